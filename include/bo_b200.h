@@ -1,0 +1,136 @@
+/*
+ * bo_b200.h -- C ABI of libbo_b200.so: the sm_100a GP Bayesian-optimisation
+ * inner loop that sits *under* pybo's pure-Python plugin surface.
+ *
+ * The reference (mwhoffman/pybo) has no FFI of its own: its policies call a
+ * duck-typed `model` object (the absent `reggie` package).  Each entry point
+ * below therefore cites the reference CALL SITE whose arithmetic it replaces.
+ * All matrices are C-contiguous row-major float64.  Pointers are host pointers
+ * unless the call's `flags` says BO_PTR_DEVICE.  Every function returns an int
+ * status (BO_OK == 0) and never throws; bo_last_error() gives the message.
+ * One host thread per handle; one CUDA stream per handle.
+ */
+#ifndef BO_B200_H
+#define BO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* status codes */
+#define BO_OK 0
+#define BO_ERR_CUDA 1      /* a CUDA runtime call or kernel failed            */
+#define BO_ERR_NOT_PD 2    /* Cholesky hit a non-positive pivot (LinAlgError) */
+#define BO_ERR_ARG 3       /* bad argument                                    */
+#define BO_ERR_STATE 4     /* call made before the state it needs exists      */
+
+/* kernel ids */
+#define BO_KERNEL_SE 0         /* rho exp(-D/2)                               */
+#define BO_KERNEL_MATERN52 1   /* rho (1 + r + r^2/3) exp(-r), r = sqrt(5 D)  */
+
+/* acquisition ids */
+#define BO_ACQ_MEAN 0   /* posterior mean            (recommenders.py:22-24)   */
+#define BO_ACQ_EI 1     /* model.get_improvement     (policies/simple.py:25)   */
+#define BO_ACQ_PI 2     /* model.get_tail            (policies/simple.py:39)   */
+#define BO_ACQ_UCB 3    /* mu + sqrt(beta s2)        (policies/simple.py:62-72)*/
+
+/* pointer flags */
+#define BO_PTR_HOST 0
+#define BO_PTR_DEVICE 1
+
+/* precision of the scoring contraction */
+#define BO_PREC_F64 0      /* FP64 tensor-core (DMMA) path                     */
+#define BO_PREC_OZAKI 1    /* error-bounded int8 slice emulation on tcgen05    */
+
+typedef struct bo_ctx bo_ctx;
+
+/* ---- lifetime ----------------------------------------------------------- */
+int bo_create(int device, bo_ctx **out);
+int bo_destroy(bo_ctx *ctx);
+const char *bo_last_error(const bo_ctx *ctx);
+/* cudaStream_t of the handle (as void*), so callers can time on it. */
+void *bo_stream(bo_ctx *ctx);
+int bo_sync(bo_ctx *ctx);
+int bo_device_props(bo_ctx *ctx, int *sm_count, int *cc_major, int *cc_minor,
+                    size_t *l2_bytes, size_t *hbm_bytes);
+
+/* ---- fit: what `model.add_data` implies (bayesopt.py:114,258,269) --------
+ * For each of S hyper-samples s (S == 1: plain GP; S > 1: the MCMC mixture of
+ * bayesopt.py:115):  K_s = k_s(X,X) + sn2_s I;  L_s = chol(K_s);
+ * alpha_s = L_s^-1 (y - bias_s); also W_s = L_s^-1 (used by the scoring
+ * contraction), beta_s = L_s^-T alpha_s and log|L_s|.
+ * X: n x d, y: n, ell: S x d, rho/sn2/bias: S.  Returns BO_ERR_NOT_PD if any
+ * factorisation fails (bo_fit_info gives sample and pivot). */
+int bo_fit(bo_ctx *ctx, int kernel, int n, int d, int S, const double *X,
+           const double *y, const double *ell, const double *rho,
+           const double *sn2, const double *bias);
+int bo_fit_shape(bo_ctx *ctx, int *kernel, int *n, int *d, int *S);
+int bo_fit_info(bo_ctx *ctx, int *info /* S */);
+/* log marginal likelihood of each hyper-sample (what every MCMC step costs) */
+int bo_loglik(bo_ctx *ctx, double *out /* S */);
+/* factor read-back, for parity tests: which = 0 L, 1 W=L^-1, 2 alpha, 3 beta */
+int bo_get_factor(bo_ctx *ctx, int s, int which, double *out);
+
+/* ---- the hot call: `finit = f(xgrid, grad=False)` (solvers/lbfgs.py:50) ---
+ * Scores M candidates Xc (M x d) with acquisition `acq`:
+ *   param = target (EI, PI), beta (UCB), ignored (MEAN).
+ * Fused on device: cross-kernel k(X, Xc) -> V = L^-1 k -> mu, s2 -> acquisition
+ * (mixture-averaged over the S hyper-samples) -> (max, first argmax).
+ * out_val (M) and out_grad (M x d) may be NULL.  best_val/best_idx may be NULL.
+ * flags: BO_PTR_DEVICE if Xc/out_val/out_grad are device pointers. */
+int bo_score(bo_ctx *ctx, int acq, double param, int64_t M, const double *Xc,
+             int flags, double *out_val, double *out_grad, double *best_val,
+             int64_t *best_idx);
+/* model.predict(X, grad) (simple.py:21,64; recommenders.py:22,24,34):
+ * mu, s2 (M) and optionally dmu, ds2 (M x d); any output may be NULL. */
+int bo_predict(bo_ctx *ctx, int64_t M, const double *Xc, int flags, double *mu,
+               double *s2, double *dmu, double *ds2);
+/* top-k of the values of the last bo_score call, descending, ties by lowest
+ * index: replaces `argsort(finit)[::-1][:nbest]` (solvers/lbfgs.py:51). */
+int bo_topk(bo_ctx *ctx, int k, int64_t *idx, double *val);
+/* choose the precision path of the scoring contraction (default BO_PREC_F64);
+ * for BO_PREC_OZAKI `tol` is the absolute error bound on V entries relative to
+ * sqrt(rho) that picks the number of int8 slices. */
+int bo_set_precision(bo_ctx *ctx, int prec, double tol);
+
+/* ---- Thompson: `model.sample_f(n, rng).get` (policies/simple.py:48) ------
+ * ndraw weight-space posterior draws
+ *   f_r(x) = bias_r + scale_r * sum_j cos(W_r[j] . x + b_r[j]) theta_r[j]
+ * with m random Fourier features each.  The frequencies/phases may be shared
+ * by all draws (nW == 1) or be per draw (nW == ndraw).
+ * W: nW x m x d, b: nW x m, theta: ndraw x m, scale/bias: ndraw. */
+int bo_thompson_set(bo_ctx *ctx, int ndraw, int nW, int m, int d, const double *W,
+                    const double *b, const double *theta, const double *scale,
+                    const double *bias);
+/* out (ndraw x M) / out_grad (ndraw x M x d) may be NULL; best_* (ndraw, host)
+ * may be NULL.  flags: BO_PTR_DEVICE if Xc/out/out_grad are device pointers. */
+int bo_thompson_eval(bo_ctx *ctx, int64_t M, const double *Xc, int flags,
+                     double *out, double *out_grad, double *best_val,
+                     int64_t *best_idx);
+
+/* ---- stand-alone pieces (metric "Cholesky GB/s", parity tests) ----------- */
+/* In-place lower Cholesky of `batch` n x n matrices (only the lower triangle
+ * is read; the strict upper triangle of the result is zeroed). info[b] = 0 or
+ * 1-based failing pivot.  Replaces scipy.linalg.cholesky (LAPACK dpotrf). */
+int bo_cholesky(bo_ctx *ctx, int n, int batch, double *A, int flags, int *info);
+/* K = k(X,X) + sn2 I  (n x n), the Gram matrix `add_data` builds. */
+int bo_gram(bo_ctx *ctx, int kernel, int n, int d, const double *X,
+            const double *ell, double rho, double sn2, double *K, int flags);
+
+/* ---- live per-kernel timing (CUDA events on the handle's stream) --------- */
+int bo_profile_enable(bo_ctx *ctx, int on);
+int bo_profile_reset(bo_ctx *ctx);
+/* number of distinct kernels seen; then name/launch-count/total ms of each */
+int bo_profile_count(bo_ctx *ctx, int *count);
+int bo_profile_get(bo_ctx *ctx, int i, char *name, int name_cap, int64_t *launches,
+                   double *total_ms);
+/* total kernel launches issued by this handle since creation */
+int bo_launch_count(bo_ctx *ctx, int64_t *launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BO_B200_H */

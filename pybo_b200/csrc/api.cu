@@ -1,0 +1,613 @@
+// api.cu -- the extern "C" boundary declared in include/bo_b200.h.
+#include <math.h>
+#include <stdarg.h>
+
+#include <algorithm>
+
+#include "common.cuh"
+
+int bo_set_err(bo_ctx *ctx, int code, const char *fmt, ...) {
+    if (ctx) {
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(ctx->err, sizeof(ctx->err), fmt, ap);
+        va_end(ap);
+    }
+    return code;
+}
+
+#define BO_ENTER(ctx)                                              \
+    do {                                                           \
+        if (!(ctx)) return BO_ERR_ARG;                             \
+        BO_CUDA(ctx, cudaSetDevice((ctx)->device));                \
+    } while (0)
+
+static int padded_dim(int d) {
+    int dp = 2;
+    while (dp < d) dp *= 2;
+    return dp;
+}
+
+// ---------------------------------------------------------------------------
+// small utility kernels
+// ---------------------------------------------------------------------------
+__global__ void pad_identity_kernel(double *A, int n, int np) {
+    // rows/cols >= n of each np x np matrix := identity
+    const int64_t boff = (int64_t)blockIdx.z * np * np;
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.y * blockDim.y + threadIdx.y;
+    if (i >= np || j >= np) return;
+    if (i >= n || j >= n) A[boff + (int64_t)i * np + j] = (i == j) ? 1.0 : 0.0;
+}
+
+__global__ void zero_upper_kernel(double *A, int n, int64_t ld, int64_t stride) {
+    const int64_t boff = (int64_t)blockIdx.z * stride;
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.y * blockDim.y + threadIdx.y;
+    if (i < n && j < n && j > i) A[boff + (int64_t)i * ld + j] = 0.0;
+}
+
+__global__ void loglik_kernel(const double *alpha, const double *logdet, int n, int np, double *out) {
+    __shared__ double red[32];
+    const int s = blockIdx.x;
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        double a = alpha[(int64_t)s * np + i];
+        acc = fma(a, a, acc);
+    }
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        double v = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : 0.0;
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (threadIdx.x == 0) out[s] = -0.5 * v - logdet[s] - 0.5 * n * 1.8378770664093453;   // log(2 pi)
+    }
+}
+
+// ---------------------------------------------------------------------------
+// lifetime
+// ---------------------------------------------------------------------------
+extern "C" int bo_create(int device, bo_ctx **out) {
+    if (!out) return BO_ERR_ARG;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) return BO_ERR_CUDA;
+    bo_ctx *ctx = new bo_ctx();
+    ctx->device = device;
+    if (cudaSetDevice(device) != cudaSuccess || cudaGetDeviceProperties(&ctx->prop, device) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete ctx;
+        return BO_ERR_CUDA;
+    }
+    ctx->sm_count = ctx->prop.multiProcessorCount;
+    int rc = bo_linalg_init(ctx);
+    if (rc == BO_OK) rc = bo_score_init(ctx);
+    if (rc != BO_OK) {
+        fprintf(stderr, "bo_create: %s\n", ctx->err);
+        cudaStreamDestroy(ctx->stream);
+        delete ctx;
+        return rc;
+    }
+    *out = ctx;
+    return BO_OK;
+}
+
+static void free_all(bo_ctx *ctx) {
+    double **ptrs[] = {&ctx->dX, &ctx->dXs, &ctx->dY, &ctx->dInvEll, &ctx->dRho, &ctx->dSn2, &ctx->dBias,
+                       &ctx->dL, &ctx->dW, &ctx->dWT, &ctx->dDinv, &ctx->dAlpha, &ctx->dBeta, &ctx->dLogdet,
+                       &ctx->dTmp, &ctx->dKs, &ctx->dV, &ctx->dU, &ctx->dQpart, &ctx->dPpart, &ctx->dMuS,
+                       &ctx->dS2S, &ctx->dDmuS, &ctx->dDs2S, &ctx->dGpart, &ctx->dXc, &ctx->dVal,
+                       &ctx->dGradOut, &ctx->dBlkVal, &ctx->th.W, &ctx->th.b, &ctx->th.theta,
+                       &ctx->th.scale, &ctx->th.bias, &ctx->th.dBestVal};
+    for (auto p : ptrs)
+        if (*p) { cudaFree(*p); *p = nullptr; }
+    if (ctx->dInfo) { cudaFree(ctx->dInfo); ctx->dInfo = nullptr; }
+    if (ctx->dBlkIdx) { cudaFree(ctx->dBlkIdx); ctx->dBlkIdx = nullptr; }
+    if (ctx->th.dBestIdx) { cudaFree(ctx->th.dBestIdx); ctx->th.dBestIdx = nullptr; }
+    if (ctx->hPinned) { cudaFreeHost(ctx->hPinned); ctx->hPinned = nullptr; }
+}
+
+static void prof_drain(bo_ctx *ctx) {
+    for (auto &e : ctx->prof) {
+        for (auto &pr : e.pending) {
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, pr.first, pr.second) == cudaSuccess) e.total_ms += ms;
+            cudaEventDestroy(pr.first);
+            cudaEventDestroy(pr.second);
+        }
+        e.pending.clear();
+    }
+}
+
+extern "C" int bo_destroy(bo_ctx *ctx) {
+    if (!ctx) return BO_OK;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    prof_drain(ctx);
+    free_all(ctx);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return BO_OK;
+}
+
+extern "C" const char *bo_last_error(const bo_ctx *ctx) { return ctx ? ctx->err : "null handle"; }
+extern "C" void *bo_stream(bo_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+
+extern "C" int bo_sync(bo_ctx *ctx) {
+    BO_ENTER(ctx);
+    BO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return BO_OK;
+}
+
+extern "C" int bo_device_props(bo_ctx *ctx, int *sm_count, int *cc_major, int *cc_minor, size_t *l2_bytes,
+                               size_t *hbm_bytes) {
+    if (!ctx) return BO_ERR_ARG;
+    if (sm_count) *sm_count = ctx->prop.multiProcessorCount;
+    if (cc_major) *cc_major = ctx->prop.major;
+    if (cc_minor) *cc_minor = ctx->prop.minor;
+    if (l2_bytes) *l2_bytes = (size_t)ctx->prop.l2CacheSize;
+    if (hbm_bytes) *hbm_bytes = ctx->prop.totalGlobalMem;
+    return BO_OK;
+}
+
+// ---------------------------------------------------------------------------
+// fit
+// ---------------------------------------------------------------------------
+template <typename T>
+static int realloc_dev(bo_ctx *ctx, T **p, size_t count) {
+    if (*p) { BO_CUDA(ctx, cudaFree(*p)); *p = nullptr; }
+    BO_CUDA(ctx, cudaMalloc((void **)p, count * sizeof(T)));
+    return BO_OK;
+}
+
+extern "C" int bo_fit(bo_ctx *ctx, int kernel, int n, int d, int S, const double *X, const double *y,
+                      const double *ell, const double *rho, const double *sn2, const double *bias) {
+    BO_ENTER(ctx);
+    if (kernel != BO_KERNEL_SE && kernel != BO_KERNEL_MATERN52)
+        return bo_set_err(ctx, BO_ERR_ARG, "unknown kernel id %d", kernel);
+    if (n < 1 || d < 1 || d > BO_MAX_D || S < 1 || !X || !y || !ell || !rho || !sn2 || !bias)
+        return bo_set_err(ctx, BO_ERR_ARG, "bo_fit: bad shape n=%d d=%d S=%d (d <= %d)", n, d, S, BO_MAX_D);
+    for (int s = 0; s < S; ++s) {
+        if (!(rho[s] > 0.0) || !(sn2[s] >= 0.0)) return bo_set_err(ctx, BO_ERR_ARG, "bo_fit: rho must be > 0, sn2 >= 0");
+        for (int k = 0; k < d; ++k)
+            if (!(ell[s * d + k] > 0.0)) return bo_set_err(ctx, BO_ERR_ARG, "bo_fit: ell must be > 0");
+    }
+    ctx->fitted = false;
+    ctx->last_val_valid = false;
+    const int np = bo_round_up(n, BO_PAD), dp = padded_dim(d), nblk64 = np / 64;
+    const size_t mat = (size_t)S * np * np;
+    if (mat > ctx->fit_capacity) {
+        BO_TRY(realloc_dev(ctx, &ctx->dL, mat));
+        BO_TRY(realloc_dev(ctx, &ctx->dW, mat));
+        BO_TRY(realloc_dev(ctx, &ctx->dWT, mat));
+        ctx->fit_capacity = mat;
+    }
+    BO_TRY(realloc_dev(ctx, &ctx->dX, (size_t)n * d));
+    BO_TRY(realloc_dev(ctx, &ctx->dY, (size_t)n));
+    BO_TRY(realloc_dev(ctx, &ctx->dXs, (size_t)S * np * dp));
+    BO_TRY(realloc_dev(ctx, &ctx->dInvEll, (size_t)S * dp));
+    BO_TRY(realloc_dev(ctx, &ctx->dRho, (size_t)S));
+    BO_TRY(realloc_dev(ctx, &ctx->dSn2, (size_t)S));
+    BO_TRY(realloc_dev(ctx, &ctx->dBias, (size_t)S));
+    BO_TRY(realloc_dev(ctx, &ctx->dDinv, (size_t)S * nblk64 * 4096));
+    BO_TRY(realloc_dev(ctx, &ctx->dAlpha, (size_t)S * np));
+    BO_TRY(realloc_dev(ctx, &ctx->dBeta, (size_t)S * np));
+    BO_TRY(realloc_dev(ctx, &ctx->dLogdet, (size_t)S));
+    BO_TRY(realloc_dev(ctx, &ctx->dInfo, (size_t)S));
+    ctx->kernel = kernel; ctx->n = n; ctx->np = np; ctx->d = d; ctx->dp = dp; ctx->S = S;
+    ctx->h_rho.assign(rho, rho + S);
+    ctx->h_sn2.assign(sn2, sn2 + S);
+    ctx->h_bias.assign(bias, bias + S);
+    ctx->h_ell.assign(ell, ell + (size_t)S * d);
+    ctx->h_info.assign(S, 0);
+
+    // scaled, zero-padded observation coordinates per hyper-sample
+    std::vector<double> xs((size_t)S * np * dp, 0.0), inv((size_t)S * dp, 0.0);
+    for (int s = 0; s < S; ++s) {
+        for (int k = 0; k < d; ++k) inv[(size_t)s * dp + k] = 1.0 / ell[s * d + k];
+        for (int i = 0; i < n; ++i)
+            for (int k = 0; k < d; ++k)
+                xs[((size_t)s * np + i) * dp + k] = X[(size_t)i * d + k] * inv[(size_t)s * dp + k];
+    }
+    cudaStream_t st = ctx->stream;
+    BO_CUDA(ctx, cudaMemcpyAsync(ctx->dX, X, sizeof(double) * n * d, cudaMemcpyHostToDevice, st));
+    BO_CUDA(ctx, cudaMemcpyAsync(ctx->dY, y, sizeof(double) * n, cudaMemcpyHostToDevice, st));
+    BO_CUDA(ctx, cudaMemcpyAsync(ctx->dXs, xs.data(), sizeof(double) * xs.size(), cudaMemcpyHostToDevice, st));
+    BO_CUDA(ctx, cudaMemcpyAsync(ctx->dInvEll, inv.data(), sizeof(double) * inv.size(), cudaMemcpyHostToDevice, st));
+    BO_CUDA(ctx, cudaMemcpyAsync(ctx->dRho, rho, sizeof(double) * S, cudaMemcpyHostToDevice, st));
+    BO_CUDA(ctx, cudaMemcpyAsync(ctx->dSn2, sn2, sizeof(double) * S, cudaMemcpyHostToDevice, st));
+    BO_CUDA(ctx, cudaMemcpyAsync(ctx->dBias, bias, sizeof(double) * S, cudaMemcpyHostToDevice, st));
+    BO_CUDA(ctx, cudaStreamSynchronize(st));   // host staging vectors go out of scope below
+
+    BO_TRY(bo_linalg_gram(ctx, kernel, n, np, dp, S, ctx->dXs, ctx->dRho, ctx->dSn2, ctx->dL));
+    BO_TRY(bo_linalg_cholesky(ctx, np, S, ctx->dL, ctx->dDinv, ctx->dInfo));
+    BO_CUDA(ctx, cudaMemcpyAsync(ctx->h_info.data(), ctx->dInfo, sizeof(int) * S, cudaMemcpyDeviceToHost, st));
+    BO_CUDA(ctx, cudaStreamSynchronize(st));
+    for (int s = 0; s < S; ++s)
+        if (ctx->h_info[s] != 0)
+            return bo_set_err(ctx, BO_ERR_NOT_PD, "Cholesky failed: hyper-sample %d, leading minor %d is not positive definite",
+                              s, ctx->h_info[s]);
+    BO_TRY(bo_linalg_trtri(ctx, np, S, ctx->dL, ctx->dDinv, ctx->dW, ctx->dWT /* scratch */));
+    BO_TRY(bo_linalg_transpose(ctx, np, S, ctx->dW, ctx->dWT));
+    BO_TRY(bo_linalg_finish_fit(ctx));
+    BO_CUDA(ctx, cudaStreamSynchronize(st));
+
+    int64_t chunk = ((int64_t)1 << 25) / np / 128 * 128;
+    ctx->chunk = std::min<int64_t>(16384, std::max<int64_t>(1024, chunk));
+    ctx->fitted = true;
+    return BO_OK;
+}
+
+extern "C" int bo_fit_shape(bo_ctx *ctx, int *kernel, int *n, int *d, int *S) {
+    if (!ctx) return BO_ERR_ARG;
+    if (!ctx->fitted) return bo_set_err(ctx, BO_ERR_STATE, "not fitted");
+    if (kernel) *kernel = ctx->kernel;
+    if (n) *n = ctx->n;
+    if (d) *d = ctx->d;
+    if (S) *S = ctx->S;
+    return BO_OK;
+}
+
+extern "C" int bo_fit_info(bo_ctx *ctx, int *info) {
+    if (!ctx || !info) return BO_ERR_ARG;
+    for (size_t s = 0; s < ctx->h_info.size(); ++s) info[s] = ctx->h_info[s];
+    return BO_OK;
+}
+
+extern "C" int bo_loglik(bo_ctx *ctx, double *out) {
+    BO_ENTER(ctx);
+    if (!ctx->fitted) return bo_set_err(ctx, BO_ERR_STATE, "bo_loglik before bo_fit");
+    double *dOut = nullptr;
+    BO_CUDA(ctx, cudaMalloc(&dOut, sizeof(double) * ctx->S));
+    {
+        BO_LAUNCH(ctx, "loglik_kernel");
+        loglik_kernel<<<ctx->S, 256, 0, ctx->stream>>>(ctx->dAlpha, ctx->dLogdet, ctx->n, ctx->np, dOut);
+    }
+    cudaError_t e = cudaMemcpyAsync(out, dOut, sizeof(double) * ctx->S, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(dOut);
+    if (e != cudaSuccess) return bo_set_err(ctx, BO_ERR_CUDA, "bo_loglik: %s", cudaGetErrorString(e));
+    return BO_OK;
+}
+
+extern "C" int bo_get_factor(bo_ctx *ctx, int s, int which, double *out) {
+    BO_ENTER(ctx);
+    if (!ctx->fitted) return bo_set_err(ctx, BO_ERR_STATE, "bo_get_factor before bo_fit");
+    if (s < 0 || s >= ctx->S || !out) return bo_set_err(ctx, BO_ERR_ARG, "bo_get_factor: bad sample index");
+    const int n = ctx->n, np = ctx->np;
+    if (which == 0 || which == 1) {
+        const double *src = (which == 0 ? ctx->dL : ctx->dW) + (size_t)s * np * np;
+        BO_CUDA(ctx, cudaMemcpy2DAsync(out, sizeof(double) * n, src, sizeof(double) * np, sizeof(double) * n, n,
+                                       cudaMemcpyDeviceToHost, ctx->stream));
+        BO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        for (int i = 0; i < n; ++i)
+            for (int j = i + 1; j < n; ++j) out[(size_t)i * n + j] = 0.0;
+    } else if (which == 2 || which == 3) {
+        const double *src = (which == 2 ? ctx->dAlpha : ctx->dBeta) + (size_t)s * np;
+        BO_CUDA(ctx, cudaMemcpyAsync(out, src, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
+        BO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    } else {
+        return bo_set_err(ctx, BO_ERR_ARG, "bo_get_factor: which must be 0..3");
+    }
+    return BO_OK;
+}
+
+// ---------------------------------------------------------------------------
+// scoring / prediction
+// ---------------------------------------------------------------------------
+static int stage_candidates(bo_ctx *ctx, int64_t M, const double *Xc, int flags, const double **dXc) {
+    if (flags & BO_PTR_DEVICE) {
+        *dXc = Xc;
+        return BO_OK;
+    }
+    BO_TRY(bo_reserve(ctx, &ctx->dXc, &ctx->xc_capacity, (size_t)M * ctx->d));
+    BO_CUDA(ctx, cudaMemcpyAsync(ctx->dXc, Xc, sizeof(double) * M * ctx->d, cudaMemcpyHostToDevice, ctx->stream));
+    *dXc = ctx->dXc;
+    return BO_OK;
+}
+
+extern "C" int bo_score(bo_ctx *ctx, int acq, double param, int64_t M, const double *Xc, int flags,
+                        double *out_val, double *out_grad, double *best_val, int64_t *best_idx) {
+    BO_ENTER(ctx);
+    if (!ctx->fitted) return bo_set_err(ctx, BO_ERR_STATE, "bo_score before bo_fit");
+    if (acq < BO_ACQ_MEAN || acq > BO_ACQ_UCB) return bo_set_err(ctx, BO_ERR_ARG, "unknown acquisition id %d", acq);
+    if (M <= 0 || !Xc) return bo_set_err(ctx, BO_ERR_ARG, "bo_score: need M > 0 candidates");
+    const bool dev = flags & BO_PTR_DEVICE;
+    ScoreRequest rq;
+    rq.mode = 0; rq.acq = acq; rq.param = param; rq.M = M;
+    BO_TRY(stage_candidates(ctx, M, Xc, flags, &rq.dXc));
+    if (dev && out_val) {
+        rq.dVal = out_val;
+    } else {
+        BO_TRY(bo_reserve(ctx, &ctx->dVal, &ctx->val_capacity, (size_t)M));
+        rq.dVal = ctx->dVal;
+    }
+    if (out_grad) {
+        if (dev) rq.dGrad = out_grad;
+        else {
+            BO_TRY(bo_reserve(ctx, &ctx->dGradOut, &ctx->gradout_capacity, (size_t)M * ctx->d));
+            rq.dGrad = ctx->dGradOut;
+        }
+    }
+    rq.want_best = (best_val != nullptr) || (best_idx != nullptr);
+    BO_TRY(bo_score_run(ctx, rq));
+    ctx->last_val_ptr = rq.dVal;
+    ctx->last_M = M;
+    ctx->last_val_valid = true;
+    cudaStream_t st = ctx->stream;
+    if (!dev && out_val)
+        BO_CUDA(ctx, cudaMemcpyAsync(out_val, rq.dVal, sizeof(double) * M, cudaMemcpyDeviceToHost, st));
+    if (!dev && out_grad)
+        BO_CUDA(ctx, cudaMemcpyAsync(out_grad, rq.dGrad, sizeof(double) * M * ctx->d, cudaMemcpyDeviceToHost, st));
+    double bv = 0.0;
+    int64_t bi = -1;
+    if (rq.want_best) {
+        BO_CUDA(ctx, cudaMemcpyAsync(&bv, ctx->dBlkVal + ctx->blk_capacity - 1, sizeof(double), cudaMemcpyDeviceToHost, st));
+        BO_CUDA(ctx, cudaMemcpyAsync(&bi, ctx->dBlkIdx + ctx->blk_capacity - 1, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    }
+    if (!dev || rq.want_best) BO_CUDA(ctx, cudaStreamSynchronize(st));
+    if (best_val) *best_val = bv;
+    if (best_idx) *best_idx = (bi == INT64_MAX) ? 0 : bi;
+    return BO_OK;
+}
+
+extern "C" int bo_predict(bo_ctx *ctx, int64_t M, const double *Xc, int flags, double *mu, double *s2,
+                          double *dmu, double *ds2) {
+    BO_ENTER(ctx);
+    if (!ctx->fitted) return bo_set_err(ctx, BO_ERR_STATE, "bo_predict before bo_fit");
+    if (M <= 0 || !Xc) return bo_set_err(ctx, BO_ERR_ARG, "bo_predict: need M > 0 points");
+    const bool dev = flags & BO_PTR_DEVICE;
+    const int d = ctx->d;
+    ScoreRequest rq;
+    rq.mode = 1; rq.M = M;
+    BO_TRY(stage_candidates(ctx, M, Xc, flags, &rq.dXc));
+    double *scratch = nullptr;
+    if (dev) {
+        rq.dMu = mu; rq.dS2 = s2; rq.dDmu = dmu; rq.dDs2 = ds2;
+    } else {
+        BO_CUDA(ctx, cudaMalloc(&scratch, sizeof(double) * M * (2 + 2 * (size_t)d)));
+        rq.dMu = scratch;
+        rq.dS2 = scratch + M;
+        if (dmu || ds2) {
+            rq.dDmu = scratch + 2 * M;
+            rq.dDs2 = scratch + 2 * M + M * d;
+        }
+    }
+    int rc = bo_score_run(ctx, rq);
+    cudaError_t e = cudaSuccess;
+    if (rc == BO_OK && !dev) {
+        cudaStream_t st = ctx->stream;
+        if (mu) e = cudaMemcpyAsync(mu, rq.dMu, sizeof(double) * M, cudaMemcpyDeviceToHost, st);
+        if (s2 && e == cudaSuccess) e = cudaMemcpyAsync(s2, rq.dS2, sizeof(double) * M, cudaMemcpyDeviceToHost, st);
+        if (dmu && e == cudaSuccess) e = cudaMemcpyAsync(dmu, rq.dDmu, sizeof(double) * M * d, cudaMemcpyDeviceToHost, st);
+        if (ds2 && e == cudaSuccess) e = cudaMemcpyAsync(ds2, rq.dDs2, sizeof(double) * M * d, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    }
+    if (scratch) {
+        cudaStreamSynchronize(ctx->stream);
+        cudaFree(scratch);
+    }
+    if (rc != BO_OK) return rc;
+    if (e != cudaSuccess) return bo_set_err(ctx, BO_ERR_CUDA, "bo_predict: %s", cudaGetErrorString(e));
+    return BO_OK;
+}
+
+extern "C" int bo_topk(bo_ctx *ctx, int k, int64_t *idx, double *val) {
+    BO_ENTER(ctx);
+    if (!ctx->last_val_valid) return bo_set_err(ctx, BO_ERR_STATE, "bo_topk before bo_score");
+    if (k < 1 || k > 4096 || !idx) return bo_set_err(ctx, BO_ERR_ARG, "bo_topk: need 1 <= k <= 4096");
+    if (k > ctx->last_M) k = (int)ctx->last_M;
+    std::vector<double> hv(k);
+    BO_TRY(bo_topk_run(ctx, ctx->last_val_ptr, ctx->last_M, k, hv.data(), idx));
+    if (val) std::copy(hv.begin(), hv.end(), val);
+    return BO_OK;
+}
+
+extern "C" int bo_set_precision(bo_ctx *ctx, int prec, double tol) {
+    if (!ctx) return BO_ERR_ARG;
+    if (prec != BO_PREC_F64) return bo_set_err(ctx, BO_ERR_ARG, "precision path %d is not available in this build", prec);
+    ctx->prec = prec;
+    ctx->prec_tol = tol;
+    return BO_OK;
+}
+
+// ---------------------------------------------------------------------------
+// Thompson
+// ---------------------------------------------------------------------------
+extern "C" int bo_thompson_set(bo_ctx *ctx, int ndraw, int nW, int m, int d, const double *W, const double *b,
+                               const double *theta, const double *scale, const double *bias) {
+    BO_ENTER(ctx);
+    if (ndraw < 1 || m < 1 || d < 1 || d > BO_MAX_D || (nW != 1 && nW != ndraw) || !W || !b || !theta || !scale || !bias)
+        return bo_set_err(ctx, BO_ERR_ARG, "bo_thompson_set: bad shape ndraw=%d nW=%d m=%d d=%d", ndraw, nW, m, d);
+    bo_thompson_state &th = ctx->th;
+    BO_TRY(realloc_dev(ctx, &th.W, (size_t)nW * m * d));
+    BO_TRY(realloc_dev(ctx, &th.b, (size_t)nW * m));
+    BO_TRY(realloc_dev(ctx, &th.theta, (size_t)ndraw * m));
+    BO_TRY(realloc_dev(ctx, &th.scale, (size_t)ndraw));
+    BO_TRY(realloc_dev(ctx, &th.bias, (size_t)ndraw));
+    BO_TRY(realloc_dev(ctx, &th.dBestVal, (size_t)ndraw));
+    BO_TRY(realloc_dev(ctx, &th.dBestIdx, (size_t)ndraw));
+    cudaStream_t st = ctx->stream;
+    BO_CUDA(ctx, cudaMemcpyAsync(th.W, W, sizeof(double) * nW * m * d, cudaMemcpyHostToDevice, st));
+    BO_CUDA(ctx, cudaMemcpyAsync(th.b, b, sizeof(double) * nW * m, cudaMemcpyHostToDevice, st));
+    BO_CUDA(ctx, cudaMemcpyAsync(th.theta, theta, sizeof(double) * ndraw * m, cudaMemcpyHostToDevice, st));
+    BO_CUDA(ctx, cudaMemcpyAsync(th.scale, scale, sizeof(double) * ndraw, cudaMemcpyHostToDevice, st));
+    BO_CUDA(ctx, cudaMemcpyAsync(th.bias, bias, sizeof(double) * ndraw, cudaMemcpyHostToDevice, st));
+    BO_CUDA(ctx, cudaStreamSynchronize(st));
+    th.ndraw = ndraw; th.nW = nW; th.m = m; th.d = d;
+    return BO_OK;
+}
+
+extern "C" int bo_thompson_eval(bo_ctx *ctx, int64_t M, const double *Xc, int flags, double *out,
+                                double *out_grad, double *best_val, int64_t *best_idx) {
+    BO_ENTER(ctx);
+    bo_thompson_state &th = ctx->th;
+    if (th.ndraw == 0) return bo_set_err(ctx, BO_ERR_STATE, "bo_thompson_eval before bo_thompson_set");
+    if (M <= 0 || !Xc) return bo_set_err(ctx, BO_ERR_ARG, "bo_thompson_eval: need M > 0 points");
+    const bool dev = flags & BO_PTR_DEVICE;
+    const double *dXc = Xc;
+    if (!dev) {
+        BO_TRY(bo_reserve(ctx, &ctx->dXc, &ctx->xc_capacity, (size_t)M * th.d));
+        BO_CUDA(ctx, cudaMemcpyAsync(ctx->dXc, Xc, sizeof(double) * M * th.d, cudaMemcpyHostToDevice, ctx->stream));
+        dXc = ctx->dXc;
+    }
+    double *dOut = out, *dGrad = out_grad;
+    if (!dev && out) {
+        BO_TRY(bo_reserve(ctx, &ctx->dVal, &ctx->val_capacity, (size_t)M * th.ndraw));
+        dOut = ctx->dVal;
+    }
+    if (!dev && out_grad) {
+        BO_TRY(bo_reserve(ctx, &ctx->dGradOut, &ctx->gradout_capacity, (size_t)M * th.ndraw * th.d));
+        dGrad = ctx->dGradOut;
+    }
+    const bool want_best = best_val || best_idx;
+    BO_TRY(bo_thompson_run(ctx, M, dXc, dOut, dGrad, want_best ? th.dBestVal : nullptr,
+                           want_best ? th.dBestIdx : nullptr));
+    ctx->last_val_valid = false;
+    cudaStream_t st = ctx->stream;
+    if (!dev && out) BO_CUDA(ctx, cudaMemcpyAsync(out, dOut, sizeof(double) * M * th.ndraw, cudaMemcpyDeviceToHost, st));
+    if (!dev && out_grad)
+        BO_CUDA(ctx, cudaMemcpyAsync(out_grad, dGrad, sizeof(double) * M * th.ndraw * th.d, cudaMemcpyDeviceToHost, st));
+    std::vector<double> bv(th.ndraw);
+    std::vector<int64_t> bi(th.ndraw);
+    if (want_best) {
+        BO_CUDA(ctx, cudaMemcpyAsync(bv.data(), th.dBestVal, sizeof(double) * th.ndraw, cudaMemcpyDeviceToHost, st));
+        BO_CUDA(ctx, cudaMemcpyAsync(bi.data(), th.dBestIdx, sizeof(int64_t) * th.ndraw, cudaMemcpyDeviceToHost, st));
+    }
+    if (!dev || want_best) BO_CUDA(ctx, cudaStreamSynchronize(st));
+    if (best_val) std::copy(bv.begin(), bv.end(), best_val);
+    if (best_idx)
+        for (int r = 0; r < th.ndraw; ++r) best_idx[r] = (bi[r] == INT64_MAX) ? 0 : bi[r];
+    return BO_OK;
+}
+
+// ---------------------------------------------------------------------------
+// stand-alone Cholesky / Gram
+// ---------------------------------------------------------------------------
+extern "C" int bo_cholesky(bo_ctx *ctx, int n, int batch, double *A, int flags, int *info) {
+    BO_ENTER(ctx);
+    if (n < 1 || batch < 1 || !A) return bo_set_err(ctx, BO_ERR_ARG, "bo_cholesky: bad shape");
+    const bool dev = flags & BO_PTR_DEVICE;
+    const int np = bo_round_up(n, 64), nblk = np / 64;
+    cudaStream_t st = ctx->stream;
+    double *dA = nullptr, *dinv = nullptr;
+    int *dInfo = nullptr;
+    const bool inplace = dev && (np == n);
+    cudaError_t e = cudaMalloc(&dinv, sizeof(double) * (size_t)batch * nblk * 4096);
+    if (e == cudaSuccess) e = cudaMalloc(&dInfo, sizeof(int) * batch);
+    if (e == cudaSuccess && !inplace) e = cudaMalloc(&dA, sizeof(double) * (size_t)batch * np * np);
+    if (e != cudaSuccess) {
+        cudaFree(dinv); cudaFree(dInfo); cudaFree(dA);
+        return bo_set_err(ctx, BO_ERR_CUDA, "bo_cholesky: %s", cudaGetErrorString(e));
+    }
+    int rc = BO_OK;
+    if (inplace) {
+        dA = A;
+    } else {
+        for (int b = 0; b < batch && e == cudaSuccess; ++b)
+            e = cudaMemcpy2DAsync(dA + (size_t)b * np * np, sizeof(double) * np, A + (size_t)b * n * n,
+                                  sizeof(double) * n, sizeof(double) * n, n,
+                                  dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess && np != n) {
+            ctx->launches++;
+            pad_identity_kernel<<<dim3((np + 31) / 32, (np + 7) / 8, batch), dim3(32, 8), 0, st>>>(dA, n, np);
+        }
+    }
+    if (e == cudaSuccess) rc = bo_linalg_cholesky(ctx, np, batch, dA, dinv, dInfo);
+    if (e == cudaSuccess && rc == BO_OK) {
+        ctx->launches++;
+        zero_upper_kernel<<<dim3((np + 31) / 32, (np + 7) / 8, batch), dim3(32, 8), 0, st>>>(dA, np, np, (int64_t)np * np);
+        if (!inplace)
+            for (int b = 0; b < batch && e == cudaSuccess; ++b)
+                e = cudaMemcpy2DAsync(A + (size_t)b * n * n, sizeof(double) * n, dA + (size_t)b * np * np,
+                                      sizeof(double) * np, sizeof(double) * n, n,
+                                      dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st);
+        std::vector<int> hinfo(batch, 0);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(hinfo.data(), dInfo, sizeof(int) * batch, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        bool bad = false;
+        for (int b = 0; b < batch; ++b) {
+            if (info) info[b] = hinfo[b];
+            bad = bad || hinfo[b] != 0;
+        }
+        if (e == cudaSuccess && bad) rc = bo_set_err(ctx, BO_ERR_NOT_PD, "bo_cholesky: matrix is not positive definite");
+    }
+    cudaStreamSynchronize(st);
+    cudaFree(dinv);
+    cudaFree(dInfo);
+    if (!inplace) cudaFree(dA);
+    if (e != cudaSuccess) return bo_set_err(ctx, BO_ERR_CUDA, "bo_cholesky: %s", cudaGetErrorString(e));
+    return rc;
+}
+
+extern "C" int bo_gram(bo_ctx *ctx, int kernel, int n, int d, const double *X, const double *ell, double rho,
+                       double sn2, double *K, int flags) {
+    BO_ENTER(ctx);
+    if (n < 1 || d < 1 || d > BO_MAX_D || !X || !ell || !K) return bo_set_err(ctx, BO_ERR_ARG, "bo_gram: bad shape");
+    if (kernel != BO_KERNEL_SE && kernel != BO_KERNEL_MATERN52) return bo_set_err(ctx, BO_ERR_ARG, "unknown kernel id");
+    const bool dev = flags & BO_PTR_DEVICE;
+    const int np = bo_round_up(n, BO_PAD), dp = padded_dim(d);
+    std::vector<double> xs((size_t)np * dp, 0.0);
+    for (int i = 0; i < n; ++i)
+        for (int k = 0; k < d; ++k) xs[(size_t)i * dp + k] = X[(size_t)i * d + k] / ell[k];
+    double *dXs = nullptr, *dK = nullptr, *dHyp = nullptr;
+    double hyp[2] = {rho, sn2};
+    cudaStream_t st = ctx->stream;
+    cudaError_t e = cudaMalloc(&dXs, sizeof(double) * xs.size());
+    if (e == cudaSuccess) e = cudaMalloc(&dK, sizeof(double) * (size_t)np * np);
+    if (e == cudaSuccess) e = cudaMalloc(&dHyp, sizeof(double) * 2);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dXs, xs.data(), sizeof(double) * xs.size(), cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dHyp, hyp, sizeof(hyp), cudaMemcpyHostToDevice, st);
+    int rc = BO_OK;
+    if (e == cudaSuccess) rc = bo_linalg_gram(ctx, kernel, n, np, dp, 1, dXs, dHyp, dHyp + 1, dK);
+    if (e == cudaSuccess && rc == BO_OK)
+        e = cudaMemcpy2DAsync(K, sizeof(double) * n, dK, sizeof(double) * np, sizeof(double) * n, n,
+                              dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(dXs); cudaFree(dK); cudaFree(dHyp);
+    if (e != cudaSuccess) return bo_set_err(ctx, BO_ERR_CUDA, "bo_gram: %s", cudaGetErrorString(e));
+    return rc;
+}
+
+// ---------------------------------------------------------------------------
+// profiler
+// ---------------------------------------------------------------------------
+extern "C" int bo_profile_enable(bo_ctx *ctx, int on) {
+    if (!ctx) return BO_ERR_ARG;
+    ctx->prof_on = on != 0;
+    return BO_OK;
+}
+
+extern "C" int bo_profile_reset(bo_ctx *ctx) {
+    BO_ENTER(ctx);
+    BO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    prof_drain(ctx);
+    ctx->prof.clear();
+    return BO_OK;
+}
+
+extern "C" int bo_profile_count(bo_ctx *ctx, int *count) {
+    BO_ENTER(ctx);
+    BO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    prof_drain(ctx);
+    if (count) *count = (int)ctx->prof.size();
+    return BO_OK;
+}
+
+extern "C" int bo_profile_get(bo_ctx *ctx, int i, char *name, int name_cap, int64_t *launches, double *total_ms) {
+    if (!ctx || i < 0 || i >= (int)ctx->prof.size()) return BO_ERR_ARG;
+    if (name && name_cap > 0) {
+        strncpy(name, ctx->prof[i].name.c_str(), name_cap - 1);
+        name[name_cap - 1] = 0;
+    }
+    if (launches) *launches = ctx->prof[i].launches;
+    if (total_ms) *total_ms = ctx->prof[i].total_ms;
+    return BO_OK;
+}
+
+extern "C" int bo_launch_count(bo_ctx *ctx, int64_t *launches) {
+    if (!ctx || !launches) return BO_ERR_ARG;
+    *launches = ctx->launches;
+    return BO_OK;
+}

@@ -1,0 +1,191 @@
+// common.cuh -- handle layout, error plumbing and the live event profiler of
+// libbo_b200.so.  sm_100a only.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <string>
+#include <vector>
+
+#include "../../include/bo_b200.h"
+
+#define BO_PAD 128           // every factor dimension is padded to a multiple of this
+#define BO_NB 64             // Cholesky panel width
+#define BO_MAX_D 32          // largest supported input dimension
+
+static inline int bo_round_up(int x, int m) { return (x + m - 1) / m * m; }
+static inline int64_t bo_round_up64(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
+
+struct bo_prof_entry {
+    std::string name;
+    int64_t launches = 0;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending;
+    double total_ms = 0.0;
+};
+
+struct bo_thompson_state {
+    int ndraw = 0, nW = 0, m = 0, d = 0;
+    double *dBestVal = nullptr;
+    int64_t *dBestIdx = nullptr;
+    double *W = nullptr, *b = nullptr, *theta = nullptr, *scale = nullptr, *bias = nullptr;
+};
+
+struct bo_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    char err[512] = {0};
+    int sm_count = 0;
+    cudaDeviceProp prop;
+
+    // ---- fit state --------------------------------------------------------
+    bool fitted = false;
+    int kernel = 0, n = 0, np = 0, d = 0, dp = 0, S = 0;
+    double *dX = nullptr;       // n x d raw observations
+    double *dXs = nullptr;      // S x np x dp : X / ell_s, zero padded
+    double *dY = nullptr;       // n
+    double *dInvEll = nullptr;  // S x dp (zero padded)
+    double *dRho = nullptr, *dSn2 = nullptr, *dBias = nullptr;   // S each
+    double *dL = nullptr;       // S x np x np   Cholesky factor (lower)
+    double *dW = nullptr;       // S x np x np   W = L^-1 (lower)
+    double *dWT = nullptr;      // S x np x np   W^T (upper) -- gradient path
+    double *dDinv = nullptr;    // S x (np/64) x 64 x 64 inverted diagonal blocks
+    double *dAlpha = nullptr;   // S x np   L^-1 (y - bias)
+    double *dBeta = nullptr;    // S x np   L^-T alpha
+    double *dLogdet = nullptr;  // S        sum log diag L
+    double *dTmp = nullptr;     // S x np x np/2 scratch for the blocked inverse
+    int *dInfo = nullptr;       // S
+    std::vector<double> h_rho, h_sn2, h_bias, h_ell;
+    std::vector<int> h_info;
+    size_t fit_capacity = 0;    // S*np*np currently allocated
+
+    // ---- scoring scratch ---------------------------------------------------
+    int64_t chunk = 0;          // candidates per chunk (multiple of 128)
+    double *dKs = nullptr;      // np x chunk cross-kernel tile
+    double *dV = nullptr;       // np x chunk (gradient path)
+    double *dU = nullptr;       // np x chunk (gradient path)
+    double *dQpart = nullptr;   // (np/128) x chunk
+    double *dPpart = nullptr;   // (np/128) x chunk
+    double *dMuS = nullptr;     // S x chunk
+    double *dS2S = nullptr;     // S x chunk
+    double *dDmuS = nullptr;    // S x chunk x d
+    double *dDs2S = nullptr;    // S x chunk x d
+    double *dGpart = nullptr;   // gradient partial sums
+    size_t ks_capacity = 0, grad_capacity = 0, mom_capacity = 0, gm_capacity = 0;
+    double *dXc = nullptr;      // staged candidates (host path)
+    size_t xc_capacity = 0;
+    double *dVal = nullptr;     // M values of the last score (device resident)
+    size_t val_capacity = 0;
+    int64_t last_M = 0;
+    bool last_val_valid = false;
+    const double *last_val_ptr = nullptr;
+    double *dGradOut = nullptr;
+    size_t gradout_capacity = 0;
+    double *dBlkVal = nullptr;  // per-block argmax staging
+    int64_t *dBlkIdx = nullptr;
+    size_t blk_capacity = 0;
+    double *hPinned = nullptr;  // pinned staging for results
+    size_t pinned_capacity = 0;
+
+    int prec = BO_PREC_F64;
+    double prec_tol = 1e-9;
+
+    bo_thompson_state th;
+
+    // ---- profiler -----------------------------------------------------------
+    bool prof_on = false;
+    std::vector<bo_prof_entry> prof;
+    int64_t launches = 0;
+};
+
+int bo_set_err(bo_ctx *ctx, int code, const char *fmt, ...);
+
+#define BO_CUDA(ctx, call)                                                          \
+    do {                                                                            \
+        cudaError_t e__ = (call);                                                   \
+        if (e__ != cudaSuccess)                                                     \
+            return bo_set_err(ctx, BO_ERR_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, \
+                              #call, cudaGetErrorString(e__));                      \
+    } while (0)
+
+#define BO_TRY(expr)                \
+    do {                            \
+        int rc__ = (expr);          \
+        if (rc__ != BO_OK) return rc__; \
+    } while (0)
+
+// Ensure a device buffer holds at least `count` elements of T.
+template <typename T>
+static inline int bo_reserve(bo_ctx *ctx, T **ptr, size_t *cap, size_t count) {
+    if (*cap >= count && *ptr) return BO_OK;
+    if (*ptr) BO_CUDA(ctx, cudaFree(*ptr));
+    *ptr = nullptr;
+    *cap = 0;
+    BO_CUDA(ctx, cudaMalloc((void **)ptr, count * sizeof(T)));
+    *cap = count;
+    return BO_OK;
+}
+
+// RAII marker around one kernel launch: counts it and, when the profiler is on,
+// brackets it with events on the handle's stream.
+struct bo_launch_scope {
+    bo_ctx *ctx;
+    cudaEvent_t a = nullptr, b = nullptr;
+    int slot = -1;
+    bo_launch_scope(bo_ctx *c, const char *name) : ctx(c) {
+        ctx->launches++;
+        if (!ctx->prof_on) return;
+        for (size_t i = 0; i < ctx->prof.size(); ++i)
+            if (ctx->prof[i].name == name) slot = (int)i;
+        if (slot < 0) {
+            ctx->prof.emplace_back();
+            ctx->prof.back().name = name;
+            slot = (int)ctx->prof.size() - 1;
+        }
+        cudaEventCreate(&a);
+        cudaEventCreate(&b);
+        cudaEventRecord(a, ctx->stream);
+    }
+    ~bo_launch_scope() {
+        if (slot < 0) return;
+        cudaEventRecord(b, ctx->stream);
+        ctx->prof[slot].launches++;
+        ctx->prof[slot].pending.emplace_back(a, b);
+    }
+};
+
+#define BO_LAUNCH(ctx, name) bo_launch_scope scope__(ctx, name)
+
+#define BO_CHECK_LAUNCH(ctx)                                                     \
+    do {                                                                         \
+        cudaError_t e__ = cudaGetLastError();                                    \
+        if (e__ != cudaSuccess)                                                  \
+            return bo_set_err(ctx, BO_ERR_CUDA, "%s:%d launch -> %s", __FILE__,  \
+                              __LINE__, cudaGetErrorString(e__));                \
+    } while (0)
+
+// ---- stage entry points implemented across the .cu files -------------------
+int bo_linalg_gram(bo_ctx *ctx, int kernel, int n, int np, int dp, int S, const double *dXs,
+                   const double *rho_dev, const double *sn2_dev, double *K);
+int bo_linalg_cholesky(bo_ctx *ctx, int np, int batch, double *A, double *dinv, int *dInfo);
+int bo_linalg_trtri(bo_ctx *ctx, int np, int batch, const double *L, const double *dinv,
+                    double *W, double *tmp);
+int bo_linalg_transpose(bo_ctx *ctx, int np, int batch, const double *A, double *AT);
+int bo_linalg_finish_fit(bo_ctx *ctx);
+int bo_linalg_init(bo_ctx *ctx);
+int bo_score_init(bo_ctx *ctx);
+
+// one scoring / prediction pass over M device-resident candidates
+struct ScoreRequest {
+    int mode = 0, acq = 0;     // mode 0: acquisition, 1: predict moments
+    double param = 0.0;
+    int64_t M = 0;
+    const double *dXc = nullptr;
+    double *dVal = nullptr, *dGrad = nullptr;
+    double *dMu = nullptr, *dS2 = nullptr, *dDmu = nullptr, *dDs2 = nullptr;
+    bool want_best = false;
+};
+int bo_score_run(bo_ctx *ctx, const ScoreRequest &rq);
+int bo_topk_run(bo_ctx *ctx, const double *vals, int64_t M, int k, double *h_val, int64_t *h_idx);
+int bo_thompson_run(bo_ctx *ctx, int64_t M, const double *dXc, double *dOut, double *dGrad,
+                    double *dBestVal, int64_t *dBestIdx);

@@ -1,0 +1,418 @@
+// linalg.cu -- the fit side of the hot path (what `model.add_data` implies,
+// reference bayesopt.py:114,258,269): Gram matrix K = k(X,X) + sn2 I, blocked
+// right-looking Cholesky (64-wide panels, FP64 DMMA trailing update), blocked
+// recursive triangular inverse W = L^-1, and alpha / beta / log-det.
+#include "common.cuh"
+#include "dgemm.cuh"
+
+typedef DTile<64, 64, 32, 32, 3, true> T64NT;
+typedef DTile<64, 64, 32, 32, 3, false> T64NN;
+typedef DTile<128, 128, 64, 32, 4, true> T128NT;
+
+// ---------------------------------------------------------------------------
+// Gram matrix.  Xs is already divided by ell (zero padded to dp columns).
+// Padded rows/cols get the identity so the factor stays well defined.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ double kern_from_sqdist(int kernel, double D, double rho) {
+    if (kernel == BO_KERNEL_SE) return rho * exp(-0.5 * D);
+    double r = sqrt(5.0 * D);
+    return rho * (1.0 + r + r * r * (1.0 / 3.0)) * exp(-r);
+}
+
+__global__ void gram_kernel(int kernel, int n, int np, int dp, const double *__restrict__ Xs,
+                            const double *__restrict__ rho, const double *__restrict__ sn2,
+                            double *__restrict__ K) {
+    const int s = blockIdx.z;
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.y * blockDim.y + threadIdx.y;
+    if (i >= np || j >= np) return;
+    double v;
+    if (i < n && j < n) {
+        const double *xi = Xs + ((int64_t)s * np + i) * dp;
+        const double *xj = Xs + ((int64_t)s * np + j) * dp;
+        double D = 0.0;
+        for (int k = 0; k < dp; ++k) {
+            double t = xi[k] - xj[k];
+            D = fma(t, t, D);
+        }
+        v = kern_from_sqdist(kernel, D, rho[s]);
+        if (i == j) v += sn2[s];
+    } else {
+        v = (i == j) ? 1.0 : 0.0;
+    }
+    K[(int64_t)s * np * np + (int64_t)i * np + j] = v;
+}
+
+int bo_linalg_gram(bo_ctx *ctx, int kernel, int n, int np, int dp, int S, const double *dXs,
+                   const double *rho_dev, const double *sn2_dev, double *K) {
+    dim3 blk(32, 8), grd((np + 31) / 32, (np + 7) / 8, S);
+    BO_LAUNCH(ctx, "gram_kernel");
+    gram_kernel<<<grd, blk, 0, ctx->stream>>>(kernel, n, np, dp, dXs, rho_dev, sn2_dev, K);
+    BO_CHECK_LAUNCH(ctx);
+    return BO_OK;
+}
+
+// ---------------------------------------------------------------------------
+// 64 x 64 diagonal block: factor in shared memory (one barrier per column) and
+// invert the factor (needed by the panel solve and by W = L^-1).
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) potrf64_kernel(double *A, int ld, int64_t strideA, int kblk,
+                                                      double *dinv, int64_t strideD, int *info) {
+    extern __shared__ __align__(16) double potrf_smem[];
+    double (*a)[65] = reinterpret_cast<double (*)[65]>(potrf_smem);
+    double (*x)[65] = reinterpret_cast<double (*)[65]>(potrf_smem + 64 * 65);
+    double *invd = potrf_smem + 2 * 64 * 65;
+    __shared__ int bad;
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    double *Ab = A + blockIdx.x * strideA + (int64_t)kblk * 64 * (ld + 1);
+    double *Db = dinv + blockIdx.x * strideD + (int64_t)kblk * 4096;
+    if (tid == 0) bad = 0;
+    for (int e = tid; e < 4096; e += 256) {
+        int i = e >> 6, j = e & 63;
+        a[i][j] = (j <= i) ? Ab[(int64_t)i * ld + j] : 0.0;
+        x[i][j] = (i == j) ? 1.0 : 0.0;
+    }
+    // LDL^T-style elimination: column j is left unscaled until the end so only
+    // one barrier per column is needed.
+    for (int j = 0; j < 64; ++j) {
+        __syncthreads();
+        const double d = a[j][j];
+        if (tid == 0 && !(d > 0.0) && bad == 0) bad = j + 1;
+        const double inv = 1.0 / d;
+#pragma unroll
+        for (int ai = 0; ai < 4; ++ai) {
+            const int i = ty + 16 * ai;
+            if (i <= j) continue;
+            const double lij = a[i][j] * inv;
+#pragma unroll
+            for (int bk = 0; bk < 4; ++bk) {
+                const int k = tx + 16 * bk;
+                if (k > j && k <= i) a[i][k] -= lij * a[k][j];
+            }
+        }
+    }
+    __syncthreads();
+    if (tid < 64) invd[tid] = 1.0 / sqrt(a[tid][tid]);
+    __syncthreads();
+    // scale columns: L[i][j] = a[i][j] / sqrt(a[j][j]);  diag = sqrt(a[j][j])
+    for (int e = tid; e < 4096; e += 256) {
+        int i = e >> 6, j = e & 63;
+        double v = 0.0;
+        if (j < i) v = a[i][j] * invd[j];
+        else if (j == i) v = sqrt(a[i][i]);
+        a[i][j] = v;
+    }
+    __syncthreads();
+    for (int e = tid; e < 4096; e += 256) {
+        int i = e >> 6, j = e & 63;
+        Ab[(int64_t)i * ld + j] = a[i][j];
+    }
+    if (tid == 0 && bad != 0) atomicCAS(&info[blockIdx.x], 0, kblk * 64 + bad);
+    // forward substitution on the identity: x = L^-1 (row k scaled at the end)
+    for (int k = 0; k < 64; ++k) {
+        __syncthreads();
+        const double ik = invd[k];   // 1 / L[k][k]
+#pragma unroll
+        for (int ai = 0; ai < 4; ++ai) {
+            const int i = ty + 16 * ai;
+            if (i <= k) continue;
+            const double lik = a[i][k] * ik;
+#pragma unroll
+            for (int bc = 0; bc < 4; ++bc) {
+                const int c = tx + 16 * bc;
+                if (c <= k) x[i][c] -= lik * x[k][c];
+            }
+        }
+    }
+    __syncthreads();
+    for (int e = tid; e < 4096; e += 256) {
+        int i = e >> 6, j = e & 63;
+        Db[e] = (j <= i) ? x[i][j] * invd[i] : 0.0;
+    }
+}
+
+#define POTRF_SMEM ((2 * 64 * 65 + 64) * 8)
+
+// Lower-triangular tile enumeration for the trailing update.
+template <class T>
+__global__ void __launch_bounds__(T::NTHREADS)
+syrk_tri_kernel(double *A22, const double *P, int ld, int64_t strideA, int ntile) {
+    extern __shared__ __align__(16) double smem[];
+    // linear index -> (tm >= tn)
+    int x = blockIdx.x;
+    int tm = (int)((sqrt(8.0 * x + 1.0) - 1.0) * 0.5);
+    while ((tm + 1) * (tm + 2) / 2 <= x) ++tm;
+    while (tm * (tm + 1) / 2 > x) --tm;
+    int tn = x - tm * (tm + 1) / 2;
+    (void)ntile;
+    const double *Pb = P + blockIdx.z * strideA;
+    double *Cb = A22 + blockIdx.z * strideA;
+    const double *Ap = Pb + (int64_t)tm * T::BM * ld;
+    const double *Bp = Pb + (int64_t)tn * T::BN * ld;
+    double *C = Cb + (int64_t)tm * T::BM * ld + (int64_t)tn * T::BN;
+    double acc[T::MI][T::NI][2];
+#pragma unroll
+    for (int mi = 0; mi < T::MI; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < T::NI; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+    T::mainloop(acc, Ap, ld, Bp, ld, 0, BO_NB, smem);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int wm = warp / T::WARPS_N, wn = warp % T::WARPS_N;
+    const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+    for (int mi = 0; mi < T::MI; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < T::NI; ++ni) {
+            int r = wm * T::WM + mi * 8 + g, c = wn * T::WN + ni * 8 + 2 * t;
+            double2 *dst = reinterpret_cast<double2 *>(&C[(int64_t)r * ld + c]);
+            double2 v = *dst;
+            v.x -= acc[mi][ni][0];
+            v.y -= acc[mi][ni][1];
+            *dst = v;
+        }
+}
+
+template <class K>
+static int set_smem(bo_ctx *ctx, K kernel, int bytes) {
+    BO_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    return BO_OK;
+}
+
+// In-place lower Cholesky of `batch` padded np x np matrices (np % 64 == 0).
+int bo_linalg_cholesky(bo_ctx *ctx, int np, int batch, double *A, double *dinv, int *dInfo) {
+    const int nblk = np / BO_NB;
+    const int64_t strideA = (int64_t)np * np, strideD = (int64_t)nblk * 4096;
+    BO_CUDA(ctx, cudaMemsetAsync(dInfo, 0, sizeof(int) * batch, ctx->stream));
+    for (int k = 0; k < nblk; ++k) {
+        {
+            BO_LAUNCH(ctx, "potrf64_kernel");
+            potrf64_kernel<<<batch, 256, POTRF_SMEM, ctx->stream>>>(A, np, strideA, k, dinv, strideD, dInfo);
+            BO_CHECK_LAUNCH(ctx);
+        }
+        const int T = nblk - k - 1;
+        if (T == 0) break;
+        double *panel = A + (int64_t)(k + 1) * BO_NB * np + (int64_t)k * BO_NB;
+        {   // panel solve: L_ik = A_ik * Dinv_k^T
+            DGemmParams p = {};
+            p.A = panel; p.lda = np; p.strideA = strideA;
+            p.B = dinv + (int64_t)k * 4096; p.ldb = 64; p.strideB = strideD;
+            p.C = panel; p.ldc = np; p.strideC = strideA;
+            p.inner = batch; p.tiles_m = T; p.tiles_n = 1; p.K = BO_NB; p.krule = KR_FULL;
+            p.alpha = 1.0; p.beta = 0.0;
+            BO_LAUNCH(ctx, "chol_trsm_kernel");
+            dgemm_kernel<T64NT><<<dim3(T, 1, batch), T64NT::NTHREADS, T64NT::SMEM_BYTES, ctx->stream>>>(p);
+            BO_CHECK_LAUNCH(ctx);
+        }
+        {   // trailing update: A22 -= L21 L21^T on the lower-triangular tiles
+            double *A22 = A + (int64_t)(k + 1) * BO_NB * (np + 1);
+            const int ntile = T * (T + 1) / 2;
+            BO_LAUNCH(ctx, "chol_syrk_kernel");
+            syrk_tri_kernel<T64NT><<<dim3(ntile, 1, batch), T64NT::NTHREADS, T64NT::SMEM_BYTES, ctx->stream>>>(
+                A22, panel, np, strideA, ntile);
+            BO_CHECK_LAUNCH(ctx);
+        }
+    }
+    return BO_OK;
+}
+
+// ---------------------------------------------------------------------------
+// W = L^-1 by recursive halving over 64-blocks:  W21 = -W22 (L21 W11).
+// All nodes of one depth run in one launch; a node's block range is recovered
+// arithmetically from (depth, index) by replaying the floor-halving.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void node_range(int nblk, int depth, int idx, int &lo, int &mid, int &hi) {
+    lo = 0;
+    hi = nblk;
+    for (int l = depth - 1; l >= 0; --l) {
+        int m = (lo + hi) >> 1;
+        if ((idx >> l) & 1) lo = m; else hi = m;
+        if (hi - lo < 1) break;
+    }
+    mid = (lo + hi) >> 1;
+}
+
+// phase 0: T21 = L21 * W11  (W11 lower: k >= column block)
+// phase 1: W21 = -W22 * T21 (W22 lower: k <= row block)
+template <int PHASE>
+__global__ void __launch_bounds__(T64NN::NTHREADS)
+trtri_node_kernel(const double *L, double *W, double *Tm, int np, int nblk, int depth, int max_side) {
+    extern __shared__ __align__(16) double smem[];
+    typedef T64NN T;
+    const int node = blockIdx.y;
+    const int64_t boff = (int64_t)blockIdx.z * np * np;
+    int lo, mid, hi;
+    node_range(nblk, depth, node, lo, mid, hi);
+    if (hi - lo < 2) return;
+    const int rows = hi - mid, cols = mid - lo;
+    const int tm = blockIdx.x / max_side, tn = blockIdx.x % max_side;
+    if (tm >= rows || tn >= cols) return;
+    const double *A, *B;
+    double *C;
+    int kbeg, kend;
+    if (PHASE == 0) {
+        A = L + boff + (int64_t)(mid + tm) * 64 * np + (int64_t)lo * 64;     // L21 row tile
+        B = W + boff + (int64_t)lo * 64 * np + (int64_t)(lo + tn) * 64;       // W11 column tile
+        C = Tm + boff + (int64_t)(mid + tm) * 64 * np + (int64_t)(lo + tn) * 64;
+        kbeg = tn * 64;
+        kend = cols * 64;
+    } else {
+        A = W + boff + (int64_t)(mid + tm) * 64 * np + (int64_t)mid * 64;    // W22 row tile
+        B = Tm + boff + (int64_t)mid * 64 * np + (int64_t)(lo + tn) * 64;     // T21 column tile
+        C = W + boff + (int64_t)(mid + tm) * 64 * np + (int64_t)(lo + tn) * 64;
+        kbeg = 0;
+        kend = (tm + 1) * 64;
+    }
+    double acc[T::MI][T::NI][2];
+#pragma unroll
+    for (int mi = 0; mi < T::MI; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < T::NI; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+    T::mainloop(acc, A, np, B, np, kbeg, kend, smem);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int wm = warp / T::WARPS_N, wn = warp % T::WARPS_N;
+    const int g = lane >> 2, t = lane & 3;
+    const double sgn = (PHASE == 0) ? 1.0 : -1.0;
+#pragma unroll
+    for (int mi = 0; mi < T::MI; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < T::NI; ++ni) {
+            int r = wm * T::WM + mi * 8 + g, c = wn * T::WN + ni * 8 + 2 * t;
+            *reinterpret_cast<double2 *>(&C[(int64_t)r * np + c]) =
+                make_double2(sgn * acc[mi][ni][0], sgn * acc[mi][ni][1]);
+        }
+}
+
+__global__ void trtri_seed_kernel(const double *dinv, double *W, int np, int nblk) {
+    // W := 0 except the diagonal 64-blocks := inverted diagonal blocks
+    const int64_t boff = (int64_t)blockIdx.z * np * np;
+    const int bi = blockIdx.y, bj = blockIdx.x;
+    double *dst = W + boff + (int64_t)bi * 64 * np + (int64_t)bj * 64;
+    const double *src = dinv + ((int64_t)blockIdx.z * nblk + bi) * 4096;
+    for (int e = threadIdx.x; e < 4096; e += blockDim.x) {
+        int i = e >> 6, j = e & 63;
+        dst[(int64_t)i * np + j] = (bi == bj) ? src[e] : 0.0;
+    }
+}
+
+int bo_linalg_trtri(bo_ctx *ctx, int np, int batch, const double *L, const double *dinv,
+                    double *W, double *tmp) {
+    const int nblk = np / 64;
+    {
+        BO_LAUNCH(ctx, "trtri_seed_kernel");
+        trtri_seed_kernel<<<dim3(nblk, nblk, batch), 256, 0, ctx->stream>>>(dinv, W, np, nblk);
+        BO_CHECK_LAUNCH(ctx);
+    }
+    int depth_max = 0;
+    while ((1 << depth_max) < nblk) ++depth_max;   // leaves live at depth <= depth_max
+    for (int depth = depth_max - 1; depth >= 0; --depth) {
+        const int nodes = 1 << depth;
+        int max_side = (nblk + nodes - 1) / nodes;      // upper bound on hi - lo
+        max_side = (max_side + 1) / 2 + 1;               // upper bound on rows / cols
+        dim3 grd(max_side * max_side, nodes, batch);
+        {
+            BO_LAUNCH(ctx, "trtri_lw_kernel");
+            trtri_node_kernel<0><<<grd, T64NN::NTHREADS, T64NN::SMEM_BYTES, ctx->stream>>>(
+                L, W, tmp, np, nblk, depth, max_side);
+            BO_CHECK_LAUNCH(ctx);
+        }
+        {
+            BO_LAUNCH(ctx, "trtri_wt_kernel");
+            trtri_node_kernel<1><<<grd, T64NN::NTHREADS, T64NN::SMEM_BYTES, ctx->stream>>>(
+                L, W, tmp, np, nblk, depth, max_side);
+            BO_CHECK_LAUNCH(ctx);
+        }
+    }
+    return BO_OK;
+}
+
+// ---------------------------------------------------------------------------
+// transpose, alpha = W r, beta = W^T alpha, logdet
+// ---------------------------------------------------------------------------
+__global__ void transpose_kernel(const double *A, double *AT, int np) {
+    __shared__ double tile[32][33];
+    const int64_t boff = (int64_t)blockIdx.z * np * np;
+    int x = blockIdx.x * 32 + threadIdx.x, y0 = blockIdx.y * 32;
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) tile[r][threadIdx.x] = A[boff + (int64_t)(y0 + r) * np + x];
+    __syncthreads();
+    int xo = blockIdx.y * 32 + threadIdx.x, yo0 = blockIdx.x * 32;
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) AT[boff + (int64_t)(yo0 + r) * np + xo] = tile[threadIdx.x][r];
+}
+
+int bo_linalg_transpose(bo_ctx *ctx, int np, int batch, const double *A, double *AT) {
+    BO_LAUNCH(ctx, "transpose_kernel");
+    transpose_kernel<<<dim3(np / 32, np / 32, batch), dim3(32, 8), 0, ctx->stream>>>(A, AT, np);
+    BO_CHECK_LAUNCH(ctx);
+    return BO_OK;
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// out[s][i] = sum_{j in [jlo(i), jhi(i))} Mx[s][i][j] * (vec[s][j] - shift[s] if j < nshift)
+// mode 0: lower rows (j <= i) with r = y - bias;  mode 1: upper rows (j >= i) with alpha.
+__global__ void trimv_kernel(int mode, const double *Mx, const double *vec, const double *bias,
+                             int n, int np, double *out) {
+    const int s = blockIdx.y;
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= np) return;
+    const double *mrow = Mx + (int64_t)s * np * np + (int64_t)row * np;
+    double acc = 0.0;
+    if (mode == 0) {
+        const double b = bias[s];
+        for (int j = lane; j <= row && j < n; j += 32) acc = fma(mrow[j], vec[j] - b, acc);
+    } else {
+        const double *v = vec + (int64_t)s * np;
+        for (int j = row + lane - (row & 31); j < np; j += 32)
+            if (j >= row) acc = fma(mrow[j], v[j], acc);
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) out[(int64_t)s * np + row] = acc;
+}
+
+__global__ void logdet_kernel(const double *L, int n, int np, double *out) {
+    __shared__ double red[32];
+    const int s = blockIdx.x;
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) acc += log(L[(int64_t)s * np * np + (int64_t)i * (np + 1)]);
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        double v = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : 0.0;
+        v = warp_sum(v);
+        if (threadIdx.x == 0) out[s] = v;
+    }
+}
+
+int bo_linalg_finish_fit(bo_ctx *ctx) {
+    const int np = ctx->np, S = ctx->S;
+    {   // alpha_s = W_s (y - bias_s)
+        BO_LAUNCH(ctx, "trimv_kernel");
+        trimv_kernel<<<dim3(np / 8, S), 256, 0, ctx->stream>>>(0, ctx->dW, ctx->dY, ctx->dBias, ctx->n, np, ctx->dAlpha);
+        BO_CHECK_LAUNCH(ctx);
+    }
+    {   // beta_s = W_s^T alpha_s
+        BO_LAUNCH(ctx, "trimv_kernel");
+        trimv_kernel<<<dim3(np / 8, S), 256, 0, ctx->stream>>>(1, ctx->dWT, ctx->dAlpha, ctx->dBias, ctx->n, np, ctx->dBeta);
+        BO_CHECK_LAUNCH(ctx);
+    }
+    {
+        BO_LAUNCH(ctx, "logdet_kernel");
+        logdet_kernel<<<S, 256, 0, ctx->stream>>>(ctx->dL, ctx->n, np, ctx->dLogdet);
+        BO_CHECK_LAUNCH(ctx);
+    }
+    return BO_OK;
+}
+
+int bo_linalg_init(bo_ctx *ctx) {
+    BO_TRY(set_smem(ctx, potrf64_kernel, POTRF_SMEM));
+    BO_TRY(set_smem(ctx, dgemm_kernel<T64NT>, T64NT::SMEM_BYTES));
+    BO_TRY(set_smem(ctx, syrk_tri_kernel<T64NT>, T64NT::SMEM_BYTES));
+    BO_TRY(set_smem(ctx, trtri_node_kernel<0>, T64NN::SMEM_BYTES));
+    BO_TRY(set_smem(ctx, trtri_node_kernel<1>, T64NN::SMEM_BYTES));
+    return BO_OK;
+}

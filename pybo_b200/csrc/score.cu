@@ -1,0 +1,612 @@
+// score.cu -- the hot call `finit = f(xgrid, grad=False)` (reference
+// solvers/lbfgs.py:50) and its gradient form (lbfgs.py:56-58), i.e. what
+// model.predict / get_improvement / get_tail do for a batch of candidates
+// (policies/simple.py:21,25,39,64):
+//
+//   K* = k(X, Xc)            kstar_kernel      (SIMT fp64, exp / Matern epilogue)
+//   V  = W K*  (W = L^-1)    score_gemm_kernel (FP64 DMMA, lower-triangular K range,
+//                                               fused column reductions |v|^2, v.alpha)
+//   mu, s2 per hyper-sample  moments_kernel
+//   U  = W^T V, dmu, ds2     dgemm_kernel + grad_partial_kernel (gradient path only)
+//   acquisition + arg max    acq_kernel / argmax_final_kernel
+//
+// Candidates are processed in chunks so K* (np x chunk) stays a bounded scratch.
+#include <math.h>
+
+#include "common.cuh"
+#include "dgemm.cuh"
+
+typedef DTile<128, 128, 64, 32, 4, false> TS;   // scoring tile, B = K* stored [k][n]
+#define GRAD_SLICES 16
+#define S2_FLOOR 1e-300
+#define INV_SQRT_2PI 0.3989422804014326779
+
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// ---------------------------------------------------------------------------
+// K*[j][m] = k(x_j, xc_m); rows j >= n and columns m >= mc are written as 0.
+// ---------------------------------------------------------------------------
+#define KS_ROWS 32
+template <int DP>
+__global__ void __launch_bounds__(128)
+kstar_kernel(int kernel, int n, int d, const double *__restrict__ Xs, const double *__restrict__ invell,
+             double rho, const double *__restrict__ Xc, int64_t c0, int mc, int mcp,
+             double *__restrict__ Ks) {
+    __shared__ double xs[KS_ROWS][DP];
+    const int tid = threadIdx.x;
+    const int m = blockIdx.x * 128 + tid;
+    const int j0 = blockIdx.y * KS_ROWS;
+    for (int e = tid; e < KS_ROWS * DP; e += 128) xs[e / DP][e % DP] = Xs[(int64_t)j0 * DP + e];
+    double xc[DP];
+    const bool live = m < mc;
+#pragma unroll
+    for (int k = 0; k < DP; ++k) xc[k] = (live && k < d) ? Xc[(c0 + m) * d + k] * invell[k] : 0.0;
+    __syncthreads();
+#pragma unroll 4
+    for (int r = 0; r < KS_ROWS; ++r) {
+        double D = 0.0;
+#pragma unroll
+        for (int k = 0; k < DP; ++k) {
+            double t = xc[k] - xs[r][k];
+            D = fma(t, t, D);
+        }
+        double v;
+        if (kernel == BO_KERNEL_SE) {
+            v = rho * exp(-0.5 * D);
+        } else {
+            double rr = sqrt(5.0 * D);
+            v = rho * (1.0 + rr + rr * rr * (1.0 / 3.0)) * exp(-rr);
+        }
+        if (!live || (j0 + r) >= n) v = 0.0;
+        Ks[(int64_t)(j0 + r) * mcp + m] = v;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// V = W K* on 128 x 128 tiles, k restricted to the lower triangle of W, with the
+// column reductions q = sum_rows v^2 and p = sum_rows v alpha fused in.
+// Tiles are issued heaviest (largest row block) first.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(TS::NTHREADS, 1)
+score_gemm_kernel(const double *__restrict__ W, int np, const double *__restrict__ Ks, int mcp,
+                  const double *__restrict__ alpha, double *__restrict__ qpart,
+                  double *__restrict__ ppart, double *__restrict__ Vout) {
+    extern __shared__ __align__(16) double smem[];
+    __shared__ double red[2][2][128];
+    typedef TS T;
+    const int ctiles = mcp / 128, nblk = np / 128;
+    const int rb = nblk - 1 - (int)(blockIdx.x / ctiles);
+    const int ct = blockIdx.x % ctiles;
+    const double *A = W + (int64_t)rb * 128 * np;
+    const double *B = Ks + (int64_t)ct * 128;
+    double acc[T::MI][T::NI][2];
+#pragma unroll
+    for (int mi = 0; mi < T::MI; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < T::NI; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+    T::mainloop(acc, A, np, B, mcp, 0, (rb + 1) * 128, smem);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int wm = warp / T::WARPS_N, wn = warp % T::WARPS_N;
+    const int g = lane >> 2, t = lane & 3;
+    const double *al = alpha + rb * 128 + wm * T::WM;
+    double qs[T::NI][2], ps[T::NI][2];
+#pragma unroll
+    for (int ni = 0; ni < T::NI; ++ni) qs[ni][0] = qs[ni][1] = ps[ni][0] = ps[ni][1] = 0.0;
+#pragma unroll
+    for (int mi = 0; mi < T::MI; ++mi) {
+        const double a_r = al[mi * 8 + g];
+#pragma unroll
+        for (int ni = 0; ni < T::NI; ++ni)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const double v = acc[mi][ni][e];
+                qs[ni][e] = fma(v, v, qs[ni][e]);
+                ps[ni][e] = fma(v, a_r, ps[ni][e]);
+            }
+    }
+#pragma unroll
+    for (int ni = 0; ni < T::NI; ++ni)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+#pragma unroll
+            for (int o = 4; o < 32; o <<= 1) {
+                qs[ni][e] += __shfl_xor_sync(0xffffffffu, qs[ni][e], o);
+                ps[ni][e] += __shfl_xor_sync(0xffffffffu, ps[ni][e], o);
+            }
+            if (g == 0) {
+                const int c = wn * T::WN + ni * 8 + 2 * t + e;
+                red[wm][0][c] = qs[ni][e];
+                red[wm][1][c] = ps[ni][e];
+            }
+        }
+    __syncthreads();
+    if (tid < 128) {
+        const int64_t o = (int64_t)rb * mcp + (int64_t)ct * 128 + tid;
+        qpart[o] = red[0][0][tid] + red[1][0][tid];
+        ppart[o] = red[0][1][tid] + red[1][1][tid];
+    }
+    if (Vout != nullptr) {
+        double *C = Vout + (int64_t)rb * 128 * mcp + (int64_t)ct * 128;
+#pragma unroll
+        for (int mi = 0; mi < T::MI; ++mi)
+#pragma unroll
+            for (int ni = 0; ni < T::NI; ++ni) {
+                int r = wm * T::WM + mi * 8 + g, c = wn * T::WN + ni * 8 + 2 * t;
+                *reinterpret_cast<double2 *>(&C[(int64_t)r * mcp + c]) =
+                    make_double2(acc[mi][ni][0], acc[mi][ni][1]);
+            }
+    }
+}
+
+__global__ void moments_kernel(int nblk, int mcp, const double *__restrict__ qpart,
+                               const double *__restrict__ ppart, double rho, double bias,
+                               double *__restrict__ mu, double *__restrict__ s2) {
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= mcp) return;
+    double q = 0.0, p = 0.0;
+    for (int i = 0; i < nblk; ++i) {
+        q += qpart[(int64_t)i * mcp + m];
+        p += ppart[(int64_t)i * mcp + m];
+    }
+    mu[m] = bias + p;
+    s2[m] = rho - q;
+}
+
+// ---------------------------------------------------------------------------
+// gradient partial sums: one warp per candidate, lanes stride the observations.
+//   gm_k = sum_j g_j beta_j (xc_k - x_jk),  gs_k = sum_j g_j U_jm (xc_k - x_jk)
+// (scaled coordinates), g = -dk/dD * 2:  SE: k,  Matern-5/2: rho 5/3 (1+r) e^-r.
+// ---------------------------------------------------------------------------
+template <int DP>
+__global__ void __launch_bounds__(256)
+grad_partial_kernel(int kernel, int n, int np, int d, const double *__restrict__ Xs,
+                    const double *__restrict__ invell, double rho, const double *__restrict__ Xc,
+                    int64_t c0, int mc, int mcp, const double *__restrict__ U,
+                    const double *__restrict__ beta, double *__restrict__ gpart) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int m = blockIdx.x * 8 + warp;
+    if (m >= mc) return;
+    const int rps = np / GRAD_SLICES, j0 = blockIdx.y * rps;
+    double xc[DP], gm[DP], gs[DP];
+#pragma unroll
+    for (int k = 0; k < DP; ++k) {
+        xc[k] = (k < d) ? Xc[(c0 + m) * d + k] * invell[k] : 0.0;
+        gm[k] = gs[k] = 0.0;
+    }
+    for (int j = j0 + lane; j < j0 + rps && j < n; j += 32) {
+        double diff[DP], D = 0.0;
+#pragma unroll
+        for (int k = 0; k < DP; ++k) {
+            diff[k] = xc[k] - Xs[(int64_t)j * DP + k];
+            D = fma(diff[k], diff[k], D);
+        }
+        double gk;
+        if (kernel == BO_KERNEL_SE) {
+            gk = rho * exp(-0.5 * D);
+        } else {
+            double rr = sqrt(5.0 * D);
+            gk = rho * (5.0 / 3.0) * (1.0 + rr) * exp(-rr);
+        }
+        const double gb = gk * beta[j], gu = gk * U[(int64_t)j * mcp + m];
+#pragma unroll
+        for (int k = 0; k < DP; ++k) {
+            gm[k] = fma(gb, diff[k], gm[k]);
+            gs[k] = fma(gu, diff[k], gs[k]);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < DP; ++k) {
+        gm[k] = warp_sum_d(gm[k]);
+        gs[k] = warp_sum_d(gs[k]);
+    }
+    if (lane == 0) {
+        double *o = gpart + ((int64_t)blockIdx.y * mcp + m) * 2 * DP;
+#pragma unroll
+        for (int k = 0; k < DP; ++k) {
+            o[k] = gm[k];
+            o[DP + k] = gs[k];
+        }
+    }
+}
+
+__global__ void grad_finish_kernel(int dp, int d, int mc, int mcp, const double *__restrict__ gpart,
+                                   const double *__restrict__ invell, double *__restrict__ dmu,
+                                   double *__restrict__ ds2) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= mc * d) return;
+    const int m = e / d, k = e % d;
+    double a = 0.0, b = 0.0;
+    for (int sl = 0; sl < GRAD_SLICES; ++sl) {
+        const double *o = gpart + ((int64_t)sl * mcp + m) * 2 * dp;
+        a += o[k];
+        b += o[dp + k];
+    }
+    dmu[e] = -invell[k] * a;
+    ds2[e] = 2.0 * invell[k] * b;
+}
+
+// ---------------------------------------------------------------------------
+// acquisition epilogue over the S hyper-samples + per-block (max, first argmax)
+// ---------------------------------------------------------------------------
+struct AcqParams {
+    int mode;          // 0: acquisition value (+grad), 1: predict moments (+grad)
+    int acq;
+    double param;
+    int S, d, mc, mcp;
+    int64_t c0;
+    const double *muS, *s2S, *dmuS, *ds2S;   // S x mcp, S x mcp x d
+    double *out_val, *out_grad;              // global arrays indexed by c0 + m
+    double *out_mu, *out_s2, *out_dmu, *out_ds2;
+    double *blkval;
+    int64_t *blkidx;
+    int64_t blk0;
+};
+
+__device__ __forceinline__ bool better(double v, int64_t i, double bv, int64_t bi) {
+    return (v > bv) || (v == bv && i < bi);
+}
+
+__global__ void __launch_bounds__(256) acq_kernel(AcqParams p) {
+    const int m = blockIdx.x * 256 + threadIdx.x;
+    const bool live = m < p.mc;
+    double val = -INFINITY;
+    if (live) {
+        const int S = p.S, d = p.d;
+        const double invS = 1.0 / S;
+        const bool want_grad = (p.mode == 0) ? (p.out_grad != nullptr) : (p.out_dmu != nullptr || p.out_ds2 != nullptr);
+        const int64_t gi = p.c0 + m;
+        if (p.mode == 0 && (p.acq == BO_ACQ_EI || p.acq == BO_ACQ_PI)) {
+            // mean over hyper-samples of the per-sample EI / PI at the common target
+            double acc = 0.0;
+            for (int s = 0; s < S; ++s) {
+                const double mu = p.muS[(int64_t)s * p.mcp + m];
+                const double s2 = fmax(p.s2S[(int64_t)s * p.mcp + m], S2_FLOOR);
+                const double sd = sqrt(s2), dl = mu - p.param, z = dl / sd;
+                const double cdf = 0.5 * erfc(-z * M_SQRT1_2);
+                const double pdf = INV_SQRT_2PI * exp(-0.5 * z * z);
+                acc += (p.acq == BO_ACQ_EI) ? (dl * cdf + sd * pdf) : cdf;
+            }
+            val = acc * invS;
+            if (want_grad) {
+                for (int k = 0; k < d; ++k) {
+                    double ga = 0.0;
+                    for (int s = 0; s < S; ++s) {
+                        const double mu = p.muS[(int64_t)s * p.mcp + m];
+                        const double s2 = fmax(p.s2S[(int64_t)s * p.mcp + m], S2_FLOOR);
+                        const double sd = sqrt(s2), z = (mu - p.param) / sd;
+                        const double cdf = 0.5 * erfc(-z * M_SQRT1_2);
+                        const double pdf = INV_SQRT_2PI * exp(-0.5 * z * z);
+                        const double dm = p.dmuS[((int64_t)s * p.mcp + m) * d + k];
+                        const double dv = p.ds2S[((int64_t)s * p.mcp + m) * d + k];
+                        ga += (p.acq == BO_ACQ_EI) ? (cdf * dm + (0.5 * pdf / sd) * dv)
+                                                   : ((pdf / sd) * (dm - (0.5 * z / sd) * dv));
+                    }
+                    p.out_grad[gi * d + k] = ga * invS;
+                }
+            }
+        } else {
+            // mixture moments: mu = mean mu_s, s2 = mean (s2_s + (mu_s - mu)^2)
+            double mub = 0.0;
+            for (int s = 0; s < S; ++s) mub += p.muS[(int64_t)s * p.mcp + m];
+            mub *= invS;
+            double s2b = 0.0;
+            for (int s = 0; s < S; ++s) {
+                const double dm = p.muS[(int64_t)s * p.mcp + m] - mub;
+                s2b += p.s2S[(int64_t)s * p.mcp + m] + dm * dm;
+            }
+            s2b *= invS;
+            if (p.mode == 1) {
+                if (p.out_mu) p.out_mu[gi] = mub;
+                if (p.out_s2) p.out_s2[gi] = s2b;
+                val = mub;
+            } else if (p.acq == BO_ACQ_MEAN) {
+                val = mub;
+            } else {   // UCB, reference policies/simple.py:72
+                val = mub + sqrt(p.param * s2b);
+            }
+            if (want_grad) {
+                for (int k = 0; k < d; ++k) {
+                    double dmb = 0.0;
+                    for (int s = 0; s < S; ++s) dmb += p.dmuS[((int64_t)s * p.mcp + m) * d + k];
+                    dmb *= invS;
+                    double dsb = 0.0;
+                    for (int s = 0; s < S; ++s) {
+                        const double dm = p.muS[(int64_t)s * p.mcp + m] - mub;
+                        dsb += p.ds2S[((int64_t)s * p.mcp + m) * d + k] +
+                               2.0 * dm * (p.dmuS[((int64_t)s * p.mcp + m) * d + k] - dmb);
+                    }
+                    dsb *= invS;
+                    if (p.mode == 1) {
+                        if (p.out_dmu) p.out_dmu[gi * d + k] = dmb;
+                        if (p.out_ds2) p.out_ds2[gi * d + k] = dsb;
+                    } else if (p.acq == BO_ACQ_MEAN) {
+                        p.out_grad[gi * d + k] = dmb;
+                    } else {   // simple.py:69-70
+                        p.out_grad[gi * d + k] = dmb + 0.5 * sqrt(p.param / s2b) * dsb;
+                    }
+                }
+            }
+        }
+        if (p.mode == 0 && p.out_val) p.out_val[gi] = val;
+    }
+    if (p.blkval == nullptr) return;
+    // block arg max, ties to the lowest index, NaN never wins
+    __shared__ double sv[8];
+    __shared__ int64_t si[8];
+    double bv = live ? val : -INFINITY;
+    int64_t bi = live ? (p.c0 + m) : INT64_MAX;
+    if (bv != bv) { bv = -INFINITY; bi = INT64_MAX; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        int64_t oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
+    }
+    if ((threadIdx.x & 31) == 0) { sv[threadIdx.x >> 5] = bv; si[threadIdx.x >> 5] = bi; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; ++w)
+            if (better(sv[w], si[w], bv, bi)) { bv = sv[w]; bi = si[w]; }
+        p.blkval[p.blk0 + blockIdx.x] = bv;
+        p.blkidx[p.blk0 + blockIdx.x] = bi;
+    }
+}
+
+// single block: reduce (val, idx) pairs; writes result[0] = val, ridx[0] = idx
+__global__ void __launch_bounds__(1024)
+argmax_final_kernel(const double *__restrict__ bval, const int64_t *__restrict__ bidx, int64_t nb,
+                    double *__restrict__ rval, int64_t *__restrict__ ridx) {
+    __shared__ double sv[32];
+    __shared__ int64_t si[32];
+    double bv = -INFINITY;
+    int64_t bi = INT64_MAX;
+    for (int64_t i = threadIdx.x; i < nb; i += 1024)
+        if (better(bval[i], bidx[i], bv, bi)) { bv = bval[i]; bi = bidx[i]; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        int64_t oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
+    }
+    if ((threadIdx.x & 31) == 0) { sv[threadIdx.x >> 5] = bv; si[threadIdx.x >> 5] = bi; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 32; ++w)
+            if (better(sv[w], si[w], bv, bi)) { bv = sv[w]; bi = si[w]; }
+        rval[0] = bv;
+        ridx[0] = bi;
+    }
+}
+
+// top-k pass: arg max over entries strictly after (prev_val, prev_idx) in the
+// (value descending, index ascending) order.
+__global__ void __launch_bounds__(256)
+topk_pass_kernel(const double *__restrict__ vals, int64_t M, const double *__restrict__ prev_val,
+                 const int64_t *__restrict__ prev_idx, int first, double *__restrict__ bval,
+                 int64_t *__restrict__ bidx) {
+    __shared__ double sv[8];
+    __shared__ int64_t si[8];
+    const double pv = first ? INFINITY : prev_val[0];
+    const int64_t pi = first ? -1 : prev_idx[0];
+    double bv = -INFINITY;
+    int64_t bi = INT64_MAX;
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < M; i += (int64_t)gridDim.x * 256) {
+        const double v = vals[i];
+        if (v != v) continue;
+        const bool eligible = first || (v < pv) || (v == pv && i > pi);
+        if (eligible && better(v, i, bv, bi)) { bv = v; bi = i; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        int64_t oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
+    }
+    if ((threadIdx.x & 31) == 0) { sv[threadIdx.x >> 5] = bv; si[threadIdx.x >> 5] = bi; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; ++w)
+            if (better(sv[w], si[w], bv, bi)) { bv = sv[w]; bi = si[w]; }
+        bval[blockIdx.x] = bv;
+        bidx[blockIdx.x] = bi;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// host orchestration
+// ---------------------------------------------------------------------------
+int bo_score_init(bo_ctx *ctx) {
+    BO_CUDA(ctx, cudaFuncSetAttribute(score_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TS::SMEM_BYTES));
+    BO_CUDA(ctx, cudaFuncSetAttribute(dgemm_kernel<TS>, cudaFuncAttributeMaxDynamicSharedMemorySize, TS::SMEM_BYTES));
+    return BO_OK;
+}
+
+template <int DP>
+static int launch_kstar(bo_ctx *ctx, int s, const double *dXc, int64_t c0, int mc, int mcp) {
+    BO_LAUNCH(ctx, "kstar_kernel");
+    kstar_kernel<DP><<<dim3(mcp / 128, ctx->np / KS_ROWS), 128, 0, ctx->stream>>>(
+        ctx->kernel, ctx->n, ctx->d, ctx->dXs + (int64_t)s * ctx->np * ctx->dp, ctx->dInvEll + (int64_t)s * ctx->dp,
+        ctx->h_rho[s], dXc, c0, mc, mcp, ctx->dKs);
+    BO_CHECK_LAUNCH(ctx);
+    return BO_OK;
+}
+
+template <int DP>
+static int launch_grad_partial(bo_ctx *ctx, int s, const double *dXc, int64_t c0, int mc, int mcp) {
+    BO_LAUNCH(ctx, "grad_partial_kernel");
+    grad_partial_kernel<DP><<<dim3((mc + 7) / 8, GRAD_SLICES), 256, 0, ctx->stream>>>(
+        ctx->kernel, ctx->n, ctx->np, ctx->d, ctx->dXs + (int64_t)s * ctx->np * ctx->dp,
+        ctx->dInvEll + (int64_t)s * ctx->dp, ctx->h_rho[s], dXc, c0, mc, mcp, ctx->dU,
+        ctx->dBeta + (int64_t)s * ctx->np, ctx->dGpart);
+    BO_CHECK_LAUNCH(ctx);
+    return BO_OK;
+}
+
+#define DISPATCH_DP(ctx, fn, ...)                                             \
+    do {                                                                      \
+        switch ((ctx)->dp) {                                                  \
+            case 2: BO_TRY(fn<2>(__VA_ARGS__)); break;                        \
+            case 4: BO_TRY(fn<4>(__VA_ARGS__)); break;                        \
+            case 8: BO_TRY(fn<8>(__VA_ARGS__)); break;                        \
+            case 16: BO_TRY(fn<16>(__VA_ARGS__)); break;                      \
+            case 32: BO_TRY(fn<32>(__VA_ARGS__)); break;                      \
+            default: return bo_set_err(ctx, BO_ERR_ARG, "unsupported padded dimension %d", (ctx)->dp); \
+        }                                                                     \
+    } while (0)
+
+int bo_score_run(bo_ctx *ctx, const ScoreRequest &rq) {
+    if (!ctx->fitted) return bo_set_err(ctx, BO_ERR_STATE, "bo_score/bo_predict before bo_fit");
+    const int np = ctx->np, S = ctx->S, d = ctx->d, dp = ctx->dp, nblk = np / 128;
+    const bool grad = (rq.mode == 0) ? (rq.dGrad != nullptr) : (rq.dDmu != nullptr || rq.dDs2 != nullptr);
+    const int64_t M = rq.M;
+    if (M <= 0) return bo_set_err(ctx, BO_ERR_ARG, "M must be positive");
+    const int64_t chunk = ctx->chunk;
+    const int64_t cap = bo_round_up64(M < chunk ? M : chunk, 128);
+
+    BO_TRY(bo_reserve(ctx, &ctx->dKs, &ctx->ks_capacity, (size_t)np * cap));
+    {
+        size_t need = (size_t)nblk * cap;
+        if (ctx->mom_capacity < need || !ctx->dQpart) {
+            size_t c1 = ctx->mom_capacity, c2 = ctx->mom_capacity;
+            BO_TRY(bo_reserve(ctx, &ctx->dQpart, &c1, need));
+            BO_TRY(bo_reserve(ctx, &ctx->dPpart, &c2, need));
+            ctx->mom_capacity = need;
+        }
+        size_t needm = (size_t)S * cap;
+        if (ctx->gm_capacity < needm || !ctx->dMuS) {
+            size_t c1 = ctx->gm_capacity, c2 = ctx->gm_capacity;
+            BO_TRY(bo_reserve(ctx, &ctx->dMuS, &c1, needm));
+            BO_TRY(bo_reserve(ctx, &ctx->dS2S, &c2, needm));
+            ctx->gm_capacity = needm;
+        }
+    }
+    if (grad) {
+        size_t need = (size_t)np * cap;
+        if (ctx->grad_capacity < need || !ctx->dV) {
+            size_t c1 = ctx->grad_capacity, c2 = ctx->grad_capacity, c3 = 0, c4 = 0, c5 = 0;
+            BO_TRY(bo_reserve(ctx, &ctx->dV, &c1, need));
+            BO_TRY(bo_reserve(ctx, &ctx->dU, &c2, need));
+            if (ctx->dGpart) { cudaFree(ctx->dGpart); ctx->dGpart = nullptr; }
+            if (ctx->dDmuS) { cudaFree(ctx->dDmuS); ctx->dDmuS = nullptr; }
+            if (ctx->dDs2S) { cudaFree(ctx->dDs2S); ctx->dDs2S = nullptr; }
+            BO_TRY(bo_reserve(ctx, &ctx->dGpart, &c3, (size_t)GRAD_SLICES * cap * 2 * dp));
+            BO_TRY(bo_reserve(ctx, &ctx->dDmuS, &c4, (size_t)S * cap * d));
+            BO_TRY(bo_reserve(ctx, &ctx->dDs2S, &c5, (size_t)S * cap * d));
+            ctx->grad_capacity = need;
+        }
+    }
+    const int64_t nchunks = (M + chunk - 1) / chunk;
+    const int64_t nblocks_total = nchunks * ((chunk + 255) / 256);
+    if (rq.want_best) {
+        size_t c1 = ctx->blk_capacity, c2 = ctx->blk_capacity;
+        if (ctx->blk_capacity < (size_t)nblocks_total + 8 || !ctx->dBlkVal) {
+            BO_TRY(bo_reserve(ctx, &ctx->dBlkVal, &c1, (size_t)nblocks_total + 8));
+            BO_TRY(bo_reserve(ctx, &ctx->dBlkIdx, &c2, (size_t)nblocks_total + 8));
+            ctx->blk_capacity = (size_t)nblocks_total + 8;
+        }
+    }
+
+    int64_t blk0 = 0;
+    for (int64_t c0 = 0; c0 < M; c0 += chunk) {
+        const int mc = (int)((M - c0) < chunk ? (M - c0) : chunk);
+        const int mcp = bo_round_up(mc, 128);
+        for (int s = 0; s < S; ++s) {
+            DISPATCH_DP(ctx, launch_kstar, ctx, s, rq.dXc, c0, mc, mcp);
+            {
+                BO_LAUNCH(ctx, "score_gemm_kernel");
+                score_gemm_kernel<<<nblk * (mcp / 128), TS::NTHREADS, TS::SMEM_BYTES, ctx->stream>>>(
+                    ctx->dW + (int64_t)s * np * np, np, ctx->dKs, mcp, ctx->dAlpha + (int64_t)s * np,
+                    ctx->dQpart, ctx->dPpart, grad ? ctx->dV : nullptr);
+                BO_CHECK_LAUNCH(ctx);
+            }
+            {
+                BO_LAUNCH(ctx, "moments_kernel");
+                moments_kernel<<<(mcp + 255) / 256, 256, 0, ctx->stream>>>(
+                    nblk, mcp, ctx->dQpart, ctx->dPpart, ctx->h_rho[s], ctx->h_bias[s],
+                    ctx->dMuS + (int64_t)s * mcp, ctx->dS2S + (int64_t)s * mcp);
+                BO_CHECK_LAUNCH(ctx);
+            }
+            if (grad) {
+                {   // U = W^T V   (W^T upper triangular: k >= row block)
+                    DGemmParams p = {};
+                    p.A = ctx->dWT + (int64_t)s * np * np; p.lda = np;
+                    p.B = ctx->dV; p.ldb = mcp;
+                    p.C = ctx->dU; p.ldc = mcp;
+                    p.inner = 1; p.tiles_m = nblk; p.tiles_n = mcp / 128; p.K = np;
+                    p.krule = KR_A_UPPER; p.alpha = 1.0; p.beta = 0.0;
+                    BO_LAUNCH(ctx, "grad_gemm_kernel");
+                    dgemm_kernel<TS><<<dim3(p.tiles_m * p.tiles_n, 1, 1), TS::NTHREADS, TS::SMEM_BYTES, ctx->stream>>>(p);
+                    BO_CHECK_LAUNCH(ctx);
+                }
+                DISPATCH_DP(ctx, launch_grad_partial, ctx, s, rq.dXc, c0, mc, mcp);
+                {
+                    BO_LAUNCH(ctx, "grad_finish_kernel");
+                    grad_finish_kernel<<<(mc * d + 255) / 256, 256, 0, ctx->stream>>>(
+                        dp, d, mc, mcp, ctx->dGpart, ctx->dInvEll + (int64_t)s * dp,
+                        ctx->dDmuS + (int64_t)s * mcp * d, ctx->dDs2S + (int64_t)s * mcp * d);
+                    BO_CHECK_LAUNCH(ctx);
+                }
+            }
+        }
+        AcqParams ap = {};
+        ap.mode = rq.mode; ap.acq = rq.acq; ap.param = rq.param;
+        ap.S = S; ap.d = d; ap.mc = mc; ap.mcp = mcp; ap.c0 = c0;
+        ap.muS = ctx->dMuS; ap.s2S = ctx->dS2S; ap.dmuS = ctx->dDmuS; ap.ds2S = ctx->dDs2S;
+        ap.out_val = rq.dVal; ap.out_grad = rq.dGrad;
+        ap.out_mu = rq.dMu; ap.out_s2 = rq.dS2; ap.out_dmu = rq.dDmu; ap.out_ds2 = rq.dDs2;
+        ap.blkval = rq.want_best ? ctx->dBlkVal : nullptr;
+        ap.blkidx = rq.want_best ? ctx->dBlkIdx : nullptr;
+        ap.blk0 = blk0;
+        const int nb = (mc + 255) / 256;
+        {
+            BO_LAUNCH(ctx, "acq_kernel");
+            acq_kernel<<<nb, 256, 0, ctx->stream>>>(ap);
+            BO_CHECK_LAUNCH(ctx);
+        }
+        blk0 += nb;
+    }
+    if (rq.want_best) {
+        BO_LAUNCH(ctx, "argmax_final_kernel");
+        argmax_final_kernel<<<1, 1024, 0, ctx->stream>>>(ctx->dBlkVal, ctx->dBlkIdx, blk0,
+                                                        ctx->dBlkVal + ctx->blk_capacity - 1,
+                                                        ctx->dBlkIdx + ctx->blk_capacity - 1);
+        BO_CHECK_LAUNCH(ctx);
+    }
+    return BO_OK;
+}
+
+// top-k of a device-resident value array; results land in dBlkVal/dBlkIdx tail
+int bo_topk_run(bo_ctx *ctx, const double *vals, int64_t M, int k, double *h_val, int64_t *h_idx) {
+    const int nb = (int)((M + 255) / 256 < 592 ? (M + 255) / 256 : 592);
+    size_t need = (size_t)nb + 2 * (size_t)k + 8;
+    if (ctx->blk_capacity < need || !ctx->dBlkVal) {
+        size_t c1 = ctx->blk_capacity, c2 = ctx->blk_capacity;
+        BO_TRY(bo_reserve(ctx, &ctx->dBlkVal, &c1, need));
+        BO_TRY(bo_reserve(ctx, &ctx->dBlkIdx, &c2, need));
+        ctx->blk_capacity = need;
+    }
+    double *rv = ctx->dBlkVal + nb;
+    int64_t *ri = ctx->dBlkIdx + nb;
+    for (int j = 0; j < k; ++j) {
+        {
+            BO_LAUNCH(ctx, "topk_pass_kernel");
+            topk_pass_kernel<<<nb, 256, 0, ctx->stream>>>(vals, M, j ? rv + j - 1 : rv, j ? ri + j - 1 : ri,
+                                                         j == 0, ctx->dBlkVal, ctx->dBlkIdx);
+            BO_CHECK_LAUNCH(ctx);
+        }
+        {
+            BO_LAUNCH(ctx, "argmax_final_kernel");
+            argmax_final_kernel<<<1, 1024, 0, ctx->stream>>>(ctx->dBlkVal, ctx->dBlkIdx, nb, rv + j, ri + j);
+            BO_CHECK_LAUNCH(ctx);
+        }
+    }
+    BO_CUDA(ctx, cudaMemcpyAsync(h_val, rv, sizeof(double) * k, cudaMemcpyDeviceToHost, ctx->stream));
+    BO_CUDA(ctx, cudaMemcpyAsync(h_idx, ri, sizeof(int64_t) * k, cudaMemcpyDeviceToHost, ctx->stream));
+    BO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return BO_OK;
+}

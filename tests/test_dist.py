@@ -1,0 +1,77 @@
+"""world_size-2 gloo tests (CPU) of the multi-GPU host logic: contiguous sharding,
+the incumbent all-reduce with the first-index tie rule, and the top-k merge."""
+
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from pybo_b200 import dist as bdist
+
+
+def test_shard_range_partitions():
+    for M in (0, 1, 7, 1024, 1000003):
+        for world in (1, 2, 3, 8):
+            blocks = [bdist.shard_range(M, r, world) for r in range(world)]
+            assert blocks[0][0] == 0 and blocks[-1][1] == M
+            assert all(blocks[i][1] == blocks[i + 1][0] for i in range(world - 1))
+            sizes = [b - a for a, b in blocks]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def _worker(rank, world, port, tmpdir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        rng = np.random.RandomState(0)
+        vals = rng.randn(1001)
+        vals[[17, 600, 900]] = 7.5                      # three-way tie across both shards
+        vals[5] = np.nan
+        lo, hi = bdist.shard_range(len(vals), rank, world)
+        local = np.where(np.isnan(vals[lo:hi]), -np.inf, vals[lo:hi])
+        li = int(np.argmax(local))
+        gv, gi = bdist.reduce_incumbent(local[li], lo + li)
+        assert gv == 7.5 and gi == 17
+        # vector form: one incumbent per draw
+        draws = rng.randn(4, 1001)
+        draws[2, [3, 999]] = 9.0
+        lv = draws[:, lo:hi].max(axis=1)
+        lidx = draws[:, lo:hi].argmax(axis=1) + lo
+        gvs, gis = bdist.reduce_incumbents(lv, lidx)
+        assert np.array_equal(gis, draws.argmax(axis=1)) and np.array_equal(gvs, draws.max(axis=1))
+        # top-k merge
+        k = 10
+        order = np.lexsort((np.arange(hi - lo), -local))[:k]
+        tv, ti = bdist.gather_topk(local[order], order + lo, k)
+        clean = np.where(np.isnan(vals), -np.inf, vals)
+        ref = np.lexsort((np.arange(len(vals)), -clean))[:k]
+        assert np.array_equal(ti, ref) and np.array_equal(tv, clean[ref])
+
+        class FakeIndex(object):
+            def best_of(self, X, kk):
+                v = -np.sum((X - 0.25) ** 2, axis=1)
+                o = np.lexsort((np.arange(len(v)), -v))[:kk]
+                return o, v[o]
+        X = np.random.RandomState(1).rand(777, 3)
+        idx, val = bdist.ShardedIndex(FakeIndex()).best_of(X, 5)
+        full = -np.sum((X - 0.25) ** 2, axis=1)
+        assert np.array_equal(idx, np.argsort(-full)[:5]) and np.allclose(val, full[idx])
+        open(os.path.join(tmpdir, "ok%d" % rank), "w").close()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(180)
+def test_incumbent_allreduce_gloo_world2(tmp_path):
+    port = 29500 + (os.getpid() % 2000)
+    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert os.path.exists(tmp_path / "ok0") and os.path.exists(tmp_path / "ok1")
+
+
+def test_single_process_paths_are_identity():
+    assert bdist.reduce_incumbent(1.5, 3) == (1.5, 3)
+    v, i = bdist.gather_topk([1.0, 3.0, 3.0], [9, 4, 2], 2)
+    assert list(i) == [2, 4] and list(v) == [3.0, 3.0]
