@@ -1,0 +1,371 @@
+#!/usr/bin/env python
+"""bench.py -- acquisition evaluations per second on the BASELINE.json headline
+shape (RBF GP, n = 4096 observations, d = 8, EI over 2^20 Sobol candidates per
+GPU), plus the n = 4096 Cholesky figure the metric also names.
+
+    python bench.py --gpus N --steps K --warmup W            (our arm)
+    python bench.py --impl reference --gpus N --steps K ...   (CPU reference arm)
+
+A step is one scoring pass of the hot path (`finit = f(xgrid)`, reference
+solvers/lbfgs.py:50) over this rank's candidate block followed by the incumbent
+reduction.  `value` times that pass with the candidates already resident in HBM
+(CUDA events on the library's stream); `e2e` times the same pass through the
+public plugin API with pinned HOST candidates, host->device copy and the
+device->host read of the top-10 inside the timed region.  Prints ONE JSON line.
+"""
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # BASELINE.json metric: "acq evals/sec (n=4096 GP, d=8)"; SURVEY 8d headline
+    "rbf_n4096_d8_ei": dict(kernel="se", n=4096, d=8, acq="ei", M=1 << 20, S=1),
+    # BASELINE.json configs[1..4] (parity cases; selectable for profiling)
+    "rbf_n1024_d4_ei": dict(kernel="se", n=1024, d=4, acq="ei", M=1 << 20, S=1),
+    "matern_n4096_d8_ucb": dict(kernel="matern52", n=4096, d=8, acq="ucb", M=1 << 20, S=1),
+    "mixture32_n2048_d8_ei": dict(kernel="se", n=2048, d=8, acq="ei", M=1 << 17, S=32),
+}
+FALLBACK_PEAKS = dict(hbm_gbs=6650.0, bf16_tflops=1590.0)
+
+
+def flop_per_eval(n, d):
+    """F(n,d) = n^2 + n(3d+2) + 4n + 30 flop per acquisition evaluation."""
+    return n * n + n * (3 * d + 2) + 4 * n + 30
+
+
+def make_problem(spec, seed=0):
+    """SURVEY 8d synthetic inputs: X ~ U[0,1]^(n x d), y = sin(sum x) + 0.01 N(0,1), hypers in the
+    reference's default regime (bayesopt.py:98-102): ell = width/4, rho = range(y), sn2 = 1e-6."""
+    rng = np.random.RandomState(seed)
+    n, d, S = spec["n"], spec["d"], spec["S"]
+    X = rng.rand(n, d)
+    y = np.sin(X.sum(axis=1)) + 0.01 * rng.randn(n)
+    ell = np.tile(0.25 * np.ones(d), (S, 1))
+    rho = np.full(S, float(y.max() - y.min()))
+    sn2 = np.full(S, 1e-6)
+    bias = np.full(S, float(y.mean()))
+    if S > 1:                                   # log-normally jittered hyper-samples, seed 0
+        ell = ell * np.exp(0.1 * rng.randn(S, d))
+        rho = rho * np.exp(0.1 * rng.randn(S))
+        sn2 = sn2 * np.exp(0.3 * rng.randn(S))
+    return X, y, ell, rho, sn2, bias
+
+
+def sobol_block(M, d, start):
+    """Candidates [start, start + M) of the unscrambled Sobol sequence in [0,1]^d."""
+    import torch
+    eng = torch.quasirandom.SobolEngine(d, scramble=False)
+    if start:
+        eng.fast_forward(start)
+    return eng.draw(M, dtype=torch.float64)
+
+
+def peaks():
+    p = dict(FALLBACK_PEAKS, source="fallback")
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            m = json.load(fh)
+        p.update(hbm_gbs=float(m["hbm_gbs"]), bf16_tflops=float(m["bf16_tflops"]),
+                 bf16_tflops_sustained=float(m.get("bf16_tflops_sustained", m["bf16_tflops"])), source="measured")
+    except Exception:
+        pass
+    return p
+
+
+class ClockSampler(threading.Thread):
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        threading.Thread.__init__(self, daemon=True)
+        self.gpu_index, self.rows, self.proc = gpu_index, [], None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu_index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([c.strip() for c in line.split(",")])
+        except Exception:
+            pass
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+        self.join(timeout=2)
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+                for name, cell in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if cell.lower().startswith("active"):
+                        reasons.add(name)
+            except (ValueError, IndexError):
+                continue
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None,
+                    reasons=sorted(reasons), samples=len(sm))
+
+
+# ----------------------------------------------------------------------------------------
+def acq_param(spec, X, predict):
+    if spec["acq"] == "ucb":
+        from pybo_b200.policies import ucb_beta
+        return 3, float(ucb_beta(spec["n"]))
+    target = float(np.max(predict(X)[0]))       # policies/simple.py:21 with xi = 0
+    return 1, target
+
+
+def our_arm(args):
+    import torch
+    import torch.distributed as dist
+    from pybo_b200 import _lib, dist as bdist, models, policies
+
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world != args.gpus:
+        raise SystemExit("launch with torchrun --nproc-per-node %d for --gpus %d" % (args.gpus, args.gpus))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    spec = WORKLOADS[args.workload]
+    n, d, M, S = spec["n"], spec["d"], (args.candidates or spec["M"]), spec["S"]
+    X, y, ell, rho, sn2, bias = make_problem(spec)
+
+    # the model behind the plugin surface (replicated fit on every rank)
+    if S == 1:
+        model = models.make_gp(sn2[0], rho[0], ell[0], bias[0], kernel=spec["kernel"], device=local)
+    else:
+        model = models.MCMC.from_samples(spec["kernel"], ell, rho, sn2, bias, device=local)
+    model.add_data(X, y) if S == 1 else models._Base.add_data(model, X, y)
+    t0 = time.perf_counter()
+    ctx = model._ensure_fit()
+    ctx.sync()
+    fit_s = time.perf_counter() - t0
+    acq, param = acq_param(spec, X, model.predict)
+    index = policies.ModelIndex(model, acq, param)
+
+    xc_dev = sobol_block(M, d, rank * M).cuda()            # this rank's block, resident in HBM
+    val_dev = torch.empty(M, dtype=torch.float64, device="cuda")
+    xc_host = xc_dev.cpu().pin_memory()
+    xc_np = xc_host.numpy()
+    torch.cuda.synchronize()
+    stream = torch.cuda.ExternalStream(ctx.stream, device=local)
+
+    def step_device():
+        bv, bi = ctx.score_device(acq, param, M, xc_dev.data_ptr(), val_dev.data_ptr(), want_best=True)
+        return bdist.reduce_incumbent(bv, bi + rank * M)
+
+    def step_e2e():
+        idx, val = index.best_of(xc_np, 10)
+        return bdist.reduce_incumbent(val[0], int(idx[0]) + rank * M)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        w0 = time.perf_counter()
+        e0.record(stream)
+        out = None
+        for _ in range(steps):
+            out = fn()
+        e1.record(stream)
+        barrier()
+        wall = time.perf_counter() - w0
+        ms = e0.elapsed_time(e1)
+        t = torch.tensor([ms, wall * 1e3], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0]), float(t[1]), out
+
+    for _ in range(args.warmup):
+        step_device()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    ctx.profile(True)
+    ctx.profile_reset()
+    l0 = ctx.launch_count()
+    dev_ms, _, incumbent = timed(step_device, args.steps)
+    launches = ctx.launch_count() - l0
+    prof = ctx.profile_report()
+    ctx.profile(False)
+    clocks = sampler.stop() if sampler else None
+
+    for _ in range(max(1, args.warmup // 2)):
+        step_e2e()
+    _, e2e_ms, incumbent_e2e = timed(step_e2e, args.steps)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    pk = peaks()
+    value = M * world * args.steps / (dev_ms * 1e-3)
+    e2e_value = M * world * args.steps / (e2e_ms * 1e-3)
+
+    # roofline of the dominant kernel: the triangular contraction V = W K* (+ fused reductions)
+    gk = prof.get("score_gemm_kernel", dict(launches=0, total_ms=0.0))
+    chunk = min(M, max(1024, min(16384, ((1 << 25) // (-(-n // 128) * 128)) // 128 * 128)))
+    alg_flop_per_launch = (n * n + 4 * n) * chunk          # n^2 substitution + 4n reductions per candidate
+    avg_ms = gk["total_ms"] / max(1, gk["launches"])
+    achieved = alg_flop_per_launch / (avg_ms * 1e-3) / 1e12 if avg_ms > 0 else 0.0
+    fp64_peak = ctx.microbench("dmma")
+    dfma_peak = ctx.microbench("dfma")
+    roofline = dict(bound="tensor", kernel="score_gemm_kernel", achieved=achieved, peak=fp64_peak, unit="TFLOP/s",
+                    frac=achieved / fp64_peak if fp64_peak else None, traffic=None,
+                    peak_source="FP64 tensor-core (DMMA m8n8k4) roof measured in this run by bo_microbench; "
+                                "MEASURED_PEAKS.json holds no FP64 figure (dfma roof %.1f TFLOP/s)" % dfma_peak,
+                    frac_of_bf16_peak=achieved / pk["bf16_tflops"], bf16_peak=pk["bf16_tflops"], peaks=pk["source"],
+                    alg_flop_per_launch=alg_flop_per_launch, avg_launch_ms=avg_ms, launches=gk["launches"],
+                    share_of_step=gk["total_ms"] / dev_ms if dev_ms else None)
+
+    chol = cholesky_metric(ctx, spec, X, ell[0], rho[0], sn2[0], pk, fp64_peak)
+    cpu = cpu_baseline(spec, X, y, ell, rho, sn2, bias, budget_s=args.cpu_seconds) if world == 1 else None
+
+    line = dict(metric="acq_evals_per_sec", value=value, unit="evals/s", n_gpus=world, steps=args.steps,
+                warmup=args.warmup, ms_per_step=dev_ms / args.steps, higher_is_better=True, scaling="weak",
+                vs_baseline=None, dtype="f64", data="synthetic",
+                config=dict(workload=args.workload, kernel=spec["kernel"], n=n, d=d, acq=spec["acq"],
+                            hyper_samples=S, candidates_per_gpu=M, candidates="unscrambled Sobol, contiguous block per rank",
+                            precision="fp64 (DMMA)", l2="inputs exceed L2: W %.0f MB + K* scratch %.0f MB + candidates %.0f MB per pass"
+                            % (n * n * 8 / 1e6, n * chunk * 8 / 1e6, M * d * 8 / 1e6), parallelism="dp%d candidate shards" % world),
+                clocks=clocks,
+                e2e=dict(value=e2e_value, unit="evals/s", ms_per_step=e2e_ms / args.steps,
+                         h2d_bytes_per_step=int(M * d * 8), d2h_bytes_per_step=int(10 * 16),
+                         api="policies.ModelIndex.best_of (score + device top-10) on pinned host candidates"),
+                gpu_launches=int(launches), roofline=roofline, cpu_baseline=cpu, cholesky=chol,
+                fit_seconds=fit_s, incumbent=dict(value=incumbent[0], index=incumbent[1]),
+                kernels={k: dict(launches=v["launches"], ms=round(v["total_ms"], 3)) for k, v in prof.items()})
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cholesky_metric(ctx, spec, X, ell, rho, sn2, pk, fp64_peak):
+    """The metric's second half: n x n Cholesky, algorithmic bytes n(n+1)*8 over its time."""
+    import torch
+    n = spec["n"]
+    K = torch.from_numpy(ctx.gram(spec["kernel"], X, ell, rho, sn2)).cuda()
+    work = torch.empty_like(K)
+    best = None
+    for rep in range(5):
+        work.copy_(K)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        ctx.cholesky_device(n, 1, work.data_ptr())
+        dt = time.perf_counter() - t0
+        best = dt if best is None or dt < best else best
+    gbs = n * (n + 1) * 8 / best / 1e9
+    tfl = n ** 3 / 3.0 / best / 1e12
+    return dict(n=n, ms=best * 1e3, algorithmic_bytes=n * (n + 1) * 8, gbs=gbs, frac_hbm=gbs / pk["hbm_gbs"],
+                hbm_peak_gbs=pk["hbm_gbs"], tflops=tfl, frac_fp64=tfl / fp64_peak if fp64_peak else None,
+                note="compute-bound: n^3/3 flop over n(n+1)*8 bytes = %.0f flop/B; the HBM fraction cannot approach 1 in fp64" % (n / 24.0))
+
+
+# ----------------------------------------------------------------------------------------
+def _blas_threads():
+    try:
+        from threadpoolctl import threadpool_info
+        return max([p.get("num_threads", 1) for p in threadpool_info()] or [1])
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def cpu_baseline(spec, X, y, ell, rho, sn2, bias, budget_s=12.0, batch=2048):
+    """The float64 NumPy/SciPy/LAPACK oracle (the calls the reference reaches through reggie)
+    timed on this host: scoring batches of Sobol candidates until `budget_s` is spent."""
+    from oracle import GPOracle, MixtureOracle
+    from oracle import ucb_beta, ucb_index
+    n, d, S = spec["n"], spec["d"], spec["S"]
+    gps = []
+    t0 = time.perf_counter()
+    for s in range(S):
+        g = GPOracle(sn2[s], rho[s], ell[s], bias[s], spec["kernel"])
+        g.add_data(X, y)
+        gps.append(g)
+    fit_s = time.perf_counter() - t0
+    model = gps[0] if S == 1 else MixtureOracle(gps)
+    target = float(np.max(model.predict(X[: min(n, 512)])[0]))
+    done, spent, start = 0, 0.0, 0
+    while spent < budget_s:
+        Xc = sobol_block(batch, d, start).numpy()
+        t0 = time.perf_counter()
+        if spec["acq"] == "ucb":
+            ucb_index(ucb_beta(n), *model.predict(Xc))
+        else:
+            model.get_improvement(target, Xc)
+        spent += time.perf_counter() - t0
+        done += batch
+        start += batch
+    return dict(value=done / spent, unit="evals/s", cores=_blas_threads(), kind="port",
+                sample="%d Sobol candidates in batches of %d (%.1f s) on the %s workload; fit %.1f s not counted"
+                       % (done, batch, spent, "n=%d d=%d" % (n, d), fit_s), host_cpus=os.cpu_count())
+
+
+def reference_arm(args):
+    """CPU reference arm: the reference's own path is NumPy/SciPy through `reggie`, which is absent;
+    the oracle port (same LAPACK/BLAS calls) is timed with every host thread it can use."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    spec = WORKLOADS[args.workload]
+    X, y, ell, rho, sn2, bias = make_problem(spec)
+    per_step = max(2.0, min(20.0, 60.0 / max(1, args.steps + args.warmup)))
+    for _ in range(min(args.warmup, 1)):
+        cpu_baseline(spec, X, y, ell, rho, sn2, bias, budget_s=1.0)
+    vals, t0 = [], time.perf_counter()
+    res = None
+    for _ in range(args.steps):
+        res = cpu_baseline(spec, X, y, ell, rho, sn2, bias, budget_s=per_step)
+        vals.append(res["value"])
+    value = float(np.mean(vals))
+    res["value"] = value
+    line = dict(impl="reference", metric="acq_evals_per_sec", value=value, unit="evals/s", n_gpus=args.gpus,
+                steps=args.steps, warmup=args.warmup, ms_per_step=(time.perf_counter() - t0) * 1e3 / max(1, args.steps),
+                higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64", data="synthetic",
+                config=dict(workload=args.workload, kernel=spec["kernel"], n=spec["n"], d=spec["d"], acq=spec["acq"],
+                            hyper_samples=spec["S"], candidates_per_gpu=spec["M"]),
+                cpu_baseline=res, e2e=dict(value=value, unit="evals/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+                gpu_launches=0)
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="rbf_n4096_d8_ei", choices=sorted(WORKLOADS))
+    ap.add_argument("--candidates", type=int, default=0, help="override candidates per GPU (profiling only)")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+    if args.impl == "reference":
+        reference_arm(args)
+    else:
+        our_arm(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -129,6 +129,9 @@ int bo_profile_get(bo_ctx *ctx, int i, char *name, int name_cap, int64_t *launch
                    double *total_ms);
 /* total kernel launches issued by this handle since creation */
 int bo_launch_count(bo_ctx *ctx, int64_t *launches);
+/* measured FP64 roof of this device: kind 0 = tensor-core DMMA m8n8k4,
+ * kind 1 = DFMA, both register resident on every SM; result in TFLOP/s. */
+int bo_microbench(bo_ctx *ctx, int kind, int iters, double *tflops);
 
 #ifdef __cplusplus
 }

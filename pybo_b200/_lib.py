@@ -25,7 +25,7 @@ EXPORTS = [
     "bo_thompson_set", "bo_thompson_eval",
     "bo_cholesky", "bo_gram",
     "bo_profile_enable", "bo_profile_reset", "bo_profile_count", "bo_profile_get",
-    "bo_launch_count",
+    "bo_launch_count", "bo_microbench",
 ]
 
 
@@ -66,6 +66,7 @@ def _declare(lib):
         "bo_profile_count": (i, [vp, _ip]),
         "bo_profile_get": (i, [vp, i, C.c_char_p, i, _lp, _dp]),
         "bo_launch_count": (i, [vp, _lp]),
+        "bo_microbench": (i, [vp, i, i, _dp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
@@ -294,6 +295,12 @@ class Context(object):
             self._check(self._lib.bo_profile_get(self._h, i, buf, 128, C.byref(launches), C.byref(ms)))
             out[buf.value.decode()] = dict(launches=launches.value, total_ms=ms.value)
         return out
+
+    def microbench(self, kind, iters=20000):
+        """Measured FP64 roof in TFLOP/s: kind 'dmma' (tensor core) or 'dfma'."""
+        v = C.c_double()
+        self._check(self._lib.bo_microbench(self._h, 0 if kind == "dmma" else 1, int(iters), C.byref(v)))
+        return v.value
 
     def launch_count(self):
         v = C.c_int64()

@@ -1,0 +1,338 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (ctypes), against the
+float64 oracle on identical seeded inputs and against the committed golden
+vectors.
+
+Tolerance (BASELINE.json north_star): outputs within 1e-6 relative of the
+reference path and identical arg-max index.  The metric is
+max |got - ref| / max(|ref|, floor) with floor = 1e-12 * max|ref| for mu and the
+acquisition values (conftest.rel_err).  For the predictive variance the floor is
+1e-9 * rho: s2 = rho - |v|^2 cancels to O(sn2) at the data, where two float64
+LAPACK builds already disagree at that level.
+"""
+
+import glob
+import os
+import pickle
+
+import numpy as np
+import pytest
+from scipy.stats import qmc
+
+from conftest import rel_err
+from oracle import GPOracle, MixtureOracle, FourierSampleOracle, ucb_beta, ucb_index, kernel_matrix
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-6
+
+
+def synth(n, d, kernel, seed=0, sn2=1e-6):
+    rng = np.random.RandomState(seed)
+    X = rng.rand(n, d)
+    y = np.sin(X.sum(axis=1)) + 0.01 * rng.randn(n)
+    gp = GPOracle(sn2, float(y.max() - y.min()), 0.25 * np.ones(d), float(y.mean()), kernel)
+    gp.add_data(X, y)
+    return gp
+
+
+def fit_ctx(ctx, gp):
+    ctx.fit(gp.kernel, gp.X, gp.Y, gp.ell[None], [gp.rho], [gp.sn2], [gp.bias])
+    return ctx
+
+
+def sobol(M, d):
+    return qmc.Sobol(d=d, scramble=False).random_base2(int(np.ceil(np.log2(M))))[:M]
+
+
+# ---- Gram / Cholesky / factors ------------------------------------------------
+@pytest.mark.parametrize("kernel", ["se", "matern52"])
+@pytest.mark.parametrize("n,d", [(1, 1), (37, 3), (128, 2), (300, 8), (513, 16)])
+def test_gram_matches_oracle(ctx, kernel, n, d):
+    rng = np.random.RandomState(n)
+    X, ell = rng.rand(n, d), 0.2 + 0.3 * rng.rand(d)
+    K = ctx.gram(kernel, X, ell, 1.7, 1e-3)
+    ref = kernel_matrix(kernel, X, X, ell, 1.7) + 1e-3 * np.eye(n)
+    assert rel_err(K, ref) < 1e-12
+
+
+@pytest.mark.parametrize("n", [1, 5, 64, 65, 200, 512, 1000])
+def test_cholesky_matches_lapack(ctx, n):
+    rng = np.random.RandomState(n)
+    B = rng.randn(n, n + 3)
+    A = B @ B.T + 0.5 * np.eye(n)
+    L = ctx.cholesky(A)
+    ref = np.linalg.cholesky(A)
+    assert np.all(np.triu(L, 1) == 0)
+    assert np.max(np.abs(L - ref)) < 1e-11 * np.max(np.abs(ref))
+    assert np.max(np.abs(L @ L.T - A)) < 1e-12 * np.max(np.abs(A)) * n
+
+
+def test_cholesky_batched_and_not_pd(ctx):
+    rng = np.random.RandomState(0)
+    A = np.array([(lambda B: B @ B.T + np.eye(96))(rng.randn(96, 100)) for _ in range(5)])
+    L = ctx.cholesky(A)
+    for b in range(5):
+        assert np.max(np.abs(L[b] - np.linalg.cholesky(A[b]))) < 1e-10
+    bad = np.eye(70)
+    bad[40, 40] = -1.0
+    with pytest.raises(np.linalg.LinAlgError):
+        ctx.cholesky(bad)
+
+
+@pytest.mark.parametrize("kernel,n,d", [("se", 40, 2), ("matern52", 333, 5), ("se", 1024, 4)])
+def test_fit_factors(ctx, kernel, n, d):
+    gp = synth(n, d, kernel, seed=n)
+    fit_ctx(ctx, gp)
+    L = ctx.factor("L")
+    assert np.max(np.abs(L - gp.L)) < 1e-9 * np.max(np.abs(gp.L))
+    W = ctx.factor("W")
+    assert np.max(np.abs(W @ gp.L - np.eye(n))) < 1e-7
+    assert rel_err(ctx.factor("alpha"), gp.alpha, 1e-9) < 1e-6
+    assert rel_err(ctx.factor("beta"), gp.beta, 1e-9) < 1e-5
+    ll = ctx.loglik()[0]
+    assert abs(ll - gp.loglikelihood()) < 1e-8 * abs(gp.loglikelihood())
+
+
+# ---- golden vectors --------------------------------------------------------------
+def test_golden_posterior_vectors(ctx, golden_dir):
+    files = sorted(glob.glob(os.path.join(golden_dir, "posterior_*.npz")))
+    assert files
+    for f in files:
+        g = np.load(f)
+        rho = float(g["rho"])
+        ctx.fit(str(g["kernel"]), g["X"], g["Y"], g["ell"][None], [rho], [float(g["sn2"])], [float(g["bias"])])
+        mu, s2, dmu, ds2 = ctx.predict(g["Xc"], grad=True)
+        assert rel_err(mu, g["mu"]) < TOL, f
+        assert np.max(np.abs(s2 - g["s2"]) / np.maximum(np.abs(g["s2"]), 1e-9 * rho)) < TOL, f
+        assert rel_err(dmu, g["dmu"], 1e-9) < TOL and rel_err(ds2, g["ds2"], 1e-9) < TOL, f
+        for acq, param, key, gkey in ((1, float(g["target"]), "ei", "dei"),
+                                      (2, float(g["target"]) + 0.05, "pi", "dpi"),
+                                      (3, float(g["beta"]), "ucb", "ducb")):
+            val, grad, best = ctx.score(acq, param, g["Xc"], grad=True, want_best=True)
+            assert rel_err(val, g[key], 1e-9) < TOL, (f, key)
+            assert rel_err(grad, g[gkey], 1e-9) < 10 * TOL, (f, key)
+            assert best[1] == int(np.argmax(g[key])) and best[0] == val[best[1]], (f, key)
+
+
+def test_golden_mixture_vectors(ctx, golden_dir):
+    g = np.load(os.path.join(golden_dir, "mixture_se_n150_d3_s5.npz"))
+    ctx.fit("se", g["X"], g["Y"], g["ell"], g["rho"], g["sn2"], g["bias"])
+    mu, s2, dmu, ds2 = ctx.predict(g["Xc"], grad=True)
+    assert rel_err(mu, g["mu"]) < TOL and rel_err(s2, g["s2"], 1e-9) < TOL
+    assert rel_err(dmu, g["dmu"], 1e-9) < TOL and rel_err(ds2, g["ds2"], 1e-9) < TOL
+    ei, dei, best = ctx.score(1, float(g["target"]), g["Xc"], grad=True, want_best=True)
+    assert rel_err(ei, g["ei"], 1e-9) < TOL and rel_err(dei, g["dei"], 1e-9) < 10 * TOL
+    assert best[1] == int(np.argmax(g["ei"]))
+
+
+# ---- scoring against the oracle on seeded inputs -----------------------------------
+@pytest.mark.parametrize("kernel,n,d,M", [("se", 1024, 4, 5000), ("matern52", 700, 8, 3000),
+                                          ("se", 20, 2, 1), ("se", 129, 16, 257), ("matern52", 64, 1, 130)])
+def test_scores_match_oracle(ctx, kernel, n, d, M):
+    gp = synth(n, d, kernel, seed=n + d)
+    fit_ctx(ctx, gp)
+    Xc = sobol(M, d)
+    mu, s2 = gp.predict(Xc)
+    target = float(gp.predict(gp.X)[0].max())
+    gmu, gs2 = ctx.predict(Xc)
+    assert rel_err(gmu, mu) < TOL
+    assert np.max(np.abs(gs2 - s2) / np.maximum(np.abs(s2), 1e-9 * gp.rho)) < TOL
+    for acq, ref in ((0, mu), (1, gp.get_improvement(target, Xc)), (2, gp.get_tail(target + 0.05, Xc)),
+                     (3, ucb_index(ucb_beta(n), mu, s2))):
+        val, _, best = ctx.score(acq, {0: 0.0, 1: target, 2: target + 0.05, 3: ucb_beta(n)}[acq], Xc, want_best=True)
+        assert rel_err(val, ref, 1e-9) < TOL, acq
+        assert best[1] == int(np.argmax(ref)), acq
+
+
+def test_predict_at_training_points_and_incumbent_target(ctx):
+    """policies/simple.py:21: target = max_i mu(x_i); recommenders.py:34-35."""
+    gp = synth(500, 4, "se", seed=9)
+    fit_ctx(ctx, gp)
+    mu, s2 = gp.predict(gp.X)
+    gmu, gs2 = ctx.predict(gp.X)
+    assert rel_err(gmu, mu) < TOL
+    assert np.max(np.abs(gs2 - s2)) < 1e-9 * gp.rho
+    assert int(np.argmax(gmu)) == int(np.argmax(mu))
+
+
+def test_ties_resolve_to_first_index(ctx):
+    """EI underflows to exactly 0 far from the data; arg max must be the first index."""
+    gp = GPOracle(1e-6, 1.0, [0.01, 0.01], 0.0, "se")
+    gp.add_data(np.array([[0.5, 0.5], [0.52, 0.5]]), np.array([1.0, 0.9]))
+    fit_ctx(ctx, gp)
+    Xc = np.random.RandomState(0).rand(4000, 2) * 0.2            # all far away: EI == 0
+    val, _, best = ctx.score(1, 5.0, Xc, want_best=True)
+    assert np.all(val == 0.0) and best == (0.0, 0)
+    Xc[1234] = Xc[77]
+    val, _, best = ctx.score(0, 0.0, Xc, want_best=True)
+    assert best[1] == int(np.argmax(val))
+    idx, tv = ctx.topk(10)
+    order = np.lexsort((np.arange(len(val)), -val))[:10]
+    assert np.array_equal(idx, order) and np.array_equal(tv, val[order])
+
+
+def test_topk_matches_argsort(ctx):
+    gp = synth(300, 3, "se", seed=4)
+    fit_ctx(ctx, gp)
+    Xc = sobol(20000, 3)
+    val, _, _ = ctx.score(3, ucb_beta(300), Xc)
+    idx, tv = ctx.topk(10)
+    order = np.argsort(val)[::-1][:10]                              # lbfgs.py:51
+    assert np.array_equal(idx, order) and np.array_equal(tv, val[order])
+
+
+def test_mixture_matches_oracle(ctx):
+    rng = np.random.RandomState(5)
+    base = synth(260, 4, "matern52", seed=5, sn2=1e-4)
+    gps = []
+    for _ in range(6):
+        g = GPOracle(base.sn2 * np.exp(0.3 * rng.randn()), base.rho * np.exp(0.2 * rng.randn()),
+                     base.ell * np.exp(0.2 * rng.randn(4)), base.bias + 0.05 * rng.randn(), "matern52")
+        g.add_data(base.X, base.Y)
+        gps.append(g)
+    mix = MixtureOracle(gps)
+    ctx.fit("matern52", base.X, base.Y, [g.ell for g in gps], [g.rho for g in gps], [g.sn2 for g in gps],
+            [g.bias for g in gps])
+    Xc = sobol(1500, 4)
+    mu, s2 = mix.predict(Xc)
+    target = float(mix.predict(base.X)[0].max())
+    gmu, gs2 = ctx.predict(Xc)
+    assert rel_err(gmu, mu) < TOL and rel_err(gs2, s2, 1e-9) < TOL
+    for acq, param, ref in ((1, target, mix.get_improvement(target, Xc)), (2, target, mix.get_tail(target, Xc)),
+                            (3, 4.0, ucb_index(4.0, mu, s2))):
+        val, _, best = ctx.score(acq, param, Xc, want_best=True)
+        assert rel_err(val, ref, 1e-9) < TOL and best[1] == int(np.argmax(ref))
+    assert np.allclose(ctx.loglik(), [g.loglikelihood() for g in gps], rtol=1e-8)
+
+
+def test_single_point_gradient_calls(ctx):
+    """The L-BFGS callback shape: f(x[None], grad=True) (solvers/lbfgs.py:56-58)."""
+    gp = synth(150, 3, "se", seed=6, sn2=1e-4)
+    fit_ctx(ctx, gp)
+    target = float(gp.predict(gp.X)[0].max())
+    for x in np.random.RandomState(1).rand(5, 3):
+        val, grad, _ = ctx.score(1, target, x[None], grad=True)
+        ref, rgrad = gp.get_improvement(target, x[None], grad=True)
+        assert rel_err(val, ref, 1e-9) < TOL and rel_err(grad, rgrad, 1e-9) < 10 * TOL
+
+
+# ---- Thompson ---------------------------------------------------------------------------
+@pytest.mark.parametrize("kernel", ["se", "matern52"])
+def test_thompson_draw_matches_oracle(ctx, kernel):
+    from pybo_b200 import models
+    gp = synth(60, 3, kernel, seed=8, sn2=1e-3)
+    ref = FourierSampleOracle(gp, 200, rng=21)
+    mine = models.GP(gp.sn2, gp.rho, gp.ell, gp.bias, kernel=kernel)
+    mine.add_data(gp.X, gp.Y)
+    draw = mine.sample_f(200, rng=21)
+    assert np.allclose(draw.theta, ref.theta, rtol=1e-9, atol=1e-12)
+    Xc = sobol(3000, 3)
+    F, G = draw.get(Xc, grad=True)
+    RF, RG = ref.get(Xc, grad=True)
+    assert rel_err(F, RF, 1e-9) < TOL and rel_err(G, RG, 1e-9) < TOL
+    bv, bi = draw.argmax(Xc)
+    assert bi == int(np.argmax(RF)) and bv == F[bi]
+
+
+def test_thompson_batch_shared_basis(ctx):
+    from pybo_b200 import models
+    gp = synth(80, 2, "se", seed=3, sn2=1e-3)
+    mine = models.GP(gp.sn2, gp.rho, gp.ell, gp.bias)
+    mine.add_data(gp.X, gp.Y)
+    tb = models.ThompsonBatch(mine, m=128, ndraw=7, rng=5)
+    Xc = sobol(1000, 2)
+    F = tb.get(Xc)
+    ref = tb.bias + (tb.scale * np.cos(Xc @ tb.W.T + tb.b)) @ tb.theta.T
+    assert rel_err(F, ref.T, 1e-9) < TOL
+    bv, bi = tb.argmax(Xc)
+    assert np.array_equal(bi, np.argmax(ref, axis=0))
+
+
+# ---- the plugin surface on the GPU model ---------------------------------------------------
+def _branin(x):
+    x = np.array(x, ndmin=2)
+    y = (x[:, 1] - (5.1 / (4 * np.pi ** 2)) * x[:, 0] ** 2 + 5 * x[:, 0] / np.pi - 6) ** 2
+    y += 10 * (1 - 1 / (8 * np.pi)) * np.cos(x[:, 0]) + 10
+    return float(-np.squeeze(y / 10.0))
+
+
+def test_policies_solver_recommender_on_gpu_model():
+    from pybo_b200 import models, policies, recommenders, solvers
+    rng = np.random.RandomState(0)
+    bounds = np.array([[-5, 10.0], [0, 15]])
+    X = bounds[:, 0] + (bounds[:, 1] - bounds[:, 0]) * rng.rand(12, 2)
+    Y = np.array([_branin(x) for x in X])
+    ell = 0.25 * (bounds[:, 1] - bounds[:, 0])
+    ref = GPOracle(1e-6, 10.0, ell, -5.0, "se")
+    ref.add_data(X, Y)
+    gpu = models.make_gp(1e-6, 10.0, ell, -5.0)
+    gpu.add_data(list(X), list(Y))
+    grid = bounds[:, 0] + (bounds[:, 1] - bounds[:, 0]) * rng.rand(4000, 2)
+    for name in ("EI", "PI", "UCB"):
+        a, b = getattr(policies, name)(gpu, bounds, list(X)), getattr(policies, name)(ref, bounds, list(X))
+        assert abs(a.param - b.param) <= 1e-6 * max(1.0, abs(b.param))
+        va, ga = a(grid, grad=True)
+        vb, gb = b(grid, grad=True)
+        assert rel_err(va, vb, 1e-9) < TOL and rel_err(ga, gb, 1e-9) < 10 * TOL
+        assert int(np.argmax(va)) == int(np.argmax(vb))
+        idx, val = a.best_of(grid, 10)
+        assert np.array_equal(idx, np.lexsort((np.arange(len(vb)), -vb))[:10])
+        xa, fa = solvers.solve_lbfgs(a, bounds, xgrid=grid)
+        xb, fb = solvers.solve_lbfgs(b, bounds, xgrid=grid)
+        assert np.allclose(xa, xb, atol=1e-4 * np.max(bounds[:, 1] - bounds[:, 0])) and abs(fa - fb) <= 1e-6 * max(1, abs(fb))
+    assert np.allclose(recommenders.best_latent(gpu, bounds, list(X)), recommenders.best_latent(ref, bounds, list(X)), atol=1e-4)
+    assert np.array_equal(recommenders.best_incumbent(gpu, bounds, list(X)), recommenders.best_incumbent(ref, bounds, list(X)))
+    # copy() shares the fitted state; add_data on the copy leaves the original alone
+    c = gpu.copy()
+    assert c._fit is gpu._fit
+    c.add_data(X[0] + 0.1, 0.0)
+    assert gpu.ndata == 12 and c.ndata == 13 and gpu._fit is not None
+    mu0 = gpu.predict(grid[:5])[0]
+    g2 = pickle.loads(pickle.dumps(gpu))
+    assert np.array_equal(g2.predict(grid[:5])[0], mu0)
+
+
+def test_bayesopt_branin_config1_gpu_vs_golden(golden_dir):
+    """BASELINE config 1 with the GPU model behind the unchanged plugin surface."""
+    import pybo_b200
+    from pybo_b200 import models
+    g = np.load(os.path.join(golden_dir, "bayesopt_branin_ei_20.npz"))
+    bounds = g["bounds"]
+    model = models.make_gp(1e-6, 10.0, 0.25 * (bounds[:, 1] - bounds[:, 0]), -5.0)
+    xbest, model, info = pybo_b200.solve_bayesopt(_branin, bounds, model=model, niter=19, policy="ei",
+                                                  solver="lbfgs", recommender="latent", rng=0)
+    assert info.x.shape == (20, 2)
+    assert np.allclose(info.x[:4], g["x"][:4], atol=1e-4) and np.allclose(info.y[:4], g["y"][:4], atol=1e-4)
+    assert info.y.max() > -0.1
+
+
+def test_default_model_mcmc_runs():
+    import pybo_b200
+    bounds = np.array([[-5, 10.0], [0, 15]])
+    xbest, model, info = pybo_b200.solve_bayesopt(_branin, bounds, niter=3, rng=1)
+    assert len(model) == 10 and info.x.shape == (4, 2) and np.all(np.isfinite(info.y))
+    assert model.ndata == 6 + 4
+
+
+# ---- size-independent properties at BASELINE sizes --------------------------------------------
+def test_full_size_properties_n4096_d8(ctx):
+    """Headline shape (RBF n=4096 d=8): W L = I, interpolation at the data, s2 in [0, rho],
+    chunk-boundary invariance of the scores, and agreement with the oracle on a slice."""
+    gp = synth(4096, 8, "se", seed=0)
+    fit_ctx(ctx, gp)
+    W, L = ctx.factor("W"), ctx.factor("L")
+    E = W[:512] @ L[:, :512]
+    assert np.max(np.abs(E[:, :512] - np.eye(512))) < 1e-8
+    mu_d, s2_d = ctx.predict(gp.X[:2048])
+    assert np.max(np.abs(mu_d - gp.Y[:2048])) < 1e-3 and np.all(s2_d < 1e-4 * gp.rho) and np.all(s2_d > -1e-9)
+    Xc = sobol(20000, 8)
+    target = float(gp.predict(gp.X)[0].max())
+    val, _, best = ctx.score(1, target, Xc, want_best=True)
+    gmu, gs2 = ctx.predict(Xc)
+    assert np.all(gs2 > 0) and np.all(gs2 <= gp.rho * (1 + 1e-12))
+    sl = slice(8000, 8400)                                  # straddles the 8192-candidate chunk edge
+    ref = gp.get_improvement(target, Xc[sl])
+    assert rel_err(val[sl], ref, 1e-9) < TOL
+    val2, _, _ = ctx.score(1, target, Xc[sl])
+    assert np.array_equal(val2, val[sl])                    # a candidate's score does not depend on its chunk
+    assert best[1] == int(np.argmax(val))
