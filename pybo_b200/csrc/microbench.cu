@@ -44,7 +44,7 @@ extern "C" int bo_microbench(bo_ctx *ctx, int kind, int iters, double *tflops) {
     cudaEventCreate(&e1);
     const int blocks = ctx->sm_count * 4, threads = 256;
     double best = 0.0;
-    for (int rep = 0; rep < 4; ++rep) {
+    for (int rep = 0; rep < 6; ++rep) {
         cudaEventRecord(e0, ctx->stream);
         ctx->launches++;
         if (kind == 0) dmma_peak_kernel<<<blocks, threads, 0, ctx->stream>>>(iters, sink);

@@ -161,7 +161,7 @@ def test_ties_resolve_to_first_index(ctx):
     gp.add_data(np.array([[0.5, 0.5], [0.52, 0.5]]), np.array([1.0, 0.9]))
     fit_ctx(ctx, gp)
     Xc = np.random.RandomState(0).rand(4000, 2) * 0.2            # all far away: EI == 0
-    val, _, best = ctx.score(1, 5.0, Xc, want_best=True)
+    val, _, best = ctx.score(1, 50.0, Xc, want_best=True)          # z = -50: phi, Phi underflow to 0
     assert np.all(val == 0.0) and best == (0.0, 0)
     Xc[1234] = Xc[77]
     val, _, best = ctx.score(0, 0.0, Xc, want_best=True)
