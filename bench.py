@@ -36,6 +36,10 @@ WORKLOADS = {
     "mixture32_n2048_d8_ei": dict(kernel="se", n=2048, d=8, acq="ei", M=1 << 17, S=32),
 }
 FALLBACK_PEAKS = dict(hbm_gbs=6650.0, bf16_tflops=1590.0)
+# dram__bytes_read.sum + dram__bytes_write.sum per score_gemm_kernel launch from the committed
+# `ncu --set full` capture (profiles/r1_fp64_score_gemm_ncu.txt); algorithmic operand bytes are
+# W (lower triangle, 67 MB) + one K* chunk (268 MB): the excess is L2 thrash, 5.5 % of DRAM peak.
+TRAFFIC_NCU = {"rbf_n4096_d8_ei": 2.005e9}
 
 
 def flop_per_eval(n, d):
@@ -229,12 +233,14 @@ def our_arm(args):
     alg_flop_per_launch = (n * n + 4 * n) * chunk          # n^2 substitution + 4n reductions per candidate
     avg_ms = gk["total_ms"] / max(1, gk["launches"])
     achieved = alg_flop_per_launch / (avg_ms * 1e-3) / 1e12 if avg_ms > 0 else 0.0
-    fp64_peak = ctx.microbench("dmma")
+    dmma_peak = ctx.microbench("dmma")
     dfma_peak = ctx.microbench("dfma")
+    fp64_peak = max(dmma_peak, dfma_peak)
     roofline = dict(bound="tensor", kernel="score_gemm_kernel", achieved=achieved, peak=fp64_peak, unit="TFLOP/s",
-                    frac=achieved / fp64_peak if fp64_peak else None, traffic=None,
-                    peak_source="FP64 tensor-core (DMMA m8n8k4) roof measured in this run by bo_microbench; "
-                                "MEASURED_PEAKS.json holds no FP64 figure (dfma roof %.1f TFLOP/s)" % dfma_peak,
+                    frac=achieved / fp64_peak if fp64_peak else None, traffic=TRAFFIC_NCU.get(args.workload),
+                    peak_source="FP64 roof measured in this run by bo_microbench (register-resident loops on every SM): "
+                                "DMMA m8n8k4 %.1f, DFMA %.1f TFLOP/s; the larger is used (ncu: both issue at 128 flop/clk/SM = "
+                                "37.2 TFLOP/s at 1965 MHz). MEASURED_PEAKS.json holds no FP64 figure" % (dmma_peak, dfma_peak),
                     frac_of_bf16_peak=achieved / pk["bf16_tflops"], bf16_peak=pk["bf16_tflops"], peaks=pk["source"],
                     alg_flop_per_launch=alg_flop_per_launch, avg_launch_ms=avg_ms, launches=gk["launches"],
                     share_of_step=gk["total_ms"] / dev_ms if dev_ms else None)

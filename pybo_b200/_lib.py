@@ -296,7 +296,7 @@ class Context(object):
             out[buf.value.decode()] = dict(launches=launches.value, total_ms=ms.value)
         return out
 
-    def microbench(self, kind, iters=200000):
+    def microbench(self, kind, iters=40000):
         """Measured FP64 roof in TFLOP/s: kind 'dmma' (tensor core) or 'dfma'."""
         v = C.c_double()
         self._check(self._lib.bo_microbench(self._h, 0 if kind == "dmma" else 1, int(iters), C.byref(v)))
