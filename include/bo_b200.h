@@ -91,9 +91,11 @@ int bo_predict(bo_ctx *ctx, int64_t M, const double *Xc, int flags, double *mu,
 /* top-k of the values of the last bo_score call, descending, ties by lowest
  * index: replaces `argsort(finit)[::-1][:nbest]` (solvers/lbfgs.py:51). */
 int bo_topk(bo_ctx *ctx, int k, int64_t *idx, double *val);
-/* choose the precision path of the scoring contraction (default BO_PREC_F64);
- * for BO_PREC_OZAKI `tol` is the absolute error bound on V entries relative to
- * sqrt(rho) that picks the number of int8 slices. */
+/* choose the precision path of the scoring contraction (default BO_PREC_F64).
+ * For BO_PREC_OZAKI, 0 < tol < 2 is the target absolute error of the entries of
+ * V = L^-1 k relative to sqrt(rho); the library picks the number of 7-bit int8
+ * slices from its a-priori error model.  tol >= 2 sets the slice count directly
+ * (2..8).  Gradient requests always run on the FP64 path. */
 int bo_set_precision(bo_ctx *ctx, int prec, double tol);
 
 /* ---- Thompson: `model.sample_f(n, rng).get` (policies/simple.py:48) ------
@@ -132,6 +134,11 @@ int bo_launch_count(bo_ctx *ctx, int64_t *launches);
 /* measured FP64 roof of this device: kind 0 = tensor-core DMMA m8n8k4,
  * kind 1 = DFMA, both register resident on every SM; result in TFLOP/s. */
 int bo_microbench(bo_ctx *ctx, int kind, int iters, double *tflops);
+/* self-test hook of the int8-slice path: runs it on hyper-sample 0 for the first mc
+ * candidates and returns mu, s2, the raw int32 group accumulators of candidate tile 0
+ * ([np/64][S][128][64]) and the slice planes, for exact comparison on the host. */
+int bo_ozaki_debug(bo_ctx *ctx, int S, int mc, const double *Xc, double *mu, double *s2,
+                   int32_t *acc, int8_t *wslices, int8_t *kslices, double *rowscale);
 
 #ifdef __cplusplus
 }

@@ -25,7 +25,7 @@ EXPORTS = [
     "bo_thompson_set", "bo_thompson_eval",
     "bo_cholesky", "bo_gram",
     "bo_profile_enable", "bo_profile_reset", "bo_profile_count", "bo_profile_get",
-    "bo_launch_count", "bo_microbench",
+    "bo_launch_count", "bo_microbench", "bo_ozaki_debug",
 ]
 
 
@@ -67,6 +67,7 @@ def _declare(lib):
         "bo_profile_get": (i, [vp, i, C.c_char_p, i, _lp, _dp]),
         "bo_launch_count": (i, [vp, _lp]),
         "bo_microbench": (i, [vp, i, i, _dp]),
+        "bo_ozaki_debug": (i, [vp, i, i, vp, vp, vp, vp, vp, vp, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
@@ -301,6 +302,21 @@ class Context(object):
         v = C.c_double()
         self._check(self._lib.bo_microbench(self._h, 0 if kind == "dmma" else 1, int(iters), C.byref(v)))
         return v.value
+
+    def ozaki_debug(self, S, X, want_acc=True, want_slices=True):
+        """Self-test hook: int8-slice path on hyper-sample 0 for candidates X."""
+        X = f64(X, 2)
+        mc = X.shape[0]
+        npad = -(-self.n // 128) * 128
+        mcp = -(-mc // 128) * 128
+        mu, s2 = np.empty(mc), np.empty(mc)
+        acc = np.empty((npad // 64, S, 128, 64), dtype=np.int32) if want_acc else None
+        ws = np.empty((S, npad, npad), dtype=np.int8) if want_slices else None
+        ks = np.empty((S, mcp, npad), dtype=np.int8) if want_slices else None
+        rs = np.empty(npad)
+        self._check(self._lib.bo_ozaki_debug(self._h, int(S), mc, _ptr(X), _ptr(mu), _ptr(s2), _ptr(acc),
+                                             _ptr(ws), _ptr(ks), _ptr(rs)))
+        return dict(mu=mu, s2=s2, acc=acc, ws=ws, ks=ks, rowscale=rs)
 
     def launch_count(self):
         v = C.c_int64()

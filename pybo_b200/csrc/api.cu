@@ -83,6 +83,7 @@ extern "C" int bo_create(int device, bo_ctx **out) {
     ctx->sm_count = ctx->prop.multiProcessorCount;
     int rc = bo_linalg_init(ctx);
     if (rc == BO_OK) rc = bo_score_init(ctx);
+    if (rc == BO_OK) rc = bo_ozaki_init(ctx);
     if (rc != BO_OK) {
         fprintf(stderr, "bo_create: %s\n", ctx->err);
         cudaStreamDestroy(ctx->stream);
@@ -103,6 +104,10 @@ static void free_all(bo_ctx *ctx) {
     for (auto p : ptrs)
         if (*p) { cudaFree(*p); *p = nullptr; }
     if (ctx->dInfo) { cudaFree(ctx->dInfo); ctx->dInfo = nullptr; }
+    if (ctx->dWs) { cudaFree(ctx->dWs); ctx->dWs = nullptr; }
+    if (ctx->dKss) { cudaFree(ctx->dKss); ctx->dKss = nullptr; }
+    if (ctx->dRowScale) { cudaFree(ctx->dRowScale); ctx->dRowScale = nullptr; }
+    if (ctx->dRowExp) { cudaFree(ctx->dRowExp); ctx->dRowExp = nullptr; }
     if (ctx->dBlkIdx) { cudaFree(ctx->dBlkIdx); ctx->dBlkIdx = nullptr; }
     if (ctx->th.dBestIdx) { cudaFree(ctx->th.dBestIdx); ctx->th.dBestIdx = nullptr; }
     if (ctx->hPinned) { cudaFreeHost(ctx->hPinned); ctx->hPinned = nullptr; }
@@ -174,6 +179,7 @@ extern "C" int bo_fit(bo_ctx *ctx, int kernel, int n, int d, int S, const double
             if (!(ell[s * d + k] > 0.0)) return bo_set_err(ctx, BO_ERR_ARG, "bo_fit: ell must be > 0");
     }
     ctx->fitted = false;
+    ctx->oz_ready = false;
     ctx->last_val_valid = false;
     const int np = bo_round_up(n, BO_PAD), dp = padded_dim(d), nblk64 = np / 64;
     const size_t mat = (size_t)S * np * np;
@@ -406,9 +412,11 @@ extern "C" int bo_topk(bo_ctx *ctx, int k, int64_t *idx, double *val) {
 
 extern "C" int bo_set_precision(bo_ctx *ctx, int prec, double tol) {
     if (!ctx) return BO_ERR_ARG;
-    if (prec != BO_PREC_F64) return bo_set_err(ctx, BO_ERR_ARG, "precision path %d is not available in this build", prec);
+    if (prec != BO_PREC_F64 && prec != BO_PREC_OZAKI) return bo_set_err(ctx, BO_ERR_ARG, "unknown precision path %d", prec);
+    if (prec == BO_PREC_OZAKI && !(tol > 0.0)) return bo_set_err(ctx, BO_ERR_ARG, "bo_set_precision: tol must be > 0");
     ctx->prec = prec;
     ctx->prec_tol = tol;
+    ctx->oz_ready = false;
     return BO_OK;
 }
 

@@ -89,6 +89,15 @@ struct bo_ctx {
 
     int prec = BO_PREC_F64;
     double prec_tol = 1e-9;
+    // int8-slice (Ozaki) path state
+    bool oz_ready = false;
+    int oz_slices = 0;
+    int8_t *dWs = nullptr;        // S_hyper x slices x np x np  slice planes of W
+    int8_t *dKss = nullptr;       // slices x chunk x np          slice planes of K*^T
+    double *dRowScale = nullptr;  // S_hyper x np   2^(e_i - 12) rho
+    int *dRowExp = nullptr;       // S_hyper x np (+ S_hyper maxima)
+    size_t ws_capacity = 0, kss_capacity = 0, rowscale_capacity = 0, rowexp_capacity = 0;
+    std::vector<int> h_emax;
 
     bo_thompson_state th;
 
@@ -174,6 +183,11 @@ int bo_linalg_transpose(bo_ctx *ctx, int np, int batch, const double *A, double 
 int bo_linalg_finish_fit(bo_ctx *ctx);
 int bo_linalg_init(bo_ctx *ctx);
 int bo_score_init(bo_ctx *ctx);
+int bo_ozaki_init(bo_ctx *ctx);
+int bo_ozaki_prepare(bo_ctx *ctx, int S);
+int bo_ozaki_choose_slices(bo_ctx *ctx, double tol);
+int bo_ozaki_moments(bo_ctx *ctx, int s, int S, const double *dXc, int64_t c0, int mc, int mcp, double *mu,
+                     double *s2, int32_t *dbg);
 
 // one scoring / prediction pass over M device-resident candidates
 struct ScoreRequest {

@@ -1,0 +1,552 @@
+// ozaki.cu -- error-bounded int8-slice emulation of the scoring contraction
+// V = W K* on the 5th-generation tensor cores (tcgen05.mma kind::i8, TMEM
+// accumulators, TMA-staged operands).
+//
+// FP64 tensor cores cap the contraction at 37 TFLOP/s; the int8 path of the same
+// SM runs 128x faster.  Both operands are cut into S signed 7-bit slices on a
+// fixed-point grid (rows of W share an exponent, K*/rho lies in [0,1]):
+//     W_ij  = 2^e_i  * sum_s a_s[i][j] 2^-(6+7s),   K*_jm = rho * sum_t b_t[m][j] 2^-(6+7t)
+// every int8 x int8 product and its int32 accumulation over j is exact, products are
+// grouped by g = s + t (pairs with g >= S are dropped), and
+//     v_im = 2^(e_i-12) rho * sum_g 2^-7g D_g[m][i]
+// is reassembled in FP64 in the epilogue, where |v|^2 and v.alpha are reduced.
+// The truncation error is bounded a priori (see bo_ozaki_choose_slices).
+//
+// Orientation: candidates are the MMA M dimension (one TMEM lane = one candidate, so
+// the row reductions are per-thread sums), rows of W are the N dimension.
+#include <cuda.h>
+#include <math.h>
+
+#include "common.cuh"
+
+#define OZ_BM 128        // candidates per CTA tile (MMA M, TMEM lanes)
+#define OZ_BN 64         // rows of W per block (MMA N)
+#define OZ_BK 64         // k bytes per stage row (one 64B swizzle atom, two K=32 MMAs)
+#define OZ_MAX_S 8
+#define OZ_A_SLICE_BYTES (OZ_BM * OZ_BK)   // 8192
+#define OZ_B_SLICE_BYTES (OZ_BN * OZ_BK)   // 4096
+#define OZ_THREADS 192   // warp 0: TMA producer, warp 1: MMA issuer, warps 2-5: epilogue
+
+// ---------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "@P1 bra.uni DONE_%=;\n\t"
+        "bra.uni WAIT_%=;\n\t"
+        "DONE_%=:\n\t"
+        "}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_3d(uint32_t smem_dst, const CUtensorMap *tmap, int c0, int c1, int c2, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+        ::"r"(smem_dst), "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *tmap) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// D[tmem] (+)= A[smem] * B[smem]^T, int8 x int8 -> int32
+__device__ __forceinline__ void umma_i8(uint32_t tmem_c, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_c), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// 32 lanes x 16 consecutive 32-bit columns
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, int32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major operand tile, rows of 64 bytes, SWIZZLE_64B: 8-row groups are 512 B apart.
+__device__ __forceinline__ uint64_t make_desc_sw64(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);        // start address
+    d |= (uint64_t)1 << 16;                             // leading byte offset (unused for swizzled K-major)
+    d |= (uint64_t)(512 >> 4) << 32;                    // stride byte offset between 8-row groups
+    d |= (uint64_t)1 << 46;                             // descriptor version (Blackwell)
+    d |= (uint64_t)4 << 61;                             // SWIZZLE_64B
+    return d;
+}
+
+// kind::i8 instruction descriptor: D = s32, A = B = signed int8, both K-major, M = 128, N = 64
+__device__ __forceinline__ uint32_t make_idesc_i8(int M, int N) {
+    return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// ---------------------------------------------------------------------------
+// slicing kernels
+// ---------------------------------------------------------------------------
+// Row exponents of W and the epilogue scale 2^(e_i - 12) * rho.
+__global__ void oz_row_exponent_kernel(const double *__restrict__ W, int np, double rho, int *__restrict__ rowexp,
+                                       double *__restrict__ rowscale, int *__restrict__ emax) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= np) return;
+    const double *w = W + (int64_t)row * np;
+    double m = 0.0;
+    for (int j = lane; j <= row; j += 32) m = fmax(m, fabs(w[j]));
+    for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (lane == 0) {
+        int e = 0;
+        if (m > 0.0) frexp(m, &e);          // m = f * 2^e, f in [0.5, 1)  =>  |w| * 2^-e < 1
+        rowexp[row] = e;
+        rowscale[row] = ldexp(rho, e - 12);
+        atomicMax(emax, e);
+    }
+}
+
+// W (lower triangle) -> S int8 slice planes [s][row][k]
+__global__ void oz_slice_w_kernel(const double *__restrict__ W, int np, int S, const int *__restrict__ rowexp,
+                                  int8_t *__restrict__ Ws) {
+    const int row = blockIdx.y;
+    const int k0 = (blockIdx.x * blockDim.x + threadIdx.x) * 16;
+    if (k0 >= np) return;
+    const double sc = ldexp(1.0, 6 - rowexp[row]);
+    const double *w = W + (int64_t)row * np + k0;
+    double r[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) r[i] = (k0 + i <= row) ? w[i] * sc : 0.0;
+    for (int s = 0; s < S; ++s) {
+        alignas(16) int8_t q[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const double t = rint(r[i]);
+            q[i] = (int8_t)(int)t;
+            r[i] = (r[i] - t) * 128.0;
+        }
+        *reinterpret_cast<int4 *>(Ws + ((int64_t)s * np + row) * np + k0) = *reinterpret_cast<const int4 *>(q);
+    }
+}
+
+// K*^T slices [s][cand][k]: kappa = k(x_j, xc_m) / rho in [0,1] on the same grid.
+// block: 64 observations x 128 candidates; thread = (candidate, 32-wide k half).
+template <int DP>
+__global__ void __launch_bounds__(256)
+oz_kstar_slices_kernel(int kernel, int n, int np, int d, int S, const double *__restrict__ Xs,
+                       const double *__restrict__ invell, const double *__restrict__ Xc, int64_t c0, int mc,
+                       int mcp, int8_t *__restrict__ Ks) {
+    __shared__ double xs[64][DP];
+    const int tid = threadIdx.x;
+    const int j0 = blockIdx.y * 64;
+    for (int e = tid; e < 64 * DP; e += 256) xs[e / DP][e % DP] = Xs[(int64_t)j0 * DP + e];
+    const int m = blockIdx.x * 128 + (tid & 127);
+    const int half = tid >> 7;
+    const bool live = m < mc;
+    double xc[DP];
+#pragma unroll
+    for (int k = 0; k < DP; ++k) xc[k] = (live && k < d) ? Xc[(c0 + m) * d + k] * invell[k] : 0.0;
+    __syncthreads();
+    for (int sub = 0; sub < 2; ++sub) {
+        const int jj0 = half * 32 + sub * 16;
+        double r[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            double D = 0.0;
+#pragma unroll
+            for (int k = 0; k < DP; ++k) {
+                const double t = xc[k] - xs[jj0 + i][k];
+                D = fma(t, t, D);
+            }
+            double v;
+            if (kernel == BO_KERNEL_SE) {
+                v = exp(-0.5 * D);
+            } else {
+                const double rr = sqrt(5.0 * D);
+                v = (1.0 + rr + rr * rr * (1.0 / 3.0)) * exp(-rr);
+            }
+            r[i] = (live && (j0 + jj0 + i) < n) ? v * 64.0 : 0.0;
+        }
+        for (int s = 0; s < S; ++s) {
+            alignas(16) int8_t q[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const double t = rint(r[i]);
+                q[i] = (int8_t)(int)t;
+                r[i] = (r[i] - t) * 128.0;
+            }
+            *reinterpret_cast<int4 *>(Ks + ((int64_t)s * mcp + m) * np + j0 + jj0) = *reinterpret_cast<const int4 *>(q);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// the contraction kernel
+// ---------------------------------------------------------------------------
+struct OzParams {
+    int np, S, nstages, ntiles;
+    const double *rowscale;   // np
+    const double *alpha;      // np
+    double rho, bias;
+    double *mu, *s2;          // ntiles * 128
+    int32_t *dbg;             // optional: [rb][g][128][64] accumulators of tile 0
+};
+
+__global__ void __launch_bounds__(OZ_THREADS, 1)
+oz_score_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB, OzParams p) {
+    extern __shared__ uint8_t oz_smem_raw[];
+    // 1024-byte aligned operand ring
+    const uint32_t raw = smem_u32(oz_smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    uint8_t *gen_base = oz_smem_raw + (base - raw);
+    const int S = p.S, G = S - 1, nst = p.nstages;
+    const uint32_t stage_bytes = (uint32_t)S * (OZ_A_SLICE_BYTES + OZ_B_SLICE_BYTES);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(gen_base + (size_t)nst * stage_bytes);
+    // bars[0..nst): full, [nst..2nst): empty, [2nst]: tmem_full, [2nst+1]: tmem_empty
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * nst + 2);
+    const uint32_t bar0 = smem_u32(bars);
+    auto full_bar = [&](int s) { return bar0 + 8u * s; };
+    auto empty_bar = [&](int s) { return bar0 + 8u * (nst + s); };
+    const uint32_t tmem_full = bar0 + 8u * (2 * nst), tmem_empty = bar0 + 8u * (2 * nst + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nb = p.np / OZ_BN;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmapA);
+        tma_prefetch_desc(&tmapB);
+        for (int s = 0; s < nst; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(empty_bar(s), 1);
+        }
+        mbar_init(tmem_full, 1);
+        mbar_init(tmem_empty, 4);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+                for (int rb = 0; rb < nb; ++rb) {
+                    for (int kb = 0; kb <= rb; ++kb) {
+                        mbar_wait(empty_bar(stage), phase ^ 1);
+                        mbar_expect_tx(full_bar(stage), stage_bytes);
+                        const uint32_t sA = base + stage * stage_bytes;
+                        const uint32_t sB = sA + S * OZ_A_SLICE_BYTES;
+                        for (int s = 0; s < S; ++s) {
+                            tma_load_3d(sA + s * OZ_A_SLICE_BYTES, &tmapA, kb * OZ_BK, tile * OZ_BM, s, full_bar(stage));
+                            tma_load_3d(sB + s * OZ_B_SLICE_BYTES, &tmapB, kb * OZ_BK, rb * OZ_BN, s, full_bar(stage));
+                        }
+                        if (++stage == nst) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc_i8(OZ_BM, OZ_BN);
+            int stage = 0;
+            uint32_t phase = 0, acc_phase = 0;
+            for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+                for (int rb = 0; rb < nb; ++rb) {
+                    mbar_wait(tmem_empty, acc_phase ^ 1);     // epilogue has drained the accumulators
+                    tc_fence_after();
+                    for (int kb = 0; kb <= rb; ++kb) {
+                        mbar_wait(full_bar(stage), phase);
+                        tc_fence_after();
+                        const uint32_t sA = base + stage * stage_bytes;
+                        const uint32_t sB = sA + S * OZ_A_SLICE_BYTES;
+#pragma unroll 1
+                        for (int kk = 0; kk < 2; ++kk) {
+#pragma unroll 1
+                            for (int s = 0; s < S; ++s) {
+                                const uint64_t adesc = make_desc_sw64(sA + s * OZ_A_SLICE_BYTES + kk * 32);
+                                const uint32_t accumulate = (kb > 0 || kk > 0 || s > 0) ? 1u : 0u;
+                                for (int t = 0; t <= G - s; ++t) {
+                                    const uint64_t bdesc = make_desc_sw64(sB + t * OZ_B_SLICE_BYTES + kk * 32);
+                                    umma_i8(tmem_base + (uint32_t)(s + t) * OZ_BN, adesc, bdesc, idesc, accumulate);
+                                }
+                            }
+                        }
+                        umma_commit(empty_bar(stage));        // smem slot free once these MMAs retire
+                        if (++stage == nst) { stage = 0; phase ^= 1; }
+                    }
+                    umma_commit(tmem_full);                   // accumulators of this row block are complete
+                    acc_phase ^= 1;
+                }
+            }
+        }
+    } else {
+        // ===================== epilogue: one candidate per thread =====================
+        const int quarter = warp & 3;                          // TMEM lane quarter this warp may access
+        const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16);
+        uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+            double q = 0.0, pm = 0.0;
+            for (int rb = 0; rb < nb; ++rb) {
+                mbar_wait(tmem_full, acc_phase);
+                tc_fence_after();
+                for (int c0 = 0; c0 < OZ_BN; c0 += 16) {
+                    double v[16];
+                    int32_t r[16];
+                    tmem_ld16(lane_base + (uint32_t)(G * OZ_BN + c0), r);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) v[i] = (double)r[i];
+                    if (p.dbg && tile == 0) {
+                        int32_t *o = p.dbg + (((int64_t)rb * S + G) * 128 + quarter * 32 + lane) * 64 + c0;
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) o[i] = r[i];
+                    }
+                    for (int g = G - 1; g >= 0; --g) {
+                        tmem_ld16(lane_base + (uint32_t)(g * OZ_BN + c0), r);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) v[i] = fma(v[i], 0.0078125, (double)r[i]);
+                        if (p.dbg && tile == 0) {
+                            int32_t *o = p.dbg + (((int64_t)rb * S + g) * 128 + quarter * 32 + lane) * 64 + c0;
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) o[i] = r[i];
+                        }
+                    }
+                    const int row0 = rb * OZ_BN + c0;
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const double vv = v[i] * __ldg(p.rowscale + row0 + i);
+                        q = fma(vv, vv, q);
+                        pm = fma(vv, __ldg(p.alpha + row0 + i), pm);
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(tmem_empty);
+                acc_phase ^= 1;
+            }
+            const int64_t cand = (int64_t)tile * OZ_BM + quarter * 32 + lane;
+            p.mu[cand] = p.bias + pm;
+            p.s2[cand] = p.rho - q;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+// ---------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                    const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode() {
+    static PFN_encodeTiled fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (PFN_encodeTiled)p;
+    }
+    return fn;
+}
+
+// 3-D int8 tensor (k, row, slice) with a (64, box_rows, 1) box and 64-byte swizzle
+static int make_tmap(bo_ctx *ctx, CUtensorMap *tm, const void *base, uint64_t kdim, uint64_t rows, uint64_t slices,
+                     uint32_t box_rows) {
+    PFN_encodeTiled enc = get_encode();
+    if (!enc) return bo_set_err(ctx, BO_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+    cuuint64_t dims[3] = {kdim, rows, slices};
+    cuuint64_t strides[2] = {kdim, kdim * rows};
+    cuuint32_t box[3] = {OZ_BK, box_rows, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void *>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return bo_set_err(ctx, BO_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return BO_OK;
+}
+
+static int oz_stage_count(int S) {
+    const int stage = S * (OZ_A_SLICE_BYTES + OZ_B_SLICE_BYTES);
+    int n = (200 * 1024) / stage;
+    return n > 4 ? 4 : (n < 2 ? 2 : n);
+}
+static size_t oz_smem_bytes(int S) {
+    return (size_t)oz_stage_count(S) * S * (OZ_A_SLICE_BYTES + OZ_B_SLICE_BYTES) + 1024 + 256;
+}
+
+int bo_ozaki_init(bo_ctx *ctx) {
+    BO_CUDA(ctx, cudaFuncSetAttribute(oz_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)oz_smem_bytes(OZ_MAX_S)));
+    return BO_OK;
+}
+
+// Build the slice planes of W for hyper-sample s (S slices) into ctx->dWs.
+int bo_ozaki_prepare(bo_ctx *ctx, int S) {
+    const int np = ctx->np, ns = ctx->S;
+    if (ctx->oz_ready && ctx->oz_slices == S) return BO_OK;
+    BO_TRY(bo_reserve(ctx, &ctx->dWs, &ctx->ws_capacity, (size_t)ns * S * np * np));
+    BO_TRY(bo_reserve(ctx, &ctx->dRowScale, &ctx->rowscale_capacity, (size_t)ns * np));
+    BO_TRY(bo_reserve(ctx, &ctx->dRowExp, &ctx->rowexp_capacity, (size_t)ns * np + ns));
+    int *emax_dev = ctx->dRowExp + (size_t)ns * np;
+    std::vector<int> init(ns, -100000);
+    BO_CUDA(ctx, cudaMemcpyAsync(emax_dev, init.data(), sizeof(int) * ns, cudaMemcpyHostToDevice, ctx->stream));
+    BO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int s = 0; s < ns; ++s) {
+        {
+            BO_LAUNCH(ctx, "oz_row_exponent_kernel");
+            oz_row_exponent_kernel<<<np / 8, 256, 0, ctx->stream>>>(ctx->dW + (size_t)s * np * np, np, ctx->h_rho[s],
+                                                                   ctx->dRowExp + (size_t)s * np,
+                                                                   ctx->dRowScale + (size_t)s * np, emax_dev + s);
+            BO_CHECK_LAUNCH(ctx);
+        }
+        {
+            BO_LAUNCH(ctx, "oz_slice_w_kernel");
+            oz_slice_w_kernel<<<dim3((np / 16 + 127) / 128, np), 128, 0, ctx->stream>>>(
+                ctx->dW + (size_t)s * np * np, np, S, ctx->dRowExp + (size_t)s * np,
+                ctx->dWs + (size_t)s * S * np * np);
+            BO_CHECK_LAUNCH(ctx);
+        }
+    }
+    ctx->h_emax.assign(ns, 0);
+    BO_CUDA(ctx, cudaMemcpyAsync(ctx->h_emax.data(), emax_dev, sizeof(int) * ns, cudaMemcpyDeviceToHost, ctx->stream));
+    BO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->oz_ready = true;
+    ctx->oz_slices = S;
+    return BO_OK;
+}
+
+// A-priori error model: |dv_i| <~ c sqrt(n) 2^e_i rho 2^-7S (round-to-nearest slices, dropped
+// pairs of weight 2^-7S); pick the smallest S whose estimate is below tol * sqrt(rho).
+int bo_ozaki_choose_slices(bo_ctx *ctx, double tol) {
+    if (tol >= 2.0) {
+        int S = (int)tol;
+        return S > OZ_MAX_S ? OZ_MAX_S : S;
+    }
+    // exponents need W: use 4 slices provisionally just to obtain e_max
+    if (!ctx->oz_ready) {
+        if (bo_ozaki_prepare(ctx, 4) != BO_OK) return -1;
+    }
+    double worst = 0.0;
+    for (int s = 0; s < ctx->S; ++s) {
+        double est = 8.0 * sqrt((double)ctx->np) * ldexp(1.0, ctx->h_emax[s]) * sqrt(ctx->h_rho[s]);
+        worst = est > worst ? est : worst;
+    }
+    for (int S = 3; S <= OZ_MAX_S; ++S)
+        if (worst * ldexp(1.0, -7 * S) <= tol) return S;
+    return OZ_MAX_S;
+}
+
+template <int DP>
+static int launch_oz_kstar(bo_ctx *ctx, int s, int S, const double *dXc, int64_t c0, int mc, int mcp) {
+    BO_LAUNCH(ctx, "oz_kstar_slices_kernel");
+    oz_kstar_slices_kernel<DP><<<dim3(mcp / 128, ctx->np / 64), 256, 0, ctx->stream>>>(
+        ctx->kernel, ctx->n, ctx->np, ctx->d, S, ctx->dXs + (int64_t)s * ctx->np * ctx->dp,
+        ctx->dInvEll + (int64_t)s * ctx->dp, dXc, c0, mc, mcp, ctx->dKss);
+    BO_CHECK_LAUNCH(ctx);
+    return BO_OK;
+}
+
+// mu_s, s2_s of candidates [c0, c0 + mc) for hyper-sample s through the int8-slice path.
+int bo_ozaki_moments(bo_ctx *ctx, int s, int S, const double *dXc, int64_t c0, int mc, int mcp, double *mu,
+                     double *s2, int32_t *dbg) {
+    const int np = ctx->np;
+    BO_TRY(bo_reserve(ctx, &ctx->dKss, &ctx->kss_capacity, (size_t)S * mcp * np));
+    switch (ctx->dp) {
+        case 2: BO_TRY(launch_oz_kstar<2>(ctx, s, S, dXc, c0, mc, mcp)); break;
+        case 4: BO_TRY(launch_oz_kstar<4>(ctx, s, S, dXc, c0, mc, mcp)); break;
+        case 8: BO_TRY(launch_oz_kstar<8>(ctx, s, S, dXc, c0, mc, mcp)); break;
+        case 16: BO_TRY(launch_oz_kstar<16>(ctx, s, S, dXc, c0, mc, mcp)); break;
+        case 32: BO_TRY(launch_oz_kstar<32>(ctx, s, S, dXc, c0, mc, mcp)); break;
+        default: return bo_set_err(ctx, BO_ERR_ARG, "unsupported padded dimension %d", ctx->dp);
+    }
+    CUtensorMap tmA, tmB;
+    BO_TRY(make_tmap(ctx, &tmA, ctx->dKss, np, mcp, S, OZ_BM));
+    BO_TRY(make_tmap(ctx, &tmB, ctx->dWs + (size_t)s * S * np * np, np, np, S, OZ_BN));
+    OzParams p;
+    p.np = np; p.S = S; p.nstages = oz_stage_count(S); p.ntiles = mcp / OZ_BM;
+    p.rowscale = ctx->dRowScale + (size_t)s * np;
+    p.alpha = ctx->dAlpha + (size_t)s * np;
+    p.rho = ctx->h_rho[s]; p.bias = ctx->h_bias[s];
+    p.mu = mu; p.s2 = s2; p.dbg = dbg;
+    const int grid = p.ntiles < ctx->sm_count ? p.ntiles : ctx->sm_count;
+    {
+        BO_LAUNCH(ctx, "oz_score_kernel");
+        oz_score_kernel<<<grid, OZ_THREADS, oz_smem_bytes(S), ctx->stream>>>(tmA, tmB, p);
+        BO_CHECK_LAUNCH(ctx);
+    }
+    return BO_OK;
+}
+
+// Debug / self-test entry point: runs the int8-slice path for the first `mc` candidates
+// of Xc (host) on hyper-sample 0 and returns mu, s2 plus the raw int32 group accumulators
+// of candidate tile 0 ([np/64][S][128][64]), the W slices and the K* slices.
+extern "C" int bo_ozaki_debug(bo_ctx *ctx, int S, int mc, const double *Xc, double *mu, double *s2, int32_t *acc,
+                              int8_t *wslices, int8_t *kslices, double *rowscale) {
+    if (!ctx) return BO_ERR_ARG;
+    BO_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (!ctx->fitted) return bo_set_err(ctx, BO_ERR_STATE, "bo_ozaki_debug before bo_fit");
+    if (S < 1 || S > OZ_MAX_S || mc < 1) return bo_set_err(ctx, BO_ERR_ARG, "bad S / mc");
+    const int np = ctx->np, mcp = bo_round_up(mc, OZ_BM), nb = np / OZ_BN;
+    ctx->oz_ready = false;
+    BO_TRY(bo_ozaki_prepare(ctx, S));
+    double *dXc = nullptr, *dmu = nullptr;
+    int32_t *dacc = nullptr;
+    BO_CUDA(ctx, cudaMalloc(&dXc, sizeof(double) * mc * ctx->d));
+    BO_CUDA(ctx, cudaMalloc(&dmu, sizeof(double) * 2 * mcp));
+    BO_CUDA(ctx, cudaMalloc(&dacc, sizeof(int32_t) * (size_t)nb * S * 128 * 64));
+    BO_CUDA(ctx, cudaMemsetAsync(dacc, 0xff, sizeof(int32_t) * (size_t)nb * S * 128 * 64, ctx->stream));
+    BO_CUDA(ctx, cudaMemcpyAsync(dXc, Xc, sizeof(double) * mc * ctx->d, cudaMemcpyHostToDevice, ctx->stream));
+    int rc = bo_ozaki_moments(ctx, 0, S, dXc, 0, mc, mcp, dmu, dmu + mcp, acc ? dacc : nullptr);
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    if (rc == BO_OK && e == cudaSuccess) {
+        if (mu) cudaMemcpy(mu, dmu, sizeof(double) * mc, cudaMemcpyDeviceToHost);
+        if (s2) cudaMemcpy(s2, dmu + mcp, sizeof(double) * mc, cudaMemcpyDeviceToHost);
+        if (acc) cudaMemcpy(acc, dacc, sizeof(int32_t) * (size_t)nb * S * 128 * 64, cudaMemcpyDeviceToHost);
+        if (wslices) cudaMemcpy(wslices, ctx->dWs, (size_t)S * np * np, cudaMemcpyDeviceToHost);
+        if (kslices) cudaMemcpy(kslices, ctx->dKss, (size_t)S * mcp * np, cudaMemcpyDeviceToHost);
+        if (rowscale) cudaMemcpy(rowscale, ctx->dRowScale, sizeof(double) * np, cudaMemcpyDeviceToHost);
+    }
+    cudaFree(dXc); cudaFree(dmu); cudaFree(dacc);
+    if (rc != BO_OK) return rc;
+    if (e != cudaSuccess) return bo_set_err(ctx, BO_ERR_CUDA, "bo_ozaki_debug: %s", cudaGetErrorString(e));
+    return BO_OK;
+}

@@ -465,10 +465,18 @@ int bo_score_run(bo_ctx *ctx, const ScoreRequest &rq) {
     const bool grad = (rq.mode == 0) ? (rq.dGrad != nullptr) : (rq.dDmu != nullptr || rq.dDs2 != nullptr);
     const int64_t M = rq.M;
     if (M <= 0) return bo_set_err(ctx, BO_ERR_ARG, "M must be positive");
-    const int64_t chunk = ctx->chunk;
+    // int8-slice path for value-only passes when selected; gradients stay on the FP64 path
+    const bool oz = (ctx->prec == BO_PREC_OZAKI) && !grad;
+    int oz_S = 0;
+    if (oz) {
+        oz_S = bo_ozaki_choose_slices(ctx, ctx->prec_tol);
+        if (oz_S < 1) return BO_ERR_CUDA;
+        BO_TRY(bo_ozaki_prepare(ctx, oz_S));
+    }
+    const int64_t chunk = oz ? (int64_t)ctx->sm_count * 128 : ctx->chunk;
     const int64_t cap = bo_round_up64(M < chunk ? M : chunk, 128);
 
-    BO_TRY(bo_reserve(ctx, &ctx->dKs, &ctx->ks_capacity, (size_t)np * cap));
+    if (!oz) BO_TRY(bo_reserve(ctx, &ctx->dKs, &ctx->ks_capacity, (size_t)np * cap));
     {
         size_t need = (size_t)nblk * cap;
         if (ctx->mom_capacity < need || !ctx->dQpart) {
@@ -516,6 +524,11 @@ int bo_score_run(bo_ctx *ctx, const ScoreRequest &rq) {
         const int mc = (int)((M - c0) < chunk ? (M - c0) : chunk);
         const int mcp = bo_round_up(mc, 128);
         for (int s = 0; s < S; ++s) {
+            if (oz) {
+                BO_TRY(bo_ozaki_moments(ctx, s, oz_S, rq.dXc, c0, mc, mcp, ctx->dMuS + (int64_t)s * mcp,
+                                        ctx->dS2S + (int64_t)s * mcp, nullptr));
+                continue;
+            }
             DISPATCH_DP(ctx, launch_kstar, ctx, s, rq.dXc, c0, mc, mcp);
             {
                 BO_LAUNCH(ctx, "score_gemm_kernel");

@@ -1,0 +1,112 @@
+"""GPU tests of the int8-slice (Ozaki) scoring path on tcgen05: exact integer checks of
+the slice planes and the TMEM group accumulators, then parity of mu / s2 / EI against the
+FP64 path and the oracle at the slice counts the error model selects."""
+
+import numpy as np
+import pytest
+from scipy.stats import qmc
+
+from conftest import rel_err
+from oracle import GPOracle, kernel_matrix
+
+pytestmark = pytest.mark.gpu
+
+
+def synth(n, d, kernel="se", seed=0):
+    rng = np.random.RandomState(seed)
+    X = rng.rand(n, d)
+    y = np.sin(X.sum(axis=1)) + 0.01 * rng.randn(n)
+    gp = GPOracle(1e-6, float(y.max() - y.min()), 0.25 * np.ones(d), float(y.mean()), kernel)
+    gp.add_data(X, y)
+    return gp
+
+
+def slices_of(x, S):
+    out, r = [], x * 64.0
+    for _ in range(S):
+        t = np.rint(r)
+        out.append(t.astype(np.int64))
+        r = (r - t) * 128.0
+    return out
+
+
+@pytest.mark.parametrize("n,d,S,mc", [(64, 2, 1, 128), (256, 4, 3, 128), (300, 8, 5, 200), (512, 3, 8, 128)])
+def test_slices_and_accumulators_exact(ctx, n, d, S, mc):
+    gp = synth(n, d, seed=n)
+    ctx.fit("se", gp.X, gp.Y, gp.ell[None], [gp.rho], [gp.sn2], [gp.bias])
+    Xc = qmc.Sobol(d=d, scramble=False).random(256)[:mc]
+    out = ctx.ozaki_debug(S, Xc)
+    npad = out["ws"].shape[1]
+    W = np.zeros((npad, npad))
+    W[:n, :n] = ctx.factor("W")
+    W[np.arange(n, npad), np.arange(n, npad)] = 1.0
+    mx = np.max(np.abs(W), axis=1)
+    _, e = np.frexp(mx)
+    assert np.allclose(out["rowscale"], gp.rho * np.exp2(e - 12.0), rtol=0, atol=0)
+    ref_ws = slices_of(W * np.exp2(-e)[:, None], S)
+    for s in range(S):
+        assert np.array_equal(out["ws"][s].astype(np.int64), ref_ws[s]), "W slice %d" % s
+    # K* slices: the device exp may differ from NumPy's in the last ulp, so compare the value they encode
+    kap = np.zeros((out["ks"].shape[1], npad))
+    kap[:mc, :n] = kernel_matrix("se", Xc, gp.X, gp.ell, 1.0)
+    enc = sum(out["ks"][s].astype(np.float64) * 2.0 ** -(6 + 7 * s) for s in range(S))
+    assert np.max(np.abs(enc - kap)) <= 0.51 * 2.0 ** -(6 + 7 * (S - 1)) + 1e-15
+    # TMEM accumulators of tile 0: exact integer contraction of the returned slices
+    ks, ws = out["ks"].astype(np.int64), out["ws"].astype(np.int64)
+    G = S - 1
+    for rb in range(npad // 64):
+        kmax = (rb + 1) * 64
+        rows = slice(rb * 64, rb * 64 + 64)
+        for g in range(S):
+            ref = sum(ks[g - s][:128, :kmax] @ ws[s][rows, :kmax].T for s in range(g + 1))
+            assert np.array_equal(out["acc"][rb, g].astype(np.int64), ref), (rb, g)
+    # reassembly + reductions
+    v = np.zeros((128, npad))
+    for rb in range(npad // 64):
+        a = np.zeros((128, 64))
+        for g in range(G, -1, -1):
+            a = a * 2.0 ** -7 + out["acc"][rb, g]
+        v[:, rb * 64:rb * 64 + 64] = a * out["rowscale"][rb * 64:rb * 64 + 64]
+    alpha = np.zeros(npad)
+    alpha[:n] = ctx.factor("alpha")
+    k = min(mc, 128)
+    assert np.allclose(out["mu"][:k], gp.bias + v[:k] @ alpha, rtol=1e-12, atol=1e-12)
+    assert np.allclose(out["s2"][:k], gp.rho - np.sum(v[:k] ** 2, axis=1), rtol=1e-12, atol=1e-12)
+
+
+@pytest.mark.parametrize("n,d,kernel", [(1024, 8, "se"), (700, 8, "matern52"), (2048, 8, "se")])
+def test_ozaki_scores_match_oracle(ctx, n, d, kernel):
+    gp = synth(n, d, kernel, seed=n + 1)
+    ctx.fit(kernel, gp.X, gp.Y, gp.ell[None], [gp.rho], [gp.sn2], [gp.bias])
+    Xc = qmc.Sobol(d=d, scramble=False).random_base2(12)[:3000]
+    target = float(gp.predict(gp.X)[0].max())
+    ref = gp.get_improvement(target, Xc)
+    mu, s2 = gp.predict(Xc)
+    f64val, _, f64best = ctx.score(1, target, Xc, want_best=True)
+    ctx.set_precision(1, 1e-8)                      # BO_PREC_OZAKI, error-model driven slice count
+    val, _, best = ctx.score(1, target, Xc, want_best=True)
+    gmu, gs2 = ctx.predict(Xc)
+    assert rel_err(gmu, mu) < 1e-6 and rel_err(gs2, s2, 1e-9) < 1e-6
+    assert rel_err(val, ref, 1e-9) < 1e-6
+    assert best[1] == int(np.argmax(ref)) == f64best[1]
+    # gradients are still served (FP64 path) while the int8 path is selected
+    v1, g1, _ = ctx.score(1, target, Xc[:5], grad=True)
+    rv, rg = gp.get_improvement(target, Xc[:5], grad=True)
+    assert rel_err(v1, rv, 1e-9) < 1e-6 and rel_err(g1, rg, 1e-9) < 1e-5
+    ctx.set_precision(0, 1e-9)
+    back, _, _ = ctx.score(1, target, Xc)
+    assert np.array_equal(back, f64val)
+
+
+def test_ozaki_slice_count_follows_tolerance(ctx):
+    gp = synth(512, 8, seed=3)
+    ctx.fit("se", gp.X, gp.Y, gp.ell[None], [gp.rho], [gp.sn2], [gp.bias])
+    Xc = qmc.Sobol(d=8, scramble=False).random_base2(9)
+    mu, s2 = gp.predict(Xc)
+    errs = []
+    for S in (3, 4, 5, 6):
+        ctx.set_precision(1, float(S))              # tol >= 2 pins the slice count
+        gmu, gs2 = ctx.predict(Xc)
+        errs.append(max(np.max(np.abs(gmu - mu)), np.max(np.abs(gs2 - s2))))
+    assert errs[0] > errs[1] > errs[2] > errs[3]
+    assert errs[3] < 1e-9 and errs[1] / errs[2] > 30    # ~2^7 per extra slice
