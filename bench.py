@@ -39,7 +39,7 @@ FALLBACK_PEAKS = dict(hbm_gbs=6650.0, bf16_tflops=1590.0)
 # dram__bytes_read.sum + dram__bytes_write.sum per score_gemm_kernel launch from the committed
 # `ncu --set full` capture (profiles/r1_fp64_score_gemm_ncu.txt); algorithmic operand bytes are
 # W (lower triangle, 67 MB) + one K* chunk (268 MB): the excess is L2 thrash, 5.5 % of DRAM peak.
-TRAFFIC_NCU = {"rbf_n4096_d8_ei": 2.005e9}
+TRAFFIC_NCU = {"rbf_n4096_d8_ei:fp64": 2.005e9}
 
 
 def flop_per_eval(n, d):
@@ -162,6 +162,8 @@ def our_arm(args):
     fit_s = time.perf_counter() - t0
     acq, param = acq_param(spec, X, model.predict)
     index = policies.ModelIndex(model, acq, param)
+    if args.precision == "ozaki":
+        ctx.set_precision(1, args.tol)
 
     xc_dev = sobol_block(M, d, rank * M).cuda()            # this rank's block, resident in HBM
     val_dev = torch.empty(M, dtype=torch.float64, device="cuda")
@@ -228,22 +230,48 @@ def our_arm(args):
     e2e_value = M * world * args.steps / (e2e_ms * 1e-3)
 
     # roofline of the dominant kernel: the triangular contraction V = W K* (+ fused reductions)
-    gk = prof.get("score_gemm_kernel", dict(launches=0, total_ms=0.0))
-    chunk = min(M, max(1024, min(16384, ((1 << 25) // (-(-n // 128) * 128)) // 128 * 128)))
-    alg_flop_per_launch = (n * n + 4 * n) * chunk          # n^2 substitution + 4n reductions per candidate
-    avg_ms = gk["total_ms"] / max(1, gk["launches"])
-    achieved = alg_flop_per_launch / (avg_ms * 1e-3) / 1e12 if avg_ms > 0 else 0.0
     dmma_peak = ctx.microbench("dmma")
     dfma_peak = ctx.microbench("dfma")
     fp64_peak = max(dmma_peak, dfma_peak)
-    roofline = dict(bound="tensor", kernel="score_gemm_kernel", achieved=achieved, peak=fp64_peak, unit="TFLOP/s",
-                    frac=achieved / fp64_peak if fp64_peak else None, traffic=TRAFFIC_NCU.get(args.workload),
-                    peak_source="FP64 roof measured in this run by bo_microbench (register-resident loops on every SM): "
-                                "DMMA m8n8k4 %.1f, DFMA %.1f TFLOP/s; the larger is used (ncu: both issue at 128 flop/clk/SM = "
-                                "37.2 TFLOP/s at 1965 MHz). MEASURED_PEAKS.json holds no FP64 figure" % (dmma_peak, dfma_peak),
-                    frac_of_bf16_peak=achieved / pk["bf16_tflops"], bf16_peak=pk["bf16_tflops"], peaks=pk["source"],
-                    alg_flop_per_launch=alg_flop_per_launch, avg_launch_ms=avg_ms, launches=gk["launches"],
-                    share_of_step=gk["total_ms"] / dev_ms if dev_ms else None)
+    npad = -(-n // 128) * 128
+    if args.precision == "ozaki":
+        kname = "oz_score_kernel"
+        gk = prof.get(kname, dict(launches=0, total_ms=0.0))
+        slices = ctx.precision_info()[1]
+        pairs = slices * (slices + 1) // 2
+        nb = npad // 64
+        # algorithmic: n^2 (forward-substitution equivalent) + 4n (reductions) flop per candidate
+        alg_flop_per_launch = (n * n + 4 * n) * (M * S * args.steps) / max(1, gk["launches"])
+        exec_ops_per_launch = 2.0 * pairs * 64 * 64 * nb * (nb + 1) / 2 * (M * S * args.steps) / max(1, gk["launches"])
+        avg_ms = gk["total_ms"] / max(1, gk["launches"])
+        achieved = alg_flop_per_launch / (avg_ms * 1e-3) / 1e12 if avg_ms > 0 else 0.0
+        executed = exec_ops_per_launch / (avg_ms * 1e-3) / 1e12 if avg_ms > 0 else 0.0
+        int8_peak = 2.0 * pk["bf16_tflops"]
+        roofline = dict(bound="tensor", kernel=kname, achieved=achieved, peak=int8_peak, unit="TFLOP/s",
+                        frac=achieved / int8_peak, traffic=TRAFFIC_NCU.get(args.workload + ":ozaki"),
+                        peak_source="int8 tensor roof = 2 x the %s bf16 figure of MEASURED_PEAKS.json (tcgen05 kind::i8 issues at "
+                                    "twice the bf16 rate: ncu peak_sustained 16384 vs 8192 op/clk/SM)" % pk["source"],
+                        int8_slices=slices, slice_pairs=pairs, executed_int8_tops=executed,
+                        frac_executed=executed / int8_peak,
+                        note="achieved counts ALGORITHMIC flop (n^2 + 4n per candidate); the emulation executes %d int8 "
+                             "products per algorithmic product, so frac_executed is the tensor-pipe utilisation" % pairs,
+                        fp64_roof=fp64_peak, achieved_over_fp64_roof=achieved / fp64_peak if fp64_peak else None,
+                        alg_flop_per_launch=alg_flop_per_launch, avg_launch_ms=avg_ms, launches=gk["launches"],
+                        share_of_step=gk["total_ms"] / dev_ms if dev_ms else None)
+    else:
+        kname = "score_gemm_kernel"
+        gk = prof.get(kname, dict(launches=0, total_ms=0.0))
+        alg_flop_per_launch = (n * n + 4 * n) * (M * S * args.steps) / max(1, gk["launches"])
+        avg_ms = gk["total_ms"] / max(1, gk["launches"])
+        achieved = alg_flop_per_launch / (avg_ms * 1e-3) / 1e12 if avg_ms > 0 else 0.0
+        roofline = dict(bound="tensor", kernel=kname, achieved=achieved, peak=fp64_peak, unit="TFLOP/s",
+                        frac=achieved / fp64_peak if fp64_peak else None, traffic=TRAFFIC_NCU.get(args.workload + ":fp64"),
+                        peak_source="FP64 roof measured in this run by bo_microbench (register-resident loops on every SM): "
+                                    "DMMA m8n8k4 %.1f, DFMA %.1f TFLOP/s; the larger is used (ncu: both issue at 128 flop/clk/SM = "
+                                    "37.2 TFLOP/s at 1965 MHz). MEASURED_PEAKS.json holds no FP64 figure" % (dmma_peak, dfma_peak),
+                        frac_of_bf16_peak=achieved / pk["bf16_tflops"], bf16_peak=pk["bf16_tflops"], peaks=pk["source"],
+                        alg_flop_per_launch=alg_flop_per_launch, avg_launch_ms=avg_ms, launches=gk["launches"],
+                        share_of_step=gk["total_ms"] / dev_ms if dev_ms else None)
 
     chol = cholesky_metric(ctx, spec, X, ell[0], rho[0], sn2[0], pk, fp64_peak)
     cpu = cpu_baseline(spec, X, y, ell, rho, sn2, bias, budget_s=args.cpu_seconds) if world == 1 else None
@@ -253,8 +281,10 @@ def our_arm(args):
                 vs_baseline=None, dtype="f64", data="synthetic",
                 config=dict(workload=args.workload, kernel=spec["kernel"], n=n, d=d, acq=spec["acq"],
                             hyper_samples=S, candidates_per_gpu=M, candidates="unscrambled Sobol, contiguous block per rank",
-                            precision="fp64 (DMMA)", l2="inputs exceed L2: W %.0f MB + K* scratch %.0f MB + candidates %.0f MB per pass"
-                            % (n * n * 8 / 1e6, n * chunk * 8 / 1e6, M * d * 8 / 1e6), parallelism="dp%d candidate shards" % world),
+                            precision=("int8 slices on tcgen05 (tol %g -> %d slices), FP64 reassembly" % (args.tol, ctx.precision_info()[1]))
+                            if args.precision == "ozaki" else "fp64 (DMMA)",
+                            l2="inputs exceed L2: W factor %.0f MB + cross-kernel scratch >= %.0f MB + candidates %.0f MB per pass"
+                            % (n * n * 8 / 1e6, n * 8192 * 8 / 1e6, M * d * 8 / 1e6), parallelism="dp%d candidate shards" % world),
                 clocks=clocks,
                 e2e=dict(value=e2e_value, unit="evals/s", ms_per_step=e2e_ms / args.steps,
                          h2d_bytes_per_step=int(M * d * 8), d2h_bytes_per_step=int(10 * 16),
@@ -365,6 +395,10 @@ def main():
     ap.add_argument("--workload", default="rbf_n4096_d8_ei", choices=sorted(WORKLOADS))
     ap.add_argument("--candidates", type=int, default=0, help="override candidates per GPU (profiling only)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--precision", default="ozaki", choices=["ozaki", "fp64"],
+                    help="scoring contraction: error-bounded int8 slices on tcgen05 (default) or FP64 DMMA")
+    ap.add_argument("--tol", type=float, default=1e-7,
+                    help="ozaki: target abs error of V entries / sqrt(rho) (>= 2: explicit slice count)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     if args.impl == "reference":

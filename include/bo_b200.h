@@ -97,6 +97,8 @@ int bo_topk(bo_ctx *ctx, int k, int64_t *idx, double *val);
  * slices from its a-priori error model.  tol >= 2 sets the slice count directly
  * (2..8).  Gradient requests always run on the FP64 path. */
 int bo_set_precision(bo_ctx *ctx, int prec, double tol);
+/* current path and, for BO_PREC_OZAKI after a scoring call, the slice count in use */
+int bo_precision_info(bo_ctx *ctx, int *prec, int *slices);
 
 /* ---- Thompson: `model.sample_f(n, rng).get` (policies/simple.py:48) ------
  * ndraw weight-space posterior draws

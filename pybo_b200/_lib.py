@@ -21,7 +21,7 @@ PTR_HOST, PTR_DEVICE = 0, 1
 EXPORTS = [
     "bo_create", "bo_destroy", "bo_last_error", "bo_stream", "bo_sync", "bo_device_props",
     "bo_fit", "bo_fit_shape", "bo_fit_info", "bo_loglik", "bo_get_factor",
-    "bo_score", "bo_predict", "bo_topk", "bo_set_precision",
+    "bo_score", "bo_predict", "bo_topk", "bo_set_precision", "bo_precision_info",
     "bo_thompson_set", "bo_thompson_eval",
     "bo_cholesky", "bo_gram",
     "bo_profile_enable", "bo_profile_reset", "bo_profile_count", "bo_profile_get",
@@ -57,6 +57,7 @@ def _declare(lib):
         "bo_predict": (i, [vp, i64, vp, i, vp, vp, vp, vp]),
         "bo_topk": (i, [vp, i, vp, vp]),
         "bo_set_precision": (i, [vp, i, d]),
+        "bo_precision_info": (i, [vp, _ip, _ip]),
         "bo_thompson_set": (i, [vp, i, i, i, i, vp, vp, vp, vp, vp]),
         "bo_thompson_eval": (i, [vp, i64, vp, i, vp, vp, vp, vp]),
         "bo_cholesky": (i, [vp, i, i, vp, i, vp]),
@@ -220,6 +221,11 @@ class Context(object):
 
     def set_precision(self, prec, tol=1e-9):
         self._check(self._lib.bo_set_precision(self._h, int(prec), float(tol)))
+
+    def precision_info(self):
+        prec, slices = C.c_int(), C.c_int()
+        self._check(self._lib.bo_precision_info(self._h, C.byref(prec), C.byref(slices)))
+        return prec.value, slices.value
 
     # -- Thompson -------------------------------------------------------------------
     def thompson_set(self, W, b, theta, scale, bias):
