@@ -98,6 +98,8 @@ struct bo_ctx {
     int *dRowExp = nullptr;       // S_hyper x np (+ S_hyper maxima)
     size_t ws_capacity = 0, kss_capacity = 0, rowscale_capacity = 0, rowexp_capacity = 0;
     std::vector<int> h_emax;
+    double *dOzQ = nullptr, *dOzP = nullptr;   // (np/64) x chunk partial reductions
+    size_t ozpart_capacity = 0;
 
     bo_thompson_state th;
 

@@ -212,13 +212,30 @@ oz_kstar_slices_kernel(int kernel, int n, int np, int d, int S, const double *__
 // the contraction kernel
 // ---------------------------------------------------------------------------
 struct OzParams {
-    int np, S, nstages, ntiles;
+    int np, S, nstages, ntiles, nacc, tiles_per_group;
+    int mcp;
     const double *rowscale;   // np
     const double *alpha;      // np
-    double rho, bias;
-    double *mu, *s2;          // ntiles * 128
+    double *qpart, *ppart;    // [np/64][mcp] partial |v|^2 and v.alpha per row block
     int32_t *dbg;             // optional: [rb][g][128][64] accumulators of tile 0
 };
+
+// Work unit = (candidate tile, 64-row block of W).  Units are ordered group by group
+// (a group = `tiles_per_group` candidate tiles whose K* slices fit in L2 next to the W
+// slices), heaviest row block first, and dealt round-robin to the persistent CTAs, so
+// the CTAs running concurrently share a small set of candidate tiles (L2 hits on the A
+// stream) and all stream the same few row blocks of W.
+struct OzUnit { int tile, rb; };
+__device__ __forceinline__ OzUnit oz_decode(int u, int nb, int T, int ntiles) {
+    const int per = T * nb;
+    const int grp = u / per, r = u - grp * per;
+    const int rem = ntiles - grp * T;
+    const int Tg = rem < T ? rem : T;
+    OzUnit o;
+    o.rb = nb - 1 - r / Tg;
+    o.tile = grp * T + r % Tg;
+    return o;
+}
 
 __global__ void __launch_bounds__(OZ_THREADS, 1)
 oz_score_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB, OzParams p) {
@@ -227,18 +244,20 @@ oz_score_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
     const uint32_t raw = smem_u32(oz_smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
     uint8_t *gen_base = oz_smem_raw + (base - raw);
-    const int S = p.S, G = S - 1, nst = p.nstages;
+    const int S = p.S, G = S - 1, nst = p.nstages, nacc = p.nacc;
     const uint32_t stage_bytes = (uint32_t)S * (OZ_A_SLICE_BYTES + OZ_B_SLICE_BYTES);
     uint64_t *bars = reinterpret_cast<uint64_t *>(gen_base + (size_t)nst * stage_bytes);
-    // bars[0..nst): full, [nst..2nst): empty, [2nst]: tmem_full, [2nst+1]: tmem_empty
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * nst + 2);
+    // bars[0..nst): full, [nst..2nst): empty, then tmem_full[2], tmem_empty[2]
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * nst + 4);
     const uint32_t bar0 = smem_u32(bars);
     auto full_bar = [&](int s) { return bar0 + 8u * s; };
     auto empty_bar = [&](int s) { return bar0 + 8u * (nst + s); };
-    const uint32_t tmem_full = bar0 + 8u * (2 * nst), tmem_empty = bar0 + 8u * (2 * nst + 1);
+    auto tmem_full = [&](int a) { return bar0 + 8u * (2 * nst + a); };
+    auto tmem_empty = [&](int a) { return bar0 + 8u * (2 * nst + 2 + a); };
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nb = p.np / OZ_BN;
+    const int nunits = p.ntiles * nb;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmapA);
@@ -247,8 +266,10 @@ oz_score_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
             mbar_init(full_bar(s), 1);
             mbar_init(empty_bar(s), 1);
         }
-        mbar_init(tmem_full, 1);
-        mbar_init(tmem_empty, 4);
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(tmem_full(a), 1);
+            mbar_init(tmem_empty(a), 4);
+        }
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 512);
@@ -262,19 +283,18 @@ oz_score_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
-                for (int rb = 0; rb < nb; ++rb) {
-                    for (int kb = 0; kb <= rb; ++kb) {
-                        mbar_wait(empty_bar(stage), phase ^ 1);
-                        mbar_expect_tx(full_bar(stage), stage_bytes);
-                        const uint32_t sA = base + stage * stage_bytes;
-                        const uint32_t sB = sA + S * OZ_A_SLICE_BYTES;
-                        for (int s = 0; s < S; ++s) {
-                            tma_load_3d(sA + s * OZ_A_SLICE_BYTES, &tmapA, kb * OZ_BK, tile * OZ_BM, s, full_bar(stage));
-                            tma_load_3d(sB + s * OZ_B_SLICE_BYTES, &tmapB, kb * OZ_BK, rb * OZ_BN, s, full_bar(stage));
-                        }
-                        if (++stage == nst) { stage = 0; phase ^= 1; }
+            for (int u = blockIdx.x; u < nunits; u += gridDim.x) {
+                const OzUnit un = oz_decode(u, nb, p.tiles_per_group, p.ntiles);
+                for (int kb = 0; kb <= un.rb; ++kb) {
+                    mbar_wait(empty_bar(stage), phase ^ 1);
+                    mbar_expect_tx(full_bar(stage), stage_bytes);
+                    const uint32_t sA = base + stage * stage_bytes;
+                    const uint32_t sB = sA + S * OZ_A_SLICE_BYTES;
+                    for (int s = 0; s < S; ++s) {
+                        tma_load_3d(sA + s * OZ_A_SLICE_BYTES, &tmapA, kb * OZ_BK, un.tile * OZ_BM, s, full_bar(stage));
+                        tma_load_3d(sB + s * OZ_B_SLICE_BYTES, &tmapB, kb * OZ_BK, un.rb * OZ_BN, s, full_bar(stage));
                     }
+                    if (++stage == nst) { stage = 0; phase ^= 1; }
                 }
             }
         }
@@ -282,91 +302,105 @@ oz_score_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
         // ===================== MMA issuer =====================
         if (lane == 0) {
             const uint32_t idesc = make_idesc_i8(OZ_BM, OZ_BN);
-            int stage = 0;
+            int stage = 0, acc = 0;
             uint32_t phase = 0, acc_phase = 0;
-            for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
-                for (int rb = 0; rb < nb; ++rb) {
-                    mbar_wait(tmem_empty, acc_phase ^ 1);     // epilogue has drained the accumulators
+            for (int u = blockIdx.x; u < nunits; u += gridDim.x) {
+                const OzUnit un = oz_decode(u, nb, p.tiles_per_group, p.ntiles);
+                mbar_wait(tmem_empty(acc), acc_phase ^ 1);    // epilogue has drained this accumulator set
+                tc_fence_after();
+                const uint32_t tacc = tmem_base + (uint32_t)(acc * S * OZ_BN);
+                for (int kb = 0; kb <= un.rb; ++kb) {
+                    mbar_wait(full_bar(stage), phase);
                     tc_fence_after();
-                    for (int kb = 0; kb <= rb; ++kb) {
-                        mbar_wait(full_bar(stage), phase);
-                        tc_fence_after();
-                        const uint32_t sA = base + stage * stage_bytes;
-                        const uint32_t sB = sA + S * OZ_A_SLICE_BYTES;
+                    const uint32_t sA = base + stage * stage_bytes;
+                    const uint32_t sB = sA + S * OZ_A_SLICE_BYTES;
 #pragma unroll 1
-                        for (int kk = 0; kk < 2; ++kk) {
+                    for (int kk = 0; kk < 2; ++kk) {
 #pragma unroll 1
-                            for (int s = 0; s < S; ++s) {
-                                const uint64_t adesc = make_desc_sw64(sA + s * OZ_A_SLICE_BYTES + kk * 32);
-                                const uint32_t accumulate = (kb > 0 || kk > 0 || s > 0) ? 1u : 0u;
-                                for (int t = 0; t <= G - s; ++t) {
-                                    const uint64_t bdesc = make_desc_sw64(sB + t * OZ_B_SLICE_BYTES + kk * 32);
-                                    umma_i8(tmem_base + (uint32_t)(s + t) * OZ_BN, adesc, bdesc, idesc, accumulate);
-                                }
+                        for (int s = 0; s < S; ++s) {
+                            const uint64_t adesc = make_desc_sw64(sA + s * OZ_A_SLICE_BYTES + kk * 32);
+                            const uint32_t accumulate = (kb > 0 || kk > 0 || s > 0) ? 1u : 0u;
+                            for (int t = 0; t <= G - s; ++t) {
+                                const uint64_t bdesc = make_desc_sw64(sB + t * OZ_B_SLICE_BYTES + kk * 32);
+                                umma_i8(tacc + (uint32_t)(s + t) * OZ_BN, adesc, bdesc, idesc, accumulate);
                             }
                         }
-                        umma_commit(empty_bar(stage));        // smem slot free once these MMAs retire
-                        if (++stage == nst) { stage = 0; phase ^= 1; }
                     }
-                    umma_commit(tmem_full);                   // accumulators of this row block are complete
-                    acc_phase ^= 1;
+                    umma_commit(empty_bar(stage));            // smem slot free once these MMAs retire
+                    if (++stage == nst) { stage = 0; phase ^= 1; }
                 }
+                umma_commit(tmem_full(acc));                  // accumulators of this unit are complete
+                if (++acc == nacc) { acc = 0; acc_phase ^= 1; }
             }
         }
     } else {
         // ===================== epilogue: one candidate per thread =====================
         const int quarter = warp & 3;                          // TMEM lane quarter this warp may access
-        const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16);
+        int acc = 0;
         uint32_t acc_phase = 0;
-        for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+        for (int u = blockIdx.x; u < nunits; u += gridDim.x) {
+            const OzUnit un = oz_decode(u, nb, p.tiles_per_group, p.ntiles);
+            const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * S * OZ_BN);
             double q = 0.0, pm = 0.0;
-            for (int rb = 0; rb < nb; ++rb) {
-                mbar_wait(tmem_full, acc_phase);
-                tc_fence_after();
-                for (int c0 = 0; c0 < OZ_BN; c0 += 16) {
-                    double v[16];
-                    int32_t r[16];
-                    tmem_ld16(lane_base + (uint32_t)(G * OZ_BN + c0), r);
+            mbar_wait(tmem_full(acc), acc_phase);
+            tc_fence_after();
+            for (int c0 = 0; c0 < OZ_BN; c0 += 16) {
+                double v[16];
+                int32_t r[16];
+                tmem_ld16(lane_base + (uint32_t)(G * OZ_BN + c0), r);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] = (double)r[i];
+                if (p.dbg && un.tile == 0) {
+                    int32_t *o = p.dbg + (((int64_t)un.rb * S + G) * 128 + quarter * 32 + lane) * 64 + c0;
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) o[i] = r[i];
+                }
+                for (int g = G - 1; g >= 0; --g) {
+                    tmem_ld16(lane_base + (uint32_t)(g * OZ_BN + c0), r);
                     tmem_ld_wait();
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) v[i] = (double)r[i];
-                    if (p.dbg && tile == 0) {
-                        int32_t *o = p.dbg + (((int64_t)rb * S + G) * 128 + quarter * 32 + lane) * 64 + c0;
+                    for (int i = 0; i < 16; ++i) v[i] = fma(v[i], 0.0078125, (double)r[i]);
+                    if (p.dbg && un.tile == 0) {
+                        int32_t *o = p.dbg + (((int64_t)un.rb * S + g) * 128 + quarter * 32 + lane) * 64 + c0;
 #pragma unroll
                         for (int i = 0; i < 16; ++i) o[i] = r[i];
                     }
-                    for (int g = G - 1; g >= 0; --g) {
-                        tmem_ld16(lane_base + (uint32_t)(g * OZ_BN + c0), r);
-                        tmem_ld_wait();
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) v[i] = fma(v[i], 0.0078125, (double)r[i]);
-                        if (p.dbg && tile == 0) {
-                            int32_t *o = p.dbg + (((int64_t)rb * S + g) * 128 + quarter * 32 + lane) * 64 + c0;
-#pragma unroll
-                            for (int i = 0; i < 16; ++i) o[i] = r[i];
-                        }
-                    }
-                    const int row0 = rb * OZ_BN + c0;
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        const double vv = v[i] * __ldg(p.rowscale + row0 + i);
-                        q = fma(vv, vv, q);
-                        pm = fma(vv, __ldg(p.alpha + row0 + i), pm);
-                    }
                 }
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(tmem_empty);
-                acc_phase ^= 1;
+                const int row0 = un.rb * OZ_BN + c0;
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const double vv = v[i] * __ldg(p.rowscale + row0 + i);
+                    q = fma(vv, vv, q);
+                    pm = fma(vv, __ldg(p.alpha + row0 + i), pm);
+                }
             }
-            const int64_t cand = (int64_t)tile * OZ_BM + quarter * 32 + lane;
-            p.mu[cand] = p.bias + pm;
-            p.s2[cand] = p.rho - q;
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tmem_empty(acc));
+            if (++acc == nacc) { acc = 0; acc_phase ^= 1; }
+            const int64_t o = (int64_t)un.rb * p.mcp + (int64_t)un.tile * OZ_BM + quarter * 32 + lane;
+            p.qpart[o] = q;
+            p.ppart[o] = pm;
         }
     }
     tc_fence_before();
     __syncthreads();
     if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+// mu = bias + sum_rb ppart, s2 = rho - sum_rb qpart (fixed summation order)
+__global__ void oz_moments_kernel(int nb, int mcp, const double *__restrict__ qpart, const double *__restrict__ ppart,
+                                  double rho, double bias, double *__restrict__ mu, double *__restrict__ s2) {
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= mcp) return;
+    double q = 0.0, pm = 0.0;
+    for (int i = 0; i < nb; ++i) {
+        q += qpart[(int64_t)i * mcp + m];
+        pm += ppart[(int64_t)i * mcp + m];
+    }
+    mu[m] = bias + pm;
+    s2[m] = rho - q;
 }
 
 // ---------------------------------------------------------------------------
@@ -501,16 +535,40 @@ int bo_ozaki_moments(bo_ctx *ctx, int s, int S, const double *dXc, int64_t c0, i
     CUtensorMap tmA, tmB;
     BO_TRY(make_tmap(ctx, &tmA, ctx->dKss, np, mcp, S, OZ_BM));
     BO_TRY(make_tmap(ctx, &tmB, ctx->dWs + (size_t)s * S * np * np, np, np, S, OZ_BN));
+    const int nb = np / OZ_BN;
+    {
+        size_t need = (size_t)nb * mcp;
+        if (ctx->ozpart_capacity < need || !ctx->dOzQ) {
+            size_t c1 = ctx->ozpart_capacity, c2 = ctx->ozpart_capacity;
+            BO_TRY(bo_reserve(ctx, &ctx->dOzQ, &c1, need));
+            BO_TRY(bo_reserve(ctx, &ctx->dOzP, &c2, need));
+            ctx->ozpart_capacity = need;
+        }
+    }
     OzParams p;
-    p.np = np; p.S = S; p.nstages = oz_stage_count(S); p.ntiles = mcp / OZ_BM;
+    p.np = np; p.S = S; p.nstages = oz_stage_count(S); p.ntiles = mcp / OZ_BM; p.mcp = mcp;
+    p.nacc = (2 * S * OZ_BN <= 512) ? 2 : 1;
+    // candidate tiles whose K* slices (S * 128 * np bytes each) share L2 with the W slices
+    {
+        const double tile_bytes = (double)S * OZ_BM * np;
+        const double budget = 0.35 * (double)ctx->prop.l2CacheSize;
+        int T = (int)(budget / tile_bytes);
+        p.tiles_per_group = T < 2 ? 2 : (T > 64 ? 64 : T);
+    }
     p.rowscale = ctx->dRowScale + (size_t)s * np;
     p.alpha = ctx->dAlpha + (size_t)s * np;
-    p.rho = ctx->h_rho[s]; p.bias = ctx->h_bias[s];
-    p.mu = mu; p.s2 = s2; p.dbg = dbg;
-    const int grid = p.ntiles < ctx->sm_count ? p.ntiles : ctx->sm_count;
+    p.qpart = ctx->dOzQ; p.ppart = ctx->dOzP; p.dbg = dbg;
+    const int nunits = p.ntiles * nb;
+    const int grid = nunits < ctx->sm_count ? nunits : ctx->sm_count;
     {
         BO_LAUNCH(ctx, "oz_score_kernel");
         oz_score_kernel<<<grid, OZ_THREADS, oz_smem_bytes(S), ctx->stream>>>(tmA, tmB, p);
+        BO_CHECK_LAUNCH(ctx);
+    }
+    {
+        BO_LAUNCH(ctx, "oz_moments_kernel");
+        oz_moments_kernel<<<(mcp + 255) / 256, 256, 0, ctx->stream>>>(nb, mcp, ctx->dOzQ, ctx->dOzP, ctx->h_rho[s],
+                                                                   ctx->h_bias[s], mu, s2);
         BO_CHECK_LAUNCH(ctx);
     }
     return BO_OK;

@@ -473,7 +473,7 @@ int bo_score_run(bo_ctx *ctx, const ScoreRequest &rq) {
         if (oz_S < 1) return BO_ERR_CUDA;
         BO_TRY(bo_ozaki_prepare(ctx, oz_S));
     }
-    const int64_t chunk = oz ? (int64_t)ctx->sm_count * 128 : ctx->chunk;
+    const int64_t chunk = oz ? (int64_t)256 * 128 : ctx->chunk;
     const int64_t cap = bo_round_up64(M < chunk ? M : chunk, 128);
 
     if (!oz) BO_TRY(bo_reserve(ctx, &ctx->dKs, &ctx->ks_capacity, (size_t)np * cap));
