@@ -107,9 +107,37 @@ __device__ __forceinline__ uint64_t make_desc_sw64(uint32_t smem_addr) {
     return d;
 }
 
-// kind::i8 instruction descriptor: D = s32, A = B = signed int8, both K-major, M = 128, N = 64
-__device__ __forceinline__ uint32_t make_idesc_i8(int M, int N) {
+// kind::i8 instruction descriptor: D = s32, A = B = signed int8, both K-major
+__host__ __device__ constexpr uint32_t make_idesc_i8(int M, int N) {
     return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+// high word of the SWIZZLE_64B K-major descriptor is constant; the low word is (addr >> 4) | LBO
+#define OZ_DESC_HI ((uint32_t)(512 >> 4) | (1u << 14) | (4u << 29))
+__device__ __forceinline__ uint64_t oz_desc(uint32_t smem_addr) {
+    return ((uint64_t)OZ_DESC_HI << 32) | (uint64_t)(((smem_addr >> 4) & 0x3FFFu) | (1u << 16));
+}
+
+// All MMAs of one pipeline stage.  For a fixed A slice s the B slices t = 0..S-1-s are
+// contiguous in shared memory and their accumulators (groups s..S-1) are contiguous in TMEM,
+// so they are issued as ONE instruction of N = 64 (S - s) columns (split at 256): the A tile is
+// read from shared memory once per s instead of once per (s, t) pair.
+template <int S>
+__device__ __forceinline__ void oz_issue_stage(uint32_t sA, uint32_t sB, uint32_t tacc, bool first) {
+#pragma unroll
+    for (int kk = 0; kk < 2; ++kk) {
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+            constexpr int dummy = 0; (void)dummy;
+            const int ntot = OZ_BN * (S - s);
+            const int n1 = ntot > 256 ? 256 : ntot;
+            const uint64_t adesc = oz_desc(sA + s * OZ_A_SLICE_BYTES + kk * 32);
+            const uint32_t accumulate = (first && kk == 0 && s == 0) ? 0u : 1u;
+            umma_i8(tacc + (uint32_t)(s * OZ_BN), adesc, oz_desc(sB + kk * 32), make_idesc_i8(OZ_BM, n1), accumulate);
+            if (ntot > 256)
+                umma_i8(tacc + (uint32_t)(s * OZ_BN + 256), adesc, oz_desc(sB + 256 * OZ_BK + kk * 32),
+                        make_idesc_i8(OZ_BM, ntot - 256), accumulate);
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------
@@ -237,6 +265,7 @@ __device__ __forceinline__ OzUnit oz_decode(int u, int nb, int T, int ntiles) {
     return o;
 }
 
+template <int S>
 __global__ void __launch_bounds__(OZ_THREADS, 1)
 oz_score_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB, OzParams p) {
     extern __shared__ uint8_t oz_smem_raw[];
@@ -244,7 +273,8 @@ oz_score_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
     const uint32_t raw = smem_u32(oz_smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
     uint8_t *gen_base = oz_smem_raw + (base - raw);
-    const int S = p.S, G = S - 1, nst = p.nstages, nacc = p.nacc;
+    constexpr int G = S - 1;
+    const int nst = p.nstages, nacc = p.nacc;
     const uint32_t stage_bytes = (uint32_t)S * (OZ_A_SLICE_BYTES + OZ_B_SLICE_BYTES);
     uint64_t *bars = reinterpret_cast<uint64_t *>(gen_base + (size_t)nst * stage_bytes);
     // bars[0..nst): full, [nst..2nst): empty, then tmem_full[2], tmem_empty[2]
@@ -301,7 +331,6 @@ oz_score_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
         if (lane == 0) {
-            const uint32_t idesc = make_idesc_i8(OZ_BM, OZ_BN);
             int stage = 0, acc = 0;
             uint32_t phase = 0, acc_phase = 0;
             for (int u = blockIdx.x; u < nunits; u += gridDim.x) {
@@ -313,19 +342,7 @@ oz_score_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
                     mbar_wait(full_bar(stage), phase);
                     tc_fence_after();
                     const uint32_t sA = base + stage * stage_bytes;
-                    const uint32_t sB = sA + S * OZ_A_SLICE_BYTES;
-#pragma unroll 1
-                    for (int kk = 0; kk < 2; ++kk) {
-#pragma unroll 1
-                        for (int s = 0; s < S; ++s) {
-                            const uint64_t adesc = make_desc_sw64(sA + s * OZ_A_SLICE_BYTES + kk * 32);
-                            const uint32_t accumulate = (kb > 0 || kk > 0 || s > 0) ? 1u : 0u;
-                            for (int t = 0; t <= G - s; ++t) {
-                                const uint64_t bdesc = make_desc_sw64(sB + t * OZ_B_SLICE_BYTES + kk * 32);
-                                umma_i8(tacc + (uint32_t)(s + t) * OZ_BN, adesc, bdesc, idesc, accumulate);
-                            }
-                        }
-                    }
+                    oz_issue_stage<S>(sA, sA + S * OZ_A_SLICE_BYTES, tacc, kb == 0);
                     umma_commit(empty_bar(stage));            // smem slot free once these MMAs retire
                     if (++stage == nst) { stage = 0; phase ^= 1; }
                 }
@@ -345,32 +362,25 @@ oz_score_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
             mbar_wait(tmem_full(acc), acc_phase);
             tc_fence_after();
             for (int c0 = 0; c0 < OZ_BN; c0 += 16) {
-                double v[16];
-                int32_t r[16];
-                tmem_ld16(lane_base + (uint32_t)(G * OZ_BN + c0), r);
+                int32_t r[S][16];
+#pragma unroll
+                for (int g = 0; g < S; ++g) tmem_ld16(lane_base + (uint32_t)(g * OZ_BN + c0), r[g]);
                 tmem_ld_wait();
-#pragma unroll
-                for (int i = 0; i < 16; ++i) v[i] = (double)r[i];
                 if (p.dbg && un.tile == 0) {
-                    int32_t *o = p.dbg + (((int64_t)un.rb * S + G) * 128 + quarter * 32 + lane) * 64 + c0;
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) o[i] = r[i];
-                }
-                for (int g = G - 1; g >= 0; --g) {
-                    tmem_ld16(lane_base + (uint32_t)(g * OZ_BN + c0), r);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) v[i] = fma(v[i], 0.0078125, (double)r[i]);
-                    if (p.dbg && un.tile == 0) {
+                    for (int g = 0; g < S; ++g) {
                         int32_t *o = p.dbg + (((int64_t)un.rb * S + g) * 128 + quarter * 32 + lane) * 64 + c0;
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) o[i] = r[i];
+                        for (int i = 0; i < 16; ++i) o[i] = r[g][i];
                     }
                 }
                 const int row0 = un.rb * OZ_BN + c0;
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
-                    const double vv = v[i] * __ldg(p.rowscale + row0 + i);
+                    double v = (double)r[G][i];
+#pragma unroll
+                    for (int g = G - 1; g >= 0; --g) v = fma(v, 0.0078125, (double)r[g][i]);
+                    const double vv = v * __ldg(p.rowscale + row0 + i);
                     q = fma(vv, vv, q);
                     pm = fma(vv, __ldg(p.alpha + row0 + i), pm);
                 }
@@ -448,8 +458,9 @@ static size_t oz_smem_bytes(int S) {
 }
 
 int bo_ozaki_init(bo_ctx *ctx) {
-    BO_CUDA(ctx, cudaFuncSetAttribute(oz_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)oz_smem_bytes(OZ_MAX_S)));
+#define OZ_ATTR(SS) BO_CUDA(ctx, cudaFuncSetAttribute(oz_score_kernel<SS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)oz_smem_bytes(SS)))
+    OZ_ATTR(2); OZ_ATTR(3); OZ_ATTR(4); OZ_ATTR(5); OZ_ATTR(6); OZ_ATTR(7); OZ_ATTR(8);
+#undef OZ_ATTR
     return BO_OK;
 }
 
@@ -493,7 +504,7 @@ int bo_ozaki_prepare(bo_ctx *ctx, int S) {
 int bo_ozaki_choose_slices(bo_ctx *ctx, double tol) {
     if (tol >= 2.0) {
         int S = (int)tol;
-        return S > OZ_MAX_S ? OZ_MAX_S : S;
+        return S > OZ_MAX_S ? OZ_MAX_S : (S < 2 ? 2 : S);
     }
     // exponents need W: use 4 slices provisionally just to obtain e_max
     if (!ctx->oz_ready) {
@@ -562,7 +573,12 @@ int bo_ozaki_moments(bo_ctx *ctx, int s, int S, const double *dXc, int64_t c0, i
     const int grid = nunits < ctx->sm_count ? nunits : ctx->sm_count;
     {
         BO_LAUNCH(ctx, "oz_score_kernel");
-        oz_score_kernel<<<grid, OZ_THREADS, oz_smem_bytes(S), ctx->stream>>>(tmA, tmB, p);
+        switch (S) {
+#define OZ_RUN(SS) case SS: oz_score_kernel<SS><<<grid, OZ_THREADS, oz_smem_bytes(SS), ctx->stream>>>(tmA, tmB, p); break
+            OZ_RUN(2); OZ_RUN(3); OZ_RUN(4); OZ_RUN(5); OZ_RUN(6); OZ_RUN(7); OZ_RUN(8);
+#undef OZ_RUN
+            default: return bo_set_err(ctx, BO_ERR_ARG, "int8 path needs 2..8 slices, got %d", S);
+        }
         BO_CHECK_LAUNCH(ctx);
     }
     {
@@ -582,7 +598,7 @@ extern "C" int bo_ozaki_debug(bo_ctx *ctx, int S, int mc, const double *Xc, doub
     if (!ctx) return BO_ERR_ARG;
     BO_CUDA(ctx, cudaSetDevice(ctx->device));
     if (!ctx->fitted) return bo_set_err(ctx, BO_ERR_STATE, "bo_ozaki_debug before bo_fit");
-    if (S < 1 || S > OZ_MAX_S || mc < 1) return bo_set_err(ctx, BO_ERR_ARG, "bad S / mc");
+    if (S < 2 || S > OZ_MAX_S || mc < 1) return bo_set_err(ctx, BO_ERR_ARG, "bad S / mc");
     const int np = ctx->np, mcp = bo_round_up(mc, OZ_BM), nb = np / OZ_BN;
     ctx->oz_ready = false;
     BO_TRY(bo_ozaki_prepare(ctx, S));

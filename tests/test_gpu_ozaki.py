@@ -30,7 +30,7 @@ def slices_of(x, S):
     return out
 
 
-@pytest.mark.parametrize("n,d,S,mc", [(64, 2, 1, 128), (256, 4, 3, 128), (300, 8, 5, 200), (512, 3, 8, 128)])
+@pytest.mark.parametrize("n,d,S,mc", [(64, 2, 2, 128), (256, 4, 3, 128), (300, 8, 5, 200), (512, 3, 8, 128), (200, 5, 6, 128), (130, 2, 7, 100), (256, 4, 4, 128)])
 def test_slices_and_accumulators_exact(ctx, n, d, S, mc):
     gp = synth(n, d, seed=n)
     ctx.fit("se", gp.X, gp.Y, gp.ell[None], [gp.rho], [gp.sn2], [gp.bias])
