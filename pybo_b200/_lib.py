@@ -99,7 +99,12 @@ def _ptr(a):
 
 
 def f64(a, ndmin=1):
-    return np.ascontiguousarray(np.array(a, dtype=np.float64, ndmin=ndmin))
+    """C-contiguous float64 view of `a` with at least `ndmin` dimensions; no copy when `a`
+    already is one (candidate grids are large and may live in pinned memory)."""
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    while a.ndim < ndmin:
+        a = a[None]
+    return a
 
 
 class Context(object):

@@ -236,6 +236,88 @@ oz_kstar_slices_kernel(int kernel, int n, int np, int d, int S, const double *__
     }
 }
 
+// Fast variant for the SE kernel and S <= 6 slices.  The FP64 pipe limits the slicer, so
+// (i) the scaled squared distance comes from one dot product, D/2 = |xc|^2/2 + |xs|^2/2 - xc.xs
+// (rounding error ~1e-14 relative in kappa, far below the 2^-41 quantum of 6 slices), (ii) exp is
+// an inline exp2 (degree-12 Taylor in ln2*f, |f| <= 1/2, error < 2e-16) whose exponent add also
+// applies the fixed-point scale, and (iii) the balanced base-128 digits are peeled off one 64-bit
+// integer on the integer pipe instead of S rint/subtract rounds on the FP64 pipe.
+__device__ __forceinline__ long long oz_fixed_exp2(double z, int shift) {
+    // rint(2^(z + shift)) for z <= 0
+    const double kd = rint(z);
+    const double f = z - kd;
+    const int ki = (int)kd + shift;
+    if (ki < -1) return 0;
+    double p = 2.5678435993488196e-11;
+    p = fma(p, f, 4.44553827187081e-10);
+    p = fma(p, f, 7.054911620801121e-09);
+    p = fma(p, f, 1.0178086009239696e-07);
+    p = fma(p, f, 1.3215486790144305e-06);
+    p = fma(p, f, 1.5252733804059838e-05);
+    p = fma(p, f, 0.00015403530393381606);
+    p = fma(p, f, 0.0013333558146428441);
+    p = fma(p, f, 0.009618129107628477);
+    p = fma(p, f, 0.055504108664821576);
+    p = fma(p, f, 0.2402265069591007);
+    p = fma(p, f, 0.6931471805599453);
+    p = fma(p, f, 1.0);
+    const double v = __longlong_as_double(__double_as_longlong(p) + ((long long)ki << 52));
+    return __double2ll_rn(v);
+}
+
+template <int DP, int S>
+__global__ void __launch_bounds__(256)
+oz_kstar_slices_fast_kernel(int n, int np, int d, const double *__restrict__ Xs, const double *__restrict__ invell,
+                            const double *__restrict__ Xc, int64_t c0, int mc, int mcp, int8_t *__restrict__ Ks) {
+    __shared__ double xs[64][DP];
+    __shared__ double hb[64];                    // |xs_j|^2 / 2
+    const int tid = threadIdx.x;
+    const int j0 = blockIdx.y * 64;
+    for (int e = tid; e < 64 * DP; e += 256) xs[e / DP][e % DP] = Xs[(int64_t)j0 * DP + e];
+    const int m = blockIdx.x * 128 + (tid & 127);
+    const int half = tid >> 7;
+    const bool live = m < mc;
+    double xc[DP], ha = 0.0;
+#pragma unroll
+    for (int k = 0; k < DP; ++k) {
+        xc[k] = (live && k < d) ? Xc[(c0 + m) * d + k] * invell[k] : 0.0;
+        ha = fma(xc[k], xc[k], ha);
+    }
+    ha *= 0.5;
+    __syncthreads();
+    if (tid < 64) {
+        double b = 0.0;
+#pragma unroll
+        for (int k = 0; k < DP; ++k) b = fma(xs[tid][k], xs[tid][k], b);
+        hb[tid] = 0.5 * b;
+    }
+    __syncthreads();
+    constexpr int SHIFT = 6 + 7 * (S - 1);
+    constexpr double LOG2E = 1.4426950408889634;
+    for (int sub = 0; sub < 2; ++sub) {
+        const int jj0 = half * 32 + sub * 16;
+        alignas(16) int8_t q[S][16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            double dot = -ha - hb[jj0 + i];
+#pragma unroll
+            for (int k = 0; k < DP; ++k) dot = fma(xc[k], xs[jj0 + i][k], dot);
+            const double z = fmin(dot, 0.0) * LOG2E;            // log2 kappa
+            long long T = (live && (j0 + jj0 + i) < n) ? oz_fixed_exp2(z, SHIFT) : 0;
+#pragma unroll
+            for (int s = S - 1; s >= 1; --s) {
+                const long long dgt = ((T + 64) & 127) - 64;    // balanced digit in [-64, 63]
+                T = (T - dgt) >> 7;
+                q[s][i] = (int8_t)dgt;
+            }
+            q[0][i] = (int8_t)T;
+        }
+#pragma unroll
+        for (int s = 0; s < S; ++s)
+            *reinterpret_cast<int4 *>(Ks + ((int64_t)s * mcp + m) * np + j0 + jj0) = *reinterpret_cast<const int4 *>(q[s]);
+    }
+}
+
 // ---------------------------------------------------------------------------
 // the contraction kernel
 // ---------------------------------------------------------------------------
@@ -520,9 +602,27 @@ int bo_ozaki_choose_slices(bo_ctx *ctx, double tol) {
     return OZ_MAX_S;
 }
 
+template <int DP, int S>
+static void launch_oz_kstar_fast(bo_ctx *ctx, int s, const double *dXc, int64_t c0, int mc, int mcp) {
+    oz_kstar_slices_fast_kernel<DP, S><<<dim3(mcp / 128, ctx->np / 64), 256, 0, ctx->stream>>>(
+        ctx->n, ctx->np, ctx->d, ctx->dXs + (int64_t)s * ctx->np * ctx->dp, ctx->dInvEll + (int64_t)s * ctx->dp,
+        dXc, c0, mc, mcp, ctx->dKss);
+}
+
 template <int DP>
 static int launch_oz_kstar(bo_ctx *ctx, int s, int S, const double *dXc, int64_t c0, int mc, int mcp) {
     BO_LAUNCH(ctx, "oz_kstar_slices_kernel");
+    if (ctx->kernel == BO_KERNEL_SE && S >= 2 && S <= 6 && DP <= 16) {
+        switch (S) {
+            case 2: launch_oz_kstar_fast<DP, 2>(ctx, s, dXc, c0, mc, mcp); break;
+            case 3: launch_oz_kstar_fast<DP, 3>(ctx, s, dXc, c0, mc, mcp); break;
+            case 4: launch_oz_kstar_fast<DP, 4>(ctx, s, dXc, c0, mc, mcp); break;
+            case 5: launch_oz_kstar_fast<DP, 5>(ctx, s, dXc, c0, mc, mcp); break;
+            default: launch_oz_kstar_fast<DP, 6>(ctx, s, dXc, c0, mc, mcp); break;
+        }
+        BO_CHECK_LAUNCH(ctx);
+        return BO_OK;
+    }
     oz_kstar_slices_kernel<DP><<<dim3(mcp / 128, ctx->np / 64), 256, 0, ctx->stream>>>(
         ctx->kernel, ctx->n, ctx->np, ctx->d, S, ctx->dXs + (int64_t)s * ctx->np * ctx->dp,
         ctx->dInvEll + (int64_t)s * ctx->dp, dXc, c0, mc, mcp, ctx->dKss);
