@@ -266,16 +266,17 @@ __device__ __forceinline__ long long oz_fixed_exp2(double z, int shift) {
 }
 
 template <int DP, int S>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(128)
 oz_kstar_slices_fast_kernel(int n, int np, int d, const double *__restrict__ Xs, const double *__restrict__ invell,
                             const double *__restrict__ Xc, int64_t c0, int mc, int mcp, int8_t *__restrict__ Ks) {
-    __shared__ double xs[64][DP];
+    // block: 64 observations x 128 candidates, one candidate per thread -> each thread writes
+    // 64 contiguous bytes (two full 32-byte sectors) per slice plane
+    __shared__ __align__(16) double xs[64][DP];
     __shared__ double hb[64];                    // |xs_j|^2 / 2
     const int tid = threadIdx.x;
     const int j0 = blockIdx.y * 64;
-    for (int e = tid; e < 64 * DP; e += 256) xs[e / DP][e % DP] = Xs[(int64_t)j0 * DP + e];
-    const int m = blockIdx.x * 128 + (tid & 127);
-    const int half = tid >> 7;
+    for (int e = tid; e < 64 * DP; e += 128) xs[e / DP][e % DP] = Xs[(int64_t)j0 * DP + e];
+    const int m = blockIdx.x * 128 + tid;
     const bool live = m < mc;
     double xc[DP], ha = 0.0;
 #pragma unroll
@@ -294,14 +295,20 @@ oz_kstar_slices_fast_kernel(int n, int np, int d, const double *__restrict__ Xs,
     __syncthreads();
     constexpr int SHIFT = 6 + 7 * (S - 1);
     constexpr double LOG2E = 1.4426950408889634;
+    int8_t *out = Ks + (int64_t)m * np + j0;
+#pragma unroll 1
     for (int sub = 0; sub < 2; ++sub) {
-        const int jj0 = half * 32 + sub * 16;
-        alignas(16) int8_t q[S][16];
+        const int jj0 = sub * 32;
+        alignas(16) int8_t q[S][32];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
+        for (int i = 0; i < 32; ++i) {
             double dot = -ha - hb[jj0 + i];
 #pragma unroll
-            for (int k = 0; k < DP; ++k) dot = fma(xc[k], xs[jj0 + i][k], dot);
+            for (int k = 0; k < DP; k += 2) {
+                const double2 x2 = *reinterpret_cast<const double2 *>(&xs[jj0 + i][k]);
+                dot = fma(xc[k], x2.x, dot);
+                dot = fma(xc[k + 1], x2.y, dot);
+            }
             const double z = fmin(dot, 0.0) * LOG2E;            // log2 kappa
             long long T = (live && (j0 + jj0 + i) < n) ? oz_fixed_exp2(z, SHIFT) : 0;
 #pragma unroll
@@ -313,8 +320,11 @@ oz_kstar_slices_fast_kernel(int n, int np, int d, const double *__restrict__ Xs,
             q[0][i] = (int8_t)T;
         }
 #pragma unroll
-        for (int s = 0; s < S; ++s)
-            *reinterpret_cast<int4 *>(Ks + ((int64_t)s * mcp + m) * np + j0 + jj0) = *reinterpret_cast<const int4 *>(q[s]);
+        for (int s = 0; s < S; ++s) {
+            int4 *dst = reinterpret_cast<int4 *>(out + (int64_t)s * mcp * np + jj0);
+            dst[0] = *reinterpret_cast<const int4 *>(&q[s][0]);
+            dst[1] = *reinterpret_cast<const int4 *>(&q[s][16]);
+        }
     }
 }
 
@@ -604,7 +614,7 @@ int bo_ozaki_choose_slices(bo_ctx *ctx, double tol) {
 
 template <int DP, int S>
 static void launch_oz_kstar_fast(bo_ctx *ctx, int s, const double *dXc, int64_t c0, int mc, int mcp) {
-    oz_kstar_slices_fast_kernel<DP, S><<<dim3(mcp / 128, ctx->np / 64), 256, 0, ctx->stream>>>(
+    oz_kstar_slices_fast_kernel<DP, S><<<dim3(mcp / 128, ctx->np / 64), 128, 0, ctx->stream>>>(
         ctx->n, ctx->np, ctx->d, ctx->dXs + (int64_t)s * ctx->np * ctx->dp, ctx->dInvEll + (int64_t)s * ctx->dp,
         dXc, c0, mc, mcp, ctx->dKss);
 }
