@@ -80,6 +80,20 @@ extern "C" int bo_create(int device, bo_ctx **out) {
         delete ctx;
         return BO_ERR_CUDA;
     }
+    {
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);       // lo = least priority (largest number)
+        cudaStreamDestroy(ctx->stream);
+        bool ok = cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, hi) == cudaSuccess &&
+                  cudaStreamCreateWithPriority(&ctx->stream2, cudaStreamNonBlocking, lo) == cudaSuccess;
+        for (int i = 0; i < 2 && ok; ++i)
+            ok = cudaEventCreateWithFlags(&ctx->ev_sliced[i], cudaEventDisableTiming) == cudaSuccess &&
+                 cudaEventCreateWithFlags(&ctx->ev_consumed[i], cudaEventDisableTiming) == cudaSuccess;
+        if (!ok) {
+            delete ctx;
+            return BO_ERR_CUDA;
+        }
+    }
     ctx->sm_count = ctx->prop.multiProcessorCount;
     int rc = bo_linalg_init(ctx);
     if (rc == BO_OK) rc = bo_score_init(ctx);
@@ -129,8 +143,14 @@ extern "C" int bo_destroy(bo_ctx *ctx) {
     if (!ctx) return BO_OK;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    if (ctx->stream2) cudaStreamSynchronize(ctx->stream2);
     prof_drain(ctx);
     free_all(ctx);
+    for (int i = 0; i < 2; ++i) {
+        if (ctx->ev_sliced[i]) cudaEventDestroy(ctx->ev_sliced[i]);
+        if (ctx->ev_consumed[i]) cudaEventDestroy(ctx->ev_consumed[i]);
+    }
+    if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
     return BO_OK;

@@ -34,6 +34,8 @@ struct bo_thompson_state {
 struct bo_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t stream2 = nullptr;       // low-priority side stream (operand slicing overlaps the contraction)
+    cudaEvent_t ev_sliced[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr};
     char err[512] = {0};
     int sm_count = 0;
     cudaDeviceProp prop;
@@ -96,7 +98,7 @@ struct bo_ctx {
     int8_t *dKss = nullptr;       // slices x chunk x np          slice planes of K*^T
     double *dRowScale = nullptr;  // S_hyper x np   2^(e_i - 12) rho
     int *dRowExp = nullptr;       // S_hyper x np (+ S_hyper maxima)
-    size_t ws_capacity = 0, kss_capacity = 0, rowscale_capacity = 0, rowexp_capacity = 0;
+    size_t ws_capacity = 0, kss_capacity = 0, kss_stride = 0, rowscale_capacity = 0, rowexp_capacity = 0;
     std::vector<int> h_emax;
     double *dOzQ = nullptr, *dOzP = nullptr;   // (np/64) x chunk partial reductions
     size_t ozpart_capacity = 0;
@@ -143,7 +145,8 @@ struct bo_launch_scope {
     bo_ctx *ctx;
     cudaEvent_t a = nullptr, b = nullptr;
     int slot = -1;
-    bo_launch_scope(bo_ctx *c, const char *name) : ctx(c) {
+    cudaStream_t st;
+    bo_launch_scope(bo_ctx *c, const char *name, cudaStream_t stream = nullptr) : ctx(c), st(stream ? stream : c->stream) {
         ctx->launches++;
         if (!ctx->prof_on) return;
         for (size_t i = 0; i < ctx->prof.size(); ++i)
@@ -155,17 +158,18 @@ struct bo_launch_scope {
         }
         cudaEventCreate(&a);
         cudaEventCreate(&b);
-        cudaEventRecord(a, ctx->stream);
+        cudaEventRecord(a, st);
     }
     ~bo_launch_scope() {
         if (slot < 0) return;
-        cudaEventRecord(b, ctx->stream);
+        cudaEventRecord(b, st);
         ctx->prof[slot].launches++;
         ctx->prof[slot].pending.emplace_back(a, b);
     }
 };
 
 #define BO_LAUNCH(ctx, name) bo_launch_scope scope__(ctx, name)
+#define BO_LAUNCH_ON(ctx, name, stream) bo_launch_scope scope__(ctx, name, stream)
 
 #define BO_CHECK_LAUNCH(ctx)                                                     \
     do {                                                                         \
@@ -188,8 +192,10 @@ int bo_score_init(bo_ctx *ctx);
 int bo_ozaki_init(bo_ctx *ctx);
 int bo_ozaki_prepare(bo_ctx *ctx, int S);
 int bo_ozaki_choose_slices(bo_ctx *ctx, double tol);
-int bo_ozaki_moments(bo_ctx *ctx, int s, int S, const double *dXc, int64_t c0, int mc, int mcp, double *mu,
-                     double *s2, int32_t *dbg);
+int bo_ozaki_slice(bo_ctx *ctx, int s, int S, const double *dXc, int64_t c0, int mc, int mcp, int buf,
+                   cudaStream_t stream);
+int bo_ozaki_contract(bo_ctx *ctx, int s, int S, int mcp, int buf, double *mu, double *s2, int32_t *dbg);
+int bo_ozaki_reserve(bo_ctx *ctx, int S, int mcp_max, int nbuf);
 
 // one scoring / prediction pass over M device-resident candidates
 struct ScoreRequest {

@@ -613,48 +613,63 @@ int bo_ozaki_choose_slices(bo_ctx *ctx, double tol) {
 }
 
 template <int DP, int S>
-static void launch_oz_kstar_fast(bo_ctx *ctx, int s, const double *dXc, int64_t c0, int mc, int mcp) {
-    oz_kstar_slices_fast_kernel<DP, S><<<dim3(mcp / 128, ctx->np / 64), 128, 0, ctx->stream>>>(
+static void launch_oz_kstar_fast(bo_ctx *ctx, int s, const double *dXc, int64_t c0, int mc, int mcp, int8_t *Kss,
+                                 cudaStream_t st) {
+    oz_kstar_slices_fast_kernel<DP, S><<<dim3(mcp / 128, ctx->np / 64), 128, 0, st>>>(
         ctx->n, ctx->np, ctx->d, ctx->dXs + (int64_t)s * ctx->np * ctx->dp, ctx->dInvEll + (int64_t)s * ctx->dp,
-        dXc, c0, mc, mcp, ctx->dKss);
+        dXc, c0, mc, mcp, Kss);
 }
 
 template <int DP>
-static int launch_oz_kstar(bo_ctx *ctx, int s, int S, const double *dXc, int64_t c0, int mc, int mcp) {
-    BO_LAUNCH(ctx, "oz_kstar_slices_kernel");
+static int launch_oz_kstar(bo_ctx *ctx, int s, int S, const double *dXc, int64_t c0, int mc, int mcp, int8_t *Kss,
+                           cudaStream_t st) {
+    BO_LAUNCH_ON(ctx, "oz_kstar_slices_kernel", st);
     if (ctx->kernel == BO_KERNEL_SE && S >= 2 && S <= 6 && DP <= 16) {
         switch (S) {
-            case 2: launch_oz_kstar_fast<DP, 2>(ctx, s, dXc, c0, mc, mcp); break;
-            case 3: launch_oz_kstar_fast<DP, 3>(ctx, s, dXc, c0, mc, mcp); break;
-            case 4: launch_oz_kstar_fast<DP, 4>(ctx, s, dXc, c0, mc, mcp); break;
-            case 5: launch_oz_kstar_fast<DP, 5>(ctx, s, dXc, c0, mc, mcp); break;
-            default: launch_oz_kstar_fast<DP, 6>(ctx, s, dXc, c0, mc, mcp); break;
+            case 2: launch_oz_kstar_fast<DP, 2>(ctx, s, dXc, c0, mc, mcp, Kss, st); break;
+            case 3: launch_oz_kstar_fast<DP, 3>(ctx, s, dXc, c0, mc, mcp, Kss, st); break;
+            case 4: launch_oz_kstar_fast<DP, 4>(ctx, s, dXc, c0, mc, mcp, Kss, st); break;
+            case 5: launch_oz_kstar_fast<DP, 5>(ctx, s, dXc, c0, mc, mcp, Kss, st); break;
+            default: launch_oz_kstar_fast<DP, 6>(ctx, s, dXc, c0, mc, mcp, Kss, st); break;
         }
         BO_CHECK_LAUNCH(ctx);
         return BO_OK;
     }
-    oz_kstar_slices_kernel<DP><<<dim3(mcp / 128, ctx->np / 64), 256, 0, ctx->stream>>>(
+    oz_kstar_slices_kernel<DP><<<dim3(mcp / 128, ctx->np / 64), 256, 0, st>>>(
         ctx->kernel, ctx->n, ctx->np, ctx->d, S, ctx->dXs + (int64_t)s * ctx->np * ctx->dp,
-        ctx->dInvEll + (int64_t)s * ctx->dp, dXc, c0, mc, mcp, ctx->dKss);
+        ctx->dInvEll + (int64_t)s * ctx->dp, dXc, c0, mc, mcp, Kss);
     BO_CHECK_LAUNCH(ctx);
     return BO_OK;
 }
 
-// mu_s, s2_s of candidates [c0, c0 + mc) for hyper-sample s through the int8-slice path.
-int bo_ozaki_moments(bo_ctx *ctx, int s, int S, const double *dXc, int64_t c0, int mc, int mcp, double *mu,
-                     double *s2, int32_t *dbg) {
-    const int np = ctx->np;
-    BO_TRY(bo_reserve(ctx, &ctx->dKss, &ctx->kss_capacity, (size_t)S * mcp * np));
+// Scratch for `nbuf` slice buffers of up to mcp_max candidates each.
+int bo_ozaki_reserve(bo_ctx *ctx, int S, int mcp_max, int nbuf) {
+    ctx->kss_stride = (size_t)S * mcp_max * ctx->np;
+    BO_TRY(bo_reserve(ctx, &ctx->dKss, &ctx->kss_capacity, ctx->kss_stride * nbuf));
+    return BO_OK;
+}
+
+// Slice planes of K*^T for candidates [c0, c0 + mc) and hyper-sample s into buffer `buf`.
+int bo_ozaki_slice(bo_ctx *ctx, int s, int S, const double *dXc, int64_t c0, int mc, int mcp, int buf,
+                   cudaStream_t st) {
+    int8_t *Kss = ctx->dKss + (size_t)buf * ctx->kss_stride;
     switch (ctx->dp) {
-        case 2: BO_TRY(launch_oz_kstar<2>(ctx, s, S, dXc, c0, mc, mcp)); break;
-        case 4: BO_TRY(launch_oz_kstar<4>(ctx, s, S, dXc, c0, mc, mcp)); break;
-        case 8: BO_TRY(launch_oz_kstar<8>(ctx, s, S, dXc, c0, mc, mcp)); break;
-        case 16: BO_TRY(launch_oz_kstar<16>(ctx, s, S, dXc, c0, mc, mcp)); break;
-        case 32: BO_TRY(launch_oz_kstar<32>(ctx, s, S, dXc, c0, mc, mcp)); break;
+        case 2: BO_TRY(launch_oz_kstar<2>(ctx, s, S, dXc, c0, mc, mcp, Kss, st)); break;
+        case 4: BO_TRY(launch_oz_kstar<4>(ctx, s, S, dXc, c0, mc, mcp, Kss, st)); break;
+        case 8: BO_TRY(launch_oz_kstar<8>(ctx, s, S, dXc, c0, mc, mcp, Kss, st)); break;
+        case 16: BO_TRY(launch_oz_kstar<16>(ctx, s, S, dXc, c0, mc, mcp, Kss, st)); break;
+        case 32: BO_TRY(launch_oz_kstar<32>(ctx, s, S, dXc, c0, mc, mcp, Kss, st)); break;
         default: return bo_set_err(ctx, BO_ERR_ARG, "unsupported padded dimension %d", ctx->dp);
     }
+    return BO_OK;
+}
+
+// mu_s, s2_s of the candidates sliced into buffer `buf`: the tcgen05 contraction + reductions.
+int bo_ozaki_contract(bo_ctx *ctx, int s, int S, int mcp, int buf, double *mu, double *s2, int32_t *dbg) {
+    const int np = ctx->np;
+    const int8_t *Kss = ctx->dKss + (size_t)buf * ctx->kss_stride;
     CUtensorMap tmA, tmB;
-    BO_TRY(make_tmap(ctx, &tmA, ctx->dKss, np, mcp, S, OZ_BM));
+    BO_TRY(make_tmap(ctx, &tmA, Kss, np, mcp, S, OZ_BM));
     BO_TRY(make_tmap(ctx, &tmB, ctx->dWs + (size_t)s * S * np * np, np, np, S, OZ_BN));
     const int nb = np / OZ_BN;
     {
@@ -719,7 +734,9 @@ extern "C" int bo_ozaki_debug(bo_ctx *ctx, int S, int mc, const double *Xc, doub
     BO_CUDA(ctx, cudaMalloc(&dacc, sizeof(int32_t) * (size_t)nb * S * 128 * 64));
     BO_CUDA(ctx, cudaMemsetAsync(dacc, 0xff, sizeof(int32_t) * (size_t)nb * S * 128 * 64, ctx->stream));
     BO_CUDA(ctx, cudaMemcpyAsync(dXc, Xc, sizeof(double) * mc * ctx->d, cudaMemcpyHostToDevice, ctx->stream));
-    int rc = bo_ozaki_moments(ctx, 0, S, dXc, 0, mc, mcp, dmu, dmu + mcp, acc ? dacc : nullptr);
+    int rc = bo_ozaki_reserve(ctx, S, mcp, 1);
+    if (rc == BO_OK) rc = bo_ozaki_slice(ctx, 0, S, dXc, 0, mc, mcp, 0, ctx->stream);
+    if (rc == BO_OK) rc = bo_ozaki_contract(ctx, 0, S, mcp, 0, dmu, dmu + mcp, acc ? dacc : nullptr);
     cudaError_t e = cudaStreamSynchronize(ctx->stream);
     if (rc == BO_OK && e == cudaSuccess) {
         if (mu) cudaMemcpy(mu, dmu, sizeof(double) * mc, cudaMemcpyDeviceToHost);

@@ -519,16 +519,75 @@ int bo_score_run(bo_ctx *ctx, const ScoreRequest &rq) {
         }
     }
 
+    if (oz) {
+        // Software pipeline over work items (chunk, hyper-sample): the operand slicer of item w+1
+        // runs on the low-priority side stream while the tcgen05 contraction of item w runs on
+        // the main stream (different pipes: FP64/ALU vs tensor).  Two slice buffers.
+        const int64_t nchunk = (M + chunk - 1) / chunk;
+        const int64_t nitems = nchunk * S;
+        BO_TRY(bo_ozaki_reserve(ctx, oz_S, (int)cap, nitems > 1 ? 2 : 1));
+        auto item = [&](int64_t w, int64_t &c0, int &mc, int &mcp, int &s) {
+            c0 = (w / S) * chunk;
+            s = (int)(w % S);
+            mc = (int)((M - c0) < chunk ? (M - c0) : chunk);
+            mcp = bo_round_up(mc, 128);
+        };
+        int64_t c0; int mc, mcp, s;
+        // candidates staged on the main stream must be visible to the side stream
+        BO_CUDA(ctx, cudaEventRecord(ctx->ev_consumed[0], ctx->stream));
+        BO_CUDA(ctx, cudaStreamWaitEvent(ctx->stream2, ctx->ev_consumed[0], 0));
+        item(0, c0, mc, mcp, s);
+        BO_TRY(bo_ozaki_slice(ctx, s, oz_S, rq.dXc, c0, mc, mcp, 0, ctx->stream2));
+        BO_CUDA(ctx, cudaEventRecord(ctx->ev_sliced[0], ctx->stream2));
+        int64_t blk0 = 0;
+        for (int64_t w = 0; w < nitems; ++w) {
+            const int buf = (int)(w & 1);
+            item(w, c0, mc, mcp, s);
+            BO_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_sliced[buf], 0));
+            BO_TRY(bo_ozaki_contract(ctx, s, oz_S, mcp, buf, ctx->dMuS + (int64_t)s * mcp, ctx->dS2S + (int64_t)s * mcp, nullptr));
+            BO_CUDA(ctx, cudaEventRecord(ctx->ev_consumed[buf], ctx->stream));
+            if (w + 1 < nitems) {
+                int64_t c1; int mc1, mcp1, s1;
+                item(w + 1, c1, mc1, mcp1, s1);
+                const int nbuf = (int)((w + 1) & 1);
+                if (w >= 1) BO_CUDA(ctx, cudaStreamWaitEvent(ctx->stream2, ctx->ev_consumed[nbuf], 0));
+                BO_TRY(bo_ozaki_slice(ctx, s1, oz_S, rq.dXc, c1, mc1, mcp1, nbuf, ctx->stream2));
+                BO_CUDA(ctx, cudaEventRecord(ctx->ev_sliced[nbuf], ctx->stream2));
+            }
+            if (s == S - 1) {
+                AcqParams ap = {};
+                ap.mode = rq.mode; ap.acq = rq.acq; ap.param = rq.param;
+                ap.S = S; ap.d = d; ap.mc = mc; ap.mcp = mcp; ap.c0 = c0;
+                ap.muS = ctx->dMuS; ap.s2S = ctx->dS2S; ap.dmuS = nullptr; ap.ds2S = nullptr;
+                ap.out_val = rq.dVal; ap.out_grad = nullptr;
+                ap.out_mu = rq.dMu; ap.out_s2 = rq.dS2; ap.out_dmu = nullptr; ap.out_ds2 = nullptr;
+                ap.blkval = rq.want_best ? ctx->dBlkVal : nullptr;
+                ap.blkidx = rq.want_best ? ctx->dBlkIdx : nullptr;
+                ap.blk0 = blk0;
+                const int nb = (mc + 255) / 256;
+                {
+                    BO_LAUNCH(ctx, "acq_kernel");
+                    acq_kernel<<<nb, 256, 0, ctx->stream>>>(ap);
+                    BO_CHECK_LAUNCH(ctx);
+                }
+                blk0 += nb;
+            }
+        }
+        if (rq.want_best) {
+            BO_LAUNCH(ctx, "argmax_final_kernel");
+            argmax_final_kernel<<<1, 1024, 0, ctx->stream>>>(ctx->dBlkVal, ctx->dBlkIdx, blk0,
+                                                            ctx->dBlkVal + ctx->blk_capacity - 1,
+                                                            ctx->dBlkIdx + ctx->blk_capacity - 1);
+            BO_CHECK_LAUNCH(ctx);
+        }
+        return BO_OK;
+    }
+
     int64_t blk0 = 0;
     for (int64_t c0 = 0; c0 < M; c0 += chunk) {
         const int mc = (int)((M - c0) < chunk ? (M - c0) : chunk);
         const int mcp = bo_round_up(mc, 128);
         for (int s = 0; s < S; ++s) {
-            if (oz) {
-                BO_TRY(bo_ozaki_moments(ctx, s, oz_S, rq.dXc, c0, mc, mcp, ctx->dMuS + (int64_t)s * mcp,
-                                        ctx->dS2S + (int64_t)s * mcp, nullptr));
-                continue;
-            }
             DISPATCH_DP(ctx, launch_kstar, ctx, s, rq.dXc, c0, mc, mcp);
             {
                 BO_LAUNCH(ctx, "score_gemm_kernel");
