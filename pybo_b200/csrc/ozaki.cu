@@ -94,6 +94,12 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, int32_t (&r)[16]) {
           "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
         : "r"(taddr) : "memory");
 }
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, int32_t (&r)[8]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+        : "r"(taddr) : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // K-major operand tile, rows of 64 bytes, SWIZZLE_64B: 8-row groups are 512 B apart.
@@ -266,7 +272,7 @@ __device__ __forceinline__ long long oz_fixed_exp2(double z, int shift) {
 }
 
 template <int DP, int S>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 6)
 oz_kstar_slices_fast_kernel(int n, int np, int d, const double *__restrict__ Xs, const double *__restrict__ invell,
                             const double *__restrict__ Xc, int64_t c0, int mc, int mcp, int8_t *__restrict__ Ks) {
     // block: 64 observations x 128 candidates, one candidate per thread -> each thread writes
@@ -297,11 +303,11 @@ oz_kstar_slices_fast_kernel(int n, int np, int d, const double *__restrict__ Xs,
     constexpr double LOG2E = 1.4426950408889634;
     int8_t *out = Ks + (int64_t)m * np + j0;
 #pragma unroll 1
-    for (int sub = 0; sub < 2; ++sub) {
-        const int jj0 = sub * 32;
-        alignas(16) int8_t q[S][32];
+    for (int sub = 0; sub < 4; ++sub) {
+        const int jj0 = sub * 16;
+        alignas(16) int8_t q[S][16];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
+        for (int i = 0; i < 16; ++i) {
             double dot = -ha - hb[jj0 + i];
 #pragma unroll
             for (int k = 0; k < DP; k += 2) {
@@ -323,7 +329,6 @@ oz_kstar_slices_fast_kernel(int n, int np, int d, const double *__restrict__ Xs,
         for (int s = 0; s < S; ++s) {
             int4 *dst = reinterpret_cast<int4 *>(out + (int64_t)s * mcp * np + jj0);
             dst[0] = *reinterpret_cast<const int4 *>(&q[s][0]);
-            dst[1] = *reinterpret_cast<const int4 *>(&q[s][16]);
         }
     }
 }
@@ -357,8 +362,10 @@ __device__ __forceinline__ OzUnit oz_decode(int u, int nb, int T, int ntiles) {
     return o;
 }
 
+// (min-blocks 2 only caps the register count at 170 so that operand-slicer CTAs of the next
+// chunk fit beside this CTA on the SM; shared memory still limits it to one CTA per SM)
 template <int S>
-__global__ void __launch_bounds__(OZ_THREADS, 1)
+__global__ void __launch_bounds__(OZ_THREADS, 2)
 oz_score_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB, OzParams p) {
     extern __shared__ uint8_t oz_smem_raw[];
     // 1024-byte aligned operand ring
@@ -453,22 +460,23 @@ oz_score_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
             double q = 0.0, pm = 0.0;
             mbar_wait(tmem_full(acc), acc_phase);
             tc_fence_after();
-            for (int c0 = 0; c0 < OZ_BN; c0 += 16) {
-                int32_t r[S][16];
+#pragma unroll 1
+            for (int c0 = 0; c0 < OZ_BN; c0 += 8) {
+                int32_t r[S][8];
 #pragma unroll
-                for (int g = 0; g < S; ++g) tmem_ld16(lane_base + (uint32_t)(g * OZ_BN + c0), r[g]);
+                for (int g = 0; g < S; ++g) tmem_ld8(lane_base + (uint32_t)(g * OZ_BN + c0), r[g]);
                 tmem_ld_wait();
                 if (p.dbg && un.tile == 0) {
 #pragma unroll
                     for (int g = 0; g < S; ++g) {
                         int32_t *o = p.dbg + (((int64_t)un.rb * S + g) * 128 + quarter * 32 + lane) * 64 + c0;
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) o[i] = r[g][i];
+                        for (int i = 0; i < 8; ++i) o[i] = r[g][i];
                     }
                 }
                 const int row0 = un.rb * OZ_BN + c0;
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
+                for (int i = 0; i < 8; ++i) {
                     double v = (double)r[G][i];
 #pragma unroll
                     for (int g = G - 1; g >= 0; --g) v = fma(v, 0.0078125, (double)r[g][i]);
