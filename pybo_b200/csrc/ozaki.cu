@@ -248,27 +248,26 @@ oz_kstar_slices_kernel(int kernel, int n, int np, int d, int S, const double *__
 // an inline exp2 (degree-12 Taylor in ln2*f, |f| <= 1/2, error < 2e-16) whose exponent add also
 // applies the fixed-point scale, and (iii) the balanced base-128 digits are peeled off one 64-bit
 // integer on the integer pipe instead of S rint/subtract rounds on the FP64 pipe.
-__device__ __forceinline__ long long oz_fixed_exp2(double z, int shift) {
-    // rint(2^(z + shift)) for z <= 0
+// Taylor coefficients ln2^i / i!, i = 12 .. 1, kept in constant memory so that each DFMA
+// takes its coefficient as a constant-bank operand (no register or uniform-register traffic)
+__constant__ double OZ_EXP2_C[12] = {
+    2.5678435993488196e-11, 4.44553827187081e-10, 7.054911620801121e-09, 1.0178086009239696e-07,
+    1.3215486790144305e-06, 1.5252733804059838e-05, 0.00015403530393381606, 0.0013333558146428441,
+    0.009618129107628477,   0.055504108664821576,  0.2402265069591007,     0.6931471805599453};
+
+// 2^(z + shift) for z <= 0 as a double (0 when it would round to 0 on the integer grid).
+// DEG 10 has relative error 2.2e-13 (enough below 2^-35, i.e. up to 5 slices), DEG 12 < 2e-16.
+template <int DEG>
+__device__ __forceinline__ double oz_exp2_scaled(double z, int shift) {
     const double kd = rint(z);
     const double f = z - kd;
     const int ki = (int)kd + shift;
-    if (ki < -1) return 0;
-    double p = 2.5678435993488196e-11;
-    p = fma(p, f, 4.44553827187081e-10);
-    p = fma(p, f, 7.054911620801121e-09);
-    p = fma(p, f, 1.0178086009239696e-07);
-    p = fma(p, f, 1.3215486790144305e-06);
-    p = fma(p, f, 1.5252733804059838e-05);
-    p = fma(p, f, 0.00015403530393381606);
-    p = fma(p, f, 0.0013333558146428441);
-    p = fma(p, f, 0.009618129107628477);
-    p = fma(p, f, 0.055504108664821576);
-    p = fma(p, f, 0.2402265069591007);
-    p = fma(p, f, 0.6931471805599453);
+    double p = OZ_EXP2_C[12 - DEG];
+#pragma unroll
+    for (int i = 12 - DEG + 1; i < 12; ++i) p = fma(p, f, OZ_EXP2_C[i]);
     p = fma(p, f, 1.0);
-    const double v = __longlong_as_double(__double_as_longlong(p) + ((long long)ki << 52));
-    return __double2ll_rn(v);
+    const double v = __hiloint2double(__double2hiint(p) + (ki << 20), __double2loint(p));
+    return ki < -1 ? 0.0 : v;
 }
 
 template <int DP, int S>
@@ -305,30 +304,73 @@ oz_kstar_slices_fast_kernel(int n, int np, int d, const double *__restrict__ Xs,
 #pragma unroll 1
     for (int sub = 0; sub < 4; ++sub) {
         const int jj0 = sub * 16;
-        alignas(16) int8_t q[S][16];
+        if (S <= 5) {
+            // kappa * 2^SHIFT = top * 2^LOW + low, low in [0, 2^LOW): the S-1 low digits are plain
+            // 7-bit fields of `low` (digits in [0,127], no carry chain), spread to byte lanes with
+            // masks/shifts and transposed to slice-major words with byte permutes.
+            constexpr int LOW = 7 * (S - 1);
+            uint32_t wlow[16], wtop[4];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            double dot = -ha - hb[jj0 + i];
+            for (int i = 0; i < 16; ++i) {
+                double dot = -ha - hb[jj0 + i];
 #pragma unroll
-            for (int k = 0; k < DP; k += 2) {
-                const double2 x2 = *reinterpret_cast<const double2 *>(&xs[jj0 + i][k]);
-                dot = fma(xc[k], x2.x, dot);
-                dot = fma(xc[k + 1], x2.y, dot);
+                for (int k = 0; k < DP; k += 2) {
+                    const double2 x2 = *reinterpret_cast<const double2 *>(&xs[jj0 + i][k]);
+                    dot = fma(xc[k], x2.x, dot);
+                    dot = fma(xc[k + 1], x2.y, dot);
+                }
+                const double z = fmin(dot, 0.0) * LOG2E;            // log2 kappa
+                const bool on = live && (j0 + jj0 + i) < n;
+                const double v = on ? oz_exp2_scaled<10>(z, SHIFT) : 0.0;
+                const double vh = floor(v * (1.0 / (double)(1 << LOW)));
+                uint32_t t = (uint32_t)__double2int_rn(fma(vh, -(double)(1 << LOW), v));   // [0, 2^LOW]
+                uint32_t top = (uint32_t)__double2int_rn(vh) + (t >> LOW);                 // rounding carry
+                t &= (1u << LOW) - 1u;
+                // byte b of wlow = digit of slice (S-1-b)
+                wlow[i] = (t & 0x7Fu) | ((t & 0x3F80u) << 1) | ((t & 0x1FC000u) << 2) | ((t & 0xFE00000u) << 3);
+                if ((i & 3) == 0) wtop[i >> 2] = top;
+                else wtop[i >> 2] |= top << (8 * (i & 3));
             }
-            const double z = fmin(dot, 0.0) * LOG2E;            // log2 kappa
-            long long T = (live && (j0 + jj0 + i) < n) ? oz_fixed_exp2(z, SHIFT) : 0;
+            int8_t *o0 = out + jj0;
+            *reinterpret_cast<uint4 *>(o0) = make_uint4(wtop[0], wtop[1], wtop[2], wtop[3]);
 #pragma unroll
-            for (int s = S - 1; s >= 1; --s) {
-                const long long dgt = ((T + 64) & 127) - 64;    // balanced digit in [-64, 63]
-                T = (T - dgt) >> 7;
-                q[s][i] = (int8_t)dgt;
+            for (int s = 1; s < S; ++s) {
+                const uint32_t b = (uint32_t)(S - 1 - s);               // byte lane holding slice s
+                const uint32_t sel2 = b | ((4u + b) << 4);             // {x.b, y.b}
+                uint32_t w[4];
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    const uint32_t lo = __byte_perm(wlow[4 * g + 0], wlow[4 * g + 1], sel2);
+                    const uint32_t hi = __byte_perm(wlow[4 * g + 2], wlow[4 * g + 3], sel2);
+                    w[g] = __byte_perm(lo, hi, 0x5410);
+                }
+                *reinterpret_cast<uint4 *>(o0 + (int64_t)s * mcp * np) = make_uint4(w[0], w[1], w[2], w[3]);
             }
-            q[0][i] = (int8_t)T;
-        }
+        } else {
+            alignas(16) int8_t q[S][16];
 #pragma unroll
-        for (int s = 0; s < S; ++s) {
-            int4 *dst = reinterpret_cast<int4 *>(out + (int64_t)s * mcp * np + jj0);
-            dst[0] = *reinterpret_cast<const int4 *>(&q[s][0]);
+            for (int i = 0; i < 16; ++i) {
+                double dot = -ha - hb[jj0 + i];
+#pragma unroll
+                for (int k = 0; k < DP; k += 2) {
+                    const double2 x2 = *reinterpret_cast<const double2 *>(&xs[jj0 + i][k]);
+                    dot = fma(xc[k], x2.x, dot);
+                    dot = fma(xc[k + 1], x2.y, dot);
+                }
+                const double z = fmin(dot, 0.0) * LOG2E;
+                const bool on = live && (j0 + jj0 + i) < n;
+                long long T = on ? __double2ll_rn(oz_exp2_scaled<12>(z, SHIFT)) : 0;
+#pragma unroll
+                for (int s = S - 1; s >= 1; --s) {
+                    const long long dgt = ((T + 64) & 127) - 64;        // balanced digit in [-64, 63]
+                    T = (T - dgt) >> 7;
+                    q[s][i] = (int8_t)dgt;
+                }
+                q[0][i] = (int8_t)T;
+            }
+#pragma unroll
+            for (int s = 0; s < S; ++s)
+                *reinterpret_cast<int4 *>(out + (int64_t)s * mcp * np + jj0) = *reinterpret_cast<const int4 *>(q[s]);
         }
     }
 }
