@@ -257,11 +257,13 @@ __constant__ double OZ_EXP2_C[12] = {
 
 // 2^(z + shift) for z <= 0 as a double (0 when it would round to 0 on the integer grid).
 // DEG 10 has relative error 2.2e-13 (enough below 2^-35, i.e. up to 5 slices), DEG 12 < 2e-16.
+// No FP64<->integer conversion instructions (F2I / FRND are very slow here): rint(z) is read from
+// the low mantissa word of z + 1.5*2^52.
 template <int DEG>
 __device__ __forceinline__ double oz_exp2_scaled(double z, int shift) {
-    const double kd = rint(z);
-    const double f = z - kd;
-    const int ki = (int)kd + shift;
+    const double zz = z + 6755399441055744.0;          // 1.5 * 2^52
+    const int ki = __double2loint(zz) + shift;         // rint(z) + shift
+    const double f = z - (zz - 6755399441055744.0);    // [-0.5, 0.5]
     double p = OZ_EXP2_C[12 - DEG];
 #pragma unroll
     for (int i = 12 - DEG + 1; i < 12; ++i) p = fma(p, f, OZ_EXP2_C[i]);
@@ -321,11 +323,12 @@ oz_kstar_slices_fast_kernel(int n, int np, int d, const double *__restrict__ Xs,
                 }
                 const double z = fmin(dot, 0.0) * LOG2E;            // log2 kappa
                 const bool on = live && (j0 + jj0 + i) < n;
-                const double v = on ? oz_exp2_scaled<10>(z, SHIFT) : 0.0;
-                const double vh = floor(v * (1.0 / (double)(1 << LOW)));
-                uint32_t t = (uint32_t)__double2int_rn(fma(vh, -(double)(1 << LOW), v));   // [0, 2^LOW]
-                uint32_t top = (uint32_t)__double2int_rn(vh) + (t >> LOW);                 // rounding carry
-                t &= (1u << LOW) - 1u;
+                const double v = on ? oz_exp2_scaled<10>(z, SHIFT) : 0.0;     // in [0, 2^SHIFT], SHIFT <= 34
+                const double vv = v + 4503599627370496.0;                   // + 2^52: mantissa = rint(v)
+                const uint32_t lo = (uint32_t)__double2loint(vv);
+                const uint32_t hi = (uint32_t)__double2hiint(vv) & 0xFFFFFu;
+                const uint32_t t = lo & ((1u << LOW) - 1u);
+                const uint32_t top = (LOW == 0) ? lo : ((lo >> LOW) | (hi << (32 - LOW)));
                 // byte b of wlow = digit of slice (S-1-b)
                 wlow[i] = (t & 0x7Fu) | ((t & 0x3F80u) << 1) | ((t & 0x1FC000u) << 2) | ((t & 0xFE00000u) << 3);
                 if ((i & 3) == 0) wtop[i >> 2] = top;
@@ -359,7 +362,11 @@ oz_kstar_slices_fast_kernel(int n, int np, int d, const double *__restrict__ Xs,
                 }
                 const double z = fmin(dot, 0.0) * LOG2E;
                 const bool on = live && (j0 + jj0 + i) < n;
-                long long T = on ? __double2ll_rn(oz_exp2_scaled<12>(z, SHIFT)) : 0;
+                long long T = 0;
+                if (on) {
+                    const double vv = oz_exp2_scaled<12>(z, SHIFT) + 4503599627370496.0;   // SHIFT <= 41 < 52
+                    T = __double_as_longlong(vv) & 0xFFFFFFFFFFFFFll;
+                }
 #pragma unroll
                 for (int s = S - 1; s >= 1; --s) {
                     const long long dgt = ((T + 64) & 127) - 64;        // balanced digit in [-64, 63]
