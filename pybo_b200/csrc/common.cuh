@@ -100,6 +100,8 @@ struct bo_ctx {
     int *dRowExp = nullptr;       // S_hyper x np (+ S_hyper maxima)
     size_t ws_capacity = 0, kss_capacity = 0, kss_stride = 0, rowscale_capacity = 0, rowexp_capacity = 0;
     std::vector<int> h_emax;
+    double *dXsHalfSq = nullptr;               // S_hyper x np   |xs_j|^2 / 2
+    size_t halfsq_capacity = 0;
     double *dOzQ = nullptr, *dOzP = nullptr;   // (np/64) x chunk partial reductions
     size_t ozpart_capacity = 0;
 

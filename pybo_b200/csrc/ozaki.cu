@@ -272,17 +272,33 @@ __device__ __forceinline__ double oz_exp2_scaled(double z, int shift) {
     return ki < -1 ? 0.0 : v;
 }
 
+#define OZ_KS_TILES 8      // observation tiles (of 64) per block
+
+__device__ __forceinline__ void oz_cp_async16(void *smem_dst, const void *gmem_src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src));
+}
+
+// block: 128 candidates (one per thread) x up to OZ_KS_TILES tiles of 64 observations; the
+// observation tiles (scaled coordinates + |xs|^2/2) are prefetched with cp.async into a double
+// buffer, so the candidate loads, barriers and global latency are amortised over 512 observations.
 template <int DP, int S>
-__global__ void __launch_bounds__(128, 6)
-oz_kstar_slices_fast_kernel(int n, int np, int d, const double *__restrict__ Xs, const double *__restrict__ invell,
-                            const double *__restrict__ Xc, int64_t c0, int mc, int mcp, int8_t *__restrict__ Ks) {
-    // block: 64 observations x 128 candidates, one candidate per thread -> each thread writes
-    // 64 contiguous bytes (two full 32-byte sectors) per slice plane
-    __shared__ __align__(16) double xs[64][DP];
-    __shared__ double hb[64];                    // |xs_j|^2 / 2
+__global__ void __launch_bounds__(128)
+oz_kstar_slices_fast_kernel(int n, int np, int d, const double *__restrict__ Xs, const double *__restrict__ XsHalfSq,
+                            const double *__restrict__ invell, const double *__restrict__ Xc, int64_t c0, int mc,
+                            int mcp, int8_t *__restrict__ Ks) {
+    __shared__ __align__(16) double xs[2][64][DP];
+    __shared__ __align__(16) double hb[2][64];
     const int tid = threadIdx.x;
-    const int j0 = blockIdx.y * 64;
-    for (int e = tid; e < 64 * DP; e += 128) xs[e / DP][e % DP] = Xs[(int64_t)j0 * DP + e];
+    const int ntile = np / 64;
+    const int t0 = blockIdx.y * OZ_KS_TILES;
+    const int t1 = (t0 + OZ_KS_TILES < ntile) ? t0 + OZ_KS_TILES : ntile;
+    auto prefetch = [&](int tile, int buf) {
+        const double *src = Xs + (int64_t)tile * 64 * DP;
+        for (int e = tid; e < 64 * DP / 2; e += 128) oz_cp_async16(&xs[buf][0][0] + 2 * e, src + 2 * e);
+        if (tid < 32) oz_cp_async16(&hb[buf][0] + 2 * tid, XsHalfSq + (int64_t)tile * 64 + 2 * tid);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    prefetch(t0, 0);
     const int m = blockIdx.x * 128 + tid;
     const bool live = m < mc;
     double xc[DP], ha = 0.0;
@@ -292,32 +308,34 @@ oz_kstar_slices_fast_kernel(int n, int np, int d, const double *__restrict__ Xs,
         ha = fma(xc[k], xc[k], ha);
     }
     ha *= 0.5;
-    __syncthreads();
-    if (tid < 64) {
-        double b = 0.0;
-#pragma unroll
-        for (int k = 0; k < DP; ++k) b = fma(xs[tid][k], xs[tid][k], b);
-        hb[tid] = 0.5 * b;
-    }
-    __syncthreads();
     constexpr int SHIFT = 6 + 7 * (S - 1);
+    constexpr int LOW = 7 * (S - 1);
     constexpr double LOG2E = 1.4426950408889634;
-    int8_t *out = Ks + (int64_t)m * np + j0;
+    static_assert(S >= 2 && S <= 5, "fast slicer handles 2..5 slices");
+    for (int tile = t0; tile < t1; ++tile) {
+        const int buf = (tile - t0) & 1;
+        if (tile + 1 < t1) {
+            prefetch(tile + 1, buf ^ 1);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
+        __syncthreads();
+        const int j0 = tile * 64;
+        int8_t *out = Ks + (int64_t)m * np + j0;
 #pragma unroll 1
-    for (int sub = 0; sub < 4; ++sub) {
-        const int jj0 = sub * 16;
-        if (S <= 5) {
-            // kappa * 2^SHIFT = top * 2^LOW + low, low in [0, 2^LOW): the S-1 low digits are plain
-            // 7-bit fields of `low` (digits in [0,127], no carry chain), spread to byte lanes with
-            // masks/shifts and transposed to slice-major words with byte permutes.
-            constexpr int LOW = 7 * (S - 1);
+        for (int sub = 0; sub < 4; ++sub) {
+            const int jj0 = sub * 16;
+            // kappa * 2^SHIFT = top * 2^LOW + low: the S-1 low digits are plain 7-bit fields of
+            // `low` (digits in [0,127], no carry chain), spread to byte lanes with masks/shifts and
+            // transposed to slice-major words with byte permutes.
             uint32_t wlow[16], wtop[4];
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
-                double dot = -ha - hb[jj0 + i];
+                double dot = -ha - hb[buf][jj0 + i];
 #pragma unroll
                 for (int k = 0; k < DP; k += 2) {
-                    const double2 x2 = *reinterpret_cast<const double2 *>(&xs[jj0 + i][k]);
+                    const double2 x2 = *reinterpret_cast<const double2 *>(&xs[buf][jj0 + i][k]);
                     dot = fma(xc[k], x2.x, dot);
                     dot = fma(xc[k + 1], x2.y, dot);
                 }
@@ -328,7 +346,7 @@ oz_kstar_slices_fast_kernel(int n, int np, int d, const double *__restrict__ Xs,
                 const uint32_t lo = (uint32_t)__double2loint(vv);
                 const uint32_t hi = (uint32_t)__double2hiint(vv) & 0xFFFFFu;
                 const uint32_t t = lo & ((1u << LOW) - 1u);
-                const uint32_t top = (LOW == 0) ? lo : ((lo >> LOW) | (hi << (32 - LOW)));
+                const uint32_t top = (lo >> LOW) | (hi << (32 - LOW));
                 // byte b of wlow = digit of slice (S-1-b)
                 wlow[i] = (t & 0x7Fu) | ((t & 0x3F80u) << 1) | ((t & 0x1FC000u) << 2) | ((t & 0xFE00000u) << 3);
                 if ((i & 3) == 0) wtop[i >> 2] = top;
@@ -343,43 +361,24 @@ oz_kstar_slices_fast_kernel(int n, int np, int d, const double *__restrict__ Xs,
                 uint32_t w[4];
 #pragma unroll
                 for (int g = 0; g < 4; ++g) {
-                    const uint32_t lo = __byte_perm(wlow[4 * g + 0], wlow[4 * g + 1], sel2);
-                    const uint32_t hi = __byte_perm(wlow[4 * g + 2], wlow[4 * g + 3], sel2);
-                    w[g] = __byte_perm(lo, hi, 0x5410);
+                    const uint32_t lo2 = __byte_perm(wlow[4 * g + 0], wlow[4 * g + 1], sel2);
+                    const uint32_t hi2 = __byte_perm(wlow[4 * g + 2], wlow[4 * g + 3], sel2);
+                    w[g] = __byte_perm(lo2, hi2, 0x5410);
                 }
                 *reinterpret_cast<uint4 *>(o0 + (int64_t)s * mcp * np) = make_uint4(w[0], w[1], w[2], w[3]);
             }
-        } else {
-            alignas(16) int8_t q[S][16];
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                double dot = -ha - hb[jj0 + i];
-#pragma unroll
-                for (int k = 0; k < DP; k += 2) {
-                    const double2 x2 = *reinterpret_cast<const double2 *>(&xs[jj0 + i][k]);
-                    dot = fma(xc[k], x2.x, dot);
-                    dot = fma(xc[k + 1], x2.y, dot);
-                }
-                const double z = fmin(dot, 0.0) * LOG2E;
-                const bool on = live && (j0 + jj0 + i) < n;
-                long long T = 0;
-                if (on) {
-                    const double vv = oz_exp2_scaled<12>(z, SHIFT) + 4503599627370496.0;   // SHIFT <= 41 < 52
-                    T = __double_as_longlong(vv) & 0xFFFFFFFFFFFFFll;
-                }
-#pragma unroll
-                for (int s = S - 1; s >= 1; --s) {
-                    const long long dgt = ((T + 64) & 127) - 64;        // balanced digit in [-64, 63]
-                    T = (T - dgt) >> 7;
-                    q[s][i] = (int8_t)dgt;
-                }
-                q[0][i] = (int8_t)T;
-            }
-#pragma unroll
-            for (int s = 0; s < S; ++s)
-                *reinterpret_cast<int4 *>(out + (int64_t)s * mcp * np + jj0) = *reinterpret_cast<const int4 *>(q[s]);
         }
+        __syncthreads();        // everyone is done with `buf` before it is refilled two tiles later
     }
+}
+
+// |xs_j|^2 / 2 per observation (once per fit)
+__global__ void oz_halfsq_kernel(const double *__restrict__ Xs, int rows, int dp, double *__restrict__ out) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= rows) return;
+    double b = 0.0;
+    for (int k = 0; k < dp; ++k) b = fma(Xs[(int64_t)j * dp + k], Xs[(int64_t)j * dp + k], b);
+    out[j] = 0.5 * b;
 }
 
 // ---------------------------------------------------------------------------
@@ -640,6 +639,12 @@ int bo_ozaki_prepare(bo_ctx *ctx, int S) {
             BO_CHECK_LAUNCH(ctx);
         }
     }
+    BO_TRY(bo_reserve(ctx, &ctx->dXsHalfSq, &ctx->halfsq_capacity, (size_t)ns * np));
+    {
+        BO_LAUNCH(ctx, "oz_halfsq_kernel");
+        oz_halfsq_kernel<<<(ns * np + 255) / 256, 256, 0, ctx->stream>>>(ctx->dXs, ns * np, ctx->dp, ctx->dXsHalfSq);
+        BO_CHECK_LAUNCH(ctx);
+    }
     ctx->h_emax.assign(ns, 0);
     BO_CUDA(ctx, cudaMemcpyAsync(ctx->h_emax.data(), emax_dev, sizeof(int) * ns, cudaMemcpyDeviceToHost, ctx->stream));
     BO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -672,22 +677,22 @@ int bo_ozaki_choose_slices(bo_ctx *ctx, double tol) {
 template <int DP, int S>
 static void launch_oz_kstar_fast(bo_ctx *ctx, int s, const double *dXc, int64_t c0, int mc, int mcp, int8_t *Kss,
                                  cudaStream_t st) {
-    oz_kstar_slices_fast_kernel<DP, S><<<dim3(mcp / 128, ctx->np / 64), 128, 0, st>>>(
-        ctx->n, ctx->np, ctx->d, ctx->dXs + (int64_t)s * ctx->np * ctx->dp, ctx->dInvEll + (int64_t)s * ctx->dp,
-        dXc, c0, mc, mcp, Kss);
+    const int ntile = ctx->np / 64;
+    oz_kstar_slices_fast_kernel<DP, S><<<dim3(mcp / 128, (ntile + OZ_KS_TILES - 1) / OZ_KS_TILES), 128, 0, st>>>(
+        ctx->n, ctx->np, ctx->d, ctx->dXs + (int64_t)s * ctx->np * ctx->dp, ctx->dXsHalfSq + (int64_t)s * ctx->np,
+        ctx->dInvEll + (int64_t)s * ctx->dp, dXc, c0, mc, mcp, Kss);
 }
 
 template <int DP>
 static int launch_oz_kstar(bo_ctx *ctx, int s, int S, const double *dXc, int64_t c0, int mc, int mcp, int8_t *Kss,
                            cudaStream_t st) {
     BO_LAUNCH_ON(ctx, "oz_kstar_slices_kernel", st);
-    if (ctx->kernel == BO_KERNEL_SE && S >= 2 && S <= 6 && DP <= 16) {
+    if (ctx->kernel == BO_KERNEL_SE && S >= 2 && S <= 5 && DP <= 16) {
         switch (S) {
             case 2: launch_oz_kstar_fast<DP, 2>(ctx, s, dXc, c0, mc, mcp, Kss, st); break;
             case 3: launch_oz_kstar_fast<DP, 3>(ctx, s, dXc, c0, mc, mcp, Kss, st); break;
             case 4: launch_oz_kstar_fast<DP, 4>(ctx, s, dXc, c0, mc, mcp, Kss, st); break;
-            case 5: launch_oz_kstar_fast<DP, 5>(ctx, s, dXc, c0, mc, mcp, Kss, st); break;
-            default: launch_oz_kstar_fast<DP, 6>(ctx, s, dXc, c0, mc, mcp, Kss, st); break;
+            default: launch_oz_kstar_fast<DP, 5>(ctx, s, dXc, c0, mc, mcp, Kss, st); break;
         }
         BO_CHECK_LAUNCH(ctx);
         return BO_OK;
