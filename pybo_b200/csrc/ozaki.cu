@@ -16,6 +16,7 @@
 // the row reductions are per-thread sums), rows of W are the N dimension.
 #include <cuda.h>
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -62,6 +63,24 @@ __device__ __forceinline__ void tma_load_3d(uint32_t smem_dst, const CUtensorMap
 }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *tmap) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
+}
+
+// 1-D bulk copy global -> shared, completion on an mbarrier (UBLKCP)
+__device__ __forceinline__ void bulk_load(uint32_t smem_dst, const void *gsrc, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_dst), "l"(gsrc), "r"(bytes), "r"(bar) : "memory");
+}
+
+// K*^T slice planes live in HBM as tile-contiguous blocks: block (slice s, candidate tile ct,
+// k block kb) is the 8 KB shared-memory image of a 128 x 64-byte K-major SWIZZLE_64B operand
+// tile (16-byte chunk c of row r sits at chunk c ^ ((r >> 1) & 3)).  The slicer writes whole
+// blocks with coalesced stores; the contraction fetches one with a single bulk copy.
+__host__ __device__ __forceinline__ size_t oz_kss_block(int s, int ct, int kb, int ntiles, int nkb) {
+    return (((size_t)s * ntiles + ct) * nkb + kb) * (size_t)OZ_A_SLICE_BYTES;
+}
+__host__ __device__ __forceinline__ size_t oz_kss_offset(int s, int m, int j, int ntiles, int nkb) {
+    const int r = m & 127, c = (j & 63) >> 4;
+    return oz_kss_block(s, m >> 7, j >> 6, ntiles, nkb) + (size_t)r * 64 + (size_t)((c ^ ((r >> 1) & 3)) << 4) + (j & 15);
 }
 
 __device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {
@@ -237,7 +256,7 @@ oz_kstar_slices_kernel(int kernel, int n, int np, int d, int S, const double *__
                 q[i] = (int8_t)(int)t;
                 r[i] = (r[i] - t) * 128.0;
             }
-            *reinterpret_cast<int4 *>(Ks + ((int64_t)s * mcp + m) * np + j0 + jj0) = *reinterpret_cast<const int4 *>(q);
+            *reinterpret_cast<int4 *>(Ks + oz_kss_offset(s, m, j0 + jj0, mcp >> 7, np >> 6)) = *reinterpret_cast<const int4 *>(q);
         }
     }
 }
@@ -278,9 +297,10 @@ __device__ __forceinline__ void oz_cp_async16(void *smem_dst, const void *gmem_s
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src));
 }
 
-// block: 128 candidates (one per thread) x up to OZ_KS_TILES tiles of 64 observations; the
-// observation tiles (scaled coordinates + |xs|^2/2) are prefetched with cp.async into a double
-// buffer, so the candidate loads, barriers and global latency are amortised over 512 observations.
+// block: one candidate tile (128 candidates, one per thread) x up to OZ_KS_TILES k blocks of 64
+// observations.  Observation tiles (scaled coordinates + |xs|^2/2) are prefetched with cp.async
+// into a double buffer; each finished 128 x 64 tile is staged in shared memory as the swizzled
+// operand image and copied out with fully coalesced 16-byte-per-lane stores (8 KB per slice).
 template <int DP, int S>
 __global__ void __launch_bounds__(128)
 oz_kstar_slices_fast_kernel(int n, int np, int d, const double *__restrict__ Xs, const double *__restrict__ XsHalfSq,
@@ -288,10 +308,11 @@ oz_kstar_slices_fast_kernel(int n, int np, int d, const double *__restrict__ Xs,
                             int mcp, int8_t *__restrict__ Ks) {
     __shared__ __align__(16) double xs[2][64][DP];
     __shared__ __align__(16) double hb[2][64];
+    extern __shared__ __align__(16) uint8_t oz_stage[];          // [S][128 rows][64 B]
     const int tid = threadIdx.x;
-    const int ntile = np / 64;
+    const int nkb = np / 64, ntiles = mcp / 128;
     const int t0 = blockIdx.y * OZ_KS_TILES;
-    const int t1 = (t0 + OZ_KS_TILES < ntile) ? t0 + OZ_KS_TILES : ntile;
+    const int t1 = (t0 + OZ_KS_TILES < nkb) ? t0 + OZ_KS_TILES : nkb;
     auto prefetch = [&](int tile, int buf) {
         const double *src = Xs + (int64_t)tile * 64 * DP;
         for (int e = tid; e < 64 * DP / 2; e += 128) oz_cp_async16(&xs[buf][0][0] + 2 * e, src + 2 * e);
@@ -312,6 +333,7 @@ oz_kstar_slices_fast_kernel(int n, int np, int d, const double *__restrict__ Xs,
     constexpr int LOW = 7 * (S - 1);
     constexpr double LOG2E = 1.4426950408889634;
     static_assert(S >= 2 && S <= 5, "fast slicer handles 2..5 slices");
+    const int swz = (tid >> 1) & 3;
     for (int tile = t0; tile < t1; ++tile) {
         const int buf = (tile - t0) & 1;
         if (tile + 1 < t1) {
@@ -320,9 +342,8 @@ oz_kstar_slices_fast_kernel(int n, int np, int d, const double *__restrict__ Xs,
         } else {
             asm volatile("cp.async.wait_group 0;" ::: "memory");
         }
-        __syncthreads();
+        __syncthreads();        // tile data landed; previous copy-out has finished reading the stage
         const int j0 = tile * 64;
-        int8_t *out = Ks + (int64_t)m * np + j0;
 #pragma unroll 1
         for (int sub = 0; sub < 4; ++sub) {
             const int jj0 = sub * 16;
@@ -352,7 +373,7 @@ oz_kstar_slices_fast_kernel(int n, int np, int d, const double *__restrict__ Xs,
                 if ((i & 3) == 0) wtop[i >> 2] = top;
                 else wtop[i >> 2] |= top << (8 * (i & 3));
             }
-            int8_t *o0 = out + jj0;
+            uint8_t *o0 = oz_stage + tid * 64 + ((sub ^ swz) << 4);
             *reinterpret_cast<uint4 *>(o0) = make_uint4(wtop[0], wtop[1], wtop[2], wtop[3]);
 #pragma unroll
             for (int s = 1; s < S; ++s) {
@@ -365,10 +386,17 @@ oz_kstar_slices_fast_kernel(int n, int np, int d, const double *__restrict__ Xs,
                     const uint32_t hi2 = __byte_perm(wlow[4 * g + 2], wlow[4 * g + 3], sel2);
                     w[g] = __byte_perm(lo2, hi2, 0x5410);
                 }
-                *reinterpret_cast<uint4 *>(o0 + (int64_t)s * mcp * np) = make_uint4(w[0], w[1], w[2], w[3]);
+                *reinterpret_cast<uint4 *>(o0 + s * OZ_A_SLICE_BYTES) = make_uint4(w[0], w[1], w[2], w[3]);
             }
         }
-        __syncthreads();        // everyone is done with `buf` before it is refilled two tiles later
+        __syncthreads();        // stage complete
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+            uint4 *dst = reinterpret_cast<uint4 *>(Ks + oz_kss_block(s, blockIdx.x, tile, ntiles, nkb));
+            const uint4 *src = reinterpret_cast<const uint4 *>(oz_stage + s * OZ_A_SLICE_BYTES);
+#pragma unroll
+            for (int e = 0; e < OZ_A_SLICE_BYTES / 16 / 128; ++e) dst[e * 128 + tid] = src[e * 128 + tid];
+        }
     }
 }
 
@@ -391,6 +419,7 @@ struct OzParams {
     const double *alpha;      // np
     double *qpart, *ppart;    // [np/64][mcp] partial |v|^2 and v.alpha per row block
     int32_t *dbg;             // optional: [rb][g][128][64] accumulators of tile 0
+    const int8_t *kss;        // K*^T slice blocks (oz_kss_block layout)
 };
 
 // Work unit = (candidate tile, 64-row block of W).  Units are ordered group by group
@@ -414,7 +443,7 @@ __device__ __forceinline__ OzUnit oz_decode(int u, int nb, int T, int ntiles) {
 // chunk fit beside this CTA on the SM; shared memory still limits it to one CTA per SM)
 template <int S>
 __global__ void __launch_bounds__(OZ_THREADS, 2)
-oz_score_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB, OzParams p) {
+oz_score_kernel(const __grid_constant__ CUtensorMap tmapB, OzParams p) {
     extern __shared__ uint8_t oz_smem_raw[];
     // 1024-byte aligned operand ring
     const uint32_t raw = smem_u32(oz_smem_raw);
@@ -437,7 +466,6 @@ oz_score_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
     const int nunits = p.ntiles * nb;
 
     if (warp == 0 && lane == 0) {
-        tma_prefetch_desc(&tmapA);
         tma_prefetch_desc(&tmapB);
         for (int s = 0; s < nst; ++s) {
             mbar_init(full_bar(s), 1);
@@ -468,7 +496,8 @@ oz_score_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
                     const uint32_t sA = base + stage * stage_bytes;
                     const uint32_t sB = sA + S * OZ_A_SLICE_BYTES;
                     for (int s = 0; s < S; ++s) {
-                        tma_load_3d(sA + s * OZ_A_SLICE_BYTES, &tmapA, kb * OZ_BK, un.tile * OZ_BM, s, full_bar(stage));
+                        bulk_load(sA + s * OZ_A_SLICE_BYTES, p.kss + oz_kss_block(s, un.tile, kb, p.ntiles, nb),
+                                  OZ_A_SLICE_BYTES, full_bar(stage));
                         tma_load_3d(sB + s * OZ_B_SLICE_BYTES, &tmapB, kb * OZ_BK, un.rb * OZ_BN, s, full_bar(stage));
                     }
                     if (++stage == nst) { stage = 0; phase ^= 1; }
@@ -609,6 +638,11 @@ int bo_ozaki_init(bo_ctx *ctx) {
 #define OZ_ATTR(SS) BO_CUDA(ctx, cudaFuncSetAttribute(oz_score_kernel<SS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)oz_smem_bytes(SS)))
     OZ_ATTR(2); OZ_ATTR(3); OZ_ATTR(4); OZ_ATTR(5); OZ_ATTR(6); OZ_ATTR(7); OZ_ATTR(8);
 #undef OZ_ATTR
+#define OZ_KATTR(DP, SS) BO_CUDA(ctx, cudaFuncSetAttribute(oz_kstar_slices_fast_kernel<DP, SS>, cudaFuncAttributeMaxDynamicSharedMemorySize, SS * OZ_A_SLICE_BYTES))
+#define OZ_KATTR_ALL(DP) OZ_KATTR(DP, 2); OZ_KATTR(DP, 3); OZ_KATTR(DP, 4); OZ_KATTR(DP, 5)
+    OZ_KATTR_ALL(2); OZ_KATTR_ALL(4); OZ_KATTR_ALL(8); OZ_KATTR_ALL(16);
+#undef OZ_KATTR_ALL
+#undef OZ_KATTR
     return BO_OK;
 }
 
@@ -678,7 +712,8 @@ template <int DP, int S>
 static void launch_oz_kstar_fast(bo_ctx *ctx, int s, const double *dXc, int64_t c0, int mc, int mcp, int8_t *Kss,
                                  cudaStream_t st) {
     const int ntile = ctx->np / 64;
-    oz_kstar_slices_fast_kernel<DP, S><<<dim3(mcp / 128, (ntile + OZ_KS_TILES - 1) / OZ_KS_TILES), 128, 0, st>>>(
+    oz_kstar_slices_fast_kernel<DP, S><<<dim3(mcp / 128, (ntile + OZ_KS_TILES - 1) / OZ_KS_TILES), 128,
+                                         S * OZ_A_SLICE_BYTES, st>>>(
         ctx->n, ctx->np, ctx->d, ctx->dXs + (int64_t)s * ctx->np * ctx->dp, ctx->dXsHalfSq + (int64_t)s * ctx->np,
         ctx->dInvEll + (int64_t)s * ctx->dp, dXc, c0, mc, mcp, Kss);
 }
@@ -730,8 +765,7 @@ int bo_ozaki_slice(bo_ctx *ctx, int s, int S, const double *dXc, int64_t c0, int
 int bo_ozaki_contract(bo_ctx *ctx, int s, int S, int mcp, int buf, double *mu, double *s2, int32_t *dbg) {
     const int np = ctx->np;
     const int8_t *Kss = ctx->dKss + (size_t)buf * ctx->kss_stride;
-    CUtensorMap tmA, tmB;
-    BO_TRY(make_tmap(ctx, &tmA, Kss, np, mcp, S, OZ_BM));
+    CUtensorMap tmB;
     BO_TRY(make_tmap(ctx, &tmB, ctx->dWs + (size_t)s * S * np * np, np, np, S, OZ_BN));
     const int nb = np / OZ_BN;
     {
@@ -755,13 +789,13 @@ int bo_ozaki_contract(bo_ctx *ctx, int s, int S, int mcp, int buf, double *mu, d
     }
     p.rowscale = ctx->dRowScale + (size_t)s * np;
     p.alpha = ctx->dAlpha + (size_t)s * np;
-    p.qpart = ctx->dOzQ; p.ppart = ctx->dOzP; p.dbg = dbg;
+    p.qpart = ctx->dOzQ; p.ppart = ctx->dOzP; p.dbg = dbg; p.kss = Kss;
     const int nunits = p.ntiles * nb;
     const int grid = nunits < ctx->sm_count ? nunits : ctx->sm_count;
     {
         BO_LAUNCH(ctx, "oz_score_kernel");
         switch (S) {
-#define OZ_RUN(SS) case SS: oz_score_kernel<SS><<<grid, OZ_THREADS, oz_smem_bytes(SS), ctx->stream>>>(tmA, tmB, p); break
+#define OZ_RUN(SS) case SS: oz_score_kernel<SS><<<grid, OZ_THREADS, oz_smem_bytes(SS), ctx->stream>>>(tmB, p); break
             OZ_RUN(2); OZ_RUN(3); OZ_RUN(4); OZ_RUN(5); OZ_RUN(6); OZ_RUN(7); OZ_RUN(8);
 #undef OZ_RUN
             default: return bo_set_err(ctx, BO_ERR_ARG, "int8 path needs 2..8 slices, got %d", S);
@@ -805,7 +839,14 @@ extern "C" int bo_ozaki_debug(bo_ctx *ctx, int S, int mc, const double *Xc, doub
         if (s2) cudaMemcpy(s2, dmu + mcp, sizeof(double) * mc, cudaMemcpyDeviceToHost);
         if (acc) cudaMemcpy(acc, dacc, sizeof(int32_t) * (size_t)nb * S * 128 * 64, cudaMemcpyDeviceToHost);
         if (wslices) cudaMemcpy(wslices, ctx->dWs, (size_t)S * np * np, cudaMemcpyDeviceToHost);
-        if (kslices) cudaMemcpy(kslices, ctx->dKss, (size_t)S * mcp * np, cudaMemcpyDeviceToHost);
+        if (kslices) {       // present the blocked / swizzled planes as plain [s][candidate][k]
+            std::vector<int8_t> raw((size_t)S * mcp * np);
+            cudaMemcpy(raw.data(), ctx->dKss, raw.size(), cudaMemcpyDeviceToHost);
+            for (int sl = 0; sl < S; ++sl)
+                for (int m = 0; m < mcp; ++m)
+                    for (int j = 0; j < np; ++j)
+                        kslices[((size_t)sl * mcp + m) * np + j] = raw[oz_kss_offset(sl, m, j, mcp >> 7, np >> 6)];
+        }
         if (rowscale) cudaMemcpy(rowscale, ctx->dRowScale, sizeof(double) * np, cudaMemcpyDeviceToHost);
     }
     cudaFree(dXc); cudaFree(dmu); cudaFree(dacc);
