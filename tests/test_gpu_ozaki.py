@@ -110,3 +110,29 @@ def test_ozaki_slice_count_follows_tolerance(ctx):
         errs.append(max(np.max(np.abs(gmu - mu)), np.max(np.abs(gs2 - s2))))
     assert errs[0] > errs[1] > errs[2] > errs[3]
     assert errs[3] < 1e-9 and errs[1] / errs[2] > 30    # ~2^7 per extra slice
+
+
+def test_full_size_headline_shape_int8_vs_fp64_and_oracle(ctx):
+    """BASELINE headline shape (RBF n=4096, d=8, EI): the int8-slice path at the bench's tolerance
+    against the FP64 path on 40k candidates (crossing the 32768-candidate chunk edge) and against
+    the oracle on a slice; identical arg max and top-10."""
+    gp = synth(4096, 8, "se", seed=0)
+    ctx.fit("se", gp.X, gp.Y, gp.ell[None], [gp.rho], [gp.sn2], [gp.bias])
+    Xc = qmc.Sobol(d=8, scramble=False).random_base2(16)[:40000]
+    target = float(gp.predict(gp.X)[0].max())
+    f64val, _, f64best = ctx.score(1, target, Xc, want_best=True)
+    top64 = ctx.topk(10)
+    ctx.set_precision(1, 1e-7)
+    val, _, best = ctx.score(1, target, Xc, want_best=True)
+    top8 = ctx.topk(10)
+    assert ctx.precision_info() == (1, 5)
+    assert rel_err(val, f64val, 1e-9) < 1e-6
+    assert best[1] == f64best[1] and np.array_equal(top8[0], top64[0])
+    sl = slice(32700, 32900)
+    ref = gp.get_improvement(target, Xc[sl])
+    assert rel_err(val[sl], ref, 1e-9) < 1e-6
+    # size-independent properties: 0 <= s2 <= rho, UCB >= mean, scores independent of chunking
+    mu, s2 = ctx.predict(Xc[:5000])
+    assert np.all(s2 > 0) and np.all(s2 <= gp.rho * (1 + 1e-9))
+    again, _, _ = ctx.score(1, target, Xc[sl])
+    assert np.array_equal(again, val[sl])
