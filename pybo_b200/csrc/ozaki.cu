@@ -366,12 +366,21 @@ oz_kstar_slices_fast_kernel(int n, int np, int d, const double *__restrict__ Xs,
                 const double vv = v + 4503599627370496.0;                   // + 2^52: mantissa = rint(v)
                 const uint32_t lo = (uint32_t)__double2loint(vv);
                 const uint32_t hi = (uint32_t)__double2hiint(vv) & 0xFFFFFu;
-                const uint32_t t = lo & ((1u << LOW) - 1u);
-                const uint32_t top = (lo >> LOW) | (hi << (32 - LOW));
-                // byte b of wlow = digit of slice (S-1-b)
-                wlow[i] = (t & 0x7Fu) | ((t & 0x3F80u) << 1) | ((t & 0x1FC000u) << 2) | ((t & 0xFE00000u) << 3);
-                if ((i & 3) == 0) wtop[i >> 2] = top;
-                else wtop[i >> 2] |= top << (8 * (i & 3));
+                int t = (int)(lo & ((1u << LOW) - 1u));
+                int top = (int)((lo >> LOW) | (hi << (32 - LOW)));
+                // balanced base-128 digits in [-64, 63] (zero-mean, so the dropped digit-pair products
+                // average out: half the error of plain 7-bit fields); byte b of wlow = slice (S-1-b)
+                uint32_t w = 0;
+#pragma unroll
+                for (int b = 0; b < S - 1; ++b) {
+                    const int dgt = ((t + 64) & 127) - 64;
+                    t = (t - dgt) >> 7;
+                    w |= ((uint32_t)dgt & 0xFFu) << (8 * b);
+                }
+                top += t;                                           // carry out of the low part: 0 or 1
+                wlow[i] = w;
+                if ((i & 3) == 0) wtop[i >> 2] = (uint32_t)top;
+                else wtop[i >> 2] |= (uint32_t)top << (8 * (i & 3));
             }
             uint8_t *o0 = oz_stage + tid * 64 + ((sub ^ swz) << 4);
             *reinterpret_cast<uint4 *>(o0) = make_uint4(wtop[0], wtop[1], wtop[2], wtop[3]);
