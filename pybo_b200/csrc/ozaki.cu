@@ -563,9 +563,19 @@ oz_score_kernel(const __grid_constant__ CUtensorMap tmapB, OzParams p) {
                 const int row0 = un.rb * OZ_BN + c0;
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                    double v = (double)r[G][i];
+                    double v;
+                    if (S <= 5) {
+                        // sum_g D_g 2^(7 (G - g)) fits int64 for <= 5 slices (|D_g| < 2^27): shift-adds on
+                        // the integer pipe and a single conversion keep the FP64 pipe for the reductions
+                        long long a = (long long)r[0][i];
 #pragma unroll
-                    for (int g = G - 1; g >= 0; --g) v = fma(v, 0.0078125, (double)r[g][i]);
+                        for (int g = 1; g <= G; ++g) a = a * 128 + (long long)r[g][i];
+                        v = (double)a * (1.0 / (double)(1ll << (7 * G)));
+                    } else {
+                        v = (double)r[G][i];
+#pragma unroll
+                        for (int g = G - 1; g >= 0; --g) v = fma(v, 0.0078125, (double)r[g][i]);
+                    }
                     const double vv = v * __ldg(p.rowscale + row0 + i);
                     q = fma(vv, vv, q);
                     pm = fma(vv, __ldg(p.alpha + row0 + i), pm);
