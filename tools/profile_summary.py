@@ -5,6 +5,7 @@ import subprocess
 import sys
 
 tag, kern = sys.argv[1], sys.argv[2]           # e.g. r1_fp64 score_gemm
+kerns = sys.argv[2:]
 rows = [r for r in csv.reader(open('gpurun_out/launches.csv')) if len(r) > 5]
 hdr = rows[0]
 ki, vi, ui = hdr.index('Kernel Name'), hdr.index('Metric Value'), hdr.index('Metric Unit')
@@ -18,7 +19,7 @@ for r in rows[1:]:
 tot = sum(a[1] for a in agg.values())
 out = ["# ncu --metrics gpu__time_duration.sum --clock-control none over a short bench.py run",
        "# (cold-cache, serialised launches: compare SHARES, not absolutes)", "kernel,launches,total_us,share"]
-STEP = ('kstar', 'score_gemm', 'moments', 'acq_kernel', 'argmax_final', 'ozaki', 'slice')
+STEP = ('kstar', 'score_gemm', 'moments', 'acq_kernel', 'argmax_final', 'oz_score', 'oz_kstar', 'oz_moments')
 step_tot = sum(t for k, (c, t) in agg.items() if any(s in k for s in STEP))
 out[2] = "kernel,launches,total_us,share_of_all,share_of_scoring_step"
 for k, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
@@ -26,21 +27,24 @@ for k, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
     out.append("%s,%d,%.1f,%.4f,%s" % (k, c, t, t / tot, ("%.4f" % (t / step_tot)) if in_step else "-"))
 open('profiles/%s_launch_shares.csv' % tag, 'w').write("\n".join(out) + "\n")
 print("\n".join(out))
-raw = subprocess.run(['ncu', '-i', 'gpurun_out/prof_%s.ncu-rep' % kern, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
-rr = list(csv.reader(raw.splitlines()))
-h, u, v = rr[0], rr[1], rr[2]
 want = ['Kernel Name', 'gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum',
         'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed', 'lts__throughput.avg.pct_of_peak_sustained_elapsed',
+        'lts__t_sector_hit_rate.pct', 'l1tex__m_xbar2l1tex_read_bytes_mem_global_op_tma_ld.sum',
         'sm__throughput.avg.pct_of_peak_sustained_elapsed', 'sm__inst_executed_pipe_tensor_subpipe_dmma.avg.pct_of_peak_sustained_active',
-        'sm__inst_executed_pipe_tensor_subpipe_imma.avg.pct_of_peak_sustained_active',
+        'sm__ops_path_tensor_op_utcimma_src_int8_sparsity_off.avg.pct_of_peak_sustained_elapsed',
+        'sm__ops_path_tensor_op_utcimma_src_int8_sparsity_off.avg.peak_sustained',
         'TPC.TriageCompute.sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed',
-        'sm__ops_path_tensor_src_fp64.avg.peak_sustained', 'sm__ops_path_tensor_op_utcimma_src_int8_sparsity_off.avg.pct_of_peak_sustained_elapsed',
-        'sm__warps_active.avg.pct_of_peak_sustained_active',
+        'sm__ops_path_tensor_src_fp64.avg.peak_sustained', 'sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active',
+        'sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active', 'sm__warps_active.avg.pct_of_peak_sustained_active',
         'launch__registers_per_thread', 'launch__grid_size', 'launch__block_size', 'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum',
-        'sm__issue_active.avg.pct_of_peak_sustained_elapsed']
-lines = ["# ncu --set full --clock-control none -k regex:%s, first captured launch" % kern, ""]
-for k in want:
-    if k in h:
-        i = h.index(k); lines.append("%s = %s %s" % (k, v[i], u[i]))
-open('profiles/%s_%s_ncu.txt' % (tag, kern), 'w').write("\n".join(lines) + "\n")
-print("\n".join(lines))
+        'sm__issue_active.avg.pct_of_peak_sustained_elapsed', 'sm__cycles_elapsed.max', 'smsp__inst_executed.sum']
+for kern in kerns:
+    raw = subprocess.run(['ncu', '-i', 'gpurun_out/prof_%s.ncu-rep' % kern, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
+    rr = list(csv.reader(raw.splitlines()))
+    h, u, v = rr[0], rr[1], rr[2]
+    lines = ["# ncu --set full --clock-control none -k regex:%s, first captured launch (bench.py --candidates 65536)" % kern, ""]
+    for k in want:
+        if k in h:
+            i = h.index(k); lines.append("%s = %s %s" % (k, v[i], u[i]))
+    open('profiles/%s_%s_ncu.txt' % (tag, kern), 'w').write("\n".join(lines) + "\n")
+    print("\n".join(lines))
