@@ -114,11 +114,12 @@ static void free_all(bo_ctx *ctx) {
                        &ctx->dTmp, &ctx->dKs, &ctx->dV, &ctx->dU, &ctx->dQpart, &ctx->dPpart, &ctx->dMuS,
                        &ctx->dS2S, &ctx->dDmuS, &ctx->dDs2S, &ctx->dGpart, &ctx->dXc, &ctx->dVal,
                        &ctx->dGradOut, &ctx->dBlkVal, &ctx->th.W, &ctx->th.b, &ctx->th.theta,
-                       &ctx->th.scale, &ctx->th.bias, &ctx->th.dBestVal, &ctx->dOzQ, &ctx->dOzP, &ctx->dXsHalfSq};
+                       &ctx->th.scale, &ctx->th.bias, &ctx->th.dBestVal, &ctx->dOzQ, &ctx->dOzP, &ctx->dXsHalfSq, &ctx->dCholDinv};
     for (auto p : ptrs)
         if (*p) { cudaFree(*p); *p = nullptr; }
     if (ctx->dInfo) { cudaFree(ctx->dInfo); ctx->dInfo = nullptr; }
     if (ctx->dWs) { cudaFree(ctx->dWs); ctx->dWs = nullptr; }
+    if (ctx->dCholInfo) { cudaFree(ctx->dCholInfo); ctx->dCholInfo = nullptr; }
     if (ctx->dKss) { cudaFree(ctx->dKss); ctx->dKss = nullptr; }
     if (ctx->dRowScale) { cudaFree(ctx->dRowScale); ctx->dRowScale = nullptr; }
     if (ctx->dRowExp) { cudaFree(ctx->dRowExp); ctx->dRowExp = nullptr; }
@@ -529,13 +530,14 @@ extern "C" int bo_cholesky(bo_ctx *ctx, int n, int batch, double *A, int flags, 
     double *dA = nullptr, *dinv = nullptr;
     int *dInfo = nullptr;
     const bool inplace = dev && (np == n);
-    cudaError_t e = cudaMalloc(&dinv, sizeof(double) * (size_t)batch * nblk * 4096);
-    if (e == cudaSuccess) e = cudaMalloc(&dInfo, sizeof(int) * batch);
-    if (e == cudaSuccess && !inplace) e = cudaMalloc(&dA, sizeof(double) * (size_t)batch * np * np);
-    if (e != cudaSuccess) {
-        cudaFree(dinv); cudaFree(dInfo); cudaFree(dA);
-        return bo_set_err(ctx, BO_ERR_CUDA, "bo_cholesky: %s", cudaGetErrorString(e));
-    }
+    // scratch (inverted diagonal blocks, info) persists in the handle: no malloc per call
+    BO_TRY(bo_reserve(ctx, &ctx->dCholDinv, &ctx->choldinv_capacity, (size_t)batch * nblk * 4096));
+    BO_TRY(bo_reserve(ctx, &ctx->dCholInfo, &ctx->cholinfo_capacity, (size_t)batch));
+    dinv = ctx->dCholDinv;
+    dInfo = ctx->dCholInfo;
+    cudaError_t e = cudaSuccess;
+    if (!inplace) e = cudaMalloc(&dA, sizeof(double) * (size_t)batch * np * np);
+    if (e != cudaSuccess) return bo_set_err(ctx, BO_ERR_CUDA, "bo_cholesky: %s", cudaGetErrorString(e));
     int rc = BO_OK;
     if (inplace) {
         dA = A;
@@ -569,8 +571,6 @@ extern "C" int bo_cholesky(bo_ctx *ctx, int n, int batch, double *A, int flags, 
         if (e == cudaSuccess && bad) rc = bo_set_err(ctx, BO_ERR_NOT_PD, "bo_cholesky: matrix is not positive definite");
     }
     cudaStreamSynchronize(st);
-    cudaFree(dinv);
-    cudaFree(dInfo);
     if (!inplace) cudaFree(dA);
     if (e != cudaSuccess) return bo_set_err(ctx, BO_ERR_CUDA, "bo_cholesky: %s", cudaGetErrorString(e));
     return rc;

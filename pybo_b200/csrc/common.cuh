@@ -57,6 +57,9 @@ struct bo_ctx {
     double *dLogdet = nullptr;  // S        sum log diag L
     double *dTmp = nullptr;     // S x np x np/2 scratch for the blocked inverse
     int *dInfo = nullptr;       // S
+    double *dCholDinv = nullptr;   // stand-alone bo_cholesky scratch
+    int *dCholInfo = nullptr;
+    size_t choldinv_capacity = 0, cholinfo_capacity = 0;
     std::vector<double> h_rho, h_sn2, h_bias, h_ell;
     std::vector<int> h_info;
     size_t fit_capacity = 0;    // S*np*np currently allocated

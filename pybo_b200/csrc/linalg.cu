@@ -61,7 +61,7 @@ __global__ void __launch_bounds__(256) potrf64_kernel(double *A, int ld, int64_t
     extern __shared__ __align__(16) double potrf_smem[];
     double (*a)[65] = reinterpret_cast<double (*)[65]>(potrf_smem);
     double (*x)[65] = reinterpret_cast<double (*)[65]>(potrf_smem + 64 * 65);
-    double *invd = potrf_smem + 2 * 64 * 65;
+    double *rs = potrf_smem + 2 * 64 * 65;            // 1 / sqrt(pivot_j)
     __shared__ int bad;
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
     double *Ab = A + blockIdx.x * strideA + (int64_t)kblk * 64 * (ld + 1);
@@ -72,63 +72,40 @@ __global__ void __launch_bounds__(256) potrf64_kernel(double *A, int ld, int64_t
         a[i][j] = (j <= i) ? Ab[(int64_t)i * ld + j] : 0.0;
         x[i][j] = (i == j) ? 1.0 : 0.0;
     }
-    // LDL^T-style elimination: column j is left unscaled until the end so only
-    // one barrier per column is needed.
+    // One loop, one barrier per column, for both the factor and its inverse.  Columns stay
+    // unscaled (a[i][j] = L[i][j] sqrt(d_j)) so the multiplier m_ij = a[i][j] / d_j serves the
+    // trailing update a[i][k] -= m_ij a[k][j] and the forward substitution on the identity
+    // x[i][c] -= m_ij x[j][c] (rows of x are scaled by 1 / L[i][i] at the end).
     for (int j = 0; j < 64; ++j) {
         __syncthreads();
         const double d = a[j][j];
         if (tid == 0 && !(d > 0.0) && bad == 0) bad = j + 1;
-        const double inv = 1.0 / d;
+        const double r = rsqrt(d);
+        const double r2 = r * r;
+        if (tid == 0) rs[j] = r;
 #pragma unroll
         for (int ai = 0; ai < 4; ++ai) {
             const int i = ty + 16 * ai;
             if (i <= j) continue;
-            const double lij = a[i][j] * inv;
+            const double mij = a[i][j] * r2;
 #pragma unroll
-            for (int bk = 0; bk < 4; ++bk) {
-                const int k = tx + 16 * bk;
-                if (k > j && k <= i) a[i][k] -= lij * a[k][j];
+            for (int b = 0; b < 4; ++b) {
+                const int k = tx + 16 * b;
+                if (k > j && k <= i) a[i][k] -= mij * a[k][j];
+                if (k <= j) x[i][k] -= mij * x[j][k];
             }
         }
     }
     __syncthreads();
-    if (tid < 64) invd[tid] = 1.0 / sqrt(a[tid][tid]);
-    __syncthreads();
-    // scale columns: L[i][j] = a[i][j] / sqrt(a[j][j]);  diag = sqrt(a[j][j])
     for (int e = tid; e < 4096; e += 256) {
         int i = e >> 6, j = e & 63;
         double v = 0.0;
-        if (j < i) v = a[i][j] * invd[j];
-        else if (j == i) v = sqrt(a[i][i]);
-        a[i][j] = v;
-    }
-    __syncthreads();
-    for (int e = tid; e < 4096; e += 256) {
-        int i = e >> 6, j = e & 63;
-        Ab[(int64_t)i * ld + j] = a[i][j];
+        if (j < i) v = a[i][j] * rs[j];
+        else if (j == i) v = a[i][i] * rs[i];          // sqrt(d) = d / sqrt(d)
+        Ab[(int64_t)i * ld + j] = v;
+        Db[e] = (j <= i) ? x[i][j] * rs[i] : 0.0;
     }
     if (tid == 0 && bad != 0) atomicCAS(&info[blockIdx.x], 0, kblk * 64 + bad);
-    // forward substitution on the identity: x = L^-1 (row k scaled at the end)
-    for (int k = 0; k < 64; ++k) {
-        __syncthreads();
-        const double ik = invd[k];   // 1 / L[k][k]
-#pragma unroll
-        for (int ai = 0; ai < 4; ++ai) {
-            const int i = ty + 16 * ai;
-            if (i <= k) continue;
-            const double lik = a[i][k] * ik;
-#pragma unroll
-            for (int bc = 0; bc < 4; ++bc) {
-                const int c = tx + 16 * bc;
-                if (c <= k) x[i][c] -= lik * x[k][c];
-            }
-        }
-    }
-    __syncthreads();
-    for (int e = tid; e < 4096; e += 256) {
-        int i = e >> 6, j = e & 63;
-        Db[e] = (j <= i) ? x[i][j] * invd[i] : 0.0;
-    }
 }
 
 #define POTRF_SMEM ((2 * 64 * 65 + 64) * 8)
