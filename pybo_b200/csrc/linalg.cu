@@ -58,57 +58,94 @@ int bo_linalg_gram(bo_ctx *ctx, int kernel, int n, int np, int dp, int S, const 
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) potrf64_kernel(double *A, int ld, int64_t strideA, int kblk,
                                                       double *dinv, int64_t strideD, int *info) {
-    extern __shared__ __align__(16) double potrf_smem[];
-    double (*a)[65] = reinterpret_cast<double (*)[65]>(potrf_smem);
-    double (*x)[65] = reinterpret_cast<double (*)[65]>(potrf_smem + 64 * 65);
-    double *rs = potrf_smem + 2 * 64 * 65;            // 1 / sqrt(pivot_j)
+    // Register-resident factorisation of a 64 x 64 diagonal block and of its inverse.
+    // Thread (ty, tx) owns a[ty + 16 ai][tx + 16 b] and x[...] (x starts as the identity) in
+    // registers for the whole kernel; per column only the pivot column of `a` and the pivot row
+    // of `x` are broadcast through double-buffered shared memory (one barrier per column).
+    // Columns stay unscaled (a[i][j] = L[i][j] sqrt(d_j)), so the multiplier m_ij = a[i][j] / d_j
+    // serves both the trailing update a[i][k] -= m_ij a[k][j] and the forward substitution
+    // x[i][c] -= m_ij x[j][c]; rows of x are scaled by 1 / L[i][i] at the end.
+    __shared__ double colbuf[2][64];
+    __shared__ double rowbuf[2][64];
+    __shared__ double rs[64];
     __shared__ int bad;
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
     double *Ab = A + blockIdx.x * strideA + (int64_t)kblk * 64 * (ld + 1);
     double *Db = dinv + blockIdx.x * strideD + (int64_t)kblk * 4096;
     if (tid == 0) bad = 0;
-    for (int e = tid; e < 4096; e += 256) {
-        int i = e >> 6, j = e & 63;
-        a[i][j] = (j <= i) ? Ab[(int64_t)i * ld + j] : 0.0;
-        x[i][j] = (i == j) ? 1.0 : 0.0;
-    }
-    // One loop, one barrier per column, for both the factor and its inverse.  Columns stay
-    // unscaled (a[i][j] = L[i][j] sqrt(d_j)) so the multiplier m_ij = a[i][j] / d_j serves the
-    // trailing update a[i][k] -= m_ij a[k][j] and the forward substitution on the identity
-    // x[i][c] -= m_ij x[j][c] (rows of x are scaled by 1 / L[i][i] at the end).
+    double ra[4][4], rx[4][4];
+#pragma unroll
+    for (int ai = 0; ai < 4; ++ai)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const int i = ty + 16 * ai, k = tx + 16 * b;
+            ra[ai][b] = (k <= i) ? Ab[(int64_t)i * ld + k] : 0.0;
+            rx[ai][b] = (i == k) ? 1.0 : 0.0;
+        }
+    int p = 0;
     for (int j = 0; j < 64; ++j) {
+        const int jb = j >> 4, jl = j & 15;
+        if (tx == jl) {            // owners of column j of a
+#pragma unroll
+            for (int ai = 0; ai < 4; ++ai) {
+                double v = ra[ai][0];
+                if (jb == 1) v = ra[ai][1];
+                if (jb == 2) v = ra[ai][2];
+                if (jb == 3) v = ra[ai][3];
+                colbuf[p][ty + 16 * ai] = v;
+            }
+        }
+        if (ty == jl) {            // owners of row j of x
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                double v = rx[0][b];
+                if (jb == 1) v = rx[1][b];
+                if (jb == 2) v = rx[2][b];
+                if (jb == 3) v = rx[3][b];
+                rowbuf[p][tx + 16 * b] = v;
+            }
+        }
         __syncthreads();
-        const double d = a[j][j];
-        if (tid == 0 && !(d > 0.0) && bad == 0) bad = j + 1;
+        const double d = colbuf[p][j];
         const double r = rsqrt(d);
         const double r2 = r * r;
-        if (tid == 0) rs[j] = r;
+        if (tid == 0) {
+            rs[j] = r;
+            if (!(d > 0.0) && bad == 0) bad = j + 1;
+        }
+        double ck[4], xk[4];
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            ck[b] = colbuf[p][tx + 16 * b];
+            xk[b] = rowbuf[p][tx + 16 * b];
+        }
 #pragma unroll
         for (int ai = 0; ai < 4; ++ai) {
             const int i = ty + 16 * ai;
             if (i <= j) continue;
-            const double mij = a[i][j] * r2;
+            const double mij = colbuf[p][i] * r2;
 #pragma unroll
             for (int b = 0; b < 4; ++b) {
                 const int k = tx + 16 * b;
-                if (k > j && k <= i) a[i][k] -= mij * a[k][j];
-                if (k <= j) x[i][k] -= mij * x[j][k];
+                if (k > j && k <= i) ra[ai][b] = fma(-mij, ck[b], ra[ai][b]);
+                if (k <= j) rx[ai][b] = fma(-mij, xk[b], rx[ai][b]);
             }
         }
+        p ^= 1;
     }
     __syncthreads();
-    for (int e = tid; e < 4096; e += 256) {
-        int i = e >> 6, j = e & 63;
-        double v = 0.0;
-        if (j < i) v = a[i][j] * rs[j];
-        else if (j == i) v = a[i][i] * rs[i];          // sqrt(d) = d / sqrt(d)
-        Ab[(int64_t)i * ld + j] = v;
-        Db[e] = (j <= i) ? x[i][j] * rs[i] : 0.0;
-    }
+#pragma unroll
+    for (int ai = 0; ai < 4; ++ai)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const int i = ty + 16 * ai, k = tx + 16 * b;
+            Ab[(int64_t)i * ld + k] = (k <= i) ? ra[ai][b] * rs[k] : 0.0;      // diag: d / sqrt(d)
+            Db[i * 64 + k] = (k <= i) ? rx[ai][b] * rs[i] : 0.0;
+        }
     if (tid == 0 && bad != 0) atomicCAS(&info[blockIdx.x], 0, kblk * 64 + bad);
 }
 
-#define POTRF_SMEM ((2 * 64 * 65 + 64) * 8)
+#define POTRF_SMEM 0
 
 // Lower-triangular tile enumeration for the trailing update.
 template <class T>
@@ -386,7 +423,6 @@ int bo_linalg_finish_fit(bo_ctx *ctx) {
 }
 
 int bo_linalg_init(bo_ctx *ctx) {
-    BO_TRY(set_smem(ctx, potrf64_kernel, POTRF_SMEM));
     BO_TRY(set_smem(ctx, dgemm_kernel<T64NT>, T64NT::SMEM_BYTES));
     BO_TRY(set_smem(ctx, syrk_tri_kernel<T64NT>, T64NT::SMEM_BYTES));
     BO_TRY(set_smem(ctx, trtri_node_kernel<0>, T64NN::SMEM_BYTES));
