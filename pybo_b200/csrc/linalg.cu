@@ -2,6 +2,8 @@
 // reference bayesopt.py:114,258,269): Gram matrix K = k(X,X) + sn2 I, blocked
 // right-looking Cholesky (64-wide panels, FP64 DMMA trailing update), blocked
 // recursive triangular inverse W = L^-1, and alpha / beta / log-det.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "dgemm.cuh"
 
@@ -57,7 +59,7 @@ int bo_linalg_gram(bo_ctx *ctx, int kernel, int n, int np, int dp, int S, const 
 // invert the factor (needed by the panel solve and by W = L^-1).
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) potrf64_kernel(double *A, int ld, int64_t strideA, int kblk,
-                                                      double *dinv, int64_t strideD, int *info) {
+                                                      double *dinv, int64_t strideD, int *info, int variant) {
     // Register-resident factorisation of a 64 x 64 diagonal block and of its inverse.
     // Thread (ty, tx) owns a[ty + 16 ai][tx + 16 b] and x[...] (x starts as the identity) in
     // registers for the whole kernel; per column only the pivot column of `a` and the pivot row
@@ -83,55 +85,54 @@ __global__ void __launch_bounds__(256) potrf64_kernel(double *A, int ld, int64_t
             rx[ai][b] = (i == k) ? 1.0 : 0.0;
         }
     int p = 0;
-    for (int j = 0; j < 64; ++j) {
-        const int jb = j >> 4, jl = j & 15;
-        if (tx == jl) {            // owners of column j of a
+    const bool tx_le_ty = tx <= ty;
+    // The column loop is unrolled over the 16-column block jb so that which register tiles take
+    // part in a step (rows below the pivot, columns right of / up to it) is known at compile time;
+    // only the comparisons against jl inside the pivot's own tile remain at run time.
 #pragma unroll
-            for (int ai = 0; ai < 4; ++ai) {
-                double v = ra[ai][0];
-                if (jb == 1) v = ra[ai][1];
-                if (jb == 2) v = ra[ai][2];
-                if (jb == 3) v = ra[ai][3];
-                colbuf[p][ty + 16 * ai] = v;
+    for (int jb = 0; jb < 4; ++jb) {
+#pragma unroll 1
+        for (int jl = 0; jl < 16; ++jl) {
+            const int j = 16 * jb + jl;
+            if (tx == jl) {            // owners of column j of a
+#pragma unroll
+                for (int ai = jb; ai < 4; ++ai) colbuf[p][ty + 16 * ai] = ra[ai][jb];
             }
-        }
-        if (ty == jl) {            // owners of row j of x
+            if (ty == jl) {            // owners of row j of x (columns <= j)
 #pragma unroll
-            for (int b = 0; b < 4; ++b) {
-                double v = rx[0][b];
-                if (jb == 1) v = rx[1][b];
-                if (jb == 2) v = rx[2][b];
-                if (jb == 3) v = rx[3][b];
-                rowbuf[p][tx + 16 * b] = v;
+                for (int b = 0; b <= jb; ++b) rowbuf[p][tx + 16 * b] = rx[jb][b];
             }
-        }
-        __syncthreads();
-        const double d = colbuf[p][j];
-        const double r = rsqrt(d);
-        const double r2 = r * r;
-        if (tid == 0) {
-            rs[j] = r;
-            if (!(d > 0.0) && bad == 0) bad = j + 1;
-        }
-        double ck[4], xk[4];
-#pragma unroll
-        for (int b = 0; b < 4; ++b) {
-            ck[b] = colbuf[p][tx + 16 * b];
-            xk[b] = rowbuf[p][tx + 16 * b];
-        }
-#pragma unroll
-        for (int ai = 0; ai < 4; ++ai) {
-            const int i = ty + 16 * ai;
-            if (i <= j) continue;
-            const double mij = colbuf[p][i] * r2;
-#pragma unroll
-            for (int b = 0; b < 4; ++b) {
-                const int k = tx + 16 * b;
-                if (k > j && k <= i) ra[ai][b] = fma(-mij, ck[b], ra[ai][b]);
-                if (k <= j) rx[ai][b] = fma(-mij, xk[b], rx[ai][b]);
+            __syncthreads();
+            const double d = colbuf[p][j];
+            const double r = (variant & 1) ? d * 0.5 : rsqrt(d);
+            const double r2 = r * r;
+            if (tid == 0) {
+                rs[j] = r;
+                if (!(d > 0.0) && bad == 0) bad = j + 1;
             }
+            const bool tx_gt_jl = tx > jl, ty_gt_jl = ty > jl;
+#pragma unroll
+            for (int ai = jb; ai < 4; ++ai) {
+                const bool row_on = (ai > jb) || ty_gt_jl;          // i > j
+                if (!row_on) continue;
+                const double mij = colbuf[p][ty + 16 * ai] * r2;
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    // trailing update: j < k <= i
+                    if (b >= jb && b <= ai) {
+                        const bool k_gt_j = (b > jb) || tx_gt_jl;
+                        const bool k_le_i = (b < ai) || tx_le_ty;
+                        if (k_gt_j && k_le_i) ra[ai][b] = fma(-mij, colbuf[p][tx + 16 * b], ra[ai][b]);
+                    }
+                    // forward substitution on the identity: k <= j
+                    if (b <= jb) {
+                        const bool k_le_j = (b < jb) || !tx_gt_jl;
+                        if (k_le_j) rx[ai][b] = fma(-mij, rowbuf[p][tx + 16 * b], rx[ai][b]);
+                    }
+                }
+            }
+            p ^= 1;
         }
-        p ^= 1;
     }
     __syncthreads();
 #pragma unroll
@@ -200,7 +201,7 @@ int bo_linalg_cholesky(bo_ctx *ctx, int np, int batch, double *A, double *dinv, 
     for (int k = 0; k < nblk; ++k) {
         {
             BO_LAUNCH(ctx, "potrf64_kernel");
-            potrf64_kernel<<<batch, 256, POTRF_SMEM, ctx->stream>>>(A, np, strideA, k, dinv, strideD, dInfo);
+            potrf64_kernel<<<batch, 256, POTRF_SMEM, ctx->stream>>>(A, np, strideA, k, dinv, strideD, dInfo, getenv("BO_POTRF_DBG") ? atoi(getenv("BO_POTRF_DBG")) : 0);
             BO_CHECK_LAUNCH(ctx);
         }
         const int T = nblk - k - 1;
