@@ -194,39 +194,79 @@ static int set_smem(bo_ctx *ctx, K kernel, int bytes) {
 }
 
 // In-place lower Cholesky of `batch` padded np x np matrices (np % 64 == 0).
+// Right-looking with a one-panel lookahead: at step k the main (high-priority) stream updates only
+// block column k+1 with panel k and goes straight on to factor and solve panel k+1, while the rest
+// of the trailing update of step k runs on the side stream.
 int bo_linalg_cholesky(bo_ctx *ctx, int np, int batch, double *A, double *dinv, int *dInfo) {
     const int nblk = np / BO_NB;
     const int64_t strideA = (int64_t)np * np, strideD = (int64_t)nblk * 4096;
-    BO_CUDA(ctx, cudaMemsetAsync(dInfo, 0, sizeof(int) * batch, ctx->stream));
-    for (int k = 0; k < nblk; ++k) {
-        {
-            BO_LAUNCH(ctx, "potrf64_kernel");
-            potrf64_kernel<<<batch, 256, POTRF_SMEM, ctx->stream>>>(A, np, strideA, k, dinv, strideD, dInfo, getenv("BO_POTRF_DBG") ? atoi(getenv("BO_POTRF_DBG")) : 0);
-            BO_CHECK_LAUNCH(ctx);
-        }
+    cudaStream_t main = ctx->stream, side = ctx->stream2;
+    const int variant = getenv("BO_POTRF_DBG") ? atoi(getenv("BO_POTRF_DBG")) : 0;
+    BO_CUDA(ctx, cudaMemsetAsync(dInfo, 0, sizeof(int) * batch, main));
+    auto potrf = [&](int k) -> int {
+        BO_LAUNCH(ctx, "potrf64_kernel");
+        potrf64_kernel<<<batch, 256, 0, main>>>(A, np, strideA, k, dinv, strideD, dInfo, variant);
+        BO_CHECK_LAUNCH(ctx);
+        return BO_OK;
+    };
+    auto trsm = [&](int k) -> int {     // L_ik = A_ik Dinv_k^T for i > k
         const int T = nblk - k - 1;
-        if (T == 0) break;
         double *panel = A + (int64_t)(k + 1) * BO_NB * np + (int64_t)k * BO_NB;
-        {   // panel solve: L_ik = A_ik * Dinv_k^T
-            DGemmParams p = {};
-            p.A = panel; p.lda = np; p.strideA = strideA;
-            p.B = dinv + (int64_t)k * 4096; p.ldb = 64; p.strideB = strideD;
-            p.C = panel; p.ldc = np; p.strideC = strideA;
-            p.inner = batch; p.tiles_m = T; p.tiles_n = 1; p.K = BO_NB; p.krule = KR_FULL;
-            p.alpha = 1.0; p.beta = 0.0;
-            BO_LAUNCH(ctx, "chol_trsm_kernel");
-            dgemm_kernel<T64NT><<<dim3(T, 1, batch), T64NT::NTHREADS, T64NT::SMEM_BYTES, ctx->stream>>>(p);
-            BO_CHECK_LAUNCH(ctx);
-        }
-        {   // trailing update: A22 -= L21 L21^T on the lower-triangular tiles
-            double *A22 = A + (int64_t)(k + 1) * BO_NB * (np + 1);
-            const int ntile = T * (T + 1) / 2;
-            BO_LAUNCH(ctx, "chol_syrk_kernel");
-            syrk_tri_kernel<T64NT><<<dim3(ntile, 1, batch), T64NT::NTHREADS, T64NT::SMEM_BYTES, ctx->stream>>>(
-                A22, panel, np, strideA, ntile);
-            BO_CHECK_LAUNCH(ctx);
-        }
+        DGemmParams p = {};
+        p.A = panel; p.lda = np; p.strideA = strideA;
+        p.B = dinv + (int64_t)k * 4096; p.ldb = 64; p.strideB = strideD;
+        p.C = panel; p.ldc = np; p.strideC = strideA;
+        p.inner = batch; p.tiles_m = T; p.tiles_n = 1; p.K = BO_NB; p.krule = KR_FULL;
+        p.alpha = 1.0; p.beta = 0.0;
+        BO_LAUNCH(ctx, "chol_trsm_kernel");
+        dgemm_kernel<T64NT><<<dim3(T, 1, batch), T64NT::NTHREADS, T64NT::SMEM_BYTES, main>>>(p);
+        BO_CHECK_LAUNCH(ctx);
+        return BO_OK;
+    };
+    auto next_column = [&](int k) -> int {   // A_{i,k+1} -= L_ik L_{k+1,k}^T for i >= k+1 (main stream)
+        const int T = nblk - k - 1;
+        double *panel = A + (int64_t)(k + 1) * BO_NB * np + (int64_t)k * BO_NB;
+        DGemmParams p = {};
+        p.A = panel; p.lda = np; p.strideA = strideA;
+        p.B = panel; p.ldb = np; p.strideB = strideA;
+        p.C = A + (int64_t)(k + 1) * BO_NB * (np + 1); p.ldc = np; p.strideC = strideA;
+        p.inner = batch; p.tiles_m = T; p.tiles_n = 1; p.K = BO_NB; p.krule = KR_FULL;
+        p.alpha = -1.0; p.beta = 1.0;
+        BO_LAUNCH(ctx, "chol_column_kernel");
+        dgemm_kernel<T64NT><<<dim3(T, 1, batch), T64NT::NTHREADS, T64NT::SMEM_BYTES, main>>>(p);
+        BO_CHECK_LAUNCH(ctx);
+        return BO_OK;
+    };
+    auto rest = [&](int k) -> int {          // A_ij -= L_ik L_jk^T for i >= j >= k+2 (side stream)
+        const int T = nblk - k - 2;
+        if (T <= 0) return BO_OK;
+        double *panel = A + (int64_t)(k + 2) * BO_NB * np + (int64_t)k * BO_NB;
+        double *A22 = A + (int64_t)(k + 2) * BO_NB * (np + 1);
+        const int ntile = T * (T + 1) / 2;
+        BO_LAUNCH_ON(ctx, "chol_syrk_kernel", side);
+        syrk_tri_kernel<T64NT><<<dim3(ntile, 1, batch), T64NT::NTHREADS, T64NT::SMEM_BYTES, side>>>(
+            A22, panel, np, strideA, ntile);
+        BO_CHECK_LAUNCH(ctx);
+        return BO_OK;
+    };
+    // the side stream must see everything queued on the main stream so far (the input matrix)
+    BO_CUDA(ctx, cudaEventRecord(ctx->ev_consumed[0], main));
+    BO_CUDA(ctx, cudaStreamWaitEvent(side, ctx->ev_consumed[0], 0));
+    BO_TRY(potrf(0));
+    if (nblk > 1) BO_TRY(trsm(0));
+    BO_CUDA(ctx, cudaEventRecord(ctx->ev_sliced[0], main));               // panel 0 ready
+    for (int k = 0; k + 1 < nblk; ++k) {
+        const int e = k & 1;
+        BO_CUDA(ctx, cudaStreamWaitEvent(side, ctx->ev_sliced[e], 0));    // panel k
+        BO_TRY(rest(k));
+        BO_CUDA(ctx, cudaEventRecord(ctx->ev_consumed[e], side));          // rest(k) done
+        if (k >= 1) BO_CUDA(ctx, cudaStreamWaitEvent(main, ctx->ev_consumed[e ^ 1], 0));   // rest(k-1) touched column k+1
+        BO_TRY(next_column(k));
+        BO_TRY(potrf(k + 1));
+        if (k + 2 < nblk) BO_TRY(trsm(k + 1));
+        BO_CUDA(ctx, cudaEventRecord(ctx->ev_sliced[e ^ 1], main));       // panel k+1 ready
     }
+    if (nblk > 1) BO_CUDA(ctx, cudaStreamWaitEvent(main, ctx->ev_consumed[(nblk - 2) & 1], 0));
     return BO_OK;
 }
 
