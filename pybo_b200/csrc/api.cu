@@ -98,6 +98,7 @@ extern "C" int bo_create(int device, bo_ctx **out) {
     int rc = bo_linalg_init(ctx);
     if (rc == BO_OK) rc = bo_score_init(ctx);
     if (rc == BO_OK) rc = bo_ozaki_init(ctx);
+    if (rc == BO_OK) rc = bo_thompson_init(ctx);
     if (rc != BO_OK) {
         fprintf(stderr, "bo_create: %s\n", ctx->err);
         cudaStreamDestroy(ctx->stream);
@@ -114,7 +115,7 @@ static void free_all(bo_ctx *ctx) {
                        &ctx->dTmp, &ctx->dKs, &ctx->dV, &ctx->dU, &ctx->dQpart, &ctx->dPpart, &ctx->dMuS,
                        &ctx->dS2S, &ctx->dDmuS, &ctx->dDs2S, &ctx->dGpart, &ctx->dXc, &ctx->dVal,
                        &ctx->dGradOut, &ctx->dBlkVal, &ctx->th.W, &ctx->th.b, &ctx->th.theta,
-                       &ctx->th.scale, &ctx->th.bias, &ctx->th.dBestVal, &ctx->dOzQ, &ctx->dOzP, &ctx->dXsHalfSq, &ctx->dCholDinv};
+                       &ctx->th.scale, &ctx->th.bias, &ctx->th.dBestVal, &ctx->th.thetaT, &ctx->dOzQ, &ctx->dOzP, &ctx->dXsHalfSq, &ctx->dCholDinv};
     for (auto p : ptrs)
         if (*p) { cudaFree(*p); *p = nullptr; }
     if (ctx->dInfo) { cudaFree(ctx->dInfo); ctx->dInfo = nullptr; }
@@ -210,18 +211,24 @@ extern "C" int bo_fit(bo_ctx *ctx, int kernel, int n, int d, int S, const double
         BO_TRY(realloc_dev(ctx, &ctx->dWT, mat));
         ctx->fit_capacity = mat;
     }
-    BO_TRY(realloc_dev(ctx, &ctx->dX, (size_t)n * d));
-    BO_TRY(realloc_dev(ctx, &ctx->dY, (size_t)n));
-    BO_TRY(realloc_dev(ctx, &ctx->dXs, (size_t)S * np * dp));
-    BO_TRY(realloc_dev(ctx, &ctx->dInvEll, (size_t)S * dp));
-    BO_TRY(realloc_dev(ctx, &ctx->dRho, (size_t)S));
-    BO_TRY(realloc_dev(ctx, &ctx->dSn2, (size_t)S));
-    BO_TRY(realloc_dev(ctx, &ctx->dBias, (size_t)S));
-    BO_TRY(realloc_dev(ctx, &ctx->dDinv, (size_t)S * nblk64 * 4096));
-    BO_TRY(realloc_dev(ctx, &ctx->dAlpha, (size_t)S * np));
-    BO_TRY(realloc_dev(ctx, &ctx->dBeta, (size_t)S * np));
-    BO_TRY(realloc_dev(ctx, &ctx->dLogdet, (size_t)S));
-    BO_TRY(realloc_dev(ctx, &ctx->dInfo, (size_t)S));
+    // small per-fit buffers grow on demand and are reused (bo_fit runs hundreds of times in the
+    // hyper-parameter sampler)
+    {
+        struct { double **p; size_t need; } small[] = {
+            {&ctx->dX, (size_t)n * d}, {&ctx->dY, (size_t)n}, {&ctx->dXs, (size_t)S * np * dp},
+            {&ctx->dInvEll, (size_t)S * dp}, {&ctx->dRho, (size_t)S}, {&ctx->dSn2, (size_t)S},
+            {&ctx->dBias, (size_t)S}, {&ctx->dDinv, (size_t)S * nblk64 * 4096}, {&ctx->dAlpha, (size_t)S * np},
+            {&ctx->dBeta, (size_t)S * np}, {&ctx->dLogdet, (size_t)S}};
+        for (size_t i = 0; i < sizeof(small) / sizeof(small[0]); ++i) {
+            if (ctx->small_capacity[i] >= small[i].need && *small[i].p) continue;
+            BO_TRY(realloc_dev(ctx, small[i].p, small[i].need));
+            ctx->small_capacity[i] = small[i].need;
+        }
+        if (ctx->info_capacity < (size_t)S || !ctx->dInfo) {
+            BO_TRY(realloc_dev(ctx, &ctx->dInfo, (size_t)S));
+            ctx->info_capacity = (size_t)S;
+        }
+    }
     ctx->kernel = kernel; ctx->n = n; ctx->np = np; ctx->d = d; ctx->dp = dp; ctx->S = S;
     ctx->h_rho.assign(rho, rho + S);
     ctx->h_sn2.assign(sn2, sn2 + S);
@@ -472,6 +479,17 @@ extern "C" int bo_thompson_set(bo_ctx *ctx, int ndraw, int nW, int m, int d, con
     BO_CUDA(ctx, cudaMemcpyAsync(th.bias, bias, sizeof(double) * ndraw, cudaMemcpyHostToDevice, st));
     BO_CUDA(ctx, cudaStreamSynchronize(st));
     th.ndraw = ndraw; th.nW = nW; th.m = m; th.d = d;
+    // transposed, zero-padded theta for the shared-basis tensor-core path
+    if (th.thetaT) { cudaFree(th.thetaT); th.thetaT = nullptr; }
+    if (nW == 1) {
+        const int mp = bo_round_up(m, 16), ndp = bo_round_up(ndraw, 256);
+        std::vector<double> tt((size_t)mp * ndp, 0.0);
+        for (int r = 0; r < ndraw; ++r)
+            for (int j = 0; j < m; ++j) tt[(size_t)j * ndp + r] = theta[(size_t)r * m + j];
+        BO_CUDA(ctx, cudaMalloc(&th.thetaT, sizeof(double) * tt.size()));
+        BO_CUDA(ctx, cudaMemcpy(th.thetaT, tt.data(), sizeof(double) * tt.size(), cudaMemcpyHostToDevice));
+        th.ndp = ndp;
+    }
     return BO_OK;
 }
 

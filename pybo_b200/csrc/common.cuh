@@ -29,6 +29,8 @@ struct bo_thompson_state {
     double *dBestVal = nullptr;
     int64_t *dBestIdx = nullptr;
     double *W = nullptr, *b = nullptr, *theta = nullptr, *scale = nullptr, *bias = nullptr;
+    double *thetaT = nullptr;   // (m padded to 16) x (ndraw padded to 256), shared-basis contraction operand
+    int ndp = 0;
 };
 
 struct bo_ctx {
@@ -63,6 +65,8 @@ struct bo_ctx {
     std::vector<double> h_rho, h_sn2, h_bias, h_ell;
     std::vector<int> h_info;
     size_t fit_capacity = 0;    // S*np*np currently allocated
+    size_t small_capacity[11] = {0};
+    size_t info_capacity = 0;
 
     // ---- scoring scratch ---------------------------------------------------
     int64_t chunk = 0;          // candidates per chunk (multiple of 128)
@@ -195,6 +199,7 @@ int bo_linalg_finish_fit(bo_ctx *ctx);
 int bo_linalg_init(bo_ctx *ctx);
 int bo_score_init(bo_ctx *ctx);
 int bo_ozaki_init(bo_ctx *ctx);
+int bo_thompson_init(bo_ctx *ctx);
 int bo_ozaki_prepare(bo_ctx *ctx, int S);
 int bo_ozaki_choose_slices(bo_ctx *ctx, double tol);
 int bo_ozaki_slice(bo_ctx *ctx, int s, int S, const double *dXc, int64_t c0, int mc, int mcp, int buf,

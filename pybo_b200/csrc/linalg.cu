@@ -2,8 +2,6 @@
 // reference bayesopt.py:114,258,269): Gram matrix K = k(X,X) + sn2 I, blocked
 // right-looking Cholesky (64-wide panels, FP64 DMMA trailing update), blocked
 // recursive triangular inverse W = L^-1, and alpha / beta / log-det.
-#include <stdlib.h>
-
 #include "common.cuh"
 #include "dgemm.cuh"
 
@@ -59,7 +57,7 @@ int bo_linalg_gram(bo_ctx *ctx, int kernel, int n, int np, int dp, int S, const 
 // invert the factor (needed by the panel solve and by W = L^-1).
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) potrf64_kernel(double *A, int ld, int64_t strideA, int kblk,
-                                                      double *dinv, int64_t strideD, int *info, int variant) {
+                                                      double *dinv, int64_t strideD, int *info) {
     // Register-resident factorisation of a 64 x 64 diagonal block and of its inverse.
     // Thread (ty, tx) owns a[ty + 16 ai][tx + 16 b] and x[...] (x starts as the identity) in
     // registers for the whole kernel; per column only the pivot column of `a` and the pivot row
@@ -104,7 +102,7 @@ __global__ void __launch_bounds__(256) potrf64_kernel(double *A, int ld, int64_t
             }
             __syncthreads();
             const double d = colbuf[p][j];
-            const double r = (variant & 1) ? d * 0.5 : rsqrt(d);
+            const double r = rsqrt(d);
             const double r2 = r * r;
             if (tid == 0) {
                 rs[j] = r;
@@ -201,11 +199,10 @@ int bo_linalg_cholesky(bo_ctx *ctx, int np, int batch, double *A, double *dinv, 
     const int nblk = np / BO_NB;
     const int64_t strideA = (int64_t)np * np, strideD = (int64_t)nblk * 4096;
     cudaStream_t main = ctx->stream, side = ctx->stream2;
-    const int variant = getenv("BO_POTRF_DBG") ? atoi(getenv("BO_POTRF_DBG")) : 0;
     BO_CUDA(ctx, cudaMemsetAsync(dInfo, 0, sizeof(int) * batch, main));
     auto potrf = [&](int k) -> int {
         BO_LAUNCH(ctx, "potrf64_kernel");
-        potrf64_kernel<<<batch, 256, 0, main>>>(A, np, strideA, k, dinv, strideD, dInfo, variant);
+        potrf64_kernel<<<batch, 256, 0, main>>>(A, np, strideA, k, dinv, strideD, dInfo);
         BO_CHECK_LAUNCH(ctx);
         return BO_OK;
     };

@@ -234,13 +234,16 @@ def test_thompson_draw_matches_oracle(ctx, kernel):
     assert bi == int(np.argmax(RF)) and bv == F[bi]
 
 
-def test_thompson_batch_shared_basis(ctx):
+@pytest.mark.parametrize("d,m,ndraw,M", [(2, 128, 7, 1000), (16, 500, 300, 4097), (5, 33, 256, 64)])
+def test_thompson_batch_shared_basis(ctx, d, m, ndraw, M):
+    """BASELINE config 4 shape family: ndraw posterior draws x M candidates on one random-feature
+    basis (tensor-core contraction with on-the-fly cosine features), per-draw arg max."""
     from pybo_b200 import models
-    gp = synth(80, 2, "se", seed=3, sn2=1e-3)
+    gp = synth(80, d, "se", seed=3, sn2=1e-3)
     mine = models.GP(gp.sn2, gp.rho, gp.ell, gp.bias)
     mine.add_data(gp.X, gp.Y)
-    tb = models.ThompsonBatch(mine, m=128, ndraw=7, rng=5)
-    Xc = sobol(1000, 2)
+    tb = models.ThompsonBatch(mine, m=m, ndraw=ndraw, rng=5)
+    Xc = sobol(M, d)
     F = tb.get(Xc)
     ref = tb.bias + (tb.scale * np.cos(Xc @ tb.W.T + tb.b)) @ tb.theta.T
     assert rel_err(F, ref.T, 1e-9) < TOL
