@@ -159,6 +159,62 @@ __global__ void moments_kernel(int nblk, int mcp, const double *__restrict__ qpa
 }
 
 // ---------------------------------------------------------------------------
+// Small batches (the L-BFGS callback shape f(x[None], grad=True), reference lbfgs.py:56-58):
+// a tiled GEMM would walk the whole k range serially in one CTA, so M <= 8 candidates use
+// bandwidth-bound triangular GEMVs instead: one warp per row of W (or W^T), MC right-hand sides.
+//   UPPER == false: out[row][m] = sum_{j <= row} Mx[row][j] rhs[j][m]     (V = W K*)
+//   UPPER == true : out[row][m] = sum_{j >= row} Mx[row][j] rhs[j][m]     (U = W^T V)
+// ---------------------------------------------------------------------------
+template <int MC, bool UPPER>
+__global__ void __launch_bounds__(256)
+trimv_small_kernel(const double *__restrict__ Mx, int np, const double *__restrict__ rhs, int ld,
+                   double *__restrict__ out) {
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= np) return;
+    const double *mrow = Mx + (int64_t)row * np;
+    double acc[MC];
+#pragma unroll
+    for (int m = 0; m < MC; ++m) acc[m] = 0.0;
+    const int jbeg = UPPER ? (row & ~31) : 0;
+    const int jend = UPPER ? np : row + 1;
+    for (int j = jbeg + lane; j < jend; j += 32) {
+        if (UPPER && j < row) continue;
+        const double w = mrow[j];
+#pragma unroll
+        for (int m = 0; m < MC; ++m) acc[m] = fma(w, rhs[(int64_t)j * ld + m], acc[m]);
+    }
+#pragma unroll
+    for (int m = 0; m < MC; ++m) {
+        acc[m] = warp_sum_d(acc[m]);
+        if (lane == 0) out[(int64_t)row * ld + m] = acc[m];
+    }
+}
+
+// mu[m] = bias + sum_i V[i][m] alpha[i], s2[m] = rho - sum_i V[i][m]^2 ; one block per candidate
+__global__ void __launch_bounds__(256)
+small_moments_kernel(const double *__restrict__ V, int np, int ld, const double *__restrict__ alpha, double rho,
+                     double bias, double *__restrict__ mu, double *__restrict__ s2) {
+    __shared__ double rq[8], rp[8];
+    const int m = blockIdx.x;
+    double q = 0.0, p = 0.0;
+    for (int i = threadIdx.x; i < np; i += 256) {
+        const double v = V[(int64_t)i * ld + m];
+        q = fma(v, v, q);
+        p = fma(v, alpha[i], p);
+    }
+    q = warp_sum_d(q);
+    p = warp_sum_d(p);
+    if ((threadIdx.x & 31) == 0) { rq[threadIdx.x >> 5] = q; rp[threadIdx.x >> 5] = p; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; ++w) { q += rq[w]; p += rp[w]; }
+        mu[m] = bias + p;
+        s2[m] = rho - q;
+    }
+}
+
+// ---------------------------------------------------------------------------
 // gradient partial sums: one warp per candidate, lanes stride the observations.
 //   gm_k = sum_j g_j beta_j (xc_k - x_jk),  gs_k = sum_j g_j U_jm (xc_k - x_jk)
 // (scaled coordinates), g = -dk/dD * 2:  SE: k,  Matern-5/2: rho 5/3 (1+r) e^-r.
@@ -467,7 +523,8 @@ int bo_score_run(bo_ctx *ctx, const ScoreRequest &rq) {
     const int64_t M = rq.M;
     if (M <= 0) return bo_set_err(ctx, BO_ERR_ARG, "M must be positive");
     // int8-slice path for value-only passes when selected; gradients stay on the FP64 path
-    const bool oz = (ctx->prec == BO_PREC_OZAKI) && !grad;
+    // (tiny batches stay on the exact FP64 GEMV/GEMM path: nothing to gain from the tensor pipe there)
+    const bool oz = (ctx->prec == BO_PREC_OZAKI) && !grad && rq.M > 64;
     int oz_S = 0;
     if (oz) {
         oz_S = bo_ozaki_choose_slices(ctx, ctx->prec_tol);
@@ -595,6 +652,62 @@ int bo_score_run(bo_ctx *ctx, const ScoreRequest &rq) {
         const int mcp = bo_round_up(mc, 128);
         for (int s = 0; s < S; ++s) {
             DISPATCH_DP(ctx, launch_kstar, ctx, s, rq.dXc, c0, mc, mcp);
+            if (mc <= 8) {
+                // small batch: triangular GEMVs (V, and U = W^T V for gradients) instead of tiled GEMMs
+                const int MC = mc <= 1 ? 1 : (mc <= 2 ? 2 : (mc <= 4 ? 4 : 8));
+                size_t need = (size_t)np * mcp;
+                if (ctx->grad_capacity < need || !ctx->dV) {
+                    size_t c1 = ctx->grad_capacity, c2 = ctx->grad_capacity, c3 = 0, c4 = 0, c5 = 0;
+                    BO_TRY(bo_reserve(ctx, &ctx->dV, &c1, need));
+                    BO_TRY(bo_reserve(ctx, &ctx->dU, &c2, need));
+                    if (ctx->dGpart) { cudaFree(ctx->dGpart); ctx->dGpart = nullptr; }
+                    if (ctx->dDmuS) { cudaFree(ctx->dDmuS); ctx->dDmuS = nullptr; }
+                    if (ctx->dDs2S) { cudaFree(ctx->dDs2S); ctx->dDs2S = nullptr; }
+                    BO_TRY(bo_reserve(ctx, &ctx->dGpart, &c3, (size_t)GRAD_SLICES * cap * 2 * dp));
+                    BO_TRY(bo_reserve(ctx, &ctx->dDmuS, &c4, (size_t)S * cap * d));
+                    BO_TRY(bo_reserve(ctx, &ctx->dDs2S, &c5, (size_t)S * cap * d));
+                    ctx->grad_capacity = need;
+                }
+                const double *Wm = ctx->dW + (int64_t)s * np * np, *WTm = ctx->dWT + (int64_t)s * np * np;
+                {
+                    BO_LAUNCH(ctx, "trimv_small_kernel");
+                    switch (MC) {
+                        case 1: trimv_small_kernel<1, false><<<np / 8, 256, 0, ctx->stream>>>(Wm, np, ctx->dKs, mcp, ctx->dV); break;
+                        case 2: trimv_small_kernel<2, false><<<np / 8, 256, 0, ctx->stream>>>(Wm, np, ctx->dKs, mcp, ctx->dV); break;
+                        case 4: trimv_small_kernel<4, false><<<np / 8, 256, 0, ctx->stream>>>(Wm, np, ctx->dKs, mcp, ctx->dV); break;
+                        default: trimv_small_kernel<8, false><<<np / 8, 256, 0, ctx->stream>>>(Wm, np, ctx->dKs, mcp, ctx->dV); break;
+                    }
+                    BO_CHECK_LAUNCH(ctx);
+                }
+                {
+                    BO_LAUNCH(ctx, "small_moments_kernel");
+                    small_moments_kernel<<<mc, 256, 0, ctx->stream>>>(ctx->dV, np, mcp, ctx->dAlpha + (int64_t)s * np,
+                                                                    ctx->h_rho[s], ctx->h_bias[s],
+                                                                    ctx->dMuS + (int64_t)s * mcp, ctx->dS2S + (int64_t)s * mcp);
+                    BO_CHECK_LAUNCH(ctx);
+                }
+                if (grad) {
+                    {
+                        BO_LAUNCH(ctx, "trimv_small_kernel");
+                        switch (MC) {
+                            case 1: trimv_small_kernel<1, true><<<np / 8, 256, 0, ctx->stream>>>(WTm, np, ctx->dV, mcp, ctx->dU); break;
+                            case 2: trimv_small_kernel<2, true><<<np / 8, 256, 0, ctx->stream>>>(WTm, np, ctx->dV, mcp, ctx->dU); break;
+                            case 4: trimv_small_kernel<4, true><<<np / 8, 256, 0, ctx->stream>>>(WTm, np, ctx->dV, mcp, ctx->dU); break;
+                            default: trimv_small_kernel<8, true><<<np / 8, 256, 0, ctx->stream>>>(WTm, np, ctx->dV, mcp, ctx->dU); break;
+                        }
+                        BO_CHECK_LAUNCH(ctx);
+                    }
+                    DISPATCH_DP(ctx, launch_grad_partial, ctx, s, rq.dXc, c0, mc, mcp);
+                    {
+                        BO_LAUNCH(ctx, "grad_finish_kernel");
+                        grad_finish_kernel<<<(mc * d + 255) / 256, 256, 0, ctx->stream>>>(
+                            dp, d, mc, mcp, ctx->dGpart, ctx->dInvEll + (int64_t)s * dp,
+                            ctx->dDmuS + (int64_t)s * mcp * d, ctx->dDs2S + (int64_t)s * mcp * d);
+                        BO_CHECK_LAUNCH(ctx);
+                    }
+                }
+                continue;
+            }
             {
                 BO_LAUNCH(ctx, "score_gemm_kernel");
                 score_gemm_kernel<<<nblk * (mcp / 128), TS::NTHREADS, TS::SMEM_BYTES, ctx->stream>>>(
