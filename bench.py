@@ -166,7 +166,7 @@ def our_arm(args):
     acq, param = acq_param(spec, X, model.predict)
     index = policies.ModelIndex(model, acq, param)
     if args.precision == "ozaki":
-        ctx.set_precision(1, args.tol)
+        model.set_precision("int8", args.tol)
 
     xc_dev = sobol_block(M, d, rank * M).cuda()            # this rank's block, resident in HBM
     val_dev = torch.empty(M, dtype=torch.float64, device="cuda")

@@ -93,6 +93,19 @@ class _Base(object):
 
     kernel = "se"
     device = None
+    _precision = ("fp64", 1e-9)
+
+    def set_precision(self, path="fp64", tol=1e-7):
+        """Arithmetic of the scoring contraction: 'fp64' (FP64 tensor cores, default) or 'int8'
+        (error-bounded int8 slices on tcgen05; `tol` is the target absolute error of V = L^-1 k
+        relative to sqrt(rho), or an explicit slice count when >= 2).  Gradients, small batches and
+        `predict` at fewer than 65 points always use FP64."""
+        if path not in ("fp64", "int8"):
+            raise ValueError("precision path must be 'fp64' or 'int8'")
+        self._precision = (path, float(tol))
+        if self._fit is not None:
+            self._fit.ctx.set_precision(1 if path == "int8" else 0, float(tol))
+        return self
 
     def _init_data(self, d):
         self._X = np.zeros((0, d))
@@ -127,6 +140,9 @@ class _Base(object):
         if self._fit is None:
             ell, rho, sn2, bias = self._hypers()
             self._fit = _Fit(self.kernel, self._X, self._Y, ell, rho, sn2, bias, self.device)
+            path, tol = self._precision
+            if path == "int8":
+                self._fit.ctx.set_precision(1, tol)
         return self._fit.ctx
 
     # pickling / checkpointing (reference bayesopt.py:39-55): device state is rebuilt lazily
@@ -199,6 +215,7 @@ class GP(_Base):
     def copy(self):
         new = GP(self.sn2, self.rho, self.ell, self.bias, self.kernel, self.device)
         new._X, new._Y, new._fit = self._X, self._Y, self._fit
+        new._precision = self._precision
         for k, p in self.params.items():
             new.params[k].prior = p.prior
         return new
