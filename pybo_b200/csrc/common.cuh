@@ -109,8 +109,11 @@ struct bo_ctx {
     std::vector<int> h_emax;
     double *dXsHalfSq = nullptr;               // S_hyper x np   |xs_j|^2 / 2
     size_t halfsq_capacity = 0;
-    double *dOzQ = nullptr, *dOzP = nullptr;   // (np/64) x chunk partial reductions
+    double *dOzQ = nullptr, *dOzP = nullptr;   // (np/64) x chunk partial |v|^2
     size_t ozpart_capacity = 0;
+    double *dOzMu = nullptr;                    // per slice buffer: (blocks) x chunk partials of kappa . beta
+    size_t ozmu_capacity = 0, ozmu_stride = 0;
+    int oz_mu_slot = 0, oz_mu_rows[2] = {0, 0};
 
     bo_thompson_state th;
 

@@ -216,7 +216,8 @@ template <int DP>
 __global__ void __launch_bounds__(256)
 oz_kstar_slices_kernel(int kernel, int n, int np, int d, int S, const double *__restrict__ Xs,
                        const double *__restrict__ invell, const double *__restrict__ Xc, int64_t c0, int mc,
-                       int mcp, int8_t *__restrict__ Ks) {
+                       int mcp, int8_t *__restrict__ Ks, const double *__restrict__ beta,
+                       double *__restrict__ mupart) {
     __shared__ double xs[64][DP];
     const int tid = threadIdx.x;
     const int j0 = blockIdx.y * 64;
@@ -228,6 +229,7 @@ oz_kstar_slices_kernel(int kernel, int n, int np, int d, int S, const double *__
 #pragma unroll
     for (int k = 0; k < DP; ++k) xc[k] = (live && k < d) ? Xc[(c0 + m) * d + k] * invell[k] : 0.0;
     __syncthreads();
+    double kb = 0.0;                              // sum_j kappa_j beta_j over this thread's 32 observations
     for (int sub = 0; sub < 2; ++sub) {
         const int jj0 = half * 32 + sub * 16;
         double r[16];
@@ -247,6 +249,7 @@ oz_kstar_slices_kernel(int kernel, int n, int np, int d, int S, const double *__
                 v = (1.0 + rr + rr * rr * (1.0 / 3.0)) * exp(-rr);
             }
             r[i] = (live && (j0 + jj0 + i) < n) ? v * 64.0 : 0.0;
+            if (live && (j0 + jj0 + i) < n) kb = fma(v, beta[j0 + jj0 + i], kb);
         }
         for (int s = 0; s < S; ++s) {
             alignas(16) int8_t q[16];
@@ -259,6 +262,8 @@ oz_kstar_slices_kernel(int kernel, int n, int np, int d, int S, const double *__
             *reinterpret_cast<int4 *>(Ks + oz_kss_offset(s, m, j0 + jj0, mcp >> 7, np >> 6)) = *reinterpret_cast<const int4 *>(q);
         }
     }
+    // partial of kappa . beta for (64-observation block, half): fixed-order sum in oz_moments_kernel
+    mupart[((int64_t)blockIdx.y * 2 + half) * mcp + m] = kb;
 }
 
 // Fast variant for the SE kernel and S <= 6 slices.  The FP64 pipe limits the slicer, so
@@ -305,9 +310,11 @@ template <int DP, int S>
 __global__ void __launch_bounds__(128)
 oz_kstar_slices_fast_kernel(int n, int np, int d, const double *__restrict__ Xs, const double *__restrict__ XsHalfSq,
                             const double *__restrict__ invell, const double *__restrict__ Xc, int64_t c0, int mc,
-                            int mcp, int8_t *__restrict__ Ks) {
+                            int mcp, int8_t *__restrict__ Ks, const double *__restrict__ beta,
+                            double *__restrict__ mupart) {
     __shared__ __align__(16) double xs[2][64][DP];
     __shared__ __align__(16) double hb[2][64];
+    __shared__ __align__(16) double bt[2][64];                      // beta of the tile
     extern __shared__ __align__(16) uint8_t oz_stage[];          // [S][128 rows][64 B]
     const int tid = threadIdx.x;
     const int nkb = np / 64, ntiles = mcp / 128;
@@ -317,6 +324,7 @@ oz_kstar_slices_fast_kernel(int n, int np, int d, const double *__restrict__ Xs,
         const double *src = Xs + (int64_t)tile * 64 * DP;
         for (int e = tid; e < 64 * DP / 2; e += 128) oz_cp_async16(&xs[buf][0][0] + 2 * e, src + 2 * e);
         if (tid < 32) oz_cp_async16(&hb[buf][0] + 2 * tid, XsHalfSq + (int64_t)tile * 64 + 2 * tid);
+        else if (tid < 64) oz_cp_async16(&bt[buf][0] + 2 * (tid - 32), beta + (int64_t)tile * 64 + 2 * (tid - 32));
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
     prefetch(t0, 0);
@@ -334,6 +342,7 @@ oz_kstar_slices_fast_kernel(int n, int np, int d, const double *__restrict__ Xs,
     constexpr double LOG2E = 1.4426950408889634;
     static_assert(S >= 2 && S <= 5, "fast slicer handles 2..5 slices");
     const int swz = (tid >> 1) & 3;
+    double kb = 0.0;                 // sum_j 2^SHIFT kappa_j beta_j over this block's observations (FP64)
     for (int tile = t0; tile < t1; ++tile) {
         const int buf = (tile - t0) & 1;
         if (tile + 1 < t1) {
@@ -363,6 +372,7 @@ oz_kstar_slices_fast_kernel(int n, int np, int d, const double *__restrict__ Xs,
                 const double z = fmin(dot, 0.0) * LOG2E;            // log2 kappa
                 const bool on = live && (j0 + jj0 + i) < n;
                 const double v = on ? oz_exp2_scaled<10>(z, SHIFT) : 0.0;     // in [0, 2^SHIFT], SHIFT <= 34
+                kb = fma(v, bt[buf][jj0 + i], kb);
                 const double vv = v + 4503599627370496.0;                   // + 2^52: mantissa = rint(v)
                 const uint32_t lo = (uint32_t)__double2loint(vv);
                 const uint32_t hi = (uint32_t)__double2hiint(vv) & 0xFFFFFu;
@@ -407,6 +417,9 @@ oz_kstar_slices_fast_kernel(int n, int np, int d, const double *__restrict__ Xs,
             for (int e = 0; e < OZ_A_SLICE_BYTES / 16 / 128; ++e) dst[e * 128 + tid] = src[e * 128 + tid];
         }
     }
+    // the posterior mean needs no contraction with W: mu = bias + rho * kappa . beta (beta = K^-1 r);
+    // per-block partials, summed in a fixed order by oz_moments_kernel
+    mupart[(int64_t)blockIdx.y * mcp + m] = kb * (1.0 / (double)(1ll << SHIFT));
 }
 
 // |xs_j|^2 / 2 per observation (once per fit)
@@ -425,8 +438,7 @@ struct OzParams {
     int np, S, nstages, ntiles, nacc, tiles_per_group;
     int mcp;
     const double *rowscale;   // np
-    const double *alpha;      // np
-    double *qpart, *ppart;    // [np/64][mcp] partial |v|^2 and v.alpha per row block
+    double *qpart;            // [np/64][mcp] partial |v|^2 per row block
     int32_t *dbg;             // optional: [rb][g][128][64] accumulators of tile 0
     const int8_t *kss;        // K*^T slice blocks (oz_kss_block layout)
 };
@@ -543,7 +555,7 @@ oz_score_kernel(const __grid_constant__ CUtensorMap tmapB, OzParams p) {
         for (int u = blockIdx.x; u < nunits; u += gridDim.x) {
             const OzUnit un = oz_decode(u, nb, p.tiles_per_group, p.ntiles);
             const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * S * OZ_BN);
-            double q = 0.0, pm = 0.0;
+            double q = 0.0;
             mbar_wait(tmem_full(acc), acc_phase);
             tc_fence_after();
 #pragma unroll 1
@@ -578,7 +590,6 @@ oz_score_kernel(const __grid_constant__ CUtensorMap tmapB, OzParams p) {
                     }
                     const double vv = v * __ldg(p.rowscale + row0 + i);
                     q = fma(vv, vv, q);
-                    pm = fma(vv, __ldg(p.alpha + row0 + i), pm);
                 }
             }
             tc_fence_before();
@@ -587,7 +598,6 @@ oz_score_kernel(const __grid_constant__ CUtensorMap tmapB, OzParams p) {
             if (++acc == nacc) { acc = 0; acc_phase ^= 1; }
             const int64_t o = (int64_t)un.rb * p.mcp + (int64_t)un.tile * OZ_BM + quarter * 32 + lane;
             p.qpart[o] = q;
-            p.ppart[o] = pm;
         }
     }
     tc_fence_before();
@@ -595,17 +605,17 @@ oz_score_kernel(const __grid_constant__ CUtensorMap tmapB, OzParams p) {
     if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
-// mu = bias + sum_rb ppart, s2 = rho - sum_rb qpart (fixed summation order)
-__global__ void oz_moments_kernel(int nb, int mcp, const double *__restrict__ qpart, const double *__restrict__ ppart,
-                                  double rho, double bias, double *__restrict__ mu, double *__restrict__ s2) {
+// s2 = rho - sum_rb qpart (int8 contraction); mu = bias + rho * sum_blocks mupart (FP64 dot product
+// kappa . beta accumulated by the slicer); both in a fixed summation order
+__global__ void oz_moments_kernel(int nb, int nmu, int mcp, const double *__restrict__ qpart,
+                                  const double *__restrict__ mupart, double rho, double bias,
+                                  double *__restrict__ mu, double *__restrict__ s2) {
     const int m = blockIdx.x * blockDim.x + threadIdx.x;
     if (m >= mcp) return;
     double q = 0.0, pm = 0.0;
-    for (int i = 0; i < nb; ++i) {
-        q += qpart[(int64_t)i * mcp + m];
-        pm += ppart[(int64_t)i * mcp + m];
-    }
-    mu[m] = bias + pm;
+    for (int i = 0; i < nb; ++i) q += qpart[(int64_t)i * mcp + m];
+    for (int i = 0; i < nmu; ++i) pm += mupart[(int64_t)i * mcp + m];
+    mu[m] = fma(rho, pm, bias);
     s2[m] = rho - q;
 }
 
@@ -734,7 +744,9 @@ static void launch_oz_kstar_fast(bo_ctx *ctx, int s, const double *dXc, int64_t 
     oz_kstar_slices_fast_kernel<DP, S><<<dim3(mcp / 128, (ntile + OZ_KS_TILES - 1) / OZ_KS_TILES), 128,
                                          S * OZ_A_SLICE_BYTES, st>>>(
         ctx->n, ctx->np, ctx->d, ctx->dXs + (int64_t)s * ctx->np * ctx->dp, ctx->dXsHalfSq + (int64_t)s * ctx->np,
-        ctx->dInvEll + (int64_t)s * ctx->dp, dXc, c0, mc, mcp, Kss);
+        ctx->dInvEll + (int64_t)s * ctx->dp, dXc, c0, mc, mcp, Kss, ctx->dBeta + (int64_t)s * ctx->np,
+        ctx->dOzMu + (size_t)ctx->oz_mu_slot * ctx->ozmu_stride);
+    ctx->oz_mu_rows[ctx->oz_mu_slot] = (ntile + OZ_KS_TILES - 1) / OZ_KS_TILES;
 }
 
 template <int DP>
@@ -753,7 +765,9 @@ static int launch_oz_kstar(bo_ctx *ctx, int s, int S, const double *dXc, int64_t
     }
     oz_kstar_slices_kernel<DP><<<dim3(mcp / 128, ctx->np / 64), 256, 0, st>>>(
         ctx->kernel, ctx->n, ctx->np, ctx->d, S, ctx->dXs + (int64_t)s * ctx->np * ctx->dp,
-        ctx->dInvEll + (int64_t)s * ctx->dp, dXc, c0, mc, mcp, Kss);
+        ctx->dInvEll + (int64_t)s * ctx->dp, dXc, c0, mc, mcp, Kss, ctx->dBeta + (int64_t)s * ctx->np,
+        ctx->dOzMu + (size_t)ctx->oz_mu_slot * ctx->ozmu_stride);
+    ctx->oz_mu_rows[ctx->oz_mu_slot] = 2 * (ctx->np / 64);
     BO_CHECK_LAUNCH(ctx);
     return BO_OK;
 }
@@ -762,6 +776,8 @@ static int launch_oz_kstar(bo_ctx *ctx, int s, int S, const double *dXc, int64_t
 int bo_ozaki_reserve(bo_ctx *ctx, int S, int mcp_max, int nbuf) {
     ctx->kss_stride = (size_t)S * mcp_max * ctx->np;
     BO_TRY(bo_reserve(ctx, &ctx->dKss, &ctx->kss_capacity, ctx->kss_stride * nbuf));
+    ctx->ozmu_stride = (size_t)2 * (ctx->np / 64) * mcp_max;       // per-buffer mean partials
+    BO_TRY(bo_reserve(ctx, &ctx->dOzMu, &ctx->ozmu_capacity, ctx->ozmu_stride * nbuf));
     return BO_OK;
 }
 
@@ -769,6 +785,7 @@ int bo_ozaki_reserve(bo_ctx *ctx, int S, int mcp_max, int nbuf) {
 int bo_ozaki_slice(bo_ctx *ctx, int s, int S, const double *dXc, int64_t c0, int mc, int mcp, int buf,
                    cudaStream_t st) {
     int8_t *Kss = ctx->dKss + (size_t)buf * ctx->kss_stride;
+    ctx->oz_mu_slot = buf;
     switch (ctx->dp) {
         case 2: BO_TRY(launch_oz_kstar<2>(ctx, s, S, dXc, c0, mc, mcp, Kss, st)); break;
         case 4: BO_TRY(launch_oz_kstar<4>(ctx, s, S, dXc, c0, mc, mcp, Kss, st)); break;
@@ -789,12 +806,7 @@ int bo_ozaki_contract(bo_ctx *ctx, int s, int S, int mcp, int buf, double *mu, d
     const int nb = np / OZ_BN;
     {
         size_t need = (size_t)nb * mcp;
-        if (ctx->ozpart_capacity < need || !ctx->dOzQ) {
-            size_t c1 = ctx->ozpart_capacity, c2 = ctx->ozpart_capacity;
-            BO_TRY(bo_reserve(ctx, &ctx->dOzQ, &c1, need));
-            BO_TRY(bo_reserve(ctx, &ctx->dOzP, &c2, need));
-            ctx->ozpart_capacity = need;
-        }
+        BO_TRY(bo_reserve(ctx, &ctx->dOzQ, &ctx->ozpart_capacity, need));
     }
     OzParams p;
     p.np = np; p.S = S; p.nstages = oz_stage_count(S); p.ntiles = mcp / OZ_BM; p.mcp = mcp;
@@ -807,8 +819,7 @@ int bo_ozaki_contract(bo_ctx *ctx, int s, int S, int mcp, int buf, double *mu, d
         p.tiles_per_group = T < 2 ? 2 : (T > 64 ? 64 : T);
     }
     p.rowscale = ctx->dRowScale + (size_t)s * np;
-    p.alpha = ctx->dAlpha + (size_t)s * np;
-    p.qpart = ctx->dOzQ; p.ppart = ctx->dOzP; p.dbg = dbg; p.kss = Kss;
+    p.qpart = ctx->dOzQ; p.dbg = dbg; p.kss = Kss;
     const int nunits = p.ntiles * nb;
     const int grid = nunits < ctx->sm_count ? nunits : ctx->sm_count;
     {
@@ -823,8 +834,9 @@ int bo_ozaki_contract(bo_ctx *ctx, int s, int S, int mcp, int buf, double *mu, d
     }
     {
         BO_LAUNCH(ctx, "oz_moments_kernel");
-        oz_moments_kernel<<<(mcp + 255) / 256, 256, 0, ctx->stream>>>(nb, mcp, ctx->dOzQ, ctx->dOzP, ctx->h_rho[s],
-                                                                   ctx->h_bias[s], mu, s2);
+        oz_moments_kernel<<<(mcp + 255) / 256, 256, 0, ctx->stream>>>(
+            nb, ctx->oz_mu_rows[buf], mcp, ctx->dOzQ, ctx->dOzMu + (size_t)buf * ctx->ozmu_stride, ctx->h_rho[s],
+            ctx->h_bias[s], mu, s2);
         BO_CHECK_LAUNCH(ctx);
     }
     return BO_OK;

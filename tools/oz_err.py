@@ -3,19 +3,20 @@ import sys, numpy as np
 sys.path.insert(0, '.')
 from scipy.stats import qmc
 from pybo_b200 import _lib
-n, d, M = 4096, 8, 40000
+import os
+n, d, M = 4096, 8, int(os.environ.get("OZ_ERR_M", "40000"))
 rng = np.random.RandomState(0)
 X = rng.rand(n, d); y = np.sin(X.sum(1)) + 0.01 * rng.randn(n)
 rho, bias = float(y.max() - y.min()), float(y.mean())
 ctx = _lib.Context(0)
 ctx.fit("se", X, y, 0.25 * np.ones((1, d)), [rho], [1e-6], [bias])
-Xc = qmc.Sobol(d=d, scramble=False).random_base2(16)[:M]
+Xc = qmc.Sobol(d=d, scramble=False).random_base2(20)[:M]
 target = float(ctx.predict(X)[0].max())
 mu0, s20 = ctx.predict(Xc)
 ei0, _, _ = ctx.score(1, target, Xc)
 z = (mu0 - target) / np.sqrt(s20)
 print("z range", z.min(), z.max(), "s2/rho range", s20.min() / rho, s20.max() / rho, "EI max", ei0.max())
-for S in (4, 5, 6):
+for S in (5, 6):
     ctx.set_precision(1, float(S))
     mu, s2 = ctx.predict(Xc)
     ei, _, _ = ctx.score(1, target, Xc)
