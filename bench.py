@@ -240,8 +240,8 @@ def our_arm(args):
     if args.precision == "ozaki":
         kname = "oz_score_kernel"
         gk = prof.get(kname, dict(launches=0, total_ms=0.0))
-        slices = ctx.precision_info()[1]
-        pairs = slices * (slices + 1) // 2
+        _, slices, extra = ctx.precision_info()
+        pairs = slices * (slices + 1) // 2 + ((slices - 1) if extra else 0)
         nb = npad // 64
         # algorithmic: n^2 (forward-substitution equivalent) + 4n (reductions) flop per candidate
         alg_flop_per_launch = (n * n + 4 * n) * (M * S * args.steps) / max(1, gk["launches"])
@@ -284,7 +284,8 @@ def our_arm(args):
                 vs_baseline=None, dtype="f64", data="synthetic",
                 config=dict(workload=args.workload, kernel=spec["kernel"], n=n, d=d, acq=spec["acq"],
                             hyper_samples=S, candidates_per_gpu=M, candidates="unscrambled Sobol, contiguous block per rank",
-                            precision=("int8 slices on tcgen05 (tol %g -> %d slices), FP64 reassembly" % (args.tol, ctx.precision_info()[1]))
+                            precision=("int8 slices on tcgen05 (tol %g -> %d slices%s), FP64 reassembly and FP64 mean"
+                                       % (args.tol, ctx.precision_info()[1], " + first dropped pair group" if ctx.precision_info()[2] else ""))
                             if args.precision == "ozaki" else "fp64 (DMMA)",
                             l2="inputs exceed L2: W factor %.0f MB + cross-kernel scratch >= %.0f MB + candidates %.0f MB per pass"
                             % (n * n * 8 / 1e6, n * 8192 * 8 / 1e6, M * d * 8 / 1e6), parallelism="dp%d candidate shards" % world),

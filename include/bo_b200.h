@@ -94,10 +94,13 @@ int bo_topk(bo_ctx *ctx, int k, int64_t *idx, double *val);
 /* choose the precision path of the scoring contraction (default BO_PREC_F64).
  * For BO_PREC_OZAKI, 0 < tol < 2 is the target absolute error of the entries of
  * V = L^-1 k relative to sqrt(rho); the library picks the number of 7-bit int8
- * slices from its a-priori error model.  tol >= 2 sets the slice count directly
- * (2..8).  Gradient requests always run on the FP64 path. */
+ * slices (and whether the first dropped pair group is accumulated as well) from its
+ * error model.  tol >= 2 pins the level: slices = floor(tol) (2..8), extra group iff the
+ * fractional part is >= 0.5 (e.g. 5.5).  Gradient requests and batches of <= 64 points
+ * always run on the FP64 path. */
 int bo_set_precision(bo_ctx *ctx, int prec, double tol);
-/* current path and, for BO_PREC_OZAKI after a scoring call, the slice count in use */
+/* current path and, for BO_PREC_OZAKI after a scoring call, the level in use encoded as
+ * 2 * slices + extra (extra = the digit pairs of group g = slices are accumulated too) */
 int bo_precision_info(bo_ctx *ctx, int *prec, int *slices);
 
 /* ---- Thompson: `model.sample_f(n, rng).get` (policies/simple.py:48) ------
@@ -138,8 +141,8 @@ int bo_launch_count(bo_ctx *ctx, int64_t *launches);
 int bo_microbench(bo_ctx *ctx, int kind, int iters, double *tflops);
 /* self-test hook of the int8-slice path: runs it on hyper-sample 0 for the first mc
  * candidates and returns mu, s2, the raw int32 group accumulators of candidate tile 0
- * ([np/64][S][128][64]) and the slice planes, for exact comparison on the host. */
-int bo_ozaki_debug(bo_ctx *ctx, int S, int mc, const double *Xc, double *mu, double *s2,
+ * ([np/64][S + extra][128][64]) and the slice planes, for exact comparison on the host. */
+int bo_ozaki_debug(bo_ctx *ctx, int S, int extra, int mc, const double *Xc, double *mu, double *s2,
                    int32_t *acc, int8_t *wslices, int8_t *kslices, double *rowscale);
 
 #ifdef __cplusplus

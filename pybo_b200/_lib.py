@@ -68,7 +68,7 @@ def _declare(lib):
         "bo_profile_get": (i, [vp, i, C.c_char_p, i, _lp, _dp]),
         "bo_launch_count": (i, [vp, _lp]),
         "bo_microbench": (i, [vp, i, i, _dp]),
-        "bo_ozaki_debug": (i, [vp, i, i, vp, vp, vp, vp, vp, vp, vp]),
+        "bo_ozaki_debug": (i, [vp, i, i, i, vp, vp, vp, vp, vp, vp, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
@@ -228,9 +228,10 @@ class Context(object):
         self._check(self._lib.bo_set_precision(self._h, int(prec), float(tol)))
 
     def precision_info(self):
-        prec, slices = C.c_int(), C.c_int()
-        self._check(self._lib.bo_precision_info(self._h, C.byref(prec), C.byref(slices)))
-        return prec.value, slices.value
+        """(path, slices, extra_group) of the scoring contraction."""
+        prec, level = C.c_int(), C.c_int()
+        self._check(self._lib.bo_precision_info(self._h, C.byref(prec), C.byref(level)))
+        return prec.value, level.value // 2, bool(level.value & 1)
 
     # -- Thompson -------------------------------------------------------------------
     def thompson_set(self, W, b, theta, scale, bias):
@@ -314,18 +315,18 @@ class Context(object):
         self._check(self._lib.bo_microbench(self._h, 0 if kind == "dmma" else 1, int(iters), C.byref(v)))
         return v.value
 
-    def ozaki_debug(self, S, X, want_acc=True, want_slices=True):
+    def ozaki_debug(self, S, X, want_acc=True, want_slices=True, extra=False):
         """Self-test hook: int8-slice path on hyper-sample 0 for candidates X."""
         X = f64(X, 2)
         mc = X.shape[0]
         npad = -(-self.n // 128) * 128
         mcp = -(-mc // 128) * 128
         mu, s2 = np.empty(mc), np.empty(mc)
-        acc = np.empty((npad // 64, S, 128, 64), dtype=np.int32) if want_acc else None
+        acc = np.empty((npad // 64, S + (1 if extra else 0), 128, 64), dtype=np.int32) if want_acc else None
         ws = np.empty((S, npad, npad), dtype=np.int8) if want_slices else None
         ks = np.empty((S, mcp, npad), dtype=np.int8) if want_slices else None
         rs = np.empty(npad)
-        self._check(self._lib.bo_ozaki_debug(self._h, int(S), mc, _ptr(X), _ptr(mu), _ptr(s2), _ptr(acc),
+        self._check(self._lib.bo_ozaki_debug(self._h, int(S), 1 if extra else 0, mc, _ptr(X), _ptr(mu), _ptr(s2), _ptr(acc),
                                              _ptr(ws), _ptr(ks), _ptr(rs)))
         return dict(mu=mu, s2=s2, acc=acc, ws=ws, ks=ks, rowscale=rs)
 

@@ -451,7 +451,7 @@ extern "C" int bo_set_precision(bo_ctx *ctx, int prec, double tol) {
 extern "C" int bo_precision_info(bo_ctx *ctx, int *prec, int *slices) {
     if (!ctx) return BO_ERR_ARG;
     if (prec) *prec = ctx->prec;
-    if (slices) *slices = (ctx->prec == BO_PREC_OZAKI) ? ctx->oz_slices : 0;
+    if (slices) *slices = (ctx->prec == BO_PREC_OZAKI) ? ctx->oz_slices * 2 + (ctx->oz_extra ? 1 : 0) : 0;
     return BO_OK;
 }
 

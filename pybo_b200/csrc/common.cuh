@@ -101,6 +101,7 @@ struct bo_ctx {
     // int8-slice (Ozaki) path state
     bool oz_ready = false;
     int oz_slices = 0;
+    bool oz_extra = false;          // also accumulate the digit pairs of group g = S
     int8_t *dWs = nullptr;        // S_hyper x slices x np x np  slice planes of W
     int8_t *dKss = nullptr;       // slices x chunk x np          slice planes of K*^T
     double *dRowScale = nullptr;  // S_hyper x np   2^(e_i - 12) rho

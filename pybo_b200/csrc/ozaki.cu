@@ -146,14 +146,16 @@ __device__ __forceinline__ uint64_t oz_desc(uint32_t smem_addr) {
 // contiguous in shared memory and their accumulators (groups s..S-1) are contiguous in TMEM,
 // so they are issued as ONE instruction of N = 64 (S - s) columns (split at 256): the A tile is
 // read from shared memory once per s instead of once per (s, t) pair.
-template <int S>
+// With EXTRA the pairs of group g = S (s + t = S, s, t >= 1) are accumulated too, into one more
+// 64-column accumulator group: the dominant dropped-pair error term disappears at +27 % MMA work
+// (S = 5: 19 pairs instead of 15) without re-slicing either operand.
+template <int S, int EXTRA>
 __device__ __forceinline__ void oz_issue_stage(uint32_t sA, uint32_t sB, uint32_t tacc, bool first) {
 #pragma unroll
     for (int kk = 0; kk < 2; ++kk) {
 #pragma unroll
         for (int s = 0; s < S; ++s) {
-            constexpr int dummy = 0; (void)dummy;
-            const int ntot = OZ_BN * (S - s);
+            const int ntot = OZ_BN * (S - s + ((EXTRA && s >= 1) ? 1 : 0));
             const int n1 = ntot > 256 ? 256 : ntot;
             const uint64_t adesc = oz_desc(sA + s * OZ_A_SLICE_BYTES + kk * 32);
             const uint32_t accumulate = (first && kk == 0 && s == 0) ? 0u : 1u;
@@ -462,7 +464,7 @@ __device__ __forceinline__ OzUnit oz_decode(int u, int nb, int T, int ntiles) {
 
 // (min-blocks 2 only caps the register count at 170 so that operand-slicer CTAs of the next
 // chunk fit beside this CTA on the SM; shared memory still limits it to one CTA per SM)
-template <int S>
+template <int S, int EXTRA>
 __global__ void __launch_bounds__(OZ_THREADS, 2)
 oz_score_kernel(const __grid_constant__ CUtensorMap tmapB, OzParams p) {
     extern __shared__ uint8_t oz_smem_raw[];
@@ -470,7 +472,8 @@ oz_score_kernel(const __grid_constant__ CUtensorMap tmapB, OzParams p) {
     const uint32_t raw = smem_u32(oz_smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
     uint8_t *gen_base = oz_smem_raw + (base - raw);
-    constexpr int G = S - 1;
+    constexpr int G = S - 1 + EXTRA;          // highest accumulator group
+    constexpr int NG = G + 1;
     const int nst = p.nstages, nacc = p.nacc;
     const uint32_t stage_bytes = (uint32_t)S * (OZ_A_SLICE_BYTES + OZ_B_SLICE_BYTES);
     uint64_t *bars = reinterpret_cast<uint64_t *>(gen_base + (size_t)nst * stage_bytes);
@@ -534,12 +537,12 @@ oz_score_kernel(const __grid_constant__ CUtensorMap tmapB, OzParams p) {
                 const OzUnit un = oz_decode(u, nb, p.tiles_per_group, p.ntiles);
                 mbar_wait(tmem_empty(acc), acc_phase ^ 1);    // epilogue has drained this accumulator set
                 tc_fence_after();
-                const uint32_t tacc = tmem_base + (uint32_t)(acc * S * OZ_BN);
+                const uint32_t tacc = tmem_base + (uint32_t)(acc * NG * OZ_BN);
                 for (int kb = 0; kb <= un.rb; ++kb) {
                     mbar_wait(full_bar(stage), phase);
                     tc_fence_after();
                     const uint32_t sA = base + stage * stage_bytes;
-                    oz_issue_stage<S>(sA, sA + S * OZ_A_SLICE_BYTES, tacc, kb == 0);
+                    oz_issue_stage<S, EXTRA>(sA, sA + S * OZ_A_SLICE_BYTES, tacc, kb == 0);
                     umma_commit(empty_bar(stage));            // smem slot free once these MMAs retire
                     if (++stage == nst) { stage = 0; phase ^= 1; }
                 }
@@ -554,20 +557,20 @@ oz_score_kernel(const __grid_constant__ CUtensorMap tmapB, OzParams p) {
         uint32_t acc_phase = 0;
         for (int u = blockIdx.x; u < nunits; u += gridDim.x) {
             const OzUnit un = oz_decode(u, nb, p.tiles_per_group, p.ntiles);
-            const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * S * OZ_BN);
+            const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * NG * OZ_BN);
             double q = 0.0;
             mbar_wait(tmem_full(acc), acc_phase);
             tc_fence_after();
 #pragma unroll 1
             for (int c0 = 0; c0 < OZ_BN; c0 += 8) {
-                int32_t r[S][8];
+                int32_t r[NG][8];
 #pragma unroll
-                for (int g = 0; g < S; ++g) tmem_ld8(lane_base + (uint32_t)(g * OZ_BN + c0), r[g]);
+                for (int g = 0; g < NG; ++g) tmem_ld8(lane_base + (uint32_t)(g * OZ_BN + c0), r[g]);
                 tmem_ld_wait();
                 if (p.dbg && un.tile == 0) {
 #pragma unroll
-                    for (int g = 0; g < S; ++g) {
-                        int32_t *o = p.dbg + (((int64_t)un.rb * S + g) * 128 + quarter * 32 + lane) * 64 + c0;
+                    for (int g = 0; g < NG; ++g) {
+                        int32_t *o = p.dbg + (((int64_t)un.rb * NG + g) * 128 + quarter * 32 + lane) * 64 + c0;
 #pragma unroll
                         for (int i = 0; i < 8; ++i) o[i] = r[g][i];
                     }
@@ -576,7 +579,7 @@ oz_score_kernel(const __grid_constant__ CUtensorMap tmapB, OzParams p) {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     double v;
-                    if (S <= 5) {
+                    if (NG <= 6 && S <= 5) {
                         // sum_g D_g 2^(7 (G - g)) fits int64 for <= 5 slices (|D_g| < 2^27): shift-adds on
                         // the integer pipe and a single conversion keep the FP64 pipe for the reductions
                         long long a = (long long)r[0][i];
@@ -664,7 +667,8 @@ static size_t oz_smem_bytes(int S) {
 }
 
 int bo_ozaki_init(bo_ctx *ctx) {
-#define OZ_ATTR(SS) BO_CUDA(ctx, cudaFuncSetAttribute(oz_score_kernel<SS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)oz_smem_bytes(SS)))
+#define OZ_ATTR(SS) BO_CUDA(ctx, cudaFuncSetAttribute(oz_score_kernel<SS, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)oz_smem_bytes(SS))); \
+                    if (SS <= 7) BO_CUDA(ctx, cudaFuncSetAttribute(oz_score_kernel<(SS <= 7 ? SS : 7), 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)oz_smem_bytes(SS)))
     OZ_ATTR(2); OZ_ATTR(3); OZ_ATTR(4); OZ_ATTR(5); OZ_ATTR(6); OZ_ATTR(7); OZ_ATTR(8);
 #undef OZ_ATTR
 #define OZ_KATTR(DP, SS) BO_CUDA(ctx, cudaFuncSetAttribute(oz_kstar_slices_fast_kernel<DP, SS>, cudaFuncAttributeMaxDynamicSharedMemorySize, SS * OZ_A_SLICE_BYTES))
@@ -716,11 +720,15 @@ int bo_ozaki_prepare(bo_ctx *ctx, int S) {
     return BO_OK;
 }
 
-// A-priori error model: |dv_i| <~ c sqrt(n) 2^e_i rho 2^-7S (round-to-nearest slices, dropped
-// pairs of weight 2^-7S); pick the smallest S whose estimate is below tol * sqrt(rho).
+// Error model (calibrated on the headline shape, tools/oz_err.py): with S slices per operand the
+// truncation term of v is ~ sqrt(n) 2^e sqrt(rho) 2^(-7S) and the dropped digit pairs of group g = S
+// are ~30x larger; accumulating that group too (`extra`) leaves only the truncation term.
+// Levels in order of cost: (S, extra) = (3,0) (3,1) (4,0) (4,1) (5,0) (5,1) (6,0) ...; pick the first
+// whose estimate is below tol * sqrt(rho).  tol >= 2 pins S = floor(tol), extra = (tol - S >= 0.5).
 int bo_ozaki_choose_slices(bo_ctx *ctx, double tol) {
     if (tol >= 2.0) {
         int S = (int)tol;
+        ctx->oz_extra = (tol - S) >= 0.5;
         return S > OZ_MAX_S ? OZ_MAX_S : (S < 2 ? 2 : S);
     }
     // exponents need W: use 4 slices provisionally just to obtain e_max
@@ -732,8 +740,12 @@ int bo_ozaki_choose_slices(bo_ctx *ctx, double tol) {
         double est = 8.0 * sqrt((double)ctx->np) * ldexp(1.0, ctx->h_emax[s]) * sqrt(ctx->h_rho[s]);
         worst = est > worst ? est : worst;
     }
-    for (int S = 3; S <= OZ_MAX_S; ++S)
-        if (worst * ldexp(1.0, -7 * S) <= tol) return S;
+    for (int S = 3; S <= OZ_MAX_S; ++S) {
+        const double base = worst * ldexp(1.0, -7 * S);
+        if (base <= tol) { ctx->oz_extra = false; return S; }
+        if (S <= 7 && base / 32.0 <= tol) { ctx->oz_extra = true; return S; }
+    }
+    ctx->oz_extra = false;
     return OZ_MAX_S;
 }
 
@@ -810,7 +822,8 @@ int bo_ozaki_contract(bo_ctx *ctx, int s, int S, int mcp, int buf, double *mu, d
     }
     OzParams p;
     p.np = np; p.S = S; p.nstages = oz_stage_count(S); p.ntiles = mcp / OZ_BM; p.mcp = mcp;
-    p.nacc = (2 * S * OZ_BN <= 512) ? 2 : 1;
+    const bool extra = ctx->oz_extra && S <= 7;
+    p.nacc = (2 * (S + (extra ? 1 : 0)) * OZ_BN <= 512) ? 2 : 1;
     // candidate tiles whose K* slices (S * 128 * np bytes each) share L2 with the W slices
     {
         const double tile_bytes = (double)S * OZ_BM * np;
@@ -825,7 +838,8 @@ int bo_ozaki_contract(bo_ctx *ctx, int s, int S, int mcp, int buf, double *mu, d
     {
         BO_LAUNCH(ctx, "oz_score_kernel");
         switch (S) {
-#define OZ_RUN(SS) case SS: oz_score_kernel<SS><<<grid, OZ_THREADS, oz_smem_bytes(SS), ctx->stream>>>(tmB, p); break
+#define OZ_RUN(SS) case SS: if (extra && SS <= 7) oz_score_kernel<(SS <= 7 ? SS : 7), 1><<<grid, OZ_THREADS, oz_smem_bytes(SS), ctx->stream>>>(tmB, p); \
+                         else oz_score_kernel<SS, 0><<<grid, OZ_THREADS, oz_smem_bytes(SS), ctx->stream>>>(tmB, p); break
             OZ_RUN(2); OZ_RUN(3); OZ_RUN(4); OZ_RUN(5); OZ_RUN(6); OZ_RUN(7); OZ_RUN(8);
 #undef OZ_RUN
             default: return bo_set_err(ctx, BO_ERR_ARG, "int8 path needs 2..8 slices, got %d", S);
@@ -845,21 +859,23 @@ int bo_ozaki_contract(bo_ctx *ctx, int s, int S, int mcp, int buf, double *mu, d
 // Debug / self-test entry point: runs the int8-slice path for the first `mc` candidates
 // of Xc (host) on hyper-sample 0 and returns mu, s2 plus the raw int32 group accumulators
 // of candidate tile 0 ([np/64][S][128][64]), the W slices and the K* slices.
-extern "C" int bo_ozaki_debug(bo_ctx *ctx, int S, int mc, const double *Xc, double *mu, double *s2, int32_t *acc,
-                              int8_t *wslices, int8_t *kslices, double *rowscale) {
+extern "C" int bo_ozaki_debug(bo_ctx *ctx, int S, int extra, int mc, const double *Xc, double *mu, double *s2,
+                              int32_t *acc, int8_t *wslices, int8_t *kslices, double *rowscale) {
     if (!ctx) return BO_ERR_ARG;
     BO_CUDA(ctx, cudaSetDevice(ctx->device));
     if (!ctx->fitted) return bo_set_err(ctx, BO_ERR_STATE, "bo_ozaki_debug before bo_fit");
     if (S < 2 || S > OZ_MAX_S || mc < 1) return bo_set_err(ctx, BO_ERR_ARG, "bad S / mc");
     const int np = ctx->np, mcp = bo_round_up(mc, OZ_BM), nb = np / OZ_BN;
     ctx->oz_ready = false;
+    ctx->oz_extra = extra != 0 && S <= 7;
+    const int NG = S + (ctx->oz_extra ? 1 : 0);
     BO_TRY(bo_ozaki_prepare(ctx, S));
     double *dXc = nullptr, *dmu = nullptr;
     int32_t *dacc = nullptr;
     BO_CUDA(ctx, cudaMalloc(&dXc, sizeof(double) * mc * ctx->d));
     BO_CUDA(ctx, cudaMalloc(&dmu, sizeof(double) * 2 * mcp));
-    BO_CUDA(ctx, cudaMalloc(&dacc, sizeof(int32_t) * (size_t)nb * S * 128 * 64));
-    BO_CUDA(ctx, cudaMemsetAsync(dacc, 0xff, sizeof(int32_t) * (size_t)nb * S * 128 * 64, ctx->stream));
+    BO_CUDA(ctx, cudaMalloc(&dacc, sizeof(int32_t) * (size_t)nb * NG * 128 * 64));
+    BO_CUDA(ctx, cudaMemsetAsync(dacc, 0xff, sizeof(int32_t) * (size_t)nb * NG * 128 * 64, ctx->stream));
     BO_CUDA(ctx, cudaMemcpyAsync(dXc, Xc, sizeof(double) * mc * ctx->d, cudaMemcpyHostToDevice, ctx->stream));
     int rc = bo_ozaki_reserve(ctx, S, mcp, 1);
     if (rc == BO_OK) rc = bo_ozaki_slice(ctx, 0, S, dXc, 0, mc, mcp, 0, ctx->stream);
@@ -868,7 +884,7 @@ extern "C" int bo_ozaki_debug(bo_ctx *ctx, int S, int mc, const double *Xc, doub
     if (rc == BO_OK && e == cudaSuccess) {
         if (mu) cudaMemcpy(mu, dmu, sizeof(double) * mc, cudaMemcpyDeviceToHost);
         if (s2) cudaMemcpy(s2, dmu + mcp, sizeof(double) * mc, cudaMemcpyDeviceToHost);
-        if (acc) cudaMemcpy(acc, dacc, sizeof(int32_t) * (size_t)nb * S * 128 * 64, cudaMemcpyDeviceToHost);
+        if (acc) cudaMemcpy(acc, dacc, sizeof(int32_t) * (size_t)nb * NG * 128 * 64, cudaMemcpyDeviceToHost);
         if (wslices) cudaMemcpy(wslices, ctx->dWs, (size_t)S * np * np, cudaMemcpyDeviceToHost);
         if (kslices) {       // present the blocked / swizzled planes as plain [s][candidate][k]
             std::vector<int8_t> raw((size_t)S * mcp * np);

@@ -30,12 +30,15 @@ def slices_of(x, S):
     return out
 
 
-@pytest.mark.parametrize("n,d,S,mc", [(64, 2, 2, 128), (256, 4, 3, 128), (300, 8, 5, 200), (512, 3, 8, 128), (200, 5, 6, 128), (130, 2, 7, 100), (256, 4, 4, 128)])
-def test_slices_and_accumulators_exact(ctx, n, d, S, mc):
+@pytest.mark.parametrize("n,d,S,mc,extra", [(64, 2, 2, 128, False), (256, 4, 3, 128, False), (300, 8, 5, 200, False),
+                                            (512, 3, 8, 128, False), (200, 5, 6, 128, False), (130, 2, 7, 100, False),
+                                            (256, 4, 4, 128, False), (300, 8, 5, 128, True), (192, 3, 3, 128, True),
+                                            (128, 2, 7, 128, True)])
+def test_slices_and_accumulators_exact(ctx, n, d, S, mc, extra):
     gp = synth(n, d, seed=n)
     ctx.fit("se", gp.X, gp.Y, gp.ell[None], [gp.rho], [gp.sn2], [gp.bias])
     Xc = qmc.Sobol(d=d, scramble=False).random(256)[:mc]
-    out = ctx.ozaki_debug(S, Xc)
+    out = ctx.ozaki_debug(S, Xc, extra=extra)
     npad = out["ws"].shape[1]
     W = np.zeros((npad, npad))
     W[:n, :n] = ctx.factor("W")
@@ -53,12 +56,12 @@ def test_slices_and_accumulators_exact(ctx, n, d, S, mc):
     assert np.max(np.abs(enc - kap)) <= 0.51 * 2.0 ** -(6 + 7 * (S - 1)) + 1e-15
     # TMEM accumulators of tile 0: exact integer contraction of the returned slices
     ks, ws = out["ks"].astype(np.int64), out["ws"].astype(np.int64)
-    G = S - 1
+    G = S - 1 + (1 if extra else 0)
     for rb in range(npad // 64):
         kmax = (rb + 1) * 64
         rows = slice(rb * 64, rb * 64 + 64)
-        for g in range(S):
-            ref = sum(ks[g - s][:128, :kmax] @ ws[s][rows, :kmax].T for s in range(g + 1))
+        for g in range(G + 1):
+            ref = sum(ks[g - s][:128, :kmax] @ ws[s][rows, :kmax].T for s in range(g + 1) if s < S and g - s < S)
             assert np.array_equal(out["acc"][rb, g].astype(np.int64), ref), (rb, g)
     # reassembly + reductions
     v = np.zeros((128, npad))
@@ -125,7 +128,7 @@ def test_full_size_headline_shape_int8_vs_fp64_and_oracle(ctx):
     ctx.set_precision(1, 1e-7)
     val, _, best = ctx.score(1, target, Xc, want_best=True)
     top8 = ctx.topk(10)
-    assert ctx.precision_info() == (1, 5)
+    assert ctx.precision_info() == (1, 5, False)
     assert rel_err(val, f64val, 1e-9) < 1e-6
     assert best[1] == f64best[1] and np.array_equal(top8[0], top64[0])
     sl = slice(32700, 32900)
