@@ -153,8 +153,30 @@ template <int S, int EXTRA>
 __device__ __forceinline__ void oz_issue_stage(uint32_t sA, uint32_t sB, uint32_t tacc, bool first) {
 #pragma unroll
     for (int kk = 0; kk < 2; ++kk) {
+        int s0 = 0;
+        if (EXTRA && kk == 0 && first) {
+            // Accumulator initialisation when the extra group exists: group S is only written by
+            // slices s >= 1, so the first MMA is slice 1 over groups 1..S with accumulate = 0; slice 0
+            // then initialises group 0 on its own and accumulates into groups 1..S-1.
+            const uint64_t a1 = oz_desc(sA + 1 * OZ_A_SLICE_BYTES);
+            const int n1tot = OZ_BN * S;
+            umma_i8(tacc + OZ_BN, a1, oz_desc(sB), make_idesc_i8(OZ_BM, n1tot > 256 ? 256 : n1tot), 0u);
+            if (n1tot > 256)
+                umma_i8(tacc + OZ_BN + 256, a1, oz_desc(sB + 256 * OZ_BK), make_idesc_i8(OZ_BM, n1tot - 256), 0u);
+            const uint64_t a0 = oz_desc(sA);
+            umma_i8(tacc, a0, oz_desc(sB), make_idesc_i8(OZ_BM, OZ_BN), 0u);
+            if (S > 1) {
+                const int n0 = OZ_BN * (S - 1);
+                umma_i8(tacc + OZ_BN, a0, oz_desc(sB + OZ_B_SLICE_BYTES), make_idesc_i8(OZ_BM, n0 > 256 ? 256 : n0), 1u);
+                if (n0 > 256)
+                    umma_i8(tacc + OZ_BN + 256, a0, oz_desc(sB + OZ_B_SLICE_BYTES + 256 * OZ_BK),
+                            make_idesc_i8(OZ_BM, n0 - 256), 1u);
+            }
+            s0 = 2;
+        }
 #pragma unroll
         for (int s = 0; s < S; ++s) {
+            if (s < s0) continue;
             const int ntot = OZ_BN * (S - s + ((EXTRA && s >= 1) ? 1 : 0));
             const int n1 = ntot > 256 ? 256 : ntot;
             const uint64_t adesc = oz_desc(sA + s * OZ_A_SLICE_BYTES + kk * 32);
@@ -294,8 +316,10 @@ __device__ __forceinline__ double oz_exp2_scaled(double z, int shift) {
 #pragma unroll
     for (int i = 12 - DEG + 1; i < 12; ++i) p = fma(p, f, OZ_EXP2_C[i]);
     p = fma(p, f, 1.0);
+    // (no cut-off at the integer grid: the caller also accumulates the FP64 mean from this value;
+    //  values below 1/2 round to a zero digit string by themselves)
     const double v = __hiloint2double(__double2hiint(p) + (ki << 20), __double2loint(p));
-    return ki < -1 ? 0.0 : v;
+    return ki < -1000 ? 0.0 : v;
 }
 
 #define OZ_KS_TILES 8      // observation tiles (of 64) per block
@@ -373,7 +397,7 @@ oz_kstar_slices_fast_kernel(int n, int np, int d, const double *__restrict__ Xs,
                 }
                 const double z = fmin(dot, 0.0) * LOG2E;            // log2 kappa
                 const bool on = live && (j0 + jj0 + i) < n;
-                const double v = on ? oz_exp2_scaled<10>(z, SHIFT) : 0.0;     // in [0, 2^SHIFT], SHIFT <= 34
+                const double v = on ? oz_exp2_scaled<12>(z, SHIFT) : 0.0;     // in [0, 2^SHIFT], SHIFT <= 34
                 kb = fma(v, bt[buf][jj0 + i], kb);
                 const double vv = v + 4503599627370496.0;                   // + 2^52: mantissa = rint(v)
                 const uint32_t lo = (uint32_t)__double2loint(vv);
