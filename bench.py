@@ -42,7 +42,7 @@ FALLBACK_PEAKS = dict(hbm_gbs=6650.0, bf16_tflops=1590.0)
 TRAFFIC_NCU = {"rbf_n4096_d8_ei:fp64": 2.005e9,
                # oz_score_kernel<5>, 32768 candidates per launch (profiles/r1_int8_oz_score_ncu.txt): the K* slice
                # planes of the chunk (671 MB) are read ~2.6x from DRAM, W slices stay in L2 (89.6 % hit rate)
-               "rbf_n4096_d8_ei:ozaki": 1.810e9}
+               "rbf_n4096_d8_ei:ozaki": 1.83e9}
 
 
 def flop_per_eval(n, d):
