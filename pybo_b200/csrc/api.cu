@@ -112,10 +112,10 @@ extern "C" int bo_create(int device, bo_ctx **out) {
 static void free_all(bo_ctx *ctx) {
     double **ptrs[] = {&ctx->dX, &ctx->dXs, &ctx->dY, &ctx->dInvEll, &ctx->dRho, &ctx->dSn2, &ctx->dBias,
                        &ctx->dL, &ctx->dW, &ctx->dWT, &ctx->dDinv, &ctx->dAlpha, &ctx->dBeta, &ctx->dLogdet,
-                       &ctx->dTmp, &ctx->dKs, &ctx->dV, &ctx->dU, &ctx->dQpart, &ctx->dPpart, &ctx->dMuS,
+                       &ctx->dKs, &ctx->dV, &ctx->dU, &ctx->dQpart, &ctx->dPpart, &ctx->dMuS,
                        &ctx->dS2S, &ctx->dDmuS, &ctx->dDs2S, &ctx->dGpart, &ctx->dXc, &ctx->dVal,
                        &ctx->dGradOut, &ctx->dBlkVal, &ctx->th.W, &ctx->th.b, &ctx->th.theta,
-                       &ctx->th.scale, &ctx->th.bias, &ctx->th.dBestVal, &ctx->th.thetaT, &ctx->dOzQ, &ctx->dOzP, &ctx->dXsHalfSq, &ctx->dCholDinv, &ctx->dOzMu};
+                       &ctx->th.scale, &ctx->th.bias, &ctx->th.dBestVal, &ctx->th.thetaT, &ctx->dOzQ, &ctx->dXsHalfSq, &ctx->dCholDinv, &ctx->dOzMu};
     for (auto p : ptrs)
         if (*p) { cudaFree(*p); *p = nullptr; }
     if (ctx->dInfo) { cudaFree(ctx->dInfo); ctx->dInfo = nullptr; }
@@ -126,7 +126,6 @@ static void free_all(bo_ctx *ctx) {
     if (ctx->dRowExp) { cudaFree(ctx->dRowExp); ctx->dRowExp = nullptr; }
     if (ctx->dBlkIdx) { cudaFree(ctx->dBlkIdx); ctx->dBlkIdx = nullptr; }
     if (ctx->th.dBestIdx) { cudaFree(ctx->th.dBestIdx); ctx->th.dBestIdx = nullptr; }
-    if (ctx->hPinned) { cudaFreeHost(ctx->hPinned); ctx->hPinned = nullptr; }
 }
 
 static void prof_drain(bo_ctx *ctx) {

@@ -57,7 +57,6 @@ struct bo_ctx {
     double *dAlpha = nullptr;   // S x np   L^-1 (y - bias)
     double *dBeta = nullptr;    // S x np   L^-T alpha
     double *dLogdet = nullptr;  // S        sum log diag L
-    double *dTmp = nullptr;     // S x np x np/2 scratch for the blocked inverse
     int *dInfo = nullptr;       // S
     double *dCholDinv = nullptr;   // stand-alone bo_cholesky scratch
     int *dCholInfo = nullptr;
@@ -93,8 +92,6 @@ struct bo_ctx {
     double *dBlkVal = nullptr;  // per-block argmax staging
     int64_t *dBlkIdx = nullptr;
     size_t blk_capacity = 0;
-    double *hPinned = nullptr;  // pinned staging for results
-    size_t pinned_capacity = 0;
 
     int prec = BO_PREC_F64;
     double prec_tol = 1e-9;
@@ -110,7 +107,7 @@ struct bo_ctx {
     std::vector<int> h_emax;
     double *dXsHalfSq = nullptr;               // S_hyper x np   |xs_j|^2 / 2
     size_t halfsq_capacity = 0;
-    double *dOzQ = nullptr, *dOzP = nullptr;   // (np/64) x chunk partial |v|^2
+    double *dOzQ = nullptr;                     // (np/64) x chunk partial |v|^2
     size_t ozpart_capacity = 0;
     double *dOzMu = nullptr;                    // per slice buffer: (blocks) x chunk partials of kappa . beta
     size_t ozmu_capacity = 0, ozmu_stride = 0;

@@ -1,0 +1,106 @@
+"""BASELINE.json configs 2-5 at their full model sizes: the GPU path (through the C ABI) against the
+oracle on seeded slices, plus size-independent properties (identical arg max between precision paths,
+0 < s2 <= rho, interpolation at the data, mixture = average of its members)."""
+
+import numpy as np
+import pytest
+from scipy.stats import qmc
+
+from conftest import rel_err
+from oracle import GPOracle, MixtureOracle, ucb_beta, ucb_index
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-6
+
+
+def problem(n, d, seed=0):
+    rng = np.random.RandomState(seed)
+    X = rng.rand(n, d)
+    y = np.sin(X.sum(axis=1)) + 0.01 * rng.randn(n)
+    return rng, X, y, float(y.max() - y.min()), float(y.mean())
+
+
+def test_config2_rbf_n1024_d4_ei(ctx):
+    """RBF GP n=1024 d=4, EI (ill-conditioned regime: s2/rho down to 1e-6): FP64 path vs oracle on
+    50k Sobol candidates; the int8 path's error model must pick a deeper level here and still agree."""
+    rng, X, y, rho, bias = problem(1024, 4)
+    gp = GPOracle(1e-6, rho, 0.25 * np.ones(4), bias, "se")
+    gp.add_data(X, y)
+    ctx.fit("se", X, y, 0.25 * np.ones((1, 4)), [rho], [1e-6], [bias])
+    Xc = qmc.Sobol(d=4, scramble=False).random_base2(16)[:50000]
+    target = float(gp.predict(X)[0].max())
+    ref = gp.get_improvement(target, Xc)
+    val, _, best = ctx.score(1, target, Xc, want_best=True)
+    assert rel_err(val, ref, 1e-9) < TOL and best[1] == int(np.argmax(ref))
+    ctx.set_precision(1, 1e-8)
+    v8, _, b8 = ctx.score(1, target, Xc, want_best=True)
+    _, slices, extra = ctx.precision_info()
+    assert slices >= 6                                            # 2^e sqrt(rho) ~ 300 here
+    assert b8[1] == best[1]
+    assert rel_err(v8, ref, 1e-6) < 1e-4                          # loose: this regime belongs to the FP64 path
+
+
+def test_config3_matern_n4096_d8_ucb(ctx):
+    rng, X, y, rho, bias = problem(4096, 8, seed=3)
+    gp = GPOracle(1e-6, rho, 0.25 * np.ones(8), bias, "matern52")
+    gp.add_data(X, y)
+    ctx.fit("matern52", X, y, 0.25 * np.ones((1, 8)), [rho], [1e-6], [bias])
+    Xc = qmc.Sobol(d=8, scramble=False).random_base2(16)[:40000]
+    beta = ucb_beta(4096)                                         # policies/simple.py:58-66 with d = len(X)
+    val, _, best = ctx.score(3, beta, Xc, want_best=True)
+    sl = slice(32600, 32900)
+    ref = ucb_index(beta, *gp.predict(Xc[sl]))
+    assert rel_err(val[sl], ref) < TOL
+    mu_d, s2_d = ctx.predict(X[:1024])
+    assert np.max(np.abs(mu_d - y[:1024])) < 1e-3 and np.all(s2_d < 1e-4 * rho)
+    ctx.set_precision(1, 1e-8)
+    v8, _, b8 = ctx.score(3, beta, Xc, want_best=True)
+    assert rel_err(v8, val) < TOL and b8[1] == best[1]
+    mu, s2 = ctx.predict(Xc[:4096])
+    assert np.all(s2 > 0) and np.all(s2 <= rho * (1 + 1e-9))
+
+
+def test_config4_thompson_n4096_d16_256_draws(ctx):
+    from pybo_b200 import models
+    rng, X, y, rho, bias = problem(4096, 16, seed=4)
+    gp = models.make_gp(1e-4, rho, 0.5 * np.ones(16), bias)
+    gp.add_data(X, y)
+    tb = models.ThompsonBatch(gp, m=512, ndraw=256, rng=7)
+    Xc = qmc.Sobol(d=16, scramble=False).random_base2(15)[:20001]
+    F = tb.get(Xc)                                                # (256, M)
+    ref = tb.bias + (tb.scale * np.cos(Xc @ tb.W.T + tb.b)) @ tb.theta.T
+    assert rel_err(F, ref.T, 1e-9) < TOL
+    bv, bi = tb.argmax(Xc)
+    assert np.array_equal(bi, np.argmax(ref, axis=0)) and np.allclose(bv, ref.max(axis=0), rtol=1e-9)
+    # the draws interpolate the data about as well as the feature basis allows: posterior-mean sanity
+    fX = tb.get(X[:256])
+    assert np.mean((fX.mean(axis=0) - y[:256]) ** 2) < np.var(y)
+
+
+def test_config5_mixture_32_samples_n2048_d8(ctx):
+    rng, X, y, rho, bias = problem(2048, 8, seed=5)
+    S = 32
+    ell = 0.25 * np.ones((S, 8)) * np.exp(0.1 * rng.randn(S, 8))
+    rhos = rho * np.exp(0.1 * rng.randn(S))
+    sn2 = 1e-6 * np.exp(0.3 * rng.randn(S))
+    biases = bias + 0.02 * rng.randn(S)
+    ctx.fit("se", X, y, ell, rhos, sn2, biases)
+    Xc = qmc.Sobol(d=8, scramble=False).random_base2(14)
+    gps = []
+    for s in range(S):
+        g = GPOracle(sn2[s], rhos[s], ell[s], biases[s], "se")
+        g.add_data(X, y)
+        gps.append(g)
+    mix = MixtureOracle(gps)
+    sl = slice(8100, 8260)
+    mu, s2 = mix.predict(Xc[sl])
+    target = float(mix.predict(X[:256])[0].max())
+    ref = mix.get_improvement(target, Xc[sl])
+    gmu, gs2 = ctx.predict(Xc)
+    assert rel_err(gmu[sl], mu) < TOL and rel_err(gs2[sl], s2, 1e-9) < TOL
+    val, _, best = ctx.score(1, target, Xc, want_best=True)
+    assert rel_err(val[sl], ref, 1e-9) < TOL
+    assert np.allclose(ctx.loglik(), [g.loglikelihood() for g in gps], rtol=1e-8)
+    ctx.set_precision(1, 1e-8)
+    v8, _, b8 = ctx.score(1, target, Xc, want_best=True)
+    assert rel_err(v8, val, 1e-9) < TOL and b8[1] == best[1]

@@ -339,3 +339,48 @@ def test_full_size_properties_n4096_d8(ctx):
     val2, _, _ = ctx.score(1, target, Xc[sl])
     assert np.array_equal(val2, val[sl])                    # a candidate's score does not depend on its chunk
     assert best[1] == int(np.argmax(val))
+
+
+# ---- error behaviour at the boundary -------------------------------------------------------
+def test_error_codes_map_to_python_exceptions(ctx):
+    """C ABI status codes -> the exceptions the reference path would raise: a failed factorisation is a
+    numpy LinAlgError (what scipy.linalg.cholesky raises inside reggie), bad arguments are ValueError,
+    calls before the state they need exists are BackendError."""
+    from pybo_b200 import _lib
+    rng = np.random.RandomState(0)
+    X = rng.rand(10, 2)
+    with pytest.raises(_lib.BackendError):
+        ctx.n, ctx.d, ctx.S = 10, 2, 1
+        ctx.predict(X)                                             # before any fit
+    with pytest.raises(ValueError):
+        ctx.fit("se", X, rng.rand(10), [[0.3, -0.1]], [1.0], [1e-6], [0.0])    # negative length scale
+    with pytest.raises(ValueError):
+        ctx.fit("se", rng.rand(10, 40), rng.rand(10), np.ones((1, 40)), [1.0], [1e-6], [0.0])   # d > 32
+    # duplicated points and no noise: K is singular -> not positive definite
+    Xd = np.vstack([X, X])
+    with pytest.raises(np.linalg.LinAlgError):
+        ctx.fit("se", Xd, rng.rand(20), [[0.3, 0.3]], [1.0], [0.0], [0.0])
+    ctx.fit("se", X, rng.rand(10), [[0.3, 0.3]], [1.0], [1e-6], [0.0])        # the handle recovers
+    with pytest.raises(ValueError):
+        ctx.score(7, 0.0, X)                                       # unknown acquisition id
+    with pytest.raises(ValueError):
+        ctx.predict(rng.rand(5, 3))                                # wrong candidate dimension
+    with pytest.raises(ValueError):
+        ctx.set_precision(5, 1e-7)                                 # unknown precision path
+    mu, s2 = ctx.predict(X)
+    assert np.all(np.isfinite(mu)) and np.all(s2 > -1e-9)
+
+
+def test_model_rejects_bad_input():
+    from pybo_b200 import models
+    gp = models.make_gp(1e-6, 1.0, [0.25, 0.25], 0.0)
+    with pytest.raises(ValueError):
+        gp.add_data(np.random.rand(3, 5), np.random.rand(3))       # wrong dimension
+    with pytest.raises(ValueError):
+        gp.add_data(np.random.rand(3, 2), np.random.rand(4))       # length mismatch
+    with pytest.raises(ValueError):
+        gp.get_improvement(0.0, np.random.rand(3, 2))              # acquisition without data
+    with pytest.raises(ValueError):
+        models.make_gp(1e-6, 1.0, [0.25], 0.0, kernel="periodic")
+    with pytest.raises(ValueError):
+        gp.set_precision("fp16")
