@@ -485,10 +485,8 @@ __device__ __forceinline__ OzUnit oz_decode(int u, int nb, int T, int ntiles) {
     return o;
 }
 
-// (min-blocks 2 only caps the register count at 170 so that operand-slicer CTAs of the next
-// chunk fit beside this CTA on the SM; shared memory still limits it to one CTA per SM)
 template <int S, int EXTRA>
-__global__ void __launch_bounds__(OZ_THREADS, 2)
+__global__ void __launch_bounds__(OZ_THREADS, 1)
 oz_score_kernel(const __grid_constant__ CUtensorMap tmapB, OzParams p) {
     extern __shared__ uint8_t oz_smem_raw[];
     // 1024-byte aligned operand ring
@@ -585,22 +583,22 @@ oz_score_kernel(const __grid_constant__ CUtensorMap tmapB, OzParams p) {
             mbar_wait(tmem_full(acc), acc_phase);
             tc_fence_after();
 #pragma unroll 1
-            for (int c0 = 0; c0 < OZ_BN; c0 += 8) {
-                int32_t r[NG][8];
+            for (int c0 = 0; c0 < OZ_BN; c0 += 16) {
+                int32_t r[NG][16];
 #pragma unroll
-                for (int g = 0; g < NG; ++g) tmem_ld8(lane_base + (uint32_t)(g * OZ_BN + c0), r[g]);
+                for (int g = 0; g < NG; ++g) tmem_ld16(lane_base + (uint32_t)(g * OZ_BN + c0), r[g]);
                 tmem_ld_wait();
                 if (p.dbg && un.tile == 0) {
 #pragma unroll
                     for (int g = 0; g < NG; ++g) {
                         int32_t *o = p.dbg + (((int64_t)un.rb * NG + g) * 128 + quarter * 32 + lane) * 64 + c0;
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) o[i] = r[g][i];
+                        for (int i = 0; i < 16; ++i) o[i] = r[g][i];
                     }
                 }
                 const int row0 = un.rb * OZ_BN + c0;
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
+                for (int i = 0; i < 16; ++i) {
                     double v;
                     if (NG <= 6 && S <= 5) {
                         // sum_g D_g 2^(7 (G - g)) fits int64 for <= 5 slices (|D_g| < 2^27): shift-adds on
