@@ -3,9 +3,9 @@
 Candidates are independent, so the M-point grid of `solve_lbfgs`
 (reference solvers/lbfgs.py:45-51) is cut into contiguous blocks, one per rank;
 the fit inputs (n x d observations, hyper-parameters) are tiny and every rank
-refits redundantly.  The only exchange is the global incumbent: a MAX all-reduce
-of the best score followed by a MIN all-reduce of the index among the ranks
-that hold that score, which reproduces `argmax`'s first-index tie rule.
+refits redundantly.  The only exchange is the global incumbent: ONE all-reduce
+(a sum over a [world, k, 3] tensor in which every rank fills only its own row),
+after which each rank picks the maximum with `argmax`'s first-index tie rule.
 `torch.distributed` is plumbing only (NCCL on GPUs, gloo in the CPU tests).
 """
 
@@ -44,42 +44,41 @@ def _comm_device(device=None):
     return torch.device("cpu")
 
 
-def reduce_incumbent(val, idx, device=None, group=None):
-    """Global (max value, lowest global index attaining it) from per-rank bests.
-    `idx` must already be a global index.  NaN scores never win."""
-    if not is_distributed():
-        return float(val), int(idx)
-    import torch
-    dist = _dist()
-    dev = _comm_device(device)
-    v = float(val)
-    if v != v:
-        v = -np.inf
-    tv = torch.tensor([v], dtype=torch.float64, device=dev)
-    dist.all_reduce(tv, op=dist.ReduceOp.MAX, group=group)
-    gmax = float(tv.item())
-    ti = torch.tensor([int(idx) if v == gmax else _INT64_MAX], dtype=torch.int64, device=dev)
-    dist.all_reduce(ti, op=dist.ReduceOp.MIN, group=group)
-    return gmax, int(ti.item())
-
-
 def reduce_incumbents(vals, idxs, device=None, group=None):
-    """Vector form (e.g. one incumbent per Thompson draw): two all-reduces in total."""
-    vals = np.array(vals, dtype=np.float64)
-    idxs = np.array(idxs, dtype=np.int64)
+    """Global (max value, lowest global index attaining it) for each of k incumbents (k = 1 for a
+    scoring pass, k = #draws for Thompson) with ONE all-reduce: every rank writes its (value, index)
+    pairs into its own row of a zero [world, k, 3] float64 tensor and the rows are summed (adding
+    zeros is exact; indices are exact in float64 up to 2^53), after which every rank holds all
+    candidates and takes the arg max with the first-index tie rule locally.  NaN never wins."""
+    vals = np.array(vals, dtype=np.float64, ndmin=1)
+    idxs = np.array(idxs, dtype=np.int64, ndmin=1)
+    vals = np.where(np.isnan(vals), -np.inf, vals)
     if not is_distributed():
         return vals, idxs
     import torch
     dist = _dist()
     dev = _comm_device(device)
-    vals = np.where(np.isnan(vals), -np.inf, vals)
-    tv = torch.from_numpy(vals.copy()).to(dev)
-    dist.all_reduce(tv, op=dist.ReduceOp.MAX, group=group)
-    gmax = tv.cpu().numpy()
-    cand = np.where(vals == gmax, idxs, _INT64_MAX)
-    ti = torch.from_numpy(cand).to(dev)
-    dist.all_reduce(ti, op=dist.ReduceOp.MIN, group=group)
-    return gmax, ti.cpu().numpy()
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    k = len(vals)
+    finite = np.isfinite(vals)
+    buf = np.zeros((world, k, 3), dtype=np.float64)
+    buf[rank, :, 0] = np.where(finite, vals, 0.0)          # +-inf would poison the sum: flag it instead
+    buf[rank, :, 1] = idxs.astype(np.float64)
+    buf[rank, :, 2] = np.where(finite, 0.0, np.where(vals > 0, 1.0, -1.0))
+    t = torch.from_numpy(buf).to(dev)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    allb = t.cpu().numpy()
+    v = np.where(allb[:, :, 2] == 0.0, allb[:, :, 0], np.where(allb[:, :, 2] > 0, np.inf, -np.inf))
+    ix = allb[:, :, 1].astype(np.int64)
+    gmax = v.max(axis=0)
+    cand = np.where(v == gmax[None, :], ix, _INT64_MAX)
+    return gmax, cand.min(axis=0)
+
+
+def reduce_incumbent(val, idx, device=None, group=None):
+    """Scalar form of `reduce_incumbents`.  `idx` must already be a global index."""
+    v, i = reduce_incumbents([val], [idx], device=device, group=group)
+    return float(v[0]), int(i[0])
 
 
 def gather_topk(vals, idxs, k, device=None, group=None):
