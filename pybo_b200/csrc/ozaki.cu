@@ -3,13 +3,17 @@
 // accumulators, TMA-staged operands).
 //
 // FP64 tensor cores cap the contraction at 37 TFLOP/s; the int8 path of the same
-// SM runs 128x faster.  Both operands are cut into S signed 7-bit slices on a
-// fixed-point grid (rows of W share an exponent, K*/rho lies in [0,1]):
-//     W_ij  = 2^e_i  * sum_s a_s[i][j] 2^-(6+7s),   K*_jm = rho * sum_t b_t[m][j] 2^-(6+7t)
+// SM runs 128x faster.  Both operands are cut into S balanced base-256 digits (the full
+// int8 range [-128, 127]) on a fixed-point grid (rows of W share an exponent, K*/rho lies in [0,1]):
+//     W_ij  = 2^e_i / 127 * sum_s a_s[i][j] 256^-s,   K*_jm = rho / 127 * sum_t b_t[m][j] 256^-t
 // every int8 x int8 product and its int32 accumulation over j is exact, products are
 // grouped by g = s + t (pairs with g >= S are dropped), and
-//     v_im = 2^(e_i-12) rho * sum_g 2^-7g D_g[m][i]
-// is reassembled in FP64 in the epilogue, where |v|^2 and v.alpha are reduced.
+//     v_im = 2^e_i rho / 127^2 * sum_g 256^-g D_g[m][i]
+// is reassembled in FP64 in the epilogue, where |v|^2 is reduced.
+// Digits: x in [-1, 1] -> X = rint(x * 127 * 256^(P-1)) (P = 7 bytes, or 5 in the fast slicer);
+// byte k of (X + sum_k 128 * 256^k), minus 128, is the balanced digit k -- one 64-bit add and one
+// XOR, no carry chain -- and the top S bytes are kept (dropping balanced low digits rounds to
+// nearest).  int32 accumulators hold S pairs * n * 2^14 < 2^31 for n * S < 2^17.
 // The truncation error is bounded a priori (see bo_ozaki_choose_slices).
 //
 // Orientation: candidates are the MMA M dimension (one TMEM lane = one candidate, so
@@ -23,7 +27,8 @@
 #define OZ_BM 128        // candidates per CTA tile (MMA M, TMEM lanes)
 #define OZ_BN 64         // rows of W per block (MMA N)
 #define OZ_BK 64         // k bytes per stage row (one 64B swizzle atom, two K=32 MMAs)
-#define OZ_MAX_S 8
+#define OZ_MAX_S 7
+#define OZ_DIGIT_BIAS7 0x0080808080808080ll   // 128 in each of the 7 digit bytes
 #define OZ_A_SLICE_BYTES (OZ_BM * OZ_BK)   // 8192
 #define OZ_B_SLICE_BYTES (OZ_BN * OZ_BK)   // 4096
 #define OZ_THREADS 192   // warp 0: TMA producer, warp 1: MMA issuer, warps 2-5: epilogue
@@ -191,7 +196,7 @@ __device__ __forceinline__ void oz_issue_stage(uint32_t sA, uint32_t sB, uint32_
 // ---------------------------------------------------------------------------
 // slicing kernels
 // ---------------------------------------------------------------------------
-// Row exponents of W and the epilogue scale 2^(e_i - 12) * rho.
+// Row exponents of W and the epilogue scale 2^e_i * rho / 127^2.
 __global__ void oz_row_exponent_kernel(const double *__restrict__ W, int np, double rho, int *__restrict__ rowexp,
                                        double *__restrict__ rowscale, int *__restrict__ emax) {
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -205,30 +210,32 @@ __global__ void oz_row_exponent_kernel(const double *__restrict__ W, int np, dou
         int e = 0;
         if (m > 0.0) frexp(m, &e);          // m = f * 2^e, f in [0.5, 1)  =>  |w| * 2^-e < 1
         rowexp[row] = e;
-        rowscale[row] = ldexp(rho, e - 12);
+        rowscale[row] = ldexp(rho, e) / 16129.0;
         atomicMax(emax, e);
     }
 }
 
-// W (lower triangle) -> S int8 slice planes [s][row][k]
+// balanced base-256 digits of x * 127 * 2^48, |x| <= 1: byte k of the result is digit k as an int8
+__device__ __forceinline__ unsigned long long oz_digits7(double x) {
+    const long long X = __double2ll_rn(x * 35747322042253312.0);      // 127 * 2^48
+    return (unsigned long long)(X + OZ_DIGIT_BIAS7) ^ (unsigned long long)OZ_DIGIT_BIAS7;
+}
+
+// W (lower triangle) -> S int8 slice planes [s][row][k]; slice s = digit byte 6 - s
 __global__ void oz_slice_w_kernel(const double *__restrict__ W, int np, int S, const int *__restrict__ rowexp,
                                   int8_t *__restrict__ Ws) {
     const int row = blockIdx.y;
     const int k0 = (blockIdx.x * blockDim.x + threadIdx.x) * 16;
     if (k0 >= np) return;
-    const double sc = ldexp(1.0, 6 - rowexp[row]);
+    const double sc = ldexp(1.0, -rowexp[row]);
     const double *w = W + (int64_t)row * np + k0;
-    double r[16];
+    unsigned long long dg[16];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) r[i] = (k0 + i <= row) ? w[i] * sc : 0.0;
+    for (int i = 0; i < 16; ++i) dg[i] = oz_digits7((k0 + i <= row) ? w[i] * sc : 0.0);
     for (int s = 0; s < S; ++s) {
         alignas(16) int8_t q[16];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            const double t = rint(r[i]);
-            q[i] = (int8_t)(int)t;
-            r[i] = (r[i] - t) * 128.0;
-        }
+        for (int i = 0; i < 16; ++i) q[i] = (int8_t)(uint8_t)(dg[i] >> (8 * (6 - s)));
         *reinterpret_cast<int4 *>(Ws + ((int64_t)s * np + row) * np + k0) = *reinterpret_cast<const int4 *>(q);
     }
 }
@@ -255,7 +262,7 @@ oz_kstar_slices_kernel(int kernel, int n, int np, int d, int S, const double *__
     double kb = 0.0;                              // sum_j kappa_j beta_j over this thread's 32 observations
     for (int sub = 0; sub < 2; ++sub) {
         const int jj0 = half * 32 + sub * 16;
-        double r[16];
+        unsigned long long dg[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
             double D = 0.0;
@@ -271,17 +278,13 @@ oz_kstar_slices_kernel(int kernel, int n, int np, int d, int S, const double *__
                 const double rr = sqrt(5.0 * D);
                 v = (1.0 + rr + rr * rr * (1.0 / 3.0)) * exp(-rr);
             }
-            r[i] = (live && (j0 + jj0 + i) < n) ? v * 64.0 : 0.0;
+            dg[i] = oz_digits7((live && (j0 + jj0 + i) < n) ? v : 0.0);
             if (live && (j0 + jj0 + i) < n) kb = fma(v, beta[j0 + jj0 + i], kb);
         }
         for (int s = 0; s < S; ++s) {
             alignas(16) int8_t q[16];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                const double t = rint(r[i]);
-                q[i] = (int8_t)(int)t;
-                r[i] = (r[i] - t) * 128.0;
-            }
+            for (int i = 0; i < 16; ++i) q[i] = (int8_t)(uint8_t)(dg[i] >> (8 * (6 - s)));
             *reinterpret_cast<int4 *>(Ks + oz_kss_offset(s, m, j0 + jj0, mcp >> 7, np >> 6)) = *reinterpret_cast<const int4 *>(q);
         }
     }
@@ -289,12 +292,12 @@ oz_kstar_slices_kernel(int kernel, int n, int np, int d, int S, const double *__
     mupart[((int64_t)blockIdx.y * 2 + half) * mcp + m] = kb;
 }
 
-// Fast variant for the SE kernel and S <= 6 slices.  The FP64 pipe limits the slicer, so
+// Fast variant for the SE kernel and S <= 5 slices.  The FP64 pipe limits the slicer, so
 // (i) the scaled squared distance comes from one dot product, D/2 = |xc|^2/2 + |xs|^2/2 - xc.xs
 // (rounding error ~1e-14 relative in kappa, far below the 2^-41 quantum of 6 slices), (ii) exp is
 // an inline exp2 (degree-12 Taylor in ln2*f, |f| <= 1/2, error < 2e-16) whose exponent add also
-// applies the fixed-point scale, and (iii) the balanced base-128 digits are peeled off one 64-bit
-// integer on the integer pipe instead of S rint/subtract rounds on the FP64 pipe.
+// applies the fixed-point scale, and (iii) the balanced base-256 digits are the bytes of one biased
+// 40-bit integer (integer pipe) instead of S rint/subtract rounds on the FP64 pipe.
 // Taylor coefficients ln2^i / i!, i = 12 .. 1, kept in constant memory so that each DFMA
 // takes its coefficient as a constant-bank operand (no register or uniform-register traffic)
 __constant__ double OZ_EXP2_C[12] = {
@@ -362,12 +365,11 @@ oz_kstar_slices_fast_kernel(int n, int np, int d, const double *__restrict__ Xs,
         ha = fma(xc[k], xc[k], ha);
     }
     ha *= 0.5;
-    constexpr int SHIFT = 6 + 7 * (S - 1);
-    constexpr int LOW = 7 * (S - 1);
     constexpr double LOG2E = 1.4426950408889634;
+    constexpr double LOG2_127 = 6.988684686772166;      // kappa * 127 * 2^32 = 2^(log2 kappa + LOG2_127 + 32)
     static_assert(S >= 2 && S <= 5, "fast slicer handles 2..5 slices");
     const int swz = (tid >> 1) & 3;
-    double kb = 0.0;                 // sum_j 2^SHIFT kappa_j beta_j over this block's observations (FP64)
+    double kb = 0.0;                 // sum_j 127 * 2^32 kappa_j beta_j over this block's observations (FP64)
     for (int tile = t0; tile < t1; ++tile) {
         const int buf = (tile - t0) & 1;
         if (tile + 1 < t1) {
@@ -381,9 +383,9 @@ oz_kstar_slices_fast_kernel(int n, int np, int d, const double *__restrict__ Xs,
 #pragma unroll 1
         for (int sub = 0; sub < 4; ++sub) {
             const int jj0 = sub * 16;
-            // kappa * 2^SHIFT = top * 2^LOW + low: the S-1 low digits are plain 7-bit fields of
-            // `low` (digits in [0,127], no carry chain), spread to byte lanes with masks/shifts and
-            // transposed to slice-major words with byte permutes.
+            // X = rint(kappa * 127 * 2^32) < 2^39 as a 5-byte integer; the bytes of X + 0x8080808080,
+            // each XOR 0x80, are its balanced base-256 digits (slice s = byte 4 - s): the low word is
+            // transposed to slice-major words with byte permutes, the top digit sits in the high word.
             uint32_t wlow[16], wtop[4];
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
@@ -394,34 +396,23 @@ oz_kstar_slices_fast_kernel(int n, int np, int d, const double *__restrict__ Xs,
                     dot = fma(xc[k], x2.x, dot);
                     dot = fma(xc[k + 1], x2.y, dot);
                 }
-                const double z = fmin(dot, 0.0) * LOG2E;            // log2 kappa
+                const double z = fma(fmin(dot, 0.0), LOG2E, LOG2_127);
                 const bool on = live && (j0 + jj0 + i) < n;
-                const double v = on ? oz_exp2_scaled<12>(z, SHIFT) : 0.0;     // in [0, 2^SHIFT], SHIFT <= 34
+                const double v = on ? oz_exp2_scaled<12>(z, 32) : 0.0;        // in [0, 127 * 2^32]
                 kb = fma(v, bt[buf][jj0 + i], kb);
                 const double vv = v + 4503599627370496.0;                   // + 2^52: mantissa = rint(v)
-                const uint32_t lo = (uint32_t)__double2loint(vv);
-                const uint32_t hi = (uint32_t)__double2hiint(vv) & 0xFFFFFu;
-                int t = (int)(lo & ((1u << LOW) - 1u));
-                int top = (int)((lo >> LOW) | (hi << (32 - LOW)));
-                // balanced base-128 digits in [-64, 63] (zero-mean, so the dropped digit-pair products
-                // average out: half the error of plain 7-bit fields); byte b of wlow = slice (S-1-b)
-                uint32_t w = 0;
-#pragma unroll
-                for (int b = 0; b < S - 1; ++b) {
-                    const int dgt = ((t + 64) & 127) - 64;
-                    t = (t - dgt) >> 7;
-                    w |= ((uint32_t)dgt & 0xFFu) << (8 * b);
-                }
-                top += t;                                           // carry out of the low part: 0 or 1
-                wlow[i] = w;
-                if ((i & 3) == 0) wtop[i >> 2] = (uint32_t)top;
-                else wtop[i >> 2] |= (uint32_t)top << (8 * (i & 3));
+                const uint32_t lo = (uint32_t)__double2loint(vv) + 0x80808080u;
+                const uint32_t hi = ((uint32_t)__double2hiint(vv) + 0x80u + (lo < 0x80808080u ? 1u : 0u)) & 0xFFu;
+                wlow[i] = lo ^ 0x80808080u;
+                const uint32_t top = hi ^ 0x80u;
+                if ((i & 3) == 0) wtop[i >> 2] = top;
+                else wtop[i >> 2] |= top << (8 * (i & 3));
             }
             uint8_t *o0 = oz_stage + tid * 64 + ((sub ^ swz) << 4);
             *reinterpret_cast<uint4 *>(o0) = make_uint4(wtop[0], wtop[1], wtop[2], wtop[3]);
 #pragma unroll
             for (int s = 1; s < S; ++s) {
-                const uint32_t b = (uint32_t)(S - 1 - s);               // byte lane holding slice s
+                const uint32_t b = (uint32_t)(4 - s);                   // byte lane holding slice s
                 const uint32_t sel2 = b | ((4u + b) << 4);             // {x.b, y.b}
                 uint32_t w[4];
 #pragma unroll
@@ -444,7 +435,7 @@ oz_kstar_slices_fast_kernel(int n, int np, int d, const double *__restrict__ Xs,
     }
     // the posterior mean needs no contraction with W: mu = bias + rho * kappa . beta (beta = K^-1 r);
     // per-block partials, summed in a fixed order by oz_moments_kernel
-    mupart[(int64_t)blockIdx.y * mcp + m] = kb * (1.0 / (double)(1ll << SHIFT));
+    mupart[(int64_t)blockIdx.y * mcp + m] = kb * (1.0 / 545460846592.0);      // 127 * 2^32
 }
 
 // |xs_j|^2 / 2 per observation (once per fit)
@@ -599,19 +590,16 @@ oz_score_kernel(const __grid_constant__ CUtensorMap tmapB, OzParams p) {
                 const int row0 = un.rb * OZ_BN + c0;
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
-                    double v;
-                    if (NG <= 6 && S <= 5) {
-                        // sum_g D_g 2^(7 (G - g)) fits int64 for <= 5 slices (|D_g| < 2^27): shift-adds on
-                        // the integer pipe and a single conversion keep the FP64 pipe for the reductions
-                        long long a = (long long)r[0][i];
+                    // sum_g D_g 256^(G - g): the first five groups fit int64 (|D_g| < 2^30): shift-adds on
+                    // the integer pipe and a single conversion keep the FP64 pipe for the reductions
+                    constexpr int GI = G < 4 ? G : 4;
+                    long long a = (long long)r[0][i];
 #pragma unroll
-                        for (int g = 1; g <= G; ++g) a = a * 128 + (long long)r[g][i];
-                        v = (double)a * (1.0 / (double)(1ll << (7 * G)));
-                    } else {
-                        v = (double)r[G][i];
+                    for (int g = 1; g <= GI; ++g) a = a * 256 + (long long)r[g][i];
+                    double v = (double)a;
 #pragma unroll
-                        for (int g = G - 1; g >= 0; --g) v = fma(v, 0.0078125, (double)r[g][i]);
-                    }
+                    for (int g = GI + 1; g <= G; ++g) v = fma(v, 256.0, (double)r[g][i]);
+                    v *= 1.0 / (double)(1ull << (8 * G));
                     const double vv = v * __ldg(p.rowscale + row0 + i);
                     q = fma(vv, vv, q);
                 }
@@ -689,8 +677,8 @@ static size_t oz_smem_bytes(int S) {
 
 int bo_ozaki_init(bo_ctx *ctx) {
 #define OZ_ATTR(SS) BO_CUDA(ctx, cudaFuncSetAttribute(oz_score_kernel<SS, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)oz_smem_bytes(SS))); \
-                    if (SS <= 7) BO_CUDA(ctx, cudaFuncSetAttribute(oz_score_kernel<(SS <= 7 ? SS : 7), 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)oz_smem_bytes(SS)))
-    OZ_ATTR(2); OZ_ATTR(3); OZ_ATTR(4); OZ_ATTR(5); OZ_ATTR(6); OZ_ATTR(7); OZ_ATTR(8);
+                    BO_CUDA(ctx, cudaFuncSetAttribute(oz_score_kernel<SS, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)oz_smem_bytes(SS)))
+    OZ_ATTR(2); OZ_ATTR(3); OZ_ATTR(4); OZ_ATTR(5); OZ_ATTR(6); OZ_ATTR(7);
 #undef OZ_ATTR
 #define OZ_KATTR(DP, SS) BO_CUDA(ctx, cudaFuncSetAttribute(oz_kstar_slices_fast_kernel<DP, SS>, cudaFuncAttributeMaxDynamicSharedMemorySize, SS * OZ_A_SLICE_BYTES))
 #define OZ_KATTR_ALL(DP) OZ_KATTR(DP, 2); OZ_KATTR(DP, 3); OZ_KATTR(DP, 4); OZ_KATTR(DP, 5)
@@ -741,8 +729,8 @@ int bo_ozaki_prepare(bo_ctx *ctx, int S) {
     return BO_OK;
 }
 
-// Error model (calibrated on the headline shape, tools/oz_err.py): with S slices per operand the
-// truncation term of v is ~ sqrt(n) 2^e sqrt(rho) 2^(-7S) and the dropped digit pairs of group g = S
+// Error model (calibrated on the headline shape, tools/oz_err.py): with S base-256 slices per operand
+// the truncation term of v is ~ sqrt(n) 2^e sqrt(rho) 2^(-8S) and the dropped digit pairs of group g = S
 // are ~30x larger; accumulating that group too (`extra`) leaves only the truncation term.
 // Levels in order of cost: (S, extra) = (3,0) (3,1) (4,0) (4,1) (5,0) (5,1) (6,0) ...; pick the first
 // whose estimate is below tol * sqrt(rho).  tol >= 2 pins S = floor(tol), extra = (tol - S >= 0.5).
@@ -762,11 +750,11 @@ int bo_ozaki_choose_slices(bo_ctx *ctx, double tol) {
         worst = est > worst ? est : worst;
     }
     for (int S = 3; S <= OZ_MAX_S; ++S) {
-        const double base = worst * ldexp(1.0, -7 * S);
+        const double base = worst * ldexp(1.0, -8 * S);
         if (base <= tol) { ctx->oz_extra = false; return S; }
-        if (S <= 7 && base / 32.0 <= tol) { ctx->oz_extra = true; return S; }
+        if (base / 32.0 <= tol) { ctx->oz_extra = true; return S; }
     }
-    ctx->oz_extra = false;
+    ctx->oz_extra = true;
     return OZ_MAX_S;
 }
 
@@ -843,7 +831,10 @@ int bo_ozaki_contract(bo_ctx *ctx, int s, int S, int mcp, int buf, double *mu, d
     }
     OzParams p;
     p.np = np; p.S = S; p.nstages = oz_stage_count(S); p.ntiles = mcp / OZ_BM; p.mcp = mcp;
-    const bool extra = ctx->oz_extra && S <= 7;
+    const bool extra = ctx->oz_extra;
+    // exact int32 accumulation: up to S digit pairs per group, |digit| <= 128, k range <= np
+    if ((int64_t)np * S >= (1 << 17))
+        return bo_set_err(ctx, BO_ERR_ARG, "int8 path: n = %d with %d slices would overflow the int32 accumulators; use the FP64 path", np, S);
     p.nacc = (2 * (S + (extra ? 1 : 0)) * OZ_BN <= 512) ? 2 : 1;
     // candidate tiles whose K* slices (S * 128 * np bytes each) share L2 with the W slices
     {
@@ -859,11 +850,11 @@ int bo_ozaki_contract(bo_ctx *ctx, int s, int S, int mcp, int buf, double *mu, d
     {
         BO_LAUNCH(ctx, "oz_score_kernel");
         switch (S) {
-#define OZ_RUN(SS) case SS: if (extra && SS <= 7) oz_score_kernel<(SS <= 7 ? SS : 7), 1><<<grid, OZ_THREADS, oz_smem_bytes(SS), ctx->stream>>>(tmB, p); \
+#define OZ_RUN(SS) case SS: if (extra) oz_score_kernel<SS, 1><<<grid, OZ_THREADS, oz_smem_bytes(SS), ctx->stream>>>(tmB, p); \
                          else oz_score_kernel<SS, 0><<<grid, OZ_THREADS, oz_smem_bytes(SS), ctx->stream>>>(tmB, p); break
-            OZ_RUN(2); OZ_RUN(3); OZ_RUN(4); OZ_RUN(5); OZ_RUN(6); OZ_RUN(7); OZ_RUN(8);
+            OZ_RUN(2); OZ_RUN(3); OZ_RUN(4); OZ_RUN(5); OZ_RUN(6); OZ_RUN(7);
 #undef OZ_RUN
-            default: return bo_set_err(ctx, BO_ERR_ARG, "int8 path needs 2..8 slices, got %d", S);
+            default: return bo_set_err(ctx, BO_ERR_ARG, "int8 path needs 2..7 slices, got %d", S);
         }
         BO_CHECK_LAUNCH(ctx);
     }
@@ -888,7 +879,7 @@ extern "C" int bo_ozaki_debug(bo_ctx *ctx, int S, int extra, int mc, const doubl
     if (S < 2 || S > OZ_MAX_S || mc < 1) return bo_set_err(ctx, BO_ERR_ARG, "bad S / mc");
     const int np = ctx->np, mcp = bo_round_up(mc, OZ_BM), nb = np / OZ_BN;
     ctx->oz_ready = false;
-    ctx->oz_extra = extra != 0 && S <= 7;
+    ctx->oz_extra = extra != 0;
     const int NG = S + (ctx->oz_extra ? 1 : 0);
     BO_TRY(bo_ozaki_prepare(ctx, S));
     double *dXc = nullptr, *dmu = nullptr;

@@ -16,13 +16,16 @@ mu0, s20 = ctx.predict(Xc)
 ei0, _, _ = ctx.score(1, target, Xc)
 z = (mu0 - target) / np.sqrt(s20)
 print("z range", z.min(), z.max(), "s2/rho range", s20.min() / rho, s20.max() / rho, "EI max", ei0.max())
-for S in (5, 5.5, 6):
+import time
+for S in (3.5, 4, 4.5, 5, 5.5, 6):
     ctx.set_precision(1, float(S))
     mu, s2 = ctx.predict(Xc)
+    ctx.sync(); t0 = time.perf_counter()
     ei, _, _ = ctx.score(1, target, Xc)
+    dt = time.perf_counter() - t0
     floor = 1e-9 * ei0.max()
     rel = np.abs(ei - ei0) / np.maximum(np.abs(ei0), floor)
     i = int(np.argmax(rel))
-    print("S=%s  max|dmu|=%.2e mean(dmu)=%.2e  max|ds2|/rho=%.2e mean(ds2)/rho=%.2e | EI rel: max=%.2e p99.9=%.2e median=%.2e | worst: z=%.2f ei0=%.3e"
-          % (S, np.abs(mu - mu0).max(), (mu - mu0).mean(), np.abs(s2 - s20).max() / rho, (s2 - s20).mean() / rho,
+    print("S=%s (%.0f ms incl. copies) argmax same=%s  max|dmu|=%.2e mean(dmu)=%.2e  max|ds2|/rho=%.2e mean(ds2)/rho=%.2e | EI rel: max=%.2e p99.9=%.2e median=%.2e | worst: z=%.2f ei0=%.3e"
+          % (S, dt * 1e3, int(np.argmax(ei)) == int(np.argmax(ei0)), np.abs(mu - mu0).max(), (mu - mu0).mean(), np.abs(s2 - s20).max() / rho, (s2 - s20).mean() / rho,
              rel.max(), np.percentile(rel, 99.9), np.median(rel), z[i], ei0[i]))
