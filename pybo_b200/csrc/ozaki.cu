@@ -387,26 +387,55 @@ oz_kstar_slices_fast_kernel(int n, int np, int d, const double *__restrict__ Xs,
             // each XOR 0x80, are its balanced base-256 digits (slice s = byte 4 - s): the low word is
             // transposed to slice-major words with byte permutes, the top digit sits in the high word.
             uint32_t wlow[16], wtop[4];
+            // four elements in lockstep: the distance dot products and the exp2 Horner chains of the
+            // four are independent, so the FP64 pipe always has work in flight (a single chain per
+            // thread left it waiting on its own latency 55 % of the time)
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                double dot = -ha - hb[buf][jj0 + i];
+            for (int q4 = 0; q4 < 4; ++q4) {
+                const int jq = jj0 + 4 * q4;
+                double dot[4], f[4], pl[4];
+                int ki[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) dot[e] = -ha - hb[buf][jq + e];
 #pragma unroll
                 for (int k = 0; k < DP; k += 2) {
-                    const double2 x2 = *reinterpret_cast<const double2 *>(&xs[buf][jj0 + i][k]);
-                    dot = fma(xc[k], x2.x, dot);
-                    dot = fma(xc[k + 1], x2.y, dot);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const double2 x2 = *reinterpret_cast<const double2 *>(&xs[buf][jq + e][k]);
+                        dot[e] = fma(xc[k], x2.x, dot[e]);
+                        dot[e] = fma(xc[k + 1], x2.y, dot[e]);
+                    }
                 }
-                const double z = fma(fmin(dot, 0.0), LOG2E, LOG2_127);
-                const bool on = live && (j0 + jj0 + i) < n;
-                const double v = on ? oz_exp2_scaled<12>(z, 32) : 0.0;        // in [0, 127 * 2^32]
-                kb = fma(v, bt[buf][jj0 + i], kb);
-                const double vv = v + 4503599627370496.0;                   // + 2^52: mantissa = rint(v)
-                const uint32_t lo = (uint32_t)__double2loint(vv) + 0x80808080u;
-                const uint32_t hi = ((uint32_t)__double2hiint(vv) + 0x80u + (lo < 0x80808080u ? 1u : 0u)) & 0xFFu;
-                wlow[i] = lo ^ 0x80808080u;
-                const uint32_t top = hi ^ 0x80u;
-                if ((i & 3) == 0) wtop[i >> 2] = top;
-                else wtop[i >> 2] |= top << (8 * (i & 3));
+                // v = 2^(z + 32), z = log2(127 kappa) (dot <= 0 up to rounding; a last-ulp excess rounds away)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const double z = fma(dot[e], LOG2E, LOG2_127);
+                    const double zz = z + 6755399441055744.0;          // 1.5 * 2^52: low word = rint(z)
+                    ki[e] = __double2loint(zz) + 32;
+                    f[e] = z - (zz - 6755399441055744.0);              // [-0.5, 0.5]
+                    pl[e] = OZ_EXP2_C[0];
+                }
+#pragma unroll
+                for (int c = 1; c < 12; ++c) {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) pl[e] = fma(pl[e], f[e], OZ_EXP2_C[c]);
+                }
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int i = 4 * q4 + e;
+                    pl[e] = fma(pl[e], f[e], 1.0);
+                    const bool on = live && (j0 + jq + e) < n && ki[e] > -960;
+                    double v = __hiloint2double(__double2hiint(pl[e]) + (ki[e] << 20), __double2loint(pl[e]));
+                    v = on ? v : 0.0;                                           // in [0, 127 * 2^32]
+                    kb = fma(v, bt[buf][jq + e], kb);
+                    const double vv = v + 4503599627370496.0;                   // + 2^52: mantissa = rint(v)
+                    const uint32_t lo = (uint32_t)__double2loint(vv) + 0x80808080u;
+                    const uint32_t hi = ((uint32_t)__double2hiint(vv) + 0x80u + (lo < 0x80808080u ? 1u : 0u)) & 0xFFu;
+                    wlow[i] = lo ^ 0x80808080u;
+                    const uint32_t top = hi ^ 0x80u;
+                    if (e == 0) wtop[q4] = top;
+                    else wtop[q4] |= top << (8 * e);
+                }
             }
             uint8_t *o0 = oz_stage + tid * 64 + ((sub ^ swz) << 4);
             *reinterpret_cast<uint4 *>(o0) = make_uint4(wtop[0], wtop[1], wtop[2], wtop[3]);
