@@ -292,6 +292,7 @@ def our_arm(args):
                         share_of_step=gk["total_ms"] / dev_ms if dev_ms else None)
 
     chol = cholesky_metric(ctx, spec, X, ell[0], rho[0], sn2[0], pk, fp64_peak)
+    append = append_metric(spec, X, y, ell[0], rho[0], sn2[0], bias[0], pk, local) if S == 1 else None
     cpu = cpu_baseline(spec, X, y, ell, rho, sn2, bias, budget_s=args.cpu_seconds) if world == 1 else None
 
     line = dict(metric="acq_evals_per_sec", value=value, unit="evals/s", n_gpus=world, steps=args.steps,
@@ -308,7 +309,7 @@ def our_arm(args):
                 e2e=dict(value=e2e_value, unit="evals/s", ms_per_step=e2e_ms / args.steps,
                          h2d_bytes_per_step=int(M * d * 8), d2h_bytes_per_step=int(10 * 16),
                          api="policies.ModelIndex.best_of (score + device top-10) on pinned host candidates"),
-                gpu_launches=int(launches), roofline=roofline, cpu_baseline=cpu, cholesky=chol,
+                gpu_launches=int(launches), roofline=roofline, cpu_baseline=cpu, cholesky=chol, incremental_refit=append,
                 fit_seconds=fit_s, incumbent=dict(value=incumbent[0], index=incumbent[1]), faster_level=fast_level,
                 kernels={k: dict(launches=v["launches"], ms=round(v["total_ms"], 3)) for k, v in prof.items()})
     print(json.dumps(line))
@@ -335,6 +336,31 @@ def cholesky_metric(ctx, spec, X, ell, rho, sn2, pk, fp64_peak):
     return dict(n=n, ms=best * 1e3, algorithmic_bytes=n * (n + 1) * 8, gbs=gbs, frac_hbm=gbs / pk["hbm_gbs"],
                 hbm_peak_gbs=pk["hbm_gbs"], tflops=tfl, frac_fp64=tfl / fp64_peak if fp64_peak else None,
                 note="compute-bound: n^3/3 flop over n(n+1)*8 bytes = %.0f flop/B; the HBM fraction cannot approach 1 in fp64" % (n / 24.0))
+
+
+def append_metric(spec, X, y, ell, rho, sn2, bias, pk, device, k=32):
+    """Incremental refit (bo_append, reference bayesopt.py:269 `model.add_data`): the last k observations
+    appended one at a time to a fit of the first n - k.  Algorithmic bytes per append: the lower triangle of
+    W and the upper triangle of W^T streamed once each = n^2 * 8 B; HBM-bound."""
+    from pybo_b200 import _lib
+    n = spec["n"]
+    c = _lib.Context(device)
+    c.fit(spec["kernel"], X[:n - k], y[:n - k], ell[None], [rho], [sn2], [bias])
+    c.append(X[n - k], y[n - k:n - k + 1])
+    c.sync()
+    t0 = time.perf_counter()
+    for i in range(n - k + 1, n):
+        c.append(X[i], y[i:i + 1])
+    c.sync()
+    dt = (time.perf_counter() - t0) / (k - 1)
+    t0 = time.perf_counter()
+    c.fit(spec["kernel"], X, y, ell[None], [rho], [sn2], [bias])
+    c.sync()
+    refit = time.perf_counter() - t0
+    c.close()
+    gbs = n * n * 8 / dt / 1e9
+    return dict(n=n, ms_per_append=dt * 1e3, full_refit_ms=refit * 1e3, algorithmic_bytes=n * n * 8, gbs=gbs,
+                frac_hbm=gbs / pk["hbm_gbs"], note="wall clock per bo_append call incl. its host sync; 4 kernels")
 
 
 # ----------------------------------------------------------------------------------------

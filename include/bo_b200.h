@@ -74,6 +74,16 @@ int bo_loglik(bo_ctx *ctx, double *out /* S */);
 /* factor read-back, for parity tests: which = 0 L, 1 W=L^-1, 2 alpha, 3 beta */
 int bo_get_factor(bo_ctx *ctx, int s, int which, double *out);
 
+/* ---- incremental refit: `model.add_data(x, y)` inside the loop (bayesopt.py:269)
+ * Appends m observations (Xnew: m x d, ynew: m) to the fitted factor set without
+ * refactorising: per point and hyper-sample l = W k, lam = sqrt(kss - |l|^2), the
+ * new rows of L, W = L^-1 and W^T, alpha, beta and log|L| (two triangular
+ * matrix-vector products, O(n^2)); the int8 slice planes get the new row too.
+ * The handle has room for bo_fit_capacity() observations (n rounded up to 128);
+ * beyond that, or after BO_ERR_NOT_PD, call bo_fit again. */
+int bo_append(bo_ctx *ctx, int m, const double *Xnew, const double *ynew);
+int bo_fit_capacity(bo_ctx *ctx, int *capacity);
+
 /* ---- the hot call: `finit = f(xgrid, grad=False)` (solvers/lbfgs.py:50) ---
  * Scores M candidates Xc (M x d) with acquisition `acq`:
  *   param = target (EI, PI), beta (UCB), ignored (MEAN).

@@ -25,7 +25,7 @@ EXPORTS = [
     "bo_thompson_set", "bo_thompson_eval",
     "bo_cholesky", "bo_gram",
     "bo_profile_enable", "bo_profile_reset", "bo_profile_count", "bo_profile_get",
-    "bo_launch_count", "bo_microbench", "bo_ozaki_debug",
+    "bo_launch_count", "bo_microbench", "bo_ozaki_debug", "bo_append", "bo_fit_capacity",
 ]
 
 
@@ -69,6 +69,8 @@ def _declare(lib):
         "bo_launch_count": (i, [vp, _lp]),
         "bo_microbench": (i, [vp, i, i, _dp]),
         "bo_ozaki_debug": (i, [vp, i, i, i, vp, vp, vp, vp, vp, vp, vp]),
+        "bo_append": (i, [vp, i, vp, vp]),
+        "bo_fit_capacity": (i, [vp, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
@@ -173,6 +175,22 @@ class Context(object):
         self.n, self.d, self.S = n, d, S
         self._check(self._lib.bo_fit(self._h, KERNEL_IDS[kernel], n, d, S, _ptr(X), _ptr(y), _ptr(ell),
                                      _ptr(rho), _ptr(sn2), _ptr(bias)))
+
+    def capacity(self):
+        """Observations the fitted handle can hold before `append` needs a refit."""
+        cap = C.c_int()
+        self._check(self._lib.bo_fit_capacity(self._h, C.byref(cap)))
+        return cap.value
+
+    def append(self, X, y):
+        """Incremental refit (bo_append): O(n^2) per new observation."""
+        X = f64(X, 2)
+        y = f64(y, 1)
+        d = getattr(self, "d", 0)
+        if d and (X.shape[1] != d or X.shape[0] != len(y)):
+            raise ValueError("append: expected (m, %d) inputs and (m,) outputs" % d)
+        self._check(self._lib.bo_append(self._h, X.shape[0], _ptr(X), _ptr(y)))
+        self.n = getattr(self, "n", 0) + X.shape[0]
 
     def loglik(self):
         out = np.empty(self.S)

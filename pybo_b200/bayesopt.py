@@ -172,7 +172,8 @@ def solve_bayesopt(objective, bounds, model=None, niter=100, policy="ei", solver
     for i in range(len(info.xbest), niter):
         index = policy(model, bounds, info.x)
         x, _ = solver(index, bounds)
-        y = objective(x)
+        del index                       # releases the policy's private model copy: add_data can then
+        y = objective(x)                # append to the device factors in place (bo_append) instead of refitting
         model.add_data(x, y)
         xbest = recommender(model, bounds, info.x)
         info.x.append(x)

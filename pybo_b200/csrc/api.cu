@@ -115,10 +115,11 @@ static void free_all(bo_ctx *ctx) {
                        &ctx->dKs, &ctx->dV, &ctx->dU, &ctx->dQpart, &ctx->dPpart, &ctx->dMuS,
                        &ctx->dS2S, &ctx->dDmuS, &ctx->dDs2S, &ctx->dGpart, &ctx->dXc, &ctx->dVal,
                        &ctx->dGradOut, &ctx->dBlkVal, &ctx->th.W, &ctx->th.b, &ctx->th.theta,
-                       &ctx->th.scale, &ctx->th.bias, &ctx->th.dBestVal, &ctx->th.thetaT, &ctx->dOzQ, &ctx->dXsHalfSq, &ctx->dCholDinv, &ctx->dOzMu};
+                       &ctx->th.scale, &ctx->th.bias, &ctx->th.dBestVal, &ctx->th.thetaT, &ctx->dOzQ, &ctx->dXsHalfSq, &ctx->dCholDinv, &ctx->dOzMu, &ctx->dAppend};
     for (auto p : ptrs)
         if (*p) { cudaFree(*p); *p = nullptr; }
     if (ctx->dInfo) { cudaFree(ctx->dInfo); ctx->dInfo = nullptr; }
+    if (ctx->dAppendInfo) { cudaFree(ctx->dAppendInfo); ctx->dAppendInfo = nullptr; }
     if (ctx->dWs) { cudaFree(ctx->dWs); ctx->dWs = nullptr; }
     if (ctx->dCholInfo) { cudaFree(ctx->dCholInfo); ctx->dCholInfo = nullptr; }
     if (ctx->dKss) { cudaFree(ctx->dKss); ctx->dKss = nullptr; }
@@ -214,7 +215,7 @@ extern "C" int bo_fit(bo_ctx *ctx, int kernel, int n, int d, int S, const double
     // hyper-parameter sampler)
     {
         struct { double **p; size_t need; } small[] = {
-            {&ctx->dX, (size_t)n * d}, {&ctx->dY, (size_t)n}, {&ctx->dXs, (size_t)S * np * dp},
+            {&ctx->dX, (size_t)np * d}, {&ctx->dY, (size_t)np}, {&ctx->dXs, (size_t)S * np * dp},
             {&ctx->dInvEll, (size_t)S * dp}, {&ctx->dRho, (size_t)S}, {&ctx->dSn2, (size_t)S},
             {&ctx->dBias, (size_t)S}, {&ctx->dDinv, (size_t)S * nblk64 * 4096}, {&ctx->dAlpha, (size_t)S * np},
             {&ctx->dBeta, (size_t)S * np}, {&ctx->dLogdet, (size_t)S}};

@@ -58,6 +58,9 @@ struct bo_ctx {
     double *dBeta = nullptr;    // S x np   L^-T alpha
     double *dLogdet = nullptr;  // S        sum log diag L
     int *dInfo = nullptr;       // S
+    double *dAppend = nullptr;  // bo_append scratch: kvec[np], lvec[np], per-sample scalars
+    int *dAppendInfo = nullptr;
+    size_t append_capacity = 0, appendinfo_capacity = 0;
     double *dCholDinv = nullptr;   // stand-alone bo_cholesky scratch
     int *dCholInfo = nullptr;
     size_t choldinv_capacity = 0, cholinfo_capacity = 0;
@@ -202,6 +205,7 @@ int bo_score_init(bo_ctx *ctx);
 int bo_ozaki_init(bo_ctx *ctx);
 int bo_thompson_init(bo_ctx *ctx);
 int bo_ozaki_prepare(bo_ctx *ctx, int S);
+int bo_ozaki_append_row(bo_ctx *ctx, int row);
 int bo_ozaki_choose_slices(bo_ctx *ctx, double tol);
 int bo_ozaki_slice(bo_ctx *ctx, int s, int S, const double *dXc, int64_t c0, int mc, int mcp, int buf,
                    cudaStream_t stream);

@@ -198,8 +198,8 @@ __device__ __forceinline__ void oz_issue_stage(uint32_t sA, uint32_t sB, uint32_
 // ---------------------------------------------------------------------------
 // Row exponents of W and the epilogue scale 2^e_i * rho / 127^2.
 __global__ void oz_row_exponent_kernel(const double *__restrict__ W, int np, double rho, int *__restrict__ rowexp,
-                                       double *__restrict__ rowscale, int *__restrict__ emax) {
-    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+                                       double *__restrict__ rowscale, int *__restrict__ emax, int row0) {
+    const int row = row0 + blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= np) return;
     const double *w = W + (int64_t)row * np;
@@ -223,8 +223,8 @@ __device__ __forceinline__ unsigned long long oz_digits7(double x) {
 
 // W (lower triangle) -> S int8 slice planes [s][row][k]; slice s = digit byte 6 - s
 __global__ void oz_slice_w_kernel(const double *__restrict__ W, int np, int S, const int *__restrict__ rowexp,
-                                  int8_t *__restrict__ Ws) {
-    const int row = blockIdx.y;
+                                  int8_t *__restrict__ Ws, int row0) {
+    const int row = row0 + blockIdx.y;
     const int k0 = (blockIdx.x * blockDim.x + threadIdx.x) * 16;
     if (k0 >= np) return;
     const double sc = ldexp(1.0, -rowexp[row]);
@@ -324,7 +324,7 @@ __device__ __forceinline__ double oz_exp2_scaled(double z, int shift) {
     return ki < -1000 ? 0.0 : v;
 }
 
-#define OZ_KS_TILES 8      // observation tiles (of 64) per block
+#define OZ_KS_TILES 4      // observation tiles (of 64) per block
 
 __device__ __forceinline__ void oz_cp_async16(void *smem_dst, const void *gmem_src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src));
@@ -733,14 +733,14 @@ int bo_ozaki_prepare(bo_ctx *ctx, int S) {
             BO_LAUNCH(ctx, "oz_row_exponent_kernel");
             oz_row_exponent_kernel<<<np / 8, 256, 0, ctx->stream>>>(ctx->dW + (size_t)s * np * np, np, ctx->h_rho[s],
                                                                    ctx->dRowExp + (size_t)s * np,
-                                                                   ctx->dRowScale + (size_t)s * np, emax_dev + s);
+                                                                   ctx->dRowScale + (size_t)s * np, emax_dev + s, 0);
             BO_CHECK_LAUNCH(ctx);
         }
         {
             BO_LAUNCH(ctx, "oz_slice_w_kernel");
             oz_slice_w_kernel<<<dim3((np / 16 + 127) / 128, np), 128, 0, ctx->stream>>>(
                 ctx->dW + (size_t)s * np * np, np, S, ctx->dRowExp + (size_t)s * np,
-                ctx->dWs + (size_t)s * S * np * np);
+                ctx->dWs + (size_t)s * S * np * np, 0);
             BO_CHECK_LAUNCH(ctx);
         }
     }
@@ -755,6 +755,35 @@ int bo_ozaki_prepare(bo_ctx *ctx, int S) {
     BO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->oz_ready = true;
     ctx->oz_slices = S;
+    return BO_OK;
+}
+
+// bo_append wrote row `row` of W (and of Xs): refresh that row's exponent, scale, slices and |xs|^2/2.
+int bo_ozaki_append_row(bo_ctx *ctx, int row) {
+    const int np = ctx->np, ns = ctx->S, S = ctx->oz_slices;
+    int *emax_dev = ctx->dRowExp + (size_t)ns * np;
+    for (int s = 0; s < ns; ++s) {
+        {
+            BO_LAUNCH(ctx, "oz_row_exponent_kernel");
+            oz_row_exponent_kernel<<<1, 32, 0, ctx->stream>>>(ctx->dW + (size_t)s * np * np, np, ctx->h_rho[s],
+                                                              ctx->dRowExp + (size_t)s * np, ctx->dRowScale + (size_t)s * np,
+                                                              emax_dev + s, row);
+            BO_CHECK_LAUNCH(ctx);
+        }
+        {
+            BO_LAUNCH(ctx, "oz_slice_w_kernel");
+            oz_slice_w_kernel<<<dim3((np / 16 + 127) / 128, 1), 128, 0, ctx->stream>>>(
+                ctx->dW + (size_t)s * np * np, np, S, ctx->dRowExp + (size_t)s * np, ctx->dWs + (size_t)s * S * np * np, row);
+            BO_CHECK_LAUNCH(ctx);
+        }
+    }
+    {
+        BO_LAUNCH(ctx, "oz_halfsq_kernel");
+        oz_halfsq_kernel<<<(ns * np + 255) / 256, 256, 0, ctx->stream>>>(ctx->dXs, ns * np, ctx->dp, ctx->dXsHalfSq);
+        BO_CHECK_LAUNCH(ctx);
+    }
+    BO_CUDA(ctx, cudaMemcpyAsync(ctx->h_emax.data(), emax_dev, sizeof(int) * ns, cudaMemcpyDeviceToHost, ctx->stream));
+    BO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return BO_OK;
 }
 

@@ -160,7 +160,7 @@ __global__ void moments_kernel(int nblk, int mcp, const double *__restrict__ qpa
 
 // ---------------------------------------------------------------------------
 // Small batches (the L-BFGS callback shape f(x[None], grad=True), reference lbfgs.py:56-58):
-// a tiled GEMM would walk the whole k range serially in one CTA, so M <= 8 candidates use
+// a tiled GEMM would walk the whole k range serially in one CTA, so M <= 16 candidates use
 // bandwidth-bound triangular GEMVs instead: one warp per row of W (or W^T), MC right-hand sides.
 //   UPPER == false: out[row][m] = sum_{j <= row} Mx[row][j] rhs[j][m]     (V = W K*)
 //   UPPER == true : out[row][m] = sum_{j >= row} Mx[row][j] rhs[j][m]     (U = W^T V)
@@ -183,6 +183,43 @@ trimv_small_kernel(const double *__restrict__ Mx, int np, const double *__restri
         const double w = mrow[j];
 #pragma unroll
         for (int m = 0; m < MC; ++m) acc[m] = fma(w, rhs[(int64_t)j * ld + m], acc[m]);
+    }
+#pragma unroll
+    for (int m = 0; m < MC; ++m) {
+        acc[m] = warp_sum_d(acc[m]);
+        if (lane == 0) out[(int64_t)row * ld + m] = acc[m];
+    }
+}
+
+// Same products for 5..16 right-hand sides (the batched multi-start refinement, solvers.py
+// `batched_lbfgs`): re-reading MC values of rhs per matrix element from L2 made the call slower
+// than the tiled GEMM, so the block stages 128 rows of rhs in shared memory per step and the
+// eight warps (eight consecutive rows) share them; the matrix is still read exactly once.
+template <int MC, bool UPPER>
+__global__ void __launch_bounds__(256)
+trimv_multi_kernel(const double *__restrict__ Mx, int np, const double *__restrict__ rhs, int ld,
+                   double *__restrict__ out) {
+    __shared__ double sr[128][MC + 1];
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int r0 = blockIdx.x * 8, row = r0 + (tid >> 5);
+    const double *mrow = Mx + (int64_t)row * np;
+    double acc[MC];
+#pragma unroll
+    for (int m = 0; m < MC; ++m) acc[m] = 0.0;
+    const int jb = UPPER ? (r0 & ~127) : 0;
+    const int je = UPPER ? np : r0 + 8;
+    for (int j0 = jb; j0 < je; j0 += 128) {
+        for (int e = tid; e < 128 * MC; e += 256) sr[e / MC][e % MC] = rhs[(int64_t)(j0 + e / MC) * ld + (e % MC)];
+        __syncthreads();
+#pragma unroll
+        for (int jj = lane; jj < 128; jj += 32) {
+            const int j = j0 + jj;
+            const bool in = UPPER ? (j >= row) : (j <= row);
+            const double w = in ? mrow[j] : 0.0;
+#pragma unroll
+            for (int m = 0; m < MC; ++m) acc[m] = fma(w, sr[jj][m], acc[m]);
+        }
+        __syncthreads();
     }
 #pragma unroll
     for (int m = 0; m < MC; ++m) {
@@ -652,9 +689,9 @@ int bo_score_run(bo_ctx *ctx, const ScoreRequest &rq) {
         const int mcp = bo_round_up(mc, 128);
         for (int s = 0; s < S; ++s) {
             DISPATCH_DP(ctx, launch_kstar, ctx, s, rq.dXc, c0, mc, mcp);
-            if (mc <= 8) {
+            if (mc <= 16) {
                 // small batch: triangular GEMVs (V, and U = W^T V for gradients) instead of tiled GEMMs
-                const int MC = mc <= 1 ? 1 : (mc <= 2 ? 2 : (mc <= 4 ? 4 : 8));
+                const int MC = mc <= 1 ? 1 : (mc <= 2 ? 2 : (mc <= 4 ? 4 : (mc <= 8 ? 8 : 16)));
                 size_t need = (size_t)np * mcp;
                 if (ctx->grad_capacity < need || !ctx->dV) {
                     size_t c1 = ctx->grad_capacity, c2 = ctx->grad_capacity, c3 = 0, c4 = 0, c5 = 0;
@@ -675,7 +712,8 @@ int bo_score_run(bo_ctx *ctx, const ScoreRequest &rq) {
                         case 1: trimv_small_kernel<1, false><<<np / 8, 256, 0, ctx->stream>>>(Wm, np, ctx->dKs, mcp, ctx->dV); break;
                         case 2: trimv_small_kernel<2, false><<<np / 8, 256, 0, ctx->stream>>>(Wm, np, ctx->dKs, mcp, ctx->dV); break;
                         case 4: trimv_small_kernel<4, false><<<np / 8, 256, 0, ctx->stream>>>(Wm, np, ctx->dKs, mcp, ctx->dV); break;
-                        default: trimv_small_kernel<8, false><<<np / 8, 256, 0, ctx->stream>>>(Wm, np, ctx->dKs, mcp, ctx->dV); break;
+                        case 8: trimv_multi_kernel<8, false><<<np / 8, 256, 0, ctx->stream>>>(Wm, np, ctx->dKs, mcp, ctx->dV); break;
+                        default: trimv_multi_kernel<16, false><<<np / 8, 256, 0, ctx->stream>>>(Wm, np, ctx->dKs, mcp, ctx->dV); break;
                     }
                     BO_CHECK_LAUNCH(ctx);
                 }
@@ -693,7 +731,8 @@ int bo_score_run(bo_ctx *ctx, const ScoreRequest &rq) {
                             case 1: trimv_small_kernel<1, true><<<np / 8, 256, 0, ctx->stream>>>(WTm, np, ctx->dV, mcp, ctx->dU); break;
                             case 2: trimv_small_kernel<2, true><<<np / 8, 256, 0, ctx->stream>>>(WTm, np, ctx->dV, mcp, ctx->dU); break;
                             case 4: trimv_small_kernel<4, true><<<np / 8, 256, 0, ctx->stream>>>(WTm, np, ctx->dV, mcp, ctx->dU); break;
-                            default: trimv_small_kernel<8, true><<<np / 8, 256, 0, ctx->stream>>>(WTm, np, ctx->dV, mcp, ctx->dU); break;
+                            case 8: trimv_multi_kernel<8, true><<<np / 8, 256, 0, ctx->stream>>>(WTm, np, ctx->dV, mcp, ctx->dU); break;
+                            default: trimv_multi_kernel<16, true><<<np / 8, 256, 0, ctx->stream>>>(WTm, np, ctx->dV, mcp, ctx->dU); break;
                         }
                         BO_CHECK_LAUNCH(ctx);
                     }

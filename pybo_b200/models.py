@@ -8,6 +8,8 @@ of libbo_b200.so.  All numerics for data-bearing models run on the device;
 without the CUDA library these classes raise `BackendError`.
 """
 
+import sys
+
 import numpy as np
 import scipy.linalg as sla
 
@@ -94,6 +96,7 @@ class _Base(object):
     kernel = "se"
     device = None
     _precision = ("fp64", 1e-9)
+    incremental = True           # add_data appends to the device factors when it can
 
     def set_precision(self, path="fp64", tol=1e-7):
         """Arithmetic of the scoring contraction: 'fp64' (FP64 tensor cores, default) or 'int8'
@@ -134,7 +137,26 @@ class _Base(object):
             raise ValueError("add_data: expected (k, %d) inputs and (k,) outputs" % d)
         self._X = np.concatenate([self._X, X], axis=0)
         self._Y = np.concatenate([self._Y, Y])
+        self._extend_fit(X, Y)
+
+    def _extend_fit(self, X, Y):
+        """Incremental refit: when this model is the only owner of its fitted handle
+        (no `copy()` still shares it) and the handle has room, the new rows of L, W, alpha, beta are
+        appended on the device in O(n^2) per point (bo_append) instead of refactorising; otherwise
+        the handle is dropped and the next use refits."""
+        fit = self._fit
         self._fit = None
+        if fit is None or not self.incremental or len(Y) == 0 or len(Y) > 8:
+            return
+        if sys.getrefcount(fit) > 2:            # `fit` here + the getrefcount argument: anyone else shares it
+            return
+        try:
+            if fit.ctx.n + len(Y) > fit.ctx.capacity():
+                return
+            fit.ctx.append(X, Y)
+        except (np.linalg.LinAlgError, _lib.BackendError):
+            return
+        self._fit = fit
 
     def _ensure_fit(self):
         if self._fit is None:
@@ -366,8 +388,11 @@ class MCMC(_Base):
         return len(self._thetas)
 
     def add_data(self, X, Y, resample=True):
+        resample = resample and self._proto is not None and any(p.prior is not None for p in self._proto.params.values())
+        if resample:
+            self._fit = None            # new hyper-samples follow: nothing to append to
         _Base.add_data(self, X, Y)
-        if resample and self._proto is not None and any(p.prior is not None for p in self._proto.params.values()):
+        if resample:
             self._resample(self._n)
 
     def copy(self):

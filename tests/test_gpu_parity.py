@@ -216,6 +216,25 @@ def test_single_point_gradient_calls(ctx):
         assert rel_err(val, ref, 1e-9) < TOL and rel_err(grad, rgrad, 1e-9) < 10 * TOL
 
 
+@pytest.mark.parametrize("kernel,n,d", [("se", 300, 4), ("matern52", 1030, 8)])
+def test_small_batch_gradient_calls(ctx, kernel, n, d):
+    """Batches of 2..17 points with gradients (the batched multi-start refinement): every small-batch
+    code path (1/2/4 right-hand sides per warp, 8/16 staged in shared memory, tiled GEMM above 16)."""
+    gp = synth(n, d, kernel, seed=n, sn2=1e-5)
+    fit_ctx(ctx, gp)
+    target = float(gp.predict(gp.X)[0].max())
+    rng = np.random.RandomState(2)
+    for M in (2, 3, 4, 5, 8, 10, 13, 16, 17):
+        X = rng.rand(M, d)
+        val, grad, _ = ctx.score(1, target, X, grad=True)
+        ref, rgrad = gp.get_improvement(target, X, grad=True)
+        assert rel_err(val, ref, 1e-9) < TOL and rel_err(grad, rgrad, 1e-9) < 10 * TOL, M
+        mu, s2, dmu, ds2 = ctx.predict(X, grad=True)
+        rmu, rs2, rdmu, rds2 = gp.predict(X, grad=True)
+        assert rel_err(mu, rmu) < TOL and rel_err(s2, rs2, 1e-9) < TOL
+        assert rel_err(dmu, rdmu, 1e-9) < 10 * TOL and rel_err(ds2, rds2, 1e-9) < 10 * TOL
+
+
 # ---- Thompson ---------------------------------------------------------------------------
 @pytest.mark.parametrize("kernel", ["se", "matern52"])
 def test_thompson_draw_matches_oracle(ctx, kernel):
@@ -283,6 +302,10 @@ def test_policies_solver_recommender_on_gpu_model():
         xa, fa = solvers.solve_lbfgs(a, bounds, xgrid=grid)
         xb, fb = solvers.solve_lbfgs(b, bounds, xgrid=grid)
         assert np.allclose(xa, xb, atol=1e-4 * np.max(bounds[:, 1] - bounds[:, 0])) and abs(fa - fb) <= 1e-6 * max(1, abs(fb))
+        # batched multi-start refinement on the device model vs the sequential SciPy runs on the oracle
+        xc, fc = solvers.solve_lbfgs_batched(a, bounds, xgrid=grid)
+        xd, fd = solvers.solve_lbfgs(b, bounds, xgrid=grid, pick="best")
+        assert abs(fc - fd) <= 1e-6 * max(1, abs(fd)) and abs(float(b(xc[None])[0]) - fc) <= 1e-6 * max(1, abs(fc))
     assert np.allclose(recommenders.best_latent(gpu, bounds, list(X)), recommenders.best_latent(ref, bounds, list(X)), atol=1e-4)
     assert np.array_equal(recommenders.best_incumbent(gpu, bounds, list(X)), recommenders.best_incumbent(ref, bounds, list(X)))
     # copy() shares the fitted state; add_data on the copy leaves the original alone

@@ -7,6 +7,7 @@ import pickle
 import re
 
 import numpy as np
+import scipy.optimize
 import pytest
 
 import pybo_b200
@@ -119,6 +120,54 @@ def test_solve_lbfgs_plain_callable_and_quirk():
     x2, f2 = solvers.solve_lbfgs(g, b, xgrid=grid, nbest=3, pick="best")
     assert np.allclose(x1, 0.5, atol=1e-4) and abs(f1 - 1.0) < 1e-6
     assert f2 >= f1
+
+
+def test_batched_multistart_solver_matches_sequential_lbfgs():
+    """solve_lbfgs_batched (SURVEY 8f-1): all starts advance in lockstep, one batched f call per step;
+    same optima as the reference's sequential fmin_l_bfgs_b runs, in far fewer callbacks."""
+    calls = {"n": 0, "rows": 0}
+
+    def f(X, grad=False):
+        X = np.array(X, ndmin=2)
+        calls["n"] += 1
+        calls["rows"] += len(X)
+        v = np.sin(3 * X[:, 0]) * np.cos(2 * X[:, 1]) - 0.1 * np.sum((X - 0.3) ** 2, axis=1)
+        if not grad:
+            return v
+        g = np.empty_like(X)
+        g[:, 0] = 3 * np.cos(3 * X[:, 0]) * np.cos(2 * X[:, 1]) - 0.2 * (X[:, 0] - 0.3)
+        g[:, 1] = -2 * np.sin(3 * X[:, 0]) * np.sin(2 * X[:, 1]) - 0.2 * (X[:, 1] - 0.3)
+        return v, g
+
+    b = np.array([[-2, 2.0], [-1, 3.0]])
+    grid = b[:, 0] + (b[:, 1] - b[:, 0]) * np.random.RandomState(0).rand(2000, 2)
+    xa, fa = solvers.solve_lbfgs(f, b, xgrid=grid, pick="best")
+    seq_calls = calls["n"]
+    calls["n"] = 0
+    xb, fb = solvers.solve_lbfgs_batched(f, b, xgrid=grid)
+    assert np.allclose(xa, xb, atol=1e-5) and abs(fa - fb) < 1e-9
+    assert calls["n"] < seq_calls / 3
+    # every start climbs to a stationary point of the box-constrained problem (which basin a start
+    # ends in may differ from SciPy's: both are local searches with different step rules)
+    starts = grid[np.argsort(-f(grid))[::200][:7]]
+    x, fx, nev = solvers.batched_lbfgs(f, starts, b)
+    v, g = f(x, grad=True)
+    pg = np.where(((x <= b[:, 0]) & (g < 0)) | ((x >= b[:, 1]) & (g > 0)), 0.0, g)
+    assert np.allclose(v, fx) and np.all(fx >= f(starts) - 1e-12) and np.max(np.abs(pg)) < 1e-4
+    assert np.all(x >= b[:, 0]) and np.all(x <= b[:, 1])
+    # optimum on the boundary of the box; pick='first' keeps the reference's result[0] choice
+    def g(X, grad=False):
+        X = np.array(X, ndmin=2)
+        v = X[:, 0] + 0.5 * X[:, 1] - X[:, 1] ** 2
+        return (v, np.column_stack([np.ones(len(X)), 0.5 - 2 * X[:, 1]])) if grad else v
+    x, fx = solvers.solve_lbfgs_batched(g, [[0, 1], [0, 1]], ngrid=100, rng=0)
+    assert np.allclose(x, [1.0, 0.25], atol=1e-6) and abs(fx - 1.0625) < 1e-10
+    x1, f1 = solvers.solve_lbfgs_batched(g, [[0, 1], [0, 1]], ngrid=100, rng=0, pick="first")
+    assert abs(f1 - 1.0625) < 1e-10
+    with pytest.raises(ValueError):
+        solvers.solve_lbfgs_batched(g, [[0, 1], [0, 1]], ngrid=10, rng=0, pick="nope")
+    s = bayesopt.get_component("lbfgs_batched", solvers, np.random.RandomState(0), lstrip="solve_")
+    assert s.func is solvers.solve_lbfgs_batched
 
 
 def test_policies_match_reference_formulas_on_oracle_model():

@@ -22,3 +22,9 @@ for M in (1, 10, 128):
 bounds = np.array([[0, 1.0]] * d)
 t0 = time.perf_counter(); xb, fb = solvers.solve_lbfgs(index, bounds, ngrid=100000, rng=0); dt = time.perf_counter() - t0
 print("solve_lbfgs(ngrid=1e5, nbest=10): %.1f ms, f=%.6f" % (1e3 * dt, fb))
+t0 = time.perf_counter(); xc, fc = solvers.solve_lbfgs_batched(index, bounds, ngrid=100000, rng=0); dt = time.perf_counter() - t0
+print("solve_lbfgs_batched(ngrid=1e5, nbest=10): %.1f ms, f=%.6f" % (1e3 * dt, fc))
+grid = rng.rand(100000, d)
+t0 = time.perf_counter(); starts, _ = index.best_of(grid, 10); t1 = time.perf_counter()
+xr, fr, nev = solvers.batched_lbfgs(index, grid[starts], bounds); t2 = time.perf_counter()
+print("grid scoring %.1f ms; batched refinement of 10 starts %.1f ms (%d batched calls), best %.6f" % (1e3 * (t1 - t0), 1e3 * (t2 - t1), nev, fr.max()))
