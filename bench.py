@@ -148,6 +148,8 @@ def our_arm(args):
         raise SystemExit("launch with torchrun --nproc-per-node %d for --gpus %d" % (args.gpus, args.gpus))
     torch.cuda.set_device(local)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"       # keep NCCL's version banner off stdout: ONE JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     spec = WORKLOADS[args.workload]
     n, d, M, S = spec["n"], spec["d"], (args.candidates or spec["M"]), spec["S"]

@@ -328,9 +328,12 @@ class Context(object):
         return out
 
     def microbench(self, kind, iters=40000):
-        """Measured FP64 roof in TFLOP/s: kind 'dmma' (tensor core) or 'dfma'."""
+        """Measured FP64 roof in TFLOP/s: kind 'dmma' (tensor core) or 'dfma'; or dependent-issue
+        latencies in cycles: 'lat_dfma', 'lat_rcp', 'lat_rsqrt', 'lat_syncthreads', 'lat_mbarrier', 'lat_dmma'."""
+        kinds = {"dmma": 0, "dfma": 1, "lat_dfma": 2, "lat_rcp": 3, "lat_rsqrt": 4, "lat_syncthreads": 5,
+                 "lat_mbarrier": 6, "lat_dmma": 7}
         v = C.c_double()
-        self._check(self._lib.bo_microbench(self._h, 0 if kind == "dmma" else 1, int(iters), C.byref(v)))
+        self._check(self._lib.bo_microbench(self._h, kinds[kind], int(iters), C.byref(v)))
         return v.value
 
     def ozaki_debug(self, S, X, want_acc=True, want_slices=True, extra=False):

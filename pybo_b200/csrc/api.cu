@@ -122,6 +122,7 @@ static void free_all(bo_ctx *ctx) {
     if (ctx->dAppendInfo) { cudaFree(ctx->dAppendInfo); ctx->dAppendInfo = nullptr; }
     if (ctx->dWs) { cudaFree(ctx->dWs); ctx->dWs = nullptr; }
     if (ctx->dCholInfo) { cudaFree(ctx->dCholInfo); ctx->dCholInfo = nullptr; }
+    if (ctx->dCholFlags) { cudaFree(ctx->dCholFlags); ctx->dCholFlags = nullptr; }
     if (ctx->dKss) { cudaFree(ctx->dKss); ctx->dKss = nullptr; }
     if (ctx->dRowScale) { cudaFree(ctx->dRowScale); ctx->dRowScale = nullptr; }
     if (ctx->dRowExp) { cudaFree(ctx->dRowExp); ctx->dRowExp = nullptr; }

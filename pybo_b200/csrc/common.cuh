@@ -63,6 +63,8 @@ struct bo_ctx {
     size_t append_capacity = 0, appendinfo_capacity = 0;
     double *dCholDinv = nullptr;   // stand-alone bo_cholesky scratch
     int *dCholInfo = nullptr;
+    int *dCholFlags = nullptr;     // per (matrix, panel) 'diagonal block factored' flags of the fused step kernel
+    size_t cholflags_capacity = 0;
     size_t choldinv_capacity = 0, cholinfo_capacity = 0;
     std::vector<double> h_rho, h_sn2, h_bias, h_ell;
     std::vector<int> h_info;

@@ -56,30 +56,38 @@ int bo_linalg_gram(bo_ctx *ctx, int kernel, int n, int np, int dp, int S, const 
 // 64 x 64 diagonal block: factor in shared memory (one barrier per column) and
 // invert the factor (needed by the panel solve and by W = L^-1).
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) potrf64_kernel(double *A, int ld, int64_t strideA, int kblk,
-                                                      double *dinv, int64_t strideD, int *info) {
-    // Register-resident factorisation of a 64 x 64 diagonal block and of its inverse.
-    // Thread (ty, tx) owns a[ty + 16 ai][tx + 16 b] and x[...] (x starts as the identity) in
-    // registers for the whole kernel; per column only the pivot column of `a` and the pivot row
-    // of `x` are broadcast through double-buffered shared memory (one barrier per column).
-    // Columns stay unscaled (a[i][j] = L[i][j] sqrt(d_j)), so the multiplier m_ij = a[i][j] / d_j
-    // serves both the trailing update a[i][k] -= m_ij a[k][j] and the forward substitution
-    // x[i][c] -= m_ij x[j][c]; rows of x are scaled by 1 / L[i][i] at the end.
-    __shared__ double colbuf[2][64];
-    __shared__ double rowbuf[2][64];
-    __shared__ double rs[64];
-    __shared__ int bad;
+typedef DTile<64, 64, 32, 16, 3, true> T64NT8;       // 256-thread variant for the fused panel step
+
+// Register-resident factorisation of a 64 x 64 diagonal block and of its inverse by one CTA of
+// 256 threads.  Thread (ty, tx) owns a[ty + 16 ai][tx + 16 b] and x[...] (x starts as the identity)
+// in registers for the whole factorisation; per column only the pivot column of `a` and the pivot
+// row of `x` are broadcast through double-buffered shared memory (one barrier per column).
+// Columns stay unscaled (a[i][j] = L[i][j] sqrt(d_j)), so the multiplier m_ij = a[i][j] / d_j
+// serves both the trailing update a[i][k] -= m_ij a[k][j] and the forward substitution
+// x[i][c] -= m_ij x[j][c]; rows of x are scaled by 1 / L[i][i] at the end.
+// `ra` holds the (already updated) block on entry; L goes to Ab, the inverse to Db.
+struct PotrfSmem {
+    double colbuf[2][64];
+    double rowbuf[2][64];
+    double rs[64];
+    int bad;
+};
+
+// (A split arrive / wait mbarrier version that publishes the next pivot column before finishing the
+//  rank-1 update was measured and is slower: the loop is bound by instruction issue -- ~170 SASS
+//  instructions per column per warp, two warps per scheduler -- not by the barrier: tools/latency.py
+//  gives 67 cycles for the smem -> __syncthreads -> smem round trip, 113 for the mbarrier one.)
+__device__ __forceinline__ void potrf64_regs(double (&ra)[4][4], PotrfSmem &sm, double *Ab, int ld, double *Db,
+                                             int *info, int kblk) {
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-    double *Ab = A + blockIdx.x * strideA + (int64_t)kblk * 64 * (ld + 1);
-    double *Db = dinv + blockIdx.x * strideD + (int64_t)kblk * 4096;
-    if (tid == 0) bad = 0;
-    double ra[4][4], rx[4][4];
+    double rx[4][4];
+    if (tid == 0) sm.bad = 0;
 #pragma unroll
     for (int ai = 0; ai < 4; ++ai)
 #pragma unroll
         for (int b = 0; b < 4; ++b) {
             const int i = ty + 16 * ai, k = tx + 16 * b;
-            ra[ai][b] = (k <= i) ? Ab[(int64_t)i * ld + k] : 0.0;
+            if (k > i) ra[ai][b] = 0.0;
             rx[ai][b] = (i == k) ? 1.0 : 0.0;
         }
     int p = 0;
@@ -94,38 +102,38 @@ __global__ void __launch_bounds__(256) potrf64_kernel(double *A, int ld, int64_t
             const int j = 16 * jb + jl;
             if (tx == jl) {            // owners of column j of a
 #pragma unroll
-                for (int ai = jb; ai < 4; ++ai) colbuf[p][ty + 16 * ai] = ra[ai][jb];
+                for (int ai = jb; ai < 4; ++ai) sm.colbuf[p][ty + 16 * ai] = ra[ai][jb];
             }
             if (ty == jl) {            // owners of row j of x (columns <= j)
 #pragma unroll
-                for (int b = 0; b <= jb; ++b) rowbuf[p][tx + 16 * b] = rx[jb][b];
+                for (int b = 0; b <= jb; ++b) sm.rowbuf[p][tx + 16 * b] = rx[jb][b];
             }
             __syncthreads();
-            const double d = colbuf[p][j];
+            const double d = sm.colbuf[p][j];
             const double r = rsqrt(d);
             const double r2 = r * r;
             if (tid == 0) {
-                rs[j] = r;
-                if (!(d > 0.0) && bad == 0) bad = j + 1;
+                sm.rs[j] = r;
+                if (!(d > 0.0) && sm.bad == 0) sm.bad = j + 1;
             }
             const bool tx_gt_jl = tx > jl, ty_gt_jl = ty > jl;
 #pragma unroll
             for (int ai = jb; ai < 4; ++ai) {
                 const bool row_on = (ai > jb) || ty_gt_jl;          // i > j
                 if (!row_on) continue;
-                const double mij = colbuf[p][ty + 16 * ai] * r2;
+                const double mij = sm.colbuf[p][ty + 16 * ai] * r2;
 #pragma unroll
                 for (int b = 0; b < 4; ++b) {
                     // trailing update: j < k <= i
                     if (b >= jb && b <= ai) {
                         const bool k_gt_j = (b > jb) || tx_gt_jl;
                         const bool k_le_i = (b < ai) || tx_le_ty;
-                        if (k_gt_j && k_le_i) ra[ai][b] = fma(-mij, colbuf[p][tx + 16 * b], ra[ai][b]);
+                        if (k_gt_j && k_le_i) ra[ai][b] = fma(-mij, sm.colbuf[p][tx + 16 * b], ra[ai][b]);
                     }
                     // forward substitution on the identity: k <= j
                     if (b <= jb) {
                         const bool k_le_j = (b < jb) || !tx_gt_jl;
-                        if (k_le_j) rx[ai][b] = fma(-mij, rowbuf[p][tx + 16 * b], rx[ai][b]);
+                        if (k_le_j) rx[ai][b] = fma(-mij, sm.rowbuf[p][tx + 16 * b], rx[ai][b]);
                     }
                 }
             }
@@ -138,13 +146,112 @@ __global__ void __launch_bounds__(256) potrf64_kernel(double *A, int ld, int64_t
 #pragma unroll
         for (int b = 0; b < 4; ++b) {
             const int i = ty + 16 * ai, k = tx + 16 * b;
-            Ab[(int64_t)i * ld + k] = (k <= i) ? ra[ai][b] * rs[k] : 0.0;      // diag: d / sqrt(d)
-            Db[i * 64 + k] = (k <= i) ? rx[ai][b] * rs[i] : 0.0;
+            Ab[(int64_t)i * ld + k] = (k <= i) ? ra[ai][b] * sm.rs[k] : 0.0;      // diag: d / sqrt(d)
+            Db[i * 64 + k] = (k <= i) ? rx[ai][b] * sm.rs[i] : 0.0;
         }
-    if (tid == 0 && bad != 0) atomicCAS(&info[blockIdx.x], 0, kblk * 64 + bad);
+    if (tid == 0 && sm.bad != 0) atomicCAS(info, 0, kblk * 64 + sm.bad);
 }
 
-#define POTRF_SMEM 0
+// One step of the blocked factorisation in ONE launch (the serial chain of the algorithm):
+//   CTA 0      : D = A_cc - L_{c,c-1} L_{c,c-1}^T (panel c-1, if any), factor D, invert it, raise flag[c];
+//   CTA x >= 1 : R = A_ic - L_{i,c-1} L_{c,c-1}^T for row tile i = c + x (DMMA), then -- once the flag is
+//                up -- L_ic = R Dinv_c^T.
+// The column update of the tiles below the diagonal overlaps the factorisation of the diagonal block;
+// CTA 0 never waits and is dispatched before the CTAs that wait for it, so the spin cannot deadlock.
+__global__ void __launch_bounds__(256)
+chol_step_kernel(double *A, int ld, int64_t strideA, int c, double *dinv, int64_t strideD, int *info, int *flags,
+                 int nblk) {
+    extern __shared__ __align__(16) double smem[];
+    const int tid = threadIdx.x;
+    double *Az = A + blockIdx.z * strideA;
+    double *Db = dinv + blockIdx.z * strideD + (int64_t)c * 4096;
+    int *flag = flags + blockIdx.z * nblk + c;
+    const bool has_prev = c > 0;
+    if (blockIdx.x == 0) {
+        PotrfSmem &sm = *reinterpret_cast<PotrfSmem *>(smem);
+        double *P = smem + (sizeof(PotrfSmem) + 7) / 8;           // [64][65] copy of L_{c,c-1}
+        const int tx = tid & 15, ty = tid >> 4;
+        double *Ab = Az + (int64_t)c * 64 * (ld + 1);
+        double ra[4][4];
+#pragma unroll
+        for (int ai = 0; ai < 4; ++ai)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) ra[ai][b] = Ab[(int64_t)(ty + 16 * ai) * ld + tx + 16 * b];
+        if (has_prev) {
+            const double *Lp = Az + (int64_t)c * 64 * ld + (int64_t)(c - 1) * 64;
+            for (int e = tid; e < 4096; e += 256) P[(e >> 6) * 65 + (e & 63)] = Lp[(int64_t)(e >> 6) * ld + (e & 63)];
+            __syncthreads();
+#pragma unroll 4
+            for (int k = 0; k < 64; ++k) {
+                double pa[4], pb[4];
+#pragma unroll
+                for (int ai = 0; ai < 4; ++ai) pa[ai] = P[(ty + 16 * ai) * 65 + k];
+#pragma unroll
+                for (int b = 0; b < 4; ++b) pb[b] = P[(tx + 16 * b) * 65 + k];
+#pragma unroll
+                for (int ai = 0; ai < 4; ++ai)
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) ra[ai][b] = fma(-pa[ai], pb[b], ra[ai][b]);
+            }
+        }
+        potrf64_regs(ra, sm, Ab, ld, Db, info + blockIdx.z, c);
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(flag), "r"(1) : "memory");
+        return;
+    }
+    typedef T64NT8 T;
+    const int i = c + blockIdx.x;
+    double *C = Az + (int64_t)i * 64 * ld + (int64_t)c * 64;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int wm = warp / T::WARPS_N, wn = warp % T::WARPS_N;
+    const int g = lane >> 2, t = lane & 3;
+    double acc[T::MI][T::NI][2];
+    if (has_prev) {
+#pragma unroll
+        for (int mi = 0; mi < T::MI; ++mi)
+#pragma unroll
+            for (int ni = 0; ni < T::NI; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+        const double *Li = Az + (int64_t)i * 64 * ld + (int64_t)(c - 1) * 64;
+        const double *Lc = Az + (int64_t)c * 64 * ld + (int64_t)(c - 1) * 64;
+        T::mainloop(acc, Li, ld, Lc, ld, 0, 64, smem);
+#pragma unroll
+        for (int mi = 0; mi < T::MI; ++mi)
+#pragma unroll
+            for (int ni = 0; ni < T::NI; ++ni) {
+                const int r = wm * T::WM + mi * 8 + g, cc = wn * T::WN + ni * 8 + 2 * t;
+                double2 *dst = reinterpret_cast<double2 *>(&C[(int64_t)r * ld + cc]);
+                double2 v = *dst;
+                v.x -= acc[mi][ni][0];
+                v.y -= acc[mi][ni][1];
+                *dst = v;
+            }
+        __threadfence();             // the tile is re-read below through cp.async (L2)
+        __syncthreads();
+    }
+    if (tid == 0) {
+        int v;
+        do {
+            asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+        } while (v == 0);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int mi = 0; mi < T::MI; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < T::NI; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+    T::mainloop(acc, C, ld, Db, 64, 0, 64, smem);
+#pragma unroll
+    for (int mi = 0; mi < T::MI; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < T::NI; ++ni) {
+            const int r = wm * T::WM + mi * 8 + g, cc = wn * T::WN + ni * 8 + 2 * t;
+            *reinterpret_cast<double2 *>(&C[(int64_t)r * ld + cc]) = make_double2(acc[mi][ni][0], acc[mi][ni][1]);
+        }
+}
+
+#define CHOL_STEP_SMEM (T64NT8::SMEM_BYTES > (int)(sizeof(PotrfSmem) + 8 + 64 * 65 * 8) ? T64NT8::SMEM_BYTES : (int)(sizeof(PotrfSmem) + 8 + 64 * 65 * 8))
+
 
 // Lower-triangular tile enumeration for the trailing update.
 template <class T>
@@ -192,45 +299,20 @@ static int set_smem(bo_ctx *ctx, K kernel, int bytes) {
 }
 
 // In-place lower Cholesky of `batch` padded np x np matrices (np % 64 == 0).
-// Right-looking with a one-panel lookahead: at step k the main (high-priority) stream updates only
-// block column k+1 with panel k and goes straight on to factor and solve panel k+1, while the rest
-// of the trailing update of step k runs on the side stream.
+// Right-looking with a one-panel lookahead: step c (chol_step_kernel, main high-priority stream)
+// applies panel c-1 to block column c, factors the diagonal block and solves the panel in one
+// launch, while the rest of the trailing update of panel c-1 (columns > c) runs on the side stream.
 int bo_linalg_cholesky(bo_ctx *ctx, int np, int batch, double *A, double *dinv, int *dInfo) {
     const int nblk = np / BO_NB;
     const int64_t strideA = (int64_t)np * np, strideD = (int64_t)nblk * 4096;
     cudaStream_t main = ctx->stream, side = ctx->stream2;
+    BO_TRY(bo_reserve(ctx, &ctx->dCholFlags, &ctx->cholflags_capacity, (size_t)batch * nblk));
     BO_CUDA(ctx, cudaMemsetAsync(dInfo, 0, sizeof(int) * batch, main));
-    auto potrf = [&](int k) -> int {
-        BO_LAUNCH(ctx, "potrf64_kernel");
-        potrf64_kernel<<<batch, 256, 0, main>>>(A, np, strideA, k, dinv, strideD, dInfo);
-        BO_CHECK_LAUNCH(ctx);
-        return BO_OK;
-    };
-    auto trsm = [&](int k) -> int {     // L_ik = A_ik Dinv_k^T for i > k
-        const int T = nblk - k - 1;
-        double *panel = A + (int64_t)(k + 1) * BO_NB * np + (int64_t)k * BO_NB;
-        DGemmParams p = {};
-        p.A = panel; p.lda = np; p.strideA = strideA;
-        p.B = dinv + (int64_t)k * 4096; p.ldb = 64; p.strideB = strideD;
-        p.C = panel; p.ldc = np; p.strideC = strideA;
-        p.inner = batch; p.tiles_m = T; p.tiles_n = 1; p.K = BO_NB; p.krule = KR_FULL;
-        p.alpha = 1.0; p.beta = 0.0;
-        BO_LAUNCH(ctx, "chol_trsm_kernel");
-        dgemm_kernel<T64NT><<<dim3(T, 1, batch), T64NT::NTHREADS, T64NT::SMEM_BYTES, main>>>(p);
-        BO_CHECK_LAUNCH(ctx);
-        return BO_OK;
-    };
-    auto next_column = [&](int k) -> int {   // A_{i,k+1} -= L_ik L_{k+1,k}^T for i >= k+1 (main stream)
-        const int T = nblk - k - 1;
-        double *panel = A + (int64_t)(k + 1) * BO_NB * np + (int64_t)k * BO_NB;
-        DGemmParams p = {};
-        p.A = panel; p.lda = np; p.strideA = strideA;
-        p.B = panel; p.ldb = np; p.strideB = strideA;
-        p.C = A + (int64_t)(k + 1) * BO_NB * (np + 1); p.ldc = np; p.strideC = strideA;
-        p.inner = batch; p.tiles_m = T; p.tiles_n = 1; p.K = BO_NB; p.krule = KR_FULL;
-        p.alpha = -1.0; p.beta = 1.0;
-        BO_LAUNCH(ctx, "chol_column_kernel");
-        dgemm_kernel<T64NT><<<dim3(T, 1, batch), T64NT::NTHREADS, T64NT::SMEM_BYTES, main>>>(p);
+    BO_CUDA(ctx, cudaMemsetAsync(ctx->dCholFlags, 0, sizeof(int) * batch * nblk, main));
+    auto step = [&](int c) -> int {
+        BO_LAUNCH(ctx, "chol_step_kernel");
+        chol_step_kernel<<<dim3(nblk - c, 1, batch), 256, CHOL_STEP_SMEM, main>>>(A, np, strideA, c, dinv, strideD, dInfo,
+                                                                                  ctx->dCholFlags, nblk);
         BO_CHECK_LAUNCH(ctx);
         return BO_OK;
     };
@@ -249,8 +331,7 @@ int bo_linalg_cholesky(bo_ctx *ctx, int np, int batch, double *A, double *dinv, 
     // the side stream must see everything queued on the main stream so far (the input matrix)
     BO_CUDA(ctx, cudaEventRecord(ctx->ev_consumed[0], main));
     BO_CUDA(ctx, cudaStreamWaitEvent(side, ctx->ev_consumed[0], 0));
-    BO_TRY(potrf(0));
-    if (nblk > 1) BO_TRY(trsm(0));
+    BO_TRY(step(0));
     BO_CUDA(ctx, cudaEventRecord(ctx->ev_sliced[0], main));               // panel 0 ready
     for (int k = 0; k + 1 < nblk; ++k) {
         const int e = k & 1;
@@ -258,9 +339,7 @@ int bo_linalg_cholesky(bo_ctx *ctx, int np, int batch, double *A, double *dinv, 
         BO_TRY(rest(k));
         BO_CUDA(ctx, cudaEventRecord(ctx->ev_consumed[e], side));          // rest(k) done
         if (k >= 1) BO_CUDA(ctx, cudaStreamWaitEvent(main, ctx->ev_consumed[e ^ 1], 0));   // rest(k-1) touched column k+1
-        BO_TRY(next_column(k));
-        BO_TRY(potrf(k + 1));
-        if (k + 2 < nblk) BO_TRY(trsm(k + 1));
+        BO_TRY(step(k + 1));
         BO_CUDA(ctx, cudaEventRecord(ctx->ev_sliced[e ^ 1], main));       // panel k+1 ready
     }
     if (nblk > 1) BO_CUDA(ctx, cudaStreamWaitEvent(main, ctx->ev_consumed[(nblk - 2) & 1], 0));
@@ -462,6 +541,7 @@ int bo_linalg_finish_fit(bo_ctx *ctx) {
 
 int bo_linalg_init(bo_ctx *ctx) {
     BO_TRY(set_smem(ctx, dgemm_kernel<T64NT>, T64NT::SMEM_BYTES));
+    BO_TRY(set_smem(ctx, chol_step_kernel, CHOL_STEP_SMEM));
     BO_TRY(set_smem(ctx, syrk_tri_kernel<T64NT>, T64NT::SMEM_BYTES));
     BO_TRY(set_smem(ctx, trtri_node_kernel<0>, T64NN::SMEM_BYTES));
     BO_TRY(set_smem(ctx, trtri_node_kernel<1>, T64NN::SMEM_BYTES));

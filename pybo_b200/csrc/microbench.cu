@@ -34,9 +34,77 @@ __global__ void __launch_bounds__(256) dfma_peak_kernel(int iters, double *sink)
     if (s == 123.456) sink[0] = s;
 }
 
+// Dependent-issue latencies (cycles per operation, one warp / one CTA, clock64 around a dependent
+// chain): the serial chain of the Cholesky diagonal-block kernel is made of exactly these.
+//   kind 2: DFMA   3: 1/x (__drcp_rn)   4: rsqrt(double)   5: smem write -> __syncthreads -> read (256 threads)
+//   kind 6: smem write -> mbarrier arrive / wait -> read (256 threads)   7: DMMA m8n8k4 dependent
+__global__ void __launch_bounds__(256) latency_kernel(int kind, int iters, double *out) {
+    __shared__ double buf[2][64];
+    __shared__ unsigned long long bar;
+    const int tid = threadIdx.x;
+    double x = 1.0 + 1e-3 * tid, y = 1.0000001;
+    const uint32_t bar_s = (uint32_t)__cvta_generic_to_shared(&bar);
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar_s), "r"(256));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    buf[0][tid & 63] = x;
+    __syncthreads();
+    uint32_t phase = 0;
+    const long long t0 = clock64();
+    if (kind == 2) {
+        for (int i = 0; i < iters; ++i) x = fma(x, y, 1e-9);
+    } else if (kind == 3) {
+        for (int i = 0; i < iters; ++i) x = __drcp_rn(x) + 0.5;
+    } else if (kind == 4) {
+        for (int i = 0; i < iters; ++i) x = rsqrt(x) + 0.5;
+    } else if (kind == 5) {
+        for (int i = 0; i < iters; ++i) {
+            if (tid == (i & 63)) buf[i & 1][tid] = x;
+            __syncthreads();
+            x += buf[i & 1][i & 63];
+        }
+    } else if (kind == 6) {
+        for (int i = 0; i < iters; ++i) {
+            if (tid == (i & 63)) buf[i & 1][tid] = x;
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_s) : "memory");
+            asm volatile(
+                "{\n\t"
+                ".reg .pred P1;\n\t"
+                "WAIT_%=:\n\t"
+                "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+                "@P1 bra.uni DONE_%=;\n\t"
+                "bra.uni WAIT_%=;\n\t"
+                "DONE_%=:\n\t"
+                "}" ::"r"(bar_s), "r"(phase) : "memory");
+            phase ^= 1;
+            x += buf[i & 1][i & 63];
+        }
+    } else {
+        double c0 = x, c1 = y;
+        for (int i = 0; i < iters; ++i) dmma884(c0, c1, c0, y);
+        x = c0 + c1;
+    }
+    const long long t1 = clock64();
+    if (tid == 0) out[0] = (double)(t1 - t0) / iters;
+    if (x == 123.456) out[1] = x;
+}
+
 extern "C" int bo_microbench(bo_ctx *ctx, int kind, int iters, double *tflops) {
     if (!ctx || !tflops) return BO_ERR_ARG;
     BO_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (kind >= 2) {
+        double *out = nullptr, h[2] = {0.0, 0.0};
+        BO_CUDA(ctx, cudaMalloc(&out, 2 * sizeof(double)));
+        ctx->launches++;
+        latency_kernel<<<1, (kind == 5 || kind == 6) ? 256 : 32, 0, ctx->stream>>>(kind, iters, out);
+        cudaError_t e = cudaStreamSynchronize(ctx->stream);
+        if (e == cudaSuccess) e = cudaMemcpy(h, out, sizeof(h), cudaMemcpyDeviceToHost);
+        cudaFree(out);
+        if (e != cudaSuccess) return bo_set_err(ctx, BO_ERR_CUDA, "bo_microbench: %s", cudaGetErrorString(e));
+        *tflops = h[0];
+        return BO_OK;
+    }
     double *sink = nullptr;
     BO_CUDA(ctx, cudaMalloc(&sink, sizeof(double)));
     cudaEvent_t e0, e1;
