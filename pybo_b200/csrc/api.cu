@@ -128,6 +128,10 @@ static void free_all(bo_ctx *ctx) {
     if (ctx->dRowExp) { cudaFree(ctx->dRowExp); ctx->dRowExp = nullptr; }
     if (ctx->dBlkIdx) { cudaFree(ctx->dBlkIdx); ctx->dBlkIdx = nullptr; }
     if (ctx->th.dBestIdx) { cudaFree(ctx->th.dBestIdx); ctx->th.dBestIdx = nullptr; }
+    if (ctx->th.ozTheta) { cudaFree(ctx->th.ozTheta); ctx->th.ozTheta = nullptr; }
+    if (ctx->th.ozPhi) { cudaFree(ctx->th.ozPhi); ctx->th.ozPhi = nullptr; }
+    if (ctx->th.ozRowScale) { cudaFree(ctx->th.ozRowScale); ctx->th.ozRowScale = nullptr; }
+    if (ctx->th.ozWp) { cudaFree(ctx->th.ozWp); ctx->th.ozWp = nullptr; }
 }
 
 static void prof_drain(bo_ctx *ctx) {
@@ -480,6 +484,15 @@ extern "C" int bo_thompson_set(bo_ctx *ctx, int ndraw, int nW, int m, int d, con
     BO_CUDA(ctx, cudaMemcpyAsync(th.bias, bias, sizeof(double) * ndraw, cudaMemcpyHostToDevice, st));
     BO_CUDA(ctx, cudaStreamSynchronize(st));
     th.ndraw = ndraw; th.nW = nW; th.m = m; th.d = d;
+    th.oz_ready = false;
+    th.h_theta.clear();
+    if (nW == 1) {      // host copies for the int8-slice path (Theta is sliced on the host)
+        th.h_theta.assign(theta, theta + (size_t)ndraw * m);
+        th.h_scale.assign(scale, scale + ndraw);
+        th.h_bias.assign(bias, bias + ndraw);
+        th.h_W.assign(W, W + (size_t)m * d);
+        th.h_b.assign(b, b + m);
+    }
     // transposed, zero-padded theta for the shared-basis tensor-core path
     if (th.thetaT) { cudaFree(th.thetaT); th.thetaT = nullptr; }
     if (nW == 1) {

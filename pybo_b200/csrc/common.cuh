@@ -31,6 +31,13 @@ struct bo_thompson_state {
     double *W = nullptr, *b = nullptr, *theta = nullptr, *scale = nullptr, *bias = nullptr;
     double *thetaT = nullptr;   // (m padded to 16) x (ndraw padded to 256), shared-basis contraction operand
     int ndp = 0;
+    // int8-slice path of the shared-basis batch (ozaki.cu): host copies, slice planes of Theta, padded basis
+    std::vector<double> h_theta, h_scale, h_bias, h_W, h_b;
+    int8_t *ozTheta = nullptr, *ozPhi = nullptr;
+    double *ozRowScale = nullptr, *ozRowBias = nullptr, *ozWp = nullptr, *ozBp = nullptr;
+    size_t ozTheta_capacity = 0, ozPhi_capacity = 0, ozRow_capacity = 0, ozWp_capacity = 0;
+    int oz_mp = 0, oz_ndp = 0, oz_dpad = 0, oz_S = 0, oz_extra = 0, oz_mp_hint = 0;
+    bool oz_ready = false;
 };
 
 struct bo_ctx {
@@ -213,6 +220,10 @@ int bo_ozaki_slice(bo_ctx *ctx, int s, int S, const double *dXc, int64_t c0, int
                    cudaStream_t stream);
 int bo_ozaki_contract(bo_ctx *ctx, int s, int S, int mcp, int buf, double *mu, double *s2, int32_t *dbg);
 int bo_ozaki_reserve(bo_ctx *ctx, int S, int mcp_max, int nbuf);
+bool bo_thompson_ozaki_usable(bo_ctx *ctx, int64_t M);
+int64_t bo_thompson_ozaki_blocks(int64_t M);
+int bo_thompson_ozaki_run(bo_ctx *ctx, int64_t M, const double *dXc, double *dOut, double *blkval, int64_t *blkidx,
+                          int64_t blk_ld);
 
 // one scoring / prediction pass over M device-resident candidates
 struct ScoreRequest {

@@ -24,6 +24,12 @@
 
 #include "common.cuh"
 
+static int ctx_padded_dim(int d) {
+    int dp = 2;
+    while (dp < d) dp *= 2;
+    return dp;
+}
+
 #define OZ_BM 128        // candidates per CTA tile (MMA M, TMEM lanes)
 #define OZ_BN 64         // rows of W per block (MMA N)
 #define OZ_BK 64         // k bytes per stage row (one 64B swizzle atom, two K=32 MMAs)
@@ -480,12 +486,21 @@ __global__ void oz_halfsq_kernel(const double *__restrict__ Xs, int rows, int dp
 // the contraction kernel
 // ---------------------------------------------------------------------------
 struct OzParams {
-    int np, S, nstages, ntiles, nacc, tiles_per_group;
+    int nrb, nkb, full_k;     // 64-row blocks of the B operand, 64-wide k blocks, 1: every unit walks all k blocks
+    int S, nstages, ntiles, nacc, tiles_per_group;
     int mcp;
-    const double *rowscale;   // np
-    double *qpart;            // [np/64][mcp] partial |v|^2 per row block
+    const double *rowscale;   // per B row: scale of the reassembled integer
+    double *qpart;            // MODE 0: [nrb][mcp] partial |v|^2 per row block
     int32_t *dbg;             // optional: [rb][g][128][64] accumulators of tile 0
-    const int8_t *kss;        // K*^T slice blocks (oz_kss_block layout)
+    const int8_t *kss;        // A operand slice blocks (oz_kss_block layout)
+    // MODE 1 (Thompson draws: B rows = draws, A = cosine features): f = rowbias + rowscale * contraction
+    const double *rowbias;
+    double *out;              // optional [row][out_ld] values
+    int64_t out_ld, c0;       // leading dimension of out (total candidates), first candidate of this chunk
+    int mc, nrows_live;
+    double *blkval;           // optional per-(row, 32-candidate block) maximum ...
+    int64_t *blkidx;          // ... and its first arg max (global candidate index)
+    int64_t blk_ld, blk0;
 };
 
 // Work unit = (candidate tile, 64-row block of W).  Units are ordered group by group
@@ -505,7 +520,9 @@ __device__ __forceinline__ OzUnit oz_decode(int u, int nb, int T, int ntiles) {
     return o;
 }
 
-template <int S, int EXTRA>
+// MODE 0: scoring (B = slices of the triangular W, k range cut at the diagonal, epilogue reduces |v|^2);
+// MODE 1: Thompson draws (B = slices of Theta, full k range, epilogue writes values / per-draw arg max).
+template <int S, int EXTRA, int MODE>
 __global__ void __launch_bounds__(OZ_THREADS, 1)
 oz_score_kernel(const __grid_constant__ CUtensorMap tmapB, OzParams p) {
     extern __shared__ uint8_t oz_smem_raw[];
@@ -527,7 +544,7 @@ oz_score_kernel(const __grid_constant__ CUtensorMap tmapB, OzParams p) {
     auto tmem_empty = [&](int a) { return bar0 + 8u * (2 * nst + 2 + a); };
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int nb = p.np / OZ_BN;
+    const int nb = p.nrb;
     const int nunits = p.ntiles * nb;
 
     if (warp == 0 && lane == 0) {
@@ -555,13 +572,14 @@ oz_score_kernel(const __grid_constant__ CUtensorMap tmapB, OzParams p) {
             uint32_t phase = 0;
             for (int u = blockIdx.x; u < nunits; u += gridDim.x) {
                 const OzUnit un = oz_decode(u, nb, p.tiles_per_group, p.ntiles);
-                for (int kb = 0; kb <= un.rb; ++kb) {
+                const int klast = (MODE == 1 || p.full_k) ? p.nkb - 1 : un.rb;
+                for (int kb = 0; kb <= klast; ++kb) {
                     mbar_wait(empty_bar(stage), phase ^ 1);
                     mbar_expect_tx(full_bar(stage), stage_bytes);
                     const uint32_t sA = base + stage * stage_bytes;
                     const uint32_t sB = sA + S * OZ_A_SLICE_BYTES;
                     for (int s = 0; s < S; ++s) {
-                        bulk_load(sA + s * OZ_A_SLICE_BYTES, p.kss + oz_kss_block(s, un.tile, kb, p.ntiles, nb),
+                        bulk_load(sA + s * OZ_A_SLICE_BYTES, p.kss + oz_kss_block(s, un.tile, kb, p.ntiles, p.nkb),
                                   OZ_A_SLICE_BYTES, full_bar(stage));
                         tma_load_3d(sB + s * OZ_B_SLICE_BYTES, &tmapB, kb * OZ_BK, un.rb * OZ_BN, s, full_bar(stage));
                     }
@@ -579,7 +597,8 @@ oz_score_kernel(const __grid_constant__ CUtensorMap tmapB, OzParams p) {
                 mbar_wait(tmem_empty(acc), acc_phase ^ 1);    // epilogue has drained this accumulator set
                 tc_fence_after();
                 const uint32_t tacc = tmem_base + (uint32_t)(acc * NG * OZ_BN);
-                for (int kb = 0; kb <= un.rb; ++kb) {
+                const int klast = (MODE == 1 || p.full_k) ? p.nkb - 1 : un.rb;
+                for (int kb = 0; kb <= klast; ++kb) {
                     mbar_wait(full_bar(stage), phase);
                     tc_fence_after();
                     const uint32_t sA = base + stage * stage_bytes;
@@ -602,8 +621,10 @@ oz_score_kernel(const __grid_constant__ CUtensorMap tmapB, OzParams p) {
             double q = 0.0;
             mbar_wait(tmem_full(acc), acc_phase);
             tc_fence_after();
-#pragma unroll 1
-            for (int c0 = 0; c0 < OZ_BN; c0 += 16) {
+            // 16 columns (rows of B) of this thread's candidate: TMEM -> sum_g D_g 256^(G - g) / 256^G.
+            // The first five groups fit int64 (|D_g| < 2^30): shift-adds on the integer pipe and a single
+            // conversion keep the FP64 pipe for the reductions.
+            auto reassemble = [&](int c0, double (&v16)[16]) {
                 int32_t r[NG][16];
 #pragma unroll
                 for (int g = 0; g < NG; ++g) tmem_ld16(lane_base + (uint32_t)(g * OZ_BN + c0), r[g]);
@@ -616,11 +637,8 @@ oz_score_kernel(const __grid_constant__ CUtensorMap tmapB, OzParams p) {
                         for (int i = 0; i < 16; ++i) o[i] = r[g][i];
                     }
                 }
-                const int row0 = un.rb * OZ_BN + c0;
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
-                    // sum_g D_g 256^(G - g): the first five groups fit int64 (|D_g| < 2^30): shift-adds on
-                    // the integer pipe and a single conversion keep the FP64 pipe for the reductions
                     constexpr int GI = G < 4 ? G : 4;
                     long long a = (long long)r[0][i];
 #pragma unroll
@@ -628,17 +646,65 @@ oz_score_kernel(const __grid_constant__ CUtensorMap tmapB, OzParams p) {
                     double v = (double)a;
 #pragma unroll
                     for (int g = GI + 1; g <= G; ++g) v = fma(v, 256.0, (double)r[g][i]);
-                    v *= 1.0 / (double)(1ull << (8 * G));
-                    const double vv = v * __ldg(p.rowscale + row0 + i);
-                    q = fma(vv, vv, q);
+                    v16[i] = v * (1.0 / (double)(1ull << (8 * G)));
+                }
+            };
+            if (MODE == 0) {
+#pragma unroll 1
+                for (int c0 = 0; c0 < OZ_BN; c0 += 16) {
+                    double v16[16];
+                    reassemble(c0, v16);
+                    const int row0 = un.rb * OZ_BN + c0;
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const double vv = v16[i] * __ldg(p.rowscale + row0 + i);
+                        q = fma(vv, vv, q);
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(tmem_empty(acc));
+                if (++acc == nacc) { acc = 0; acc_phase ^= 1; }
+                const int64_t o = (int64_t)un.rb * p.mcp + (int64_t)un.tile * OZ_BM + quarter * 32 + lane;
+                p.qpart[o] = q;
+            } else {
+                // drain all 64 columns into registers first so the accumulators go back to the MMA warp
+                // before the stores and the per-draw arg max
+                double vcol[4][16];
+#pragma unroll
+                for (int cb = 0; cb < 4; ++cb) reassemble(cb * 16, vcol[cb]);
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(tmem_empty(acc));
+                if (++acc == nacc) { acc = 0; acc_phase ^= 1; }
+                const int cand = un.tile * OZ_BM + quarter * 32 + lane;
+#pragma unroll
+                for (int cb = 0; cb < 4; ++cb) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const int row = un.rb * OZ_BN + cb * 16 + i;
+                        const bool live = cand < p.mc && row < p.nrows_live;
+                        const double f = fma(vcol[cb][i], __ldg(p.rowscale + row), __ldg(p.rowbias + row));
+                        if (p.out && live) p.out[(int64_t)row * p.out_ld + p.c0 + cand] = f;
+                        if (p.blkval) {
+                            // first arg max over the warp's 32 consecutive candidates (NaN never wins)
+                            double bv = (live && f == f) ? f : -INFINITY;
+                            int bi = (live && f == f) ? cand : 0x7fffffff;
+#pragma unroll
+                            for (int o = 16; o > 0; o >>= 1) {
+                                const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+                                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                                if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+                            }
+                            if (lane == 0 && row < p.nrows_live) {
+                                const int64_t o = (int64_t)row * p.blk_ld + p.blk0 + un.tile * 4 + quarter;
+                                p.blkval[o] = bv;
+                                p.blkidx[o] = bi == 0x7fffffff ? INT64_MAX : p.c0 + bi;
+                            }
+                        }
+                    }
                 }
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(tmem_empty(acc));
-            if (++acc == nacc) { acc = 0; acc_phase ^= 1; }
-            const int64_t o = (int64_t)un.rb * p.mcp + (int64_t)un.tile * OZ_BM + quarter * 32 + lane;
-            p.qpart[o] = q;
         }
     }
     tc_fence_before();
@@ -705,10 +771,11 @@ static size_t oz_smem_bytes(int S) {
 }
 
 int bo_ozaki_init(bo_ctx *ctx) {
-#define OZ_ATTR(SS) BO_CUDA(ctx, cudaFuncSetAttribute(oz_score_kernel<SS, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)oz_smem_bytes(SS))); \
-                    BO_CUDA(ctx, cudaFuncSetAttribute(oz_score_kernel<SS, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)oz_smem_bytes(SS)))
+#define OZ_ATTR1(SS, EE, MM) BO_CUDA(ctx, cudaFuncSetAttribute(oz_score_kernel<SS, EE, MM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)oz_smem_bytes(SS)))
+#define OZ_ATTR(SS) OZ_ATTR1(SS, 0, 0); OZ_ATTR1(SS, 1, 0); OZ_ATTR1(SS, 0, 1); OZ_ATTR1(SS, 1, 1)
     OZ_ATTR(2); OZ_ATTR(3); OZ_ATTR(4); OZ_ATTR(5); OZ_ATTR(6); OZ_ATTR(7);
 #undef OZ_ATTR
+#undef OZ_ATTR1
 #define OZ_KATTR(DP, SS) BO_CUDA(ctx, cudaFuncSetAttribute(oz_kstar_slices_fast_kernel<DP, SS>, cudaFuncAttributeMaxDynamicSharedMemorySize, SS * OZ_A_SLICE_BYTES))
 #define OZ_KATTR_ALL(DP) OZ_KATTR(DP, 2); OZ_KATTR(DP, 3); OZ_KATTR(DP, 4); OZ_KATTR(DP, 5)
     OZ_KATTR_ALL(2); OZ_KATTR_ALL(4); OZ_KATTR_ALL(8); OZ_KATTR_ALL(16);
@@ -887,8 +954,9 @@ int bo_ozaki_contract(bo_ctx *ctx, int s, int S, int mcp, int buf, double *mu, d
         size_t need = (size_t)nb * mcp;
         BO_TRY(bo_reserve(ctx, &ctx->dOzQ, &ctx->ozpart_capacity, need));
     }
-    OzParams p;
-    p.np = np; p.S = S; p.nstages = oz_stage_count(S); p.ntiles = mcp / OZ_BM; p.mcp = mcp;
+    OzParams p = {};
+    p.nrb = np / OZ_BN; p.nkb = np / OZ_BK; p.full_k = 0;
+    p.S = S; p.nstages = oz_stage_count(S); p.ntiles = mcp / OZ_BM; p.mcp = mcp;
     const bool extra = ctx->oz_extra;
     // exact int32 accumulation: up to S digit pairs per group, |digit| <= 128, k range <= np
     if ((int64_t)np * S >= (1 << 17))
@@ -908,8 +976,8 @@ int bo_ozaki_contract(bo_ctx *ctx, int s, int S, int mcp, int buf, double *mu, d
     {
         BO_LAUNCH(ctx, "oz_score_kernel");
         switch (S) {
-#define OZ_RUN(SS) case SS: if (extra) oz_score_kernel<SS, 1><<<grid, OZ_THREADS, oz_smem_bytes(SS), ctx->stream>>>(tmB, p); \
-                         else oz_score_kernel<SS, 0><<<grid, OZ_THREADS, oz_smem_bytes(SS), ctx->stream>>>(tmB, p); break
+#define OZ_RUN(SS) case SS: if (extra) oz_score_kernel<SS, 1, 0><<<grid, OZ_THREADS, oz_smem_bytes(SS), ctx->stream>>>(tmB, p); \
+                         else oz_score_kernel<SS, 0, 0><<<grid, OZ_THREADS, oz_smem_bytes(SS), ctx->stream>>>(tmB, p); break
             OZ_RUN(2); OZ_RUN(3); OZ_RUN(4); OZ_RUN(5); OZ_RUN(6); OZ_RUN(7);
 #undef OZ_RUN
             default: return bo_set_err(ctx, BO_ERR_ARG, "int8 path needs 2..7 slices, got %d", S);
@@ -922,6 +990,302 @@ int bo_ozaki_contract(bo_ctx *ctx, int s, int S, int mcp, int buf, double *mu, d
             nb, ctx->oz_mu_rows[buf], mcp, ctx->dOzQ, ctx->dOzMu + (size_t)buf * ctx->ozmu_stride, ctx->h_rho[s],
             ctx->h_bias[s], mu, s2);
         BO_CHECK_LAUNCH(ctx);
+    }
+    return BO_OK;
+}
+
+// ---------------------------------------------------------------------------
+// Thompson draws on the same int8 machinery (shared spectral basis):
+//   F[r][i] = bias_r + scale_r * sum_j cos(w_j . x_i + b_j) theta_r[j]
+// A operand = balanced base-256 digits of the cosine features (values in [-1, 1], generated and
+// sliced on the fly per candidate chunk), B operand = digits of Theta (rows = draws, one exponent per
+// draw, sliced once on the host when the draws are set), K = features.  MODE 1 of the contraction
+// kernel writes the values and / or the per-draw first arg max.
+// ---------------------------------------------------------------------------
+// cos(a) for |a| < ~1e5: Cody-Waite reduction by pi/2 in two pieces, Taylor polynomials on |r| <= pi/4
+// (cos to r^16, sin to r^15: truncation < 2e-17); no FP64 <-> integer conversion instructions.
+__constant__ double OZ_COS_C[8] = {4.779477332387385e-14, -1.1470745597729725e-11, 2.08767569878681e-09, -2.755731922398589e-07,
+                                   2.48015873015873e-05, -0.001388888888888889, 0.041666666666666664, -0.5};
+__constant__ double OZ_SIN_C[7] = {-7.647163731819816e-13, 1.6059043836821613e-10, -2.505210838544172e-08, 2.7557319223985893e-06,
+                                   -0.0001984126984126984, 0.008333333333333333, -0.16666666666666666};
+
+__device__ __forceinline__ void oz_cos4(const double (&a)[4], double (&out)[4]) {
+    double r[4], r2[4], pc[4], ps[4];
+    int q[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const double zz = fma(a[e], 0.6366197723675814, 6755399441055744.0);       // a * 2/pi + 1.5 * 2^52
+        q[e] = __double2loint(zz);
+        const double qd = zz - 6755399441055744.0;
+        r[e] = fma(-qd, 1.5707963267948966, a[e]);
+        r[e] = fma(-qd, 6.123233995736766e-17, r[e]);
+        r2[e] = r[e] * r[e];
+        pc[e] = OZ_COS_C[0];
+        ps[e] = OZ_SIN_C[0];
+    }
+#pragma unroll
+    for (int c = 1; c < 8; ++c) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) pc[e] = fma(pc[e], r2[e], OZ_COS_C[c]);
+    }
+#pragma unroll
+    for (int c = 1; c < 7; ++c) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) ps[e] = fma(ps[e], r2[e], OZ_SIN_C[c]);
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const double cs = fma(pc[e], r2[e], 1.0);                 // cos r
+        const double sn = fma(ps[e] * r2[e], r[e], r[e]);        // sin r
+        const double v = (q[e] & 1) ? sn : cs;                    // cos(r + q pi/2): cs, -sn, -cs, sn
+        out[e] = ((q[e] + 1) & 2) ? -v : v;
+    }
+}
+
+// block: one candidate tile (128 candidates, one per thread) x up to OZ_KS_TILES blocks of 64 features;
+// same staging and layout as oz_kstar_slices_fast_kernel.
+template <int DP, int S>
+__global__ void __launch_bounds__(128)
+oz_cosine_slices_kernel(int m, int mp, int d, const double *__restrict__ Wp, const double *__restrict__ bp,
+                        const double *__restrict__ Xc, int64_t c0, int mc, int mcp, int8_t *__restrict__ Ks) {
+    __shared__ __align__(16) double ws[2][64][DP];
+    __shared__ __align__(16) double bs[2][64];
+    extern __shared__ __align__(16) uint8_t oz_stage[];          // [S][128 rows][64 B]
+    const int tid = threadIdx.x;
+    const int nkb = mp / 64, ntiles = mcp / 128;
+    const int t0 = blockIdx.y * OZ_KS_TILES;
+    const int t1 = (t0 + OZ_KS_TILES < nkb) ? t0 + OZ_KS_TILES : nkb;
+    auto prefetch = [&](int tile, int buf) {
+        const double *src = Wp + (int64_t)tile * 64 * DP;
+        for (int e = tid; e < 64 * DP / 2; e += 128) oz_cp_async16(&ws[buf][0][0] + 2 * e, src + 2 * e);
+        if (tid < 32) oz_cp_async16(&bs[buf][0] + 2 * tid, bp + (int64_t)tile * 64 + 2 * tid);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    prefetch(t0, 0);
+    const int mm = blockIdx.x * 128 + tid;
+    const bool live = mm < mc;
+    double x[DP];
+#pragma unroll
+    for (int k = 0; k < DP; ++k) x[k] = (live && k < d) ? Xc[(c0 + mm) * d + k] : 0.0;
+    const int swz = (tid >> 1) & 3;
+    for (int tile = t0; tile < t1; ++tile) {
+        const int buf = (tile - t0) & 1;
+        if (tile + 1 < t1) {
+            prefetch(tile + 1, buf ^ 1);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
+        __syncthreads();
+        const int j0 = tile * 64;
+#pragma unroll 1
+        for (int sub = 0; sub < 4; ++sub) {
+            const int jj0 = sub * 16;
+            uint32_t wlow[16], wtop[4];
+#pragma unroll
+            for (int q4 = 0; q4 < 4; ++q4) {
+                const int jq = jj0 + 4 * q4;
+                double a[4], cv[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) a[e] = bs[buf][jq + e];
+#pragma unroll
+                for (int k = 0; k < DP; k += 2) {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const double2 w2 = *reinterpret_cast<const double2 *>(&ws[buf][jq + e][k]);
+                        a[e] = fma(x[k], w2.x, a[e]);
+                        a[e] = fma(x[k + 1], w2.y, a[e]);
+                    }
+                }
+                oz_cos4(a, cv);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int i = 4 * q4 + e;
+                    const bool on = live && (j0 + jq + e) < m;
+                    // X = rint(cos * 127 * 2^32) as a 40-bit two's complement integer (low mantissa bits of
+                    // v + 1.5 * 2^52); bytes of X + 0x8080808080, each XOR 0x80, are its balanced digits
+                    const double vv = fma(on ? cv[e] : 0.0, 545460846592.0, 6755399441055744.0);
+                    const uint32_t lo = (uint32_t)__double2loint(vv) + 0x80808080u;
+                    const uint32_t hi = ((uint32_t)__double2hiint(vv) + 0x80u + (lo < 0x80808080u ? 1u : 0u)) & 0xFFu;
+                    wlow[i] = lo ^ 0x80808080u;
+                    const uint32_t top = hi ^ 0x80u;
+                    if (e == 0) wtop[q4] = top;
+                    else wtop[q4] |= top << (8 * e);
+                }
+            }
+            uint8_t *o0 = oz_stage + tid * 64 + ((sub ^ swz) << 4);
+            *reinterpret_cast<uint4 *>(o0) = make_uint4(wtop[0], wtop[1], wtop[2], wtop[3]);
+#pragma unroll
+            for (int s = 1; s < S; ++s) {
+                const uint32_t b = (uint32_t)(4 - s);                   // byte lane holding slice s
+                const uint32_t sel2 = b | ((4u + b) << 4);
+                uint32_t w[4];
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    const uint32_t lo2 = __byte_perm(wlow[4 * g + 0], wlow[4 * g + 1], sel2);
+                    const uint32_t hi2 = __byte_perm(wlow[4 * g + 2], wlow[4 * g + 3], sel2);
+                    w[g] = __byte_perm(lo2, hi2, 0x5410);
+                }
+                *reinterpret_cast<uint4 *>(o0 + s * OZ_A_SLICE_BYTES) = make_uint4(w[0], w[1], w[2], w[3]);
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+            uint4 *dst = reinterpret_cast<uint4 *>(Ks + oz_kss_block(s, blockIdx.x, tile, ntiles, nkb));
+            const uint4 *src = reinterpret_cast<const uint4 *>(oz_stage + s * OZ_A_SLICE_BYTES);
+#pragma unroll
+            for (int e = 0; e < OZ_A_SLICE_BYTES / 16 / 128; ++e) dst[e * 128 + tid] = src[e * 128 + tid];
+        }
+    }
+}
+
+template <int DP>
+static int launch_oz_cosine(bo_ctx *ctx, int S, const double *dXc, int64_t c0, int mc, int mcp) {
+    bo_thompson_state &th = ctx->th;
+    const int nkb = th.oz_mp / 64;
+    const dim3 grid(mcp / 128, (nkb + OZ_KS_TILES - 1) / OZ_KS_TILES);
+    BO_LAUNCH(ctx, "oz_cosine_slices_kernel");
+#define OZ_COS_RUN(SS) case SS: BO_CUDA(ctx, cudaFuncSetAttribute(oz_cosine_slices_kernel<DP, SS>, cudaFuncAttributeMaxDynamicSharedMemorySize, SS * OZ_A_SLICE_BYTES)); \
+                       oz_cosine_slices_kernel<DP, SS><<<grid, 128, SS * OZ_A_SLICE_BYTES, ctx->stream>>>(th.m, th.oz_mp, th.d, th.ozWp, th.ozBp, dXc, c0, mc, mcp, th.ozPhi); break
+    switch (S) {
+        OZ_COS_RUN(3); OZ_COS_RUN(4); OZ_COS_RUN(5);
+        default: return bo_set_err(ctx, BO_ERR_ARG, "Thompson int8 path handles 3..5 slices, got %d", S);
+    }
+#undef OZ_COS_RUN
+    BO_CHECK_LAUNCH(ctx);
+    return BO_OK;
+}
+
+// Level (slices, extra group) for the draws: the truncation error of F_r is ~ 8 sqrt(m) scale_r 2^e_r 256^-S
+// (/32 with the extra group); `tol` is relative to the prior standard deviation of a draw,
+// scale_r sqrt(m / 2) = sqrt(rho) -- the same reference as the scoring path.  (Posterior weights of an
+// ill-conditioned feature system are large and cancel; their exponent, not their sum, sets the error.)
+static void th_oz_choose(bo_ctx *ctx, int *S_out, int *extra_out) {
+    bo_thompson_state &th = ctx->th;
+    const double tol = ctx->prec_tol;
+    if (tol >= 2.0) {
+        int S = (int)tol;
+        *extra_out = (tol - S) >= 0.5;
+        *S_out = S > 5 ? 5 : (S < 3 ? 3 : S);
+        return;
+    }
+    double mx = 0.0;
+    for (size_t i = 0; i < th.h_theta.size(); ++i) mx = fabs(th.h_theta[i]) > mx ? fabs(th.h_theta[i]) : mx;
+    int e = 0;
+    if (mx > 0.0) frexp(mx, &e);
+    const double worst = 8.0 * sqrt((double)th.oz_mp_hint) * ldexp(1.0, e) * sqrt(2.0 / (double)th.m);
+    for (int S = 3; S <= 5; ++S) {
+        const double base = worst * ldexp(1.0, -8 * S);
+        if (base <= tol) { *S_out = S; *extra_out = 0; return; }
+        if (base / 32.0 <= tol) { *S_out = S; *extra_out = 1; return; }
+    }
+    *S_out = 5;
+    *extra_out = 1;
+}
+
+// Slice Theta on the host (ndraw x m values: microseconds) and upload the planes, scales and the padded basis.
+static int th_oz_prepare(bo_ctx *ctx, int S) {
+    bo_thompson_state &th = ctx->th;
+    if (th.oz_ready && th.oz_S == S) return BO_OK;
+    const int mp = bo_round_up(th.m, 64), ndp = bo_round_up(th.ndraw, 64), dpad = ctx_padded_dim(th.d);
+    std::vector<int8_t> planes((size_t)S * ndp * mp, 0);
+    std::vector<double> rs(ndp, 0.0), rb(ndp, 0.0);
+    for (int r = 0; r < th.ndraw; ++r) {
+        const double *t = th.h_theta.data() + (size_t)r * th.m;
+        double mx = 0.0;
+        for (int j = 0; j < th.m; ++j) mx = fabs(t[j]) > mx ? fabs(t[j]) : mx;
+        int e = 0;
+        if (mx > 0.0) frexp(mx, &e);
+        const double sc = ldexp(1.0, -e);
+        for (int j = 0; j < th.m; ++j) {
+            const long long X = llrint(t[j] * sc * 35747322042253312.0);              // 127 * 2^48
+            const unsigned long long Y = (unsigned long long)(X + OZ_DIGIT_BIAS7) ^ (unsigned long long)OZ_DIGIT_BIAS7;
+            for (int s = 0; s < S; ++s) planes[((size_t)s * ndp + r) * mp + j] = (int8_t)(uint8_t)(Y >> (8 * (6 - s)));
+        }
+        rs[r] = th.h_scale[r] * ldexp(1.0, e) / 16129.0;
+        rb[r] = th.h_bias[r];
+    }
+    std::vector<double> wp((size_t)mp * dpad, 0.0), bpv(mp, 0.0);
+    for (int j = 0; j < th.m; ++j) {
+        for (int k = 0; k < th.d; ++k) wp[(size_t)j * dpad + k] = th.h_W[(size_t)j * th.d + k];
+        bpv[j] = th.h_b[j];
+    }
+    BO_TRY(bo_reserve(ctx, &th.ozTheta, &th.ozTheta_capacity, planes.size()));
+    BO_TRY(bo_reserve(ctx, &th.ozRowScale, &th.ozRow_capacity, (size_t)2 * ndp));
+    BO_TRY(bo_reserve(ctx, &th.ozWp, &th.ozWp_capacity, wp.size() + bpv.size()));
+    th.ozRowBias = th.ozRowScale + ndp;
+    th.ozBp = th.ozWp + wp.size();
+    BO_CUDA(ctx, cudaMemcpyAsync(th.ozTheta, planes.data(), planes.size(), cudaMemcpyHostToDevice, ctx->stream));
+    BO_CUDA(ctx, cudaMemcpyAsync(th.ozRowScale, rs.data(), sizeof(double) * ndp, cudaMemcpyHostToDevice, ctx->stream));
+    BO_CUDA(ctx, cudaMemcpyAsync(th.ozRowBias, rb.data(), sizeof(double) * ndp, cudaMemcpyHostToDevice, ctx->stream));
+    BO_CUDA(ctx, cudaMemcpyAsync(th.ozWp, wp.data(), sizeof(double) * wp.size(), cudaMemcpyHostToDevice, ctx->stream));
+    BO_CUDA(ctx, cudaMemcpyAsync(th.ozBp, bpv.data(), sizeof(double) * bpv.size(), cudaMemcpyHostToDevice, ctx->stream));
+    BO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    th.oz_mp = mp; th.oz_ndp = ndp; th.oz_dpad = dpad; th.oz_S = S; th.oz_ready = true;
+    return BO_OK;
+}
+
+// 32-candidate blocks the int8 path reports per draw for M candidates
+int64_t bo_thompson_ozaki_blocks(int64_t M) {
+    const int64_t chunk = 256 * 128;
+    const int64_t full = M / chunk, rem = M - full * chunk;
+    return full * (chunk / 32) + bo_round_up64(rem, 128) / 32;
+}
+
+bool bo_thompson_ozaki_usable(bo_ctx *ctx, int64_t M) {
+    const bo_thompson_state &th = ctx->th;
+    return ctx->prec == BO_PREC_OZAKI && th.nW == 1 && M >= 1024 && !th.h_theta.empty() &&
+           (int64_t)bo_round_up(th.m, 64) * 5 < (1 << 17);
+}
+
+int bo_thompson_ozaki_run(bo_ctx *ctx, int64_t M, const double *dXc, double *dOut, double *blkval, int64_t *blkidx,
+                          int64_t blk_ld) {
+    bo_thompson_state &th = ctx->th;
+    int S = 5, extra = 0;
+    th.oz_mp_hint = bo_round_up(th.m, 64);
+    th_oz_choose(ctx, &S, &extra);
+    BO_TRY(th_oz_prepare(ctx, S));
+    th.oz_extra = extra;
+    const int mp = th.oz_mp, ndp = th.oz_ndp;
+    const int64_t chunk = 256 * 128;
+    const int64_t cap = bo_round_up64(M < chunk ? M : chunk, 128);
+    BO_TRY(bo_reserve(ctx, &th.ozPhi, &th.ozPhi_capacity, (size_t)S * cap * mp));
+    CUtensorMap tmB;
+    BO_TRY(make_tmap(ctx, &tmB, th.ozTheta, mp, ndp, S, OZ_BN));
+    int64_t blk0 = 0;
+    for (int64_t c0 = 0; c0 < M; c0 += chunk) {
+        const int mc = (int)((M - c0) < chunk ? (M - c0) : chunk);
+        const int mcp = bo_round_up(mc, 128);
+        switch (th.oz_dpad) {
+            case 2: BO_TRY(launch_oz_cosine<2>(ctx, S, dXc, c0, mc, mcp)); break;
+            case 4: BO_TRY(launch_oz_cosine<4>(ctx, S, dXc, c0, mc, mcp)); break;
+            case 8: BO_TRY(launch_oz_cosine<8>(ctx, S, dXc, c0, mc, mcp)); break;
+            case 16: BO_TRY(launch_oz_cosine<16>(ctx, S, dXc, c0, mc, mcp)); break;
+            default: BO_TRY(launch_oz_cosine<32>(ctx, S, dXc, c0, mc, mcp)); break;
+        }
+        OzParams p = {};
+        p.nrb = ndp / OZ_BN; p.nkb = mp / OZ_BK; p.full_k = 1;
+        p.S = S; p.nstages = oz_stage_count(S); p.ntiles = mcp / OZ_BM; p.mcp = mcp;
+        p.nacc = (2 * (S + extra) * OZ_BN <= 512) ? 2 : 1;
+        p.tiles_per_group = 64;
+        p.rowscale = th.ozRowScale; p.rowbias = th.ozRowBias; p.kss = th.ozPhi;
+        p.out = dOut; p.out_ld = M; p.c0 = c0; p.mc = mc; p.nrows_live = th.ndraw;
+        p.blkval = blkval; p.blkidx = blkidx; p.blk_ld = blk_ld; p.blk0 = blk0;
+        const int nunits = p.ntiles * p.nrb;
+        const int grid = nunits < ctx->sm_count ? nunits : ctx->sm_count;
+        {
+            BO_LAUNCH(ctx, "oz_thompson_kernel");
+            switch (S) {
+#define OZ_TRUN(SS) case SS: if (extra) oz_score_kernel<SS, 1, 1><<<grid, OZ_THREADS, oz_smem_bytes(SS), ctx->stream>>>(tmB, p); \
+                          else oz_score_kernel<SS, 0, 1><<<grid, OZ_THREADS, oz_smem_bytes(SS), ctx->stream>>>(tmB, p); break
+                OZ_TRUN(3); OZ_TRUN(4); OZ_TRUN(5);
+#undef OZ_TRUN
+                default: return bo_set_err(ctx, BO_ERR_ARG, "Thompson int8 path handles 3..5 slices, got %d", S);
+            }
+            BO_CHECK_LAUNCH(ctx);
+        }
+        blk0 += mcp / 32;
     }
     return BO_OK;
 }

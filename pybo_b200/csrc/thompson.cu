@@ -243,7 +243,10 @@ int bo_thompson_run(bo_ctx *ctx, int64_t M, const double *dXc, double *dOut, dou
     bo_thompson_state &th = ctx->th;
     if (th.ndraw == 0) return bo_set_err(ctx, BO_ERR_STATE, "bo_thompson_eval before bo_thompson_set");
     const bool gemm_path = (th.nW == 1) && (dGrad == nullptr) && th.thetaT != nullptr;
-    const int nb = gemm_path ? (int)((M + TG_BM - 1) / TG_BM) : (int)((M + 127) / 128);
+    // shared basis, values only, int8 path selected: tcgen05 contraction of sliced cosine features (ozaki.cu)
+    const bool oz_path = gemm_path && bo_thompson_ozaki_usable(ctx, M);
+    const int nb = oz_path ? (int)bo_thompson_ozaki_blocks(M)
+                           : (gemm_path ? (int)((M + TG_BM - 1) / TG_BM) : (int)((M + 127) / 128));
     double *blkval = nullptr;
     int64_t *blkidx = nullptr;
     if (dBestVal != nullptr) {
@@ -257,7 +260,9 @@ int bo_thompson_run(bo_ctx *ctx, int64_t M, const double *dXc, double *dOut, dou
         blkval = ctx->dBlkVal;
         blkidx = ctx->dBlkIdx;
     }
-    if (gemm_path) {
+    if (oz_path) {
+        BO_TRY(bo_thompson_ozaki_run(ctx, M, dXc, dOut, blkval, blkidx, nb));
+    } else if (gemm_path) {
         BO_LAUNCH(ctx, "thompson_gemm_kernel");
         thompson_gemm_kernel<<<dim3(nb, th.ndp / TG_BN), 256, TG_SMEM_BYTES, ctx->stream>>>(
             th.m, th.d, th.ndraw, th.ndp, th.W, th.b, th.thetaT, th.scale, th.bias, M, dXc, dOut, blkval, blkidx);

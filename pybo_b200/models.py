@@ -501,11 +501,27 @@ class ThompsonBatch(object):
             self.theta = noise
         self._ctx = None
 
+    _precision = ("fp64", 1e-9)
+
+    def set_precision(self, path="fp64", tol=1e-8):
+        """'fp64': FP64 tensor-core contraction with on-the-fly cosine features (default); 'int8': the
+        features and Theta are cut into balanced base-256 int8 slices and contracted on tcgen05 (batches of
+        >= 1024 candidates; `tol` is the target error relative to a draw's own scale, >= 2 pins the level)."""
+        if path not in ("fp64", "int8"):
+            raise ValueError("precision path must be 'fp64' or 'int8'")
+        self._precision = (path, float(tol))
+        if self._ctx is not None:
+            self._ctx.set_precision(1 if path == "int8" else 0, float(tol))
+        return self
+
     def _context(self):
         if self._ctx is None:
             ctx = _lib.Context(self.device)
             ctx.thompson_set(self.W[None], self.b[None], self.theta,
                              np.full(self.ndraw, self.scale), np.full(self.ndraw, self.bias))
+            path, tol = self._precision
+            if path == "int8":
+                ctx.set_precision(1, tol)
             self._ctx = ctx
         return self._ctx
 

@@ -148,3 +148,35 @@ def test_full_size_headline_shape_int8_vs_fp64_and_oracle(ctx):
     fast, _, fbest = ctx.score(1, target, Xc, want_best=True)
     assert ctx.precision_info() == (1, 4, True) and fbest[1] == f64best[1]
     assert rel_err(fast, f64val, 1e-9) < 1e-6           # measured: 4.2e-7 over 2^20 candidates
+
+
+@pytest.mark.parametrize("d,m,ndraw,M", [(2, 128, 7, 1500), (16, 500, 300, 4097), (8, 1024, 256, 40000), (5, 33, 64, 1024)])
+def test_thompson_batch_int8_path(d, m, ndraw, M):
+    """Thompson draws on a shared basis (BASELINE config 4 family) through the int8-slice contraction
+    (sliced cosine features x sliced Theta on tcgen05): values and per-draw first arg max against the
+    NumPy restatement and the FP64 tensor-core path."""
+    from pybo_b200 import models
+    gp = synth(80, d, "se", seed=3)
+    mine = models.GP(1e-3, gp.rho, gp.ell, gp.bias)
+    mine.add_data(gp.X, gp.Y)
+    tb = models.ThompsonBatch(mine, m=m, ndraw=ndraw, rng=5)
+    Xc = qmc.Sobol(d=d, scramble=False).random_base2(int(np.ceil(np.log2(M))))[:M]
+    ref = (tb.bias + (tb.scale * np.cos(Xc @ tb.W.T + tb.b)) @ tb.theta.T).T
+    F64 = tb.get(Xc)
+    bv64, bi64 = tb.argmax(Xc)
+    tb.set_precision("int8", 1e-8)
+    F8 = tb.get(Xc)
+    bv8, bi8 = tb.argmax(Xc)
+    assert tb._context().launch_count() > 0
+    # draws change sign, so the error is measured against the draws' scale (max |F|), not element by element:
+    # tol = 1e-8 is the int8 path's target relative to the prior standard deviation sqrt(rho)
+    scale = np.max(np.abs(ref))
+    assert np.max(np.abs(F8 - ref)) < 1e-7 * scale and np.max(np.abs(F8 - F64)) < 1e-7 * scale
+    assert np.array_equal(bi8, np.argmax(ref, axis=1)) and np.array_equal(bi8, bi64)
+    assert np.allclose(bv8, F8[np.arange(ndraw), bi8], rtol=0, atol=0)
+    # pinned levels: error shrinks by ~2^8 per slice
+    errs = []
+    for lvl in (3.0, 4.0, 5.0):
+        tb.set_precision("int8", lvl)
+        errs.append(np.max(np.abs(tb.get(Xc) - ref)))
+    assert errs[0] > errs[1] > errs[2] and errs[0] / errs[1] > 50

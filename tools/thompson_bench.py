@@ -16,3 +16,18 @@ torch.cuda.synchronize(); t0 = time.perf_counter()
 for _ in range(3): bv, bi = ctx.thompson_eval_device(M, xc.data_ptr())
 dt = (time.perf_counter() - t0) / 3
 print("m=%d: %.1f ms per pass, %.3e draw-evals/s, %.1f TFLOP/s fp64" % (m, dt * 1e3, ndraw * M / dt, 2.0 * ndraw * M * m / dt / 1e12))
+F64 = None
+if M <= (1 << 20):
+    small = xc[: 1 << 14].cpu().numpy()
+    F64 = tb.get(small)
+tb.set_precision("int8", 1e-8)
+for _ in range(2): ctx.thompson_eval_device(M, xc.data_ptr())
+torch.cuda.synchronize(); t0 = time.perf_counter()
+for _ in range(3): bv8, bi8 = ctx.thompson_eval_device(M, xc.data_ptr())
+dt = (time.perf_counter() - t0) / 3
+print("int8 path: %.1f ms per pass, %.3e draw-evals/s (%.1f algorithmic TFLOP/s); arg max identical for %d of %d draws"
+      % (dt * 1e3, ndraw * M / dt, 2.0 * ndraw * M * m / dt / 1e12, int(np.sum(bi8 == bi)), ndraw))
+F8 = tb.get(small)
+print("max |F8 - F64| / max|F64| on 2^14 candidates: %.2e" % (np.abs(F8 - F64).max() / np.abs(F64).max()))
+ctx.profile(True); ctx.profile_reset(); ctx.thompson_eval_device(M, xc.data_ptr()); ctx.sync()
+for k, v in ctx.profile_report().items(): print("  %-26s launches %4d total %.2f ms" % (k, v["launches"], v["total_ms"]))
