@@ -537,6 +537,7 @@ oz_score_kernel(const __grid_constant__ CUtensorMap tmapB, OzParams p) {
     uint64_t *bars = reinterpret_cast<uint64_t *>(gen_base + (size_t)nst * stage_bytes);
     // bars[0..nst): full, [nst..2nst): empty, then tmem_full[2], tmem_empty[2]
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * nst + 4);
+    double *row_sm = reinterpret_cast<double *>(bars + 2 * nst + 6);      // MODE 1: [2][nrb * 64] row scale, row bias
     const uint32_t bar0 = smem_u32(bars);
     auto full_bar = [&](int s) { return bar0 + 8u * s; };
     auto empty_bar = [&](int s) { return bar0 + 8u * (nst + s); };
@@ -560,6 +561,12 @@ oz_score_kernel(const __grid_constant__ CUtensorMap tmapB, OzParams p) {
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 512);
+    if (MODE == 1) {
+        for (int i = threadIdx.x; i < p.nrb * OZ_BN; i += OZ_THREADS) {
+            row_sm[i] = p.rowscale[i];
+            row_sm[p.nrb * OZ_BN + i] = p.rowbias[i];
+        }
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -670,37 +677,64 @@ oz_score_kernel(const __grid_constant__ CUtensorMap tmapB, OzParams p) {
             } else {
                 // drain all 64 columns into registers first so the accumulators go back to the MMA warp
                 // before the stores and the per-draw arg max
-                double vcol[4][16];
+                double vcol[64];
 #pragma unroll
-                for (int cb = 0; cb < 4; ++cb) reassemble(cb * 16, vcol[cb]);
+                for (int cb = 0; cb < 4; ++cb) {
+                    double v16[16];
+                    reassemble(cb * 16, v16);
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) vcol[cb * 16 + i] = v16[i];
+                }
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(tmem_empty(acc));
                 if (++acc == nacc) { acc = 0; acc_phase ^= 1; }
                 const int cand = un.tile * OZ_BM + quarter * 32 + lane;
+                const bool cand_live = cand < p.mc;
+                const int rowb = un.rb * OZ_BN;
 #pragma unroll
-                for (int cb = 0; cb < 4; ++cb) {
+                for (int c = 0; c < 64; ++c) {
+                    vcol[c] = fma(vcol[c], row_sm[rowb + c], row_sm[p.nrb * OZ_BN + rowb + c]);
+                    if (p.out && cand_live && rowb + c < p.nrows_live) p.out[(int64_t)(rowb + c) * p.out_ld + p.c0 + cand] = vcol[c];
+                }
+                if (p.blkval) {
+                    // Per-draw first arg max over the warp's 32 consecutive candidates as a butterfly that
+                    // halves the column set every round (a lane keeps the half selected by its lane bit and
+                    // hands the other half to its partner): 62 exchanges per lane instead of 64 x 5, and every
+                    // lane ends up owning two draws.  NaN never wins; ties go to the lower candidate.
+                    int bi[64];
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        const int row = un.rb * OZ_BN + cb * 16 + i;
-                        const bool live = cand < p.mc && row < p.nrows_live;
-                        const double f = fma(vcol[cb][i], __ldg(p.rowscale + row), __ldg(p.rowbias + row));
-                        if (p.out && live) p.out[(int64_t)row * p.out_ld + p.c0 + cand] = f;
-                        if (p.blkval) {
-                            // first arg max over the warp's 32 consecutive candidates (NaN never wins)
-                            double bv = (live && f == f) ? f : -INFINITY;
-                            int bi = (live && f == f) ? cand : 0x7fffffff;
+                    for (int c = 0; c < 64; ++c) {
+                        const bool ok = cand_live && vcol[c] == vcol[c];
+                        bi[c] = ok ? cand : 0x7fffffff;
+                        if (!ok) vcol[c] = -INFINITY;
+                    }
 #pragma unroll
-                            for (int o = 16; o > 0; o >>= 1) {
-                                const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
-                                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-                                if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
-                            }
-                            if (lane == 0 && row < p.nrows_live) {
-                                const int64_t o = (int64_t)row * p.blk_ld + p.blk0 + un.tile * 4 + quarter;
-                                p.blkval[o] = bv;
-                                p.blkidx[o] = bi == 0x7fffffff ? INT64_MAX : p.c0 + bi;
-                            }
+                    for (int rd = 0; rd < 5; ++rd) {
+                        const int o = 16 >> rd, half = 32 >> rd;
+                        const bool up = (lane & o) != 0;
+#pragma unroll
+                        for (int j = 0; j < half; ++j) {
+                            const double sv = up ? vcol[j] : vcol[j + half];
+                            const int si = up ? bi[j] : bi[j + half];
+                            const double kv = up ? vcol[j + half] : vcol[j];
+                            const int ki = up ? bi[j + half] : bi[j];
+                            const double ov = __shfl_xor_sync(0xffffffffu, sv, o);
+                            const int oi = __shfl_xor_sync(0xffffffffu, si, o);
+                            const bool take = ov > kv || (ov == kv && oi < ki);
+                            vcol[j] = take ? ov : kv;
+                            bi[j] = take ? oi : ki;
+                        }
+                    }
+                    const int colb = 32 * ((lane >> 4) & 1) + 16 * ((lane >> 3) & 1) + 8 * ((lane >> 2) & 1) +
+                                     4 * ((lane >> 1) & 1) + 2 * (lane & 1);
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                        const int row = rowb + colb + j;
+                        if (row < p.nrows_live) {
+                            const int64_t o = (int64_t)row * p.blk_ld + p.blk0 + un.tile * 4 + quarter;
+                            p.blkval[o] = vcol[j];
+                            p.blkidx[o] = bi[j] == 0x7fffffff ? INT64_MAX : p.c0 + bi[j];
                         }
                     }
                 }
@@ -766,12 +800,13 @@ static int oz_stage_count(int S) {
     int n = (200 * 1024) / stage;
     return n > 4 ? 4 : (n < 2 ? 2 : n);
 }
+#define OZ_ROW_SMEM 8192      // MODE 1: row scale + bias of up to 512 draws
 static size_t oz_smem_bytes(int S) {
     return (size_t)oz_stage_count(S) * S * (OZ_A_SLICE_BYTES + OZ_B_SLICE_BYTES) + 1024 + 256;
 }
 
 int bo_ozaki_init(bo_ctx *ctx) {
-#define OZ_ATTR1(SS, EE, MM) BO_CUDA(ctx, cudaFuncSetAttribute(oz_score_kernel<SS, EE, MM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)oz_smem_bytes(SS)))
+#define OZ_ATTR1(SS, EE, MM) BO_CUDA(ctx, cudaFuncSetAttribute(oz_score_kernel<SS, EE, MM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)oz_smem_bytes(SS) + MM * OZ_ROW_SMEM))
 #define OZ_ATTR(SS) OZ_ATTR1(SS, 0, 0); OZ_ATTR1(SS, 1, 0); OZ_ATTR1(SS, 0, 1); OZ_ATTR1(SS, 1, 1)
     OZ_ATTR(2); OZ_ATTR(3); OZ_ATTR(4); OZ_ATTR(5); OZ_ATTR(6); OZ_ATTR(7);
 #undef OZ_ATTR
@@ -1235,7 +1270,7 @@ int64_t bo_thompson_ozaki_blocks(int64_t M) {
 
 bool bo_thompson_ozaki_usable(bo_ctx *ctx, int64_t M) {
     const bo_thompson_state &th = ctx->th;
-    return ctx->prec == BO_PREC_OZAKI && th.nW == 1 && M >= 1024 && !th.h_theta.empty() &&
+    return ctx->prec == BO_PREC_OZAKI && th.nW == 1 && M >= 1024 && !th.h_theta.empty() && th.ndraw <= 512 &&
            (int64_t)bo_round_up(th.m, 64) * 5 < (1 << 17);
 }
 
@@ -1277,8 +1312,8 @@ int bo_thompson_ozaki_run(bo_ctx *ctx, int64_t M, const double *dXc, double *dOu
         {
             BO_LAUNCH(ctx, "oz_thompson_kernel");
             switch (S) {
-#define OZ_TRUN(SS) case SS: if (extra) oz_score_kernel<SS, 1, 1><<<grid, OZ_THREADS, oz_smem_bytes(SS), ctx->stream>>>(tmB, p); \
-                          else oz_score_kernel<SS, 0, 1><<<grid, OZ_THREADS, oz_smem_bytes(SS), ctx->stream>>>(tmB, p); break
+#define OZ_TRUN(SS) case SS: if (extra) oz_score_kernel<SS, 1, 1><<<grid, OZ_THREADS, oz_smem_bytes(SS) + OZ_ROW_SMEM, ctx->stream>>>(tmB, p); \
+                          else oz_score_kernel<SS, 0, 1><<<grid, OZ_THREADS, oz_smem_bytes(SS) + OZ_ROW_SMEM, ctx->stream>>>(tmB, p); break
                 OZ_TRUN(3); OZ_TRUN(4); OZ_TRUN(5);
 #undef OZ_TRUN
                 default: return bo_set_err(ctx, BO_ERR_ARG, "Thompson int8 path handles 3..5 slices, got %d", S);
