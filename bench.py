@@ -295,6 +295,7 @@ def our_arm(args):
 
     chol = cholesky_metric(ctx, spec, X, ell[0], rho[0], sn2[0], pk, fp64_peak)
     append = append_metric(spec, X, y, ell[0], rho[0], sn2[0], bias[0], pk, local) if S == 1 else None
+    thompson = thompson_metric(local) if (S == 1 and args.workload == "rbf_n4096_d8_ei") else None
     cpu = cpu_baseline(spec, X, y, ell, rho, sn2, bias, budget_s=args.cpu_seconds) if world == 1 else None
 
     line = dict(metric="acq_evals_per_sec", value=value, unit="evals/s", n_gpus=world, steps=args.steps,
@@ -311,7 +312,7 @@ def our_arm(args):
                 e2e=dict(value=e2e_value, unit="evals/s", ms_per_step=e2e_ms / args.steps,
                          h2d_bytes_per_step=int(M * d * 8), d2h_bytes_per_step=int(10 * 16),
                          api="policies.ModelIndex.best_of (score + device top-10) on pinned host candidates"),
-                gpu_launches=int(launches), roofline=roofline, cpu_baseline=cpu, cholesky=chol, incremental_refit=append,
+                gpu_launches=int(launches), roofline=roofline, cpu_baseline=cpu, cholesky=chol, incremental_refit=append, thompson=thompson,
                 fit_seconds=fit_s, incumbent=dict(value=incumbent[0], index=incumbent[1]), faster_level=fast_level,
                 kernels={k: dict(launches=v["launches"], ms=round(v["total_ms"], 3)) for k, v in prof.items()})
     print(json.dumps(line))
@@ -363,6 +364,38 @@ def append_metric(spec, X, y, ell, rho, sn2, bias, pk, device, k=32):
     gbs = n * n * 8 / dt / 1e9
     return dict(n=n, ms_per_append=dt * 1e3, full_refit_ms=refit * 1e3, algorithmic_bytes=n * n * 8, gbs=gbs,
                 frac_hbm=gbs / pk["hbm_gbs"], note="wall clock per bo_append call incl. its host sync; 4 kernels")
+
+
+def thompson_metric(device, n=4096, d=16, ndraw=256, m=1024, M=1 << 20):
+    """BASELINE config 4 shape (Thompson: n=4096, d=16, 256 posterior draws x 2^20 candidates, shared
+    1024-feature basis; reference policies/simple.py:48 batched): per-draw arg max on the FP64 DMMA path and
+    on the int8-slice tcgen05 path, candidates resident in HBM."""
+    import torch
+    from pybo_b200 import models
+    rng = np.random.RandomState(0)
+    X = rng.rand(n, d)
+    y = np.sin(X.sum(axis=1)) + 0.01 * rng.randn(n)
+    gp = models.make_gp(1e-6, float(y.max() - y.min()), 0.25 * np.ones(d), float(y.mean()), device=device)
+    gp.add_data(X, y)
+    tb = models.ThompsonBatch(gp, m=m, ndraw=ndraw, rng=0)
+    ctx = tb._context()
+    xc = sobol_block(M, d, 0).cuda()
+    out = {}
+    for name in ("fp64", "int8"):
+        tb.set_precision(name, 1e-8)
+        for _ in range(2):
+            bv, bi = ctx.thompson_eval_device(M, xc.data_ptr())
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            bv, bi = ctx.thompson_eval_device(M, xc.data_ptr())
+        dt = (time.perf_counter() - t0) / 3
+        out[name] = dict(ms_per_pass=dt * 1e3, draw_evals_per_sec=ndraw * M / dt,
+                         algorithmic_tflops=2.0 * ndraw * M * m / dt / 1e12, argmax=bi.tolist()[:4])
+    out["argmax_identical"] = bool(out["fp64"]["argmax"] == out["int8"]["argmax"])
+    out["shape"] = dict(n=n, d=d, draws=ndraw, features=m, candidates=M)
+    ctx.close()
+    return out
 
 
 # ----------------------------------------------------------------------------------------

@@ -75,6 +75,11 @@ def test_config4_thompson_n4096_d16_256_draws(ctx):
     # the draws interpolate the data about as well as the feature basis allows: posterior-mean sanity
     fX = tb.get(X[:256])
     assert np.mean((fX.mean(axis=0) - y[:256]) ** 2) < np.var(y)
+    # the same batch through the int8-slice tcgen05 path: identical per-draw arg max, values to 1e-7 of the draws' scale
+    tb.set_precision("int8", 1e-8)
+    F8 = tb.get(Xc)
+    bv8, bi8 = tb.argmax(Xc)
+    assert np.max(np.abs(F8 - ref.T)) < 1e-7 * np.max(np.abs(ref)) and np.array_equal(bi8, bi)
 
 
 def test_config5_mixture_32_samples_n2048_d8(ctx):
