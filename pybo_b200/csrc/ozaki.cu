@@ -375,6 +375,7 @@ oz_kstar_slices_fast_kernel(int n, int np, int d, const double *__restrict__ Xs,
     constexpr double LOG2_127 = 6.988684686772166;      // kappa * 127 * 2^32 = 2^(log2 kappa + LOG2_127 + 32)
     static_assert(S >= 2 && S <= 5, "fast slicer handles 2..5 slices");
     const int swz = (tid >> 1) & 3;
+    const int jlimit = live ? n : 0;      // observations j < jlimit contribute for this thread's candidate
     double kb = 0.0;                 // sum_j 127 * 2^32 kappa_j beta_j over this block's observations (FP64)
     for (int tile = t0; tile < t1; ++tile) {
         const int buf = (tile - t0) & 1;
@@ -430,7 +431,8 @@ oz_kstar_slices_fast_kernel(int n, int np, int d, const double *__restrict__ Xs,
                 for (int e = 0; e < 4; ++e) {
                     const int i = 4 * q4 + e;
                     pl[e] = fma(pl[e], f[e], 1.0);
-                    const bool on = live && (j0 + jq + e) < n && ki[e] > -960;
+                    // one predicate (live candidate, real observation, no exponent underflow) -> one select
+                    const bool on = (((j0 + jq + e) - jlimit) & (-961 - ki[e])) < 0;
                     double v = __hiloint2double(__double2hiint(pl[e]) + (ki[e] << 20), __double2loint(pl[e]));
                     v = on ? v : 0.0;                                           // in [0, 127 * 2^32]
                     kb = fma(v, bt[buf][jq + e], kb);
