@@ -356,6 +356,21 @@ def append_metric(spec, X, y, ell, rho, sn2, bias, pk, device, k=32):
         c.append(X[i], y[i:i + 1])
     c.sync()
     dt = (time.perf_counter() - t0) / (k - 1)
+    # the two matrix-vector kernels alone (CUDA events): the last 8 appends again on a fresh fit
+    c.fit(spec["kernel"], X[:n - 8], y[:n - 8], ell[None], [rho], [sn2], [bias])
+    c.profile(True)
+    c.profile_reset()
+    for i in range(n - 8, n):
+        c.append(X[i], y[i:i + 1])
+    c.sync()
+    prof = c.profile_report()
+    c.profile(False)
+    kern = {}
+    for name in ("append_wk_kernel", "append_wrow_kernel"):
+        if name in prof and prof[name]["launches"]:
+            us = 1e3 * prof[name]["total_ms"] / prof[name]["launches"]
+            kgbs = (n - 4) * (n - 4) * 4 / (us * 1e-6) / 1e9        # one triangle of doubles
+            kern[name] = dict(us=us, gbs=kgbs, frac_hbm=kgbs / pk["hbm_gbs"])
     t0 = time.perf_counter()
     c.fit(spec["kernel"], X, y, ell[None], [rho], [sn2], [bias])
     c.sync()
@@ -363,7 +378,9 @@ def append_metric(spec, X, y, ell, rho, sn2, bias, pk, device, k=32):
     c.close()
     gbs = n * n * 8 / dt / 1e9
     return dict(n=n, ms_per_append=dt * 1e3, full_refit_ms=refit * 1e3, algorithmic_bytes=n * n * 8, gbs=gbs,
-                frac_hbm=gbs / pk["hbm_gbs"], note="wall clock per bo_append call incl. its host sync; 4 kernels")
+                frac_hbm=gbs / pk["hbm_gbs"], kernels=kern,
+                note="ms_per_append / gbs: wall clock per bo_append call incl. its host sync (4 kernels); "
+                     "kernels: the two triangular matrix-vector products alone, CUDA events")
 
 
 def thompson_metric(device, n=4096, d=16, ndraw=256, m=1024, M=1 << 20):

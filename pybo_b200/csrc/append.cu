@@ -28,9 +28,15 @@ __device__ __forceinline__ double ap_kernel_value(int kernel, double D, double r
 }
 
 // kvec[j] = k(x_j, x_new) for j < n, 0 on [n, np); also stores the new scaled row of Xs.
+// (`raw` = {x[d], y} of the new observation, appended to the raw copies dX / dY by the first sample's launch)
 __global__ void append_kvec_kernel(int kernel, int n, int np, int dp, double rho, double *__restrict__ Xs,
-                                   const double *__restrict__ xnew, double *__restrict__ kvec) {
+                                   const double *__restrict__ xnew, double *__restrict__ kvec, const double *__restrict__ raw,
+                                   int d, double *__restrict__ dX, double *__restrict__ dY) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (raw != nullptr && blockIdx.x == 0 && threadIdx.x <= d) {
+        if (threadIdx.x < d) dX[(int64_t)n * d + threadIdx.x] = raw[threadIdx.x];
+        else dY[n] = raw[d];
+    }
     if (j >= np) return;
     double v = 0.0;
     if (j < n) {
@@ -46,28 +52,52 @@ __global__ void append_kvec_kernel(int kernel, int n, int np, int dp, double rho
         for (int k = 0; k < dp; ++k) Xs[(int64_t)n * dp + k] = xnew[k];
 }
 
-// lvec[i] = sum_{j <= i} W[i][j] kvec[j] for i < n (one warp per row, coalesced along the row);
-// lvec[i] = 0 on [n, np).
+// Dot product of one triangular row with a vector: elements [lo, hi) of `row` (lo, hi arbitrary; the
+// 16-byte loads start at the even index below lo and are masked at both ends), four independent
+// 16-byte loads per lane in flight.
+__device__ __forceinline__ double ap_row_dot(const double *__restrict__ row, const double *__restrict__ vec, int lo, int hi,
+                                             int lane) {
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    const int beg = lo & ~1;
+    int j = beg + 2 * lane;
+    for (; j + 64 < hi; j += 128) {
+        const double2 w0 = *reinterpret_cast<const double2 *>(row + j);
+        const double2 w1 = *reinterpret_cast<const double2 *>(row + j + 64);
+        const double2 v0 = *reinterpret_cast<const double2 *>(vec + j);
+        const double2 v1 = *reinterpret_cast<const double2 *>(vec + j + 64);
+        a0 = fma(j >= lo ? w0.x : 0.0, v0.x, a0);
+        a1 = fma(w0.y, v0.y, a1);
+        a2 = fma(w1.x, v1.x, a2);
+        a3 = fma(j + 65 < hi ? w1.y : 0.0, v1.y, a3);
+    }
+    if (j < hi) {
+        const double2 w0 = *reinterpret_cast<const double2 *>(row + j);
+        const double2 v0 = *reinterpret_cast<const double2 *>(vec + j);
+        a0 = fma(j >= lo ? w0.x : 0.0, v0.x, a0);
+        a1 = fma(j + 1 < hi ? w0.y : 0.0, v0.y, a1);
+    }
+    return ap_warp_sum((a0 + a1) + (a2 + a3));
+}
+
+// lvec[i] = sum_{j <= i} W[i][j] kvec[j] for i < n (coalesced along the rows), lvec[i] = 0 on [n, np).
+// A warp takes rows r and n - 1 - r, so every warp streams n + 1 elements whatever r is.
 __global__ void __launch_bounds__(32 * AP_ROWS)
 append_wk_kernel(const double *__restrict__ W, const double *__restrict__ kvec, int n, int np, double *__restrict__ lvec) {
-    const int row = blockIdx.x * AP_ROWS + (threadIdx.x >> 5);
+    const int r = blockIdx.x * AP_ROWS + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
-    if (row >= np) return;
-    double acc = 0.0;
-    if (row < n) {
-        const double *w = W + (int64_t)row * np;
-        // two independent accumulators of 16-byte loads keep more of the row in flight
-        double a0 = 0.0, a1 = 0.0;
-        const int jend = (row + 2) & ~1;               // even upper bound; the element past the diagonal is masked
-        for (int j = 2 * lane; j < jend; j += 64) {
-            const double2 w2 = *reinterpret_cast<const double2 *>(w + j);
-            const double2 k2 = *reinterpret_cast<const double2 *>(kvec + j);
-            a0 = fma(w2.x, k2.x, a0);
-            a1 = fma(j + 1 <= row ? w2.y : 0.0, k2.y, a1);
+    const int half = (n + 1) >> 1;
+    if (r < half) {
+        const int r2 = n - 1 - r;
+        const double d0 = ap_row_dot(W + (int64_t)r * np, kvec, 0, r + 1, lane);
+        if (lane == 0) lvec[r] = d0;
+        if (r2 != r) {
+            const double d1 = ap_row_dot(W + (int64_t)r2 * np, kvec, 0, r2 + 1, lane);
+            if (lane == 0) lvec[r2] = d1;
         }
-        acc = ap_warp_sum(a0 + a1);
     }
-    if (lane == 0) lvec[row] = acc;
+    // zero the padding once (first block)
+    if (blockIdx.x == 0)
+        for (int i = n + threadIdx.x; i < np; i += blockDim.x) lvec[i] = 0.0;
 }
 
 // One block: lam, a, the new row of L, alpha[n], log|L|.  scal = {lam, a, 1/lam}; info = n + 1 when
@@ -117,40 +147,33 @@ __global__ void append_pivot_kernel(const double *__restrict__ lvec, double *__r
     if (tid == 0) row[n] = lam;
 }
 
-// w_j = -(sum_{i = j}^{n-1} WT[j][i] l_i) / lam for j < n (one warp per row of W^T), written to row n
-// of W and column n of W^T; beta_j += a w_j.  j == n closes the diagonal.
+// w_j = -(sum_{i = j}^{n-1} WT[j][i] l_i) / lam for j < n (rows of W^T, paired j / n - 1 - j per warp),
+// written to row n of W and column n of W^T; beta_j += a w_j.  The last block closes the diagonal.
 __global__ void __launch_bounds__(32 * AP_ROWS)
 append_wrow_kernel(double *__restrict__ W, double *__restrict__ WT, const double *__restrict__ lvec,
                    const double *__restrict__ scal, const int *__restrict__ info, double *__restrict__ beta, int n, int np) {
     if (*info != 0) return;
-    const int j = blockIdx.x * AP_ROWS + (threadIdx.x >> 5);
+    const int r = blockIdx.x * AP_ROWS + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
-    if (j > n) return;
     const double lam_inv = scal[2], a = scal[1];
-    if (j == n) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        W[(int64_t)n * np + n] = lam_inv;
+        WT[(int64_t)n * np + n] = lam_inv;
+        beta[n] = a * lam_inv;
+    }
+    const int half = (n + 1) >> 1;
+    if (r >= half) return;
+#pragma unroll 1
+    for (int t = 0; t < 2; ++t) {
+        const int j = t == 0 ? r : n - 1 - r;
+        if (t == 1 && j == r) break;
+        const double acc = ap_row_dot(WT + (int64_t)j * np, lvec, j, n, lane);
         if (lane == 0) {
-            W[(int64_t)n * np + n] = lam_inv;
-            WT[(int64_t)n * np + n] = lam_inv;
-            beta[n] = a * lam_inv;
+            const double w = -acc * lam_inv;
+            W[(int64_t)n * np + j] = w;
+            WT[(int64_t)j * np + n] = w;
+            beta[j] = fma(a, w, beta[j]);
         }
-        return;
-    }
-    const double *wt = WT + (int64_t)j * np;
-    double a0 = 0.0, a1 = 0.0;
-    const int i0 = j & ~1;                              // even lower bound; elements outside [j, n) are masked
-    const int iend = (n + 1) & ~1;
-    for (int i = i0 + 2 * lane; i < iend; i += 64) {
-        const double2 w2 = *reinterpret_cast<const double2 *>(wt + i);
-        const double2 l2 = *reinterpret_cast<const double2 *>(lvec + i);
-        a0 = fma(i >= j ? w2.x : 0.0, l2.x, a0);
-        a1 = fma(i + 1 < n ? w2.y : 0.0, l2.y, a1);
-    }
-    const double acc = ap_warp_sum(a0 + a1);
-    if (lane == 0) {
-        const double w = -acc * lam_inv;
-        W[(int64_t)n * np + j] = w;
-        WT[(int64_t)j * np + n] = w;
-        beta[j] = fma(a, w, beta[j]);
     }
 }
 
@@ -172,12 +195,12 @@ extern "C" int bo_append(bo_ctx *ctx, int m, const double *Xnew, const double *y
         return bo_set_err(ctx, BO_ERR_STATE, "bo_append: %d + %d observations exceed the padded capacity %d; refit", ctx->n, m, ctx->np);
     const int np = ctx->np, dp = ctx->dp, d = ctx->d, S = ctx->S;
     cudaStream_t st = ctx->stream;
-    // scratch: kvec[np], lvec[np], S x (xnew[dp] + scal[4]), info[S]
+    // scratch: kvec[np], lvec[np], S x (xnew[dp] + scal[4]), raw {x[d], y}, info[S]
     const size_t per = (size_t)dp + 4;
-    BO_TRY(bo_reserve(ctx, &ctx->dAppend, &ctx->append_capacity, (size_t)2 * np + S * per));
+    BO_TRY(bo_reserve(ctx, &ctx->dAppend, &ctx->append_capacity, (size_t)2 * np + S * per + d + 1));
     BO_TRY(bo_reserve(ctx, &ctx->dAppendInfo, &ctx->appendinfo_capacity, (size_t)S + S));
     double *kvec = ctx->dAppend, *lvec = kvec + np, *small = lvec + np;
-    std::vector<double> h_small((size_t)S * per, 0.0);
+    std::vector<double> h_small((size_t)S * per + d + 1, 0.0);
     std::vector<int> h_info(2 * S, 0);
     ctx->last_val_valid = false;
     for (int p = 0; p < m; ++p) {
@@ -185,20 +208,21 @@ extern "C" int bo_append(bo_ctx *ctx, int m, const double *Xnew, const double *y
         const double *x = Xnew + (size_t)p * d;
         for (int s = 0; s < S; ++s)
             for (int k = 0; k < d; ++k) h_small[s * per + k] = x[k] / ctx->h_ell[(size_t)s * d + k];
+        for (int k = 0; k < d; ++k) h_small[(size_t)S * per + k] = x[k];
+        h_small[(size_t)S * per + d] = ynew[p];
         BO_CUDA(ctx, cudaMemcpyAsync(small, h_small.data(), sizeof(double) * h_small.size(), cudaMemcpyHostToDevice, st));
-        BO_CUDA(ctx, cudaMemcpyAsync(ctx->dX + (size_t)n * d, x, sizeof(double) * d, cudaMemcpyHostToDevice, st));
-        BO_CUDA(ctx, cudaMemcpyAsync(ctx->dY + n, ynew + p, sizeof(double), cudaMemcpyHostToDevice, st));
         for (int s = 0; s < S; ++s) {
             const size_t mo = (size_t)s * np * np;
             double *xs = ctx->dXs + (size_t)s * np * dp, *sm = small + s * per;
             {
                 BO_LAUNCH(ctx, "append_kvec_kernel");
-                append_kvec_kernel<<<(np + 255) / 256, 256, 0, st>>>(ctx->kernel, n, np, dp, ctx->h_rho[s], xs, sm, kvec);
+                append_kvec_kernel<<<(np + 255) / 256, 256, 0, st>>>(ctx->kernel, n, np, dp, ctx->h_rho[s], xs, sm, kvec,
+                                                                    s == 0 ? small + (size_t)S * per : nullptr, d, ctx->dX, ctx->dY);
                 BO_CHECK_LAUNCH(ctx);
             }
             {
                 BO_LAUNCH(ctx, "append_wk_kernel");
-                append_wk_kernel<<<np / AP_ROWS, 32 * AP_ROWS, 0, st>>>(ctx->dW + mo, kvec, n, np, lvec);
+                append_wk_kernel<<<((n + 1) / 2 + AP_ROWS - 1) / AP_ROWS + 1, 32 * AP_ROWS, 0, st>>>(ctx->dW + mo, kvec, n, np, lvec);
                 BO_CHECK_LAUNCH(ctx);
             }
             {
@@ -210,7 +234,7 @@ extern "C" int bo_append(bo_ctx *ctx, int m, const double *Xnew, const double *y
             }
             {
                 BO_LAUNCH(ctx, "append_wrow_kernel");
-                append_wrow_kernel<<<(n + 1 + AP_ROWS - 1) / AP_ROWS, 32 * AP_ROWS, 0, st>>>(
+                append_wrow_kernel<<<((n + 1) / 2 + AP_ROWS - 1) / AP_ROWS + 1, 32 * AP_ROWS, 0, st>>>(
                     ctx->dW + mo, ctx->dWT + mo, lvec, sm + dp, ctx->dAppendInfo + s, ctx->dBeta + (size_t)s * np, n, np);
                 BO_CHECK_LAUNCH(ctx);
             }
