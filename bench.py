@@ -226,6 +226,16 @@ def our_arm(args):
         step_e2e()
     _, e2e_ms, incumbent_e2e = timed(step_e2e, args.steps)
 
+    # the same pass with the Sobol block generated on the device (bo_candidates_sobol): no candidate copy at all
+    unit_box = np.array([[0.0, 1.0]] * d)
+
+    def step_grid():
+        pts, val, idx = index.best_of_sobol(unit_box, M, 10, start=rank * M)
+        return bdist.reduce_incumbent(val[0], int(idx[0]))
+
+    step_grid()
+    _, grid_ms, incumbent_grid = timed(step_grid, args.steps)
+
     # for the record: the next-cheaper precision level (4 slices + first dropped pair group), same timed loop
     fast_level = None
     if args.precision == "ozaki" and args.tol == 1e-8:
@@ -312,6 +322,9 @@ def our_arm(args):
                 e2e=dict(value=e2e_value, unit="evals/s", ms_per_step=e2e_ms / args.steps,
                          h2d_bytes_per_step=int(M * d * 8), d2h_bytes_per_step=int(10 * 16),
                          api="policies.ModelIndex.best_of (score + device top-10) on pinned host candidates"),
+                e2e_device_grid=dict(value=M * world * args.steps / (grid_ms * 1e-3), unit="evals/s", ms_per_step=grid_ms / args.steps,
+                                     h2d_bytes_per_step=0, d2h_bytes_per_step=int(10 * 16), incumbent_index=incumbent_grid[1],
+                                     api="policies.ModelIndex.best_of_sobol: Sobol block generated on the device, scored, device top-10"),
                 gpu_launches=int(launches), roofline=roofline, cpu_baseline=cpu, cholesky=chol, incremental_refit=append, thompson=thompson,
                 fit_seconds=fit_s, incumbent=dict(value=incumbent[0], index=incumbent[1]), faster_level=fast_level,
                 kernels={k: dict(launches=v["launches"], ms=round(v["total_ms"], 3)) for k, v in prof.items()})

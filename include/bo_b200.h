@@ -40,6 +40,7 @@ extern "C" {
 /* pointer flags */
 #define BO_PTR_HOST 0
 #define BO_PTR_DEVICE 1
+#define BO_PTR_STAGED 2  /* candidates were generated into the handle by bo_candidates_sobol; Xc is ignored */
 
 /* precision of the scoring contraction */
 #define BO_PREC_F64 0      /* FP64 tensor-core (DMMA) path                     */
@@ -73,6 +74,16 @@ int bo_fit_info(bo_ctx *ctx, int *info /* S */);
 int bo_loglik(bo_ctx *ctx, double *out /* S */);
 /* factor read-back, for parity tests: which = 0 L, 1 W=L^-1, 2 alpha, 3 beta */
 int bo_get_factor(bo_ctx *ctx, int s, int which, double *out);
+
+/* ---- device-side candidate grid (solvers/lbfgs.py:42-45 builds xgrid on the host; the TODO there asks
+ * for a low-discrepancy grid).  Points [start, start + M) of the unscrambled Sobol sequence in the box
+ * [lo, hi] (NULL: unit cube) from `bits` direction numbers per dimension (sv: d x bits, e.g. SciPy's
+ * qmc.Sobol(d)._sv): x_i = XOR_{b in gray(i)} sv[k][b] / 2^bits -- bit-identical to SciPy / torch.
+ * out == NULL: the grid stays in the handle and the next bo_score / bo_predict call passes
+ * flags = BO_PTR_STAGED instead of a pointer (no host-to-device copy of candidates at all);
+ * otherwise out receives the M x d points (host, or device with BO_PTR_DEVICE). */
+int bo_candidates_sobol(bo_ctx *ctx, int d, int bits, const uint32_t *sv, const double *lo,
+                        const double *hi, int64_t start, int64_t M, double *out, int flags);
 
 /* ---- incremental refit: `model.add_data(x, y)` inside the loop (bayesopt.py:269)
  * Appends m observations (Xnew: m x d, ynew: m) to the fitted factor set without

@@ -15,7 +15,7 @@ LIBPATH = os.path.join(HERE, "lib", "libbo_b200.so")
 BO_OK, BO_ERR_CUDA, BO_ERR_NOT_PD, BO_ERR_ARG, BO_ERR_STATE = 0, 1, 2, 3, 4
 KERNEL_IDS = {"se": 0, "matern52": 1}
 ACQ_MEAN, ACQ_EI, ACQ_PI, ACQ_UCB = 0, 1, 2, 3
-PTR_HOST, PTR_DEVICE = 0, 1
+PTR_HOST, PTR_DEVICE, PTR_STAGED = 0, 1, 2
 
 # every symbol include/bo_b200.h declares
 EXPORTS = [
@@ -25,7 +25,7 @@ EXPORTS = [
     "bo_thompson_set", "bo_thompson_eval",
     "bo_cholesky", "bo_gram",
     "bo_profile_enable", "bo_profile_reset", "bo_profile_count", "bo_profile_get",
-    "bo_launch_count", "bo_microbench", "bo_ozaki_debug", "bo_append", "bo_fit_capacity",
+    "bo_launch_count", "bo_microbench", "bo_ozaki_debug", "bo_append", "bo_fit_capacity", "bo_candidates_sobol",
 ]
 
 
@@ -71,6 +71,7 @@ def _declare(lib):
         "bo_ozaki_debug": (i, [vp, i, i, i, vp, vp, vp, vp, vp, vp, vp]),
         "bo_append": (i, [vp, i, vp, vp]),
         "bo_fit_capacity": (i, [vp, vp]),
+        "bo_candidates_sobol": (i, [vp, i, i, vp, vp, vp, i64, i64, vp, i]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
@@ -98,6 +99,34 @@ def _ptr(a):
     if isinstance(a, (int, np.integer)):
         return C.c_void_p(int(a))
     return a.ctypes.data_as(C.c_void_p)
+
+
+_SOBOL_SV = {}
+
+
+def sobol_directions(d):
+    """(sv, bits): direction numbers (d x bits, uint32) of SciPy's unscrambled Sobol generator."""
+    if d not in _SOBOL_SV:
+        from scipy.stats import qmc
+        eng = qmc.Sobol(d=d, scramble=False)
+        _SOBOL_SV[d] = (np.ascontiguousarray(eng._sv, dtype=np.uint32), int(eng.bits))
+    return _SOBOL_SV[d]
+
+
+def sobol_points(d, indices, bounds=None):
+    """Host restatement of the device generator for a few indices (gray-code XOR of direction numbers)."""
+    sv, bits = sobol_directions(d)
+    idx = np.asarray(indices, dtype=np.uint64)
+    g = idx ^ (idx >> np.uint64(1))
+    x = np.zeros((len(idx), d), dtype=np.uint64)
+    for b in range(bits):
+        on = ((g >> np.uint64(b)) & np.uint64(1)).astype(bool)
+        x[on] ^= sv[:, b].astype(np.uint64)
+    u = x.astype(np.float64) * 2.0 ** -bits
+    if bounds is None:
+        return u
+    bnd = np.array(bounds, dtype=np.float64, ndmin=2)
+    return bnd[:, 0] + (bnd[:, 1] - bnd[:, 0]) * u
 
 
 def f64(a, ndmin=1):
@@ -224,6 +253,29 @@ class Context(object):
                                        _ptr(val_ptr), _ptr(grad_ptr),
                                        C.byref(bv) if want_best else None, C.byref(bi) if want_best else None))
         return (bv.value, bi.value) if want_best else None
+
+    # -- device-side candidate grid ---------------------------------------------------
+    def sobol(self, d, start, M, bounds=None, out="host"):
+        """Points [start, start + M) of the unscrambled Sobol sequence in `bounds` ((d, 2), default unit
+        cube), generated on the device from SciPy's direction numbers.  out='host' returns the (M, d)
+        array; out='staged' leaves the grid in the handle for `score_staged` (no candidate copy at all)."""
+        sv, bits = sobol_directions(d)
+        lo = hi = None
+        if bounds is not None:
+            b = f64(bounds, 2)
+            lo, hi = np.ascontiguousarray(b[:, 0]), np.ascontiguousarray(b[:, 1])
+        res = np.empty((M, d)) if out == "host" else None
+        self._check(self._lib.bo_candidates_sobol(self._h, int(d), int(bits), _ptr(sv), _ptr(lo), _ptr(hi),
+                                                  int(start), int(M), _ptr(res), PTR_HOST))
+        return res
+
+    def score_staged(self, acq, param, M, want_values=False, want_best=True):
+        """Score the grid left in the handle by `sobol(..., out='staged')`."""
+        val = np.empty(M) if want_values else None
+        bv, bi = C.c_double(), C.c_int64()
+        self._check(self._lib.bo_score(self._h, int(acq), float(param), int(M), None, PTR_STAGED, _ptr(val), None,
+                                       C.byref(bv) if want_best else None, C.byref(bi) if want_best else None))
+        return val, ((bv.value, bi.value) if want_best else None)
 
     def predict(self, X, grad=False):
         X = f64(X, 2)

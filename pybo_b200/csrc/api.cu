@@ -115,7 +115,7 @@ static void free_all(bo_ctx *ctx) {
                        &ctx->dKs, &ctx->dV, &ctx->dU, &ctx->dQpart, &ctx->dPpart, &ctx->dMuS,
                        &ctx->dS2S, &ctx->dDmuS, &ctx->dDs2S, &ctx->dGpart, &ctx->dXc, &ctx->dVal,
                        &ctx->dGradOut, &ctx->dBlkVal, &ctx->th.W, &ctx->th.b, &ctx->th.theta,
-                       &ctx->th.scale, &ctx->th.bias, &ctx->th.dBestVal, &ctx->th.thetaT, &ctx->dOzQ, &ctx->dXsHalfSq, &ctx->dCholDinv, &ctx->dOzMu, &ctx->dAppend};
+                       &ctx->th.scale, &ctx->th.bias, &ctx->th.dBestVal, &ctx->th.thetaT, &ctx->dOzQ, &ctx->dXsHalfSq, &ctx->dCholDinv, &ctx->dOzMu, &ctx->dAppend, &ctx->dSobol};
     for (auto p : ptrs)
         if (*p) { cudaFree(*p); *p = nullptr; }
     if (ctx->dInfo) { cudaFree(ctx->dInfo); ctx->dInfo = nullptr; }
@@ -335,7 +335,86 @@ extern "C" int bo_get_factor(bo_ctx *ctx, int s, int which, double *out) {
 // ---------------------------------------------------------------------------
 // scoring / prediction
 // ---------------------------------------------------------------------------
+// ---------------------------------------------------------------------------
+// device-side candidate grid: points [start, start + M) of the unscrambled Sobol sequence,
+// x_i = XOR over the set bits b of gray(i) = i ^ (i >> 1) of the direction numbers sv[k][b], scaled to the
+// box.  One thread per coordinate (coalesced row-major M x d output).
+// ---------------------------------------------------------------------------
+__global__ void sobol_kernel(int d, int bits, const uint32_t *__restrict__ sv, const double *__restrict__ lohi,
+                             int64_t start, int64_t M, double *__restrict__ out) {
+    __shared__ uint32_t ssv[BO_MAX_D * 32];
+    __shared__ double slo[BO_MAX_D], sw[BO_MAX_D];
+    for (int e = threadIdx.x; e < d * bits; e += blockDim.x) ssv[e] = sv[e];
+    for (int k = threadIdx.x; k < d; k += blockDim.x) {
+        slo[k] = lohi[k];
+        sw[k] = lohi[d + k] - lohi[k];
+    }
+    __syncthreads();
+    const double unit = 1.0 / (double)(1ull << bits);
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < M * d; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = e / d;
+        const int k = (int)(e - i * d);
+        const uint64_t idx = (uint64_t)(start + i);
+        uint32_t g = (uint32_t)(idx ^ (idx >> 1)), x = 0;
+        while (g) {
+            const int b = __ffs(g) - 1;
+            x ^= ssv[k * bits + b];
+            g &= g - 1;
+        }
+        out[e] = fma((double)x * unit, sw[k], slo[k]);
+    }
+}
+
+extern "C" int bo_candidates_sobol(bo_ctx *ctx, int d, int bits, const uint32_t *sv, const double *lo, const double *hi,
+                                   int64_t start, int64_t M, double *out, int flags) {
+    BO_ENTER(ctx);
+    if (d < 1 || d > BO_MAX_D || bits < 1 || bits > 32 || !sv || M <= 0 || start < 0 ||
+        (uint64_t)(start + M) > (1ull << bits))
+        return bo_set_err(ctx, BO_ERR_ARG, "bo_candidates_sobol: bad arguments (d=%d bits=%d start=%lld M=%lld)", d, bits,
+                          (long long)start, (long long)M);
+    const bool dev = (flags & BO_PTR_DEVICE) && out;
+    double *dst = dev ? out : nullptr;
+    if (!dst) {
+        BO_TRY(bo_reserve(ctx, &ctx->dXc, &ctx->xc_capacity, (size_t)M * d));
+        dst = ctx->dXc;
+    }
+    BO_TRY(bo_reserve(ctx, &ctx->dSobol, &ctx->sobol_capacity, (size_t)BO_MAX_D * 32 / 2 + 2 * BO_MAX_D));
+    std::vector<double> lohi(2 * d);
+    for (int k = 0; k < d; ++k) {
+        lohi[k] = lo ? lo[k] : 0.0;
+        lohi[d + k] = hi ? hi[k] : 1.0;
+    }
+    double *dLoHi = ctx->dSobol;
+    uint32_t *dSv = reinterpret_cast<uint32_t *>(ctx->dSobol + 2 * BO_MAX_D);
+    cudaStream_t st = ctx->stream;
+    BO_CUDA(ctx, cudaMemcpyAsync(dLoHi, lohi.data(), sizeof(double) * 2 * d, cudaMemcpyHostToDevice, st));
+    BO_CUDA(ctx, cudaMemcpyAsync(dSv, sv, sizeof(uint32_t) * d * bits, cudaMemcpyHostToDevice, st));
+    BO_CUDA(ctx, cudaStreamSynchronize(st));        // `lohi` is a host temporary
+    {
+        BO_LAUNCH(ctx, "sobol_kernel");
+        const int64_t want = (M * d + 255) / 256;
+        const int grid = (int)(want < (int64_t)ctx->sm_count * 16 ? want : (int64_t)ctx->sm_count * 16);
+        sobol_kernel<<<grid, 256, 0, st>>>(d, bits, dSv, dLoHi, start, M, dst);
+        BO_CHECK_LAUNCH(ctx);
+    }
+    ctx->staged_M = dev ? 0 : M;
+    ctx->staged_d = dev ? 0 : d;
+    if (out && !dev) {
+        BO_CUDA(ctx, cudaMemcpyAsync(out, dst, sizeof(double) * M * d, cudaMemcpyDeviceToHost, st));
+        BO_CUDA(ctx, cudaStreamSynchronize(st));
+    }
+    return BO_OK;
+}
+
 static int stage_candidates(bo_ctx *ctx, int64_t M, const double *Xc, int flags, const double **dXc) {
+    if (flags & BO_PTR_STAGED) {       // grid generated into the handle by bo_candidates_sobol
+        if (ctx->staged_M != M || ctx->staged_d != ctx->d || !ctx->dXc)
+            return bo_set_err(ctx, BO_ERR_STATE, "BO_PTR_STAGED: the handle holds %lld staged candidates of dimension %d, asked for %lld x %d",
+                              (long long)ctx->staged_M, ctx->staged_d, (long long)M, ctx->d);
+        *dXc = ctx->dXc;
+        return BO_OK;
+    }
+    ctx->staged_M = 0;
     if (flags & BO_PTR_DEVICE) {
         *dXc = Xc;
         return BO_OK;
@@ -351,7 +430,7 @@ extern "C" int bo_score(bo_ctx *ctx, int acq, double param, int64_t M, const dou
     BO_ENTER(ctx);
     if (!ctx->fitted) return bo_set_err(ctx, BO_ERR_STATE, "bo_score before bo_fit");
     if (acq < BO_ACQ_MEAN || acq > BO_ACQ_UCB) return bo_set_err(ctx, BO_ERR_ARG, "unknown acquisition id %d", acq);
-    if (M <= 0 || !Xc) return bo_set_err(ctx, BO_ERR_ARG, "bo_score: need M > 0 candidates");
+    if (M <= 0 || (!Xc && !(flags & BO_PTR_STAGED))) return bo_set_err(ctx, BO_ERR_ARG, "bo_score: need M > 0 candidates");
     const bool dev = flags & BO_PTR_DEVICE;
     ScoreRequest rq;
     rq.mode = 0; rq.acq = acq; rq.param = param; rq.M = M;
@@ -395,7 +474,7 @@ extern "C" int bo_predict(bo_ctx *ctx, int64_t M, const double *Xc, int flags, d
                           double *dmu, double *ds2) {
     BO_ENTER(ctx);
     if (!ctx->fitted) return bo_set_err(ctx, BO_ERR_STATE, "bo_predict before bo_fit");
-    if (M <= 0 || !Xc) return bo_set_err(ctx, BO_ERR_ARG, "bo_predict: need M > 0 points");
+    if (M <= 0 || (!Xc && !(flags & BO_PTR_STAGED))) return bo_set_err(ctx, BO_ERR_ARG, "bo_predict: need M > 0 points");
     const bool dev = flags & BO_PTR_DEVICE;
     const int d = ctx->d;
     ScoreRequest rq;

@@ -57,6 +57,18 @@ class ModelIndex(object):
         ctx.score(self.acq, self.param, X, want_values=False)
         return ctx.topk(min(int(k), len(X)))
 
+    def best_of_sobol(self, bounds, M, k, start=0):
+        """Same reduction over points [start, start + M) of the unscrambled Sobol sequence in `bounds`,
+        generated on the device (no candidate array crosses the PCIe bus in either direction).  Returns
+        (points (k, d), values (k,), sequence indices (k,))."""
+        ctx = self.model._ensure_fit()
+        bounds = np.array(bounds, dtype=np.float64, ndmin=2)
+        d = bounds.shape[0]
+        ctx.sobol(d, int(start), int(M), bounds, out="staged")
+        ctx.score_staged(self.acq, self.param, int(M), want_best=False)
+        idx, val = ctx.topk(min(int(k), int(M)))
+        return _lib.sobol_points(d, idx + int(start), bounds), val, idx + int(start)
+
 
 def _incumbent_target(model, X, xi):
     """max_i mu(x_i) + xi over the observed points (simple.py:21,35)."""

@@ -28,7 +28,30 @@ def _top_indices(values, k):
     return order[:k]
 
 
-def solve_lbfgs(f, bounds, nbest=10, ngrid=10000, xgrid=None, rng=None, pick="first"):
+def _grid_starts(f, bounds, nbest, ngrid, xgrid, rng, grid):
+    """The `nbest` best points of the candidate grid (reference lbfgs.py:42-51).  grid='uniform' is the
+    reference's `init_uniform(bounds, ngrid, rng)`; grid='sobol' is the low-discrepancy grid its TODO
+    (lbfgs.py:43-44) asks for -- for a device-backed index it is generated, scored and reduced on the
+    GPU, so no candidate array is built on the host at all.  An explicit `xgrid` wins."""
+    if grid not in ("uniform", "sobol"):
+        raise ValueError("grid must be 'uniform' or 'sobol'")
+    if xgrid is None and grid == "sobol":
+        if getattr(f, "fused", False) and hasattr(f, "best_of_sobol"):
+            return f.best_of_sobol(bounds, ngrid, nbest)[0]
+        from ._lib import sobol_points
+        xgrid = sobol_points(len(bounds), np.arange(ngrid), bounds)
+    elif xgrid is None:
+        xgrid = init_uniform(bounds, ngrid, rng)
+    else:
+        xgrid = np.array(xgrid, dtype=float, ndmin=2)
+    if getattr(f, "fused", False):
+        starts, _ = f.best_of(xgrid, nbest)
+    else:
+        starts = _top_indices(np.asarray(f(xgrid, grad=False), dtype=float), nbest)
+    return xgrid[starts]
+
+
+def solve_lbfgs(f, bounds, nbest=10, ngrid=10000, xgrid=None, rng=None, pick="first", grid="uniform"):
     """Maximise `f` over the box.
 
     pick='first' reproduces the reference exactly: its final selection
@@ -37,23 +60,15 @@ def solve_lbfgs(f, bounds, nbest=10, ngrid=10000, xgrid=None, rng=None, pick="fi
     refined point with the highest value instead.
     """
     bounds = as_bounds(bounds)
-    if xgrid is None:
-        xgrid = init_uniform(bounds, ngrid, rng)
-    else:
-        xgrid = np.array(xgrid, dtype=float, ndmin=2)
-
-    if getattr(f, "fused", False):
-        starts, _ = f.best_of(xgrid, nbest)
-    else:
-        starts = _top_indices(np.asarray(f(xgrid, grad=False), dtype=float), nbest)
+    x0 = _grid_starts(f, bounds, nbest, ngrid, xgrid, rng, grid)
 
     def negated(x):
         fx, gx = f(x[None], grad=True)
         return -float(fx[0]), -np.asarray(gx[0], dtype=float)
 
     refined = []
-    for x0 in xgrid[starts]:
-        x, fmin, _ = scipy.optimize.fmin_l_bfgs_b(negated, x0, bounds=bounds)
+    for start in x0:
+        x, fmin, _ = scipy.optimize.fmin_l_bfgs_b(negated, start, bounds=bounds)
         refined.append((x, fmin))
 
     if pick == "first":
@@ -156,21 +171,14 @@ def batched_lbfgs(f, x0, bounds, maxiter=100, history=10, pgtol=1e-5, ftol=2.2e-
     return x, -fx, nev
 
 
-def solve_lbfgs_batched(f, bounds, nbest=10, ngrid=10000, xgrid=None, rng=None, pick="best", maxiter=100):
+def solve_lbfgs_batched(f, bounds, nbest=10, ngrid=10000, xgrid=None, rng=None, pick="best", maxiter=100,
+                        grid="uniform"):
     """Maximise `f` over the box: grid scoring and top-`nbest` selection as in `solve_lbfgs`
     (reference lbfgs.py:42-51), then all `nbest` starts refined together by `batched_lbfgs`.
     pick='best' (default) returns the highest refined value; pick='first' keeps the reference's
     `result[0]` selection (lbfgs.py:65).  Same return contract: `(xbest (d,), f(xbest))`."""
     bounds = as_bounds(bounds)
-    if xgrid is None:
-        xgrid = init_uniform(bounds, ngrid, rng)
-    else:
-        xgrid = np.array(xgrid, dtype=float, ndmin=2)
-    if getattr(f, "fused", False):
-        starts, _ = f.best_of(xgrid, nbest)
-    else:
-        starts = _top_indices(np.asarray(f(xgrid, grad=False), dtype=float), nbest)
-    x, fx, _ = batched_lbfgs(f, xgrid[starts], bounds, maxiter=maxiter)
+    x, fx, _ = batched_lbfgs(f, _grid_starts(f, bounds, nbest, ngrid, xgrid, rng, grid), bounds, maxiter=maxiter)
     if pick == "first":
         k = 0
     elif pick == "best":

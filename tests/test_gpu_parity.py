@@ -144,6 +144,72 @@ def test_scores_match_oracle(ctx, kernel, n, d, M):
         assert best[1] == int(np.argmax(ref)), acq
 
 
+@pytest.mark.parametrize("kernel,n,d,M", [("se", 2100, 32, 700), ("matern52", 150, 31, 300), ("se", 8190, 8, 600)])
+def test_edge_shapes_max_dimension_and_large_ragged_n(ctx, kernel, n, d, M):
+    """Largest supported input dimension (32, and 31 padded to it) and a large factor whose order is not a
+    multiple of the 128 padding (n = 8190): both precision paths against the oracle."""
+    rng = np.random.RandomState(n + d)
+    X = rng.rand(n, d)
+    y = np.sin(X.sum(axis=1)) + 0.01 * rng.randn(n)
+    # lengthscale grows with sqrt(d) so that candidates stay correlated with the data in 32 dimensions
+    gp = GPOracle(1e-4, float(y.max() - y.min()), 0.25 * max(1.0, np.sqrt(d / 8.0)) * np.ones(d), float(y.mean()), kernel)
+    gp.add_data(X, y)
+    fit_ctx(ctx, gp)
+    Xc = sobol(M, d)
+    mu, s2 = gp.predict(Xc)
+    target = float(gp.predict(gp.X[:200])[0].max())
+    ref = gp.get_improvement(target, Xc)
+    gmu, gs2 = ctx.predict(Xc)
+    assert rel_err(gmu, mu) < TOL and np.max(np.abs(gs2 - s2) / np.maximum(np.abs(s2), 1e-9 * gp.rho)) < TOL
+    val, _, best = ctx.score(1, target, Xc, want_best=True)
+    assert rel_err(val, ref, 1e-9) < TOL and best[1] == int(np.argmax(ref))
+    ctx.set_precision(1, 1e-9)
+    v8, _, b8 = ctx.score(1, target, Xc, want_best=True)
+    assert rel_err(v8, ref, 1e-8) < TOL and b8[1] == best[1]
+    v1, g1, _ = ctx.score(1, target, Xc[:3], grad=True)
+    rv, rg = gp.get_improvement(target, Xc[:3], grad=True)
+    assert rel_err(v1, rv, 1e-9) < TOL and rel_err(g1, rg, 1e-9) < 10 * TOL
+
+
+def test_device_sobol_grid_bit_exact_and_staged_scoring(ctx):
+    """bo_candidates_sobol: the device generator reproduces SciPy's unscrambled Sobol points bit for bit
+    (any offset), and scoring the grid staged in the handle equals scoring the same points from the host."""
+    from scipy.stats import qmc
+    from pybo_b200 import _lib, models, policies, solvers
+    for d in (1, 4, 16, 32):
+        ref = qmc.Sobol(d=d, scramble=False).random_base2(13)
+        assert np.array_equal(ctx.sobol(d, 0, 8192), ref)
+        assert np.array_equal(ctx.sobol(d, 1000, 3001), ref[1000:4001])
+    b = np.array([[-5, 10.0], [0, 15]])
+    assert np.allclose(ctx.sobol(2, 5, 100, b), _lib.sobol_points(2, np.arange(5, 105), b), rtol=1e-15, atol=0)
+    with pytest.raises(ValueError):
+        ctx.sobol(3, 2 ** 30 - 10, 100)
+    gp = synth(400, 4, "se", seed=12)
+    fit_ctx(ctx, gp)
+    target = float(gp.predict(gp.X)[0].max())
+    pts = ctx.sobol(4, 64, 20000)
+    val, _, best = ctx.score(1, target, pts, want_best=True)
+    ctx.sobol(4, 64, 20000, out="staged")
+    sval, sbest = ctx.score_staged(1, target, 20000, want_values=True)
+    assert np.array_equal(sval, val) and sbest == best
+    with pytest.raises(_lib.BackendError):
+        ctx.score_staged(1, target, 19999)                 # the handle holds a different grid
+    ctx.score(1, target, pts[:10])                          # a host-pointer call un-stages the grid
+    with pytest.raises(_lib.BackendError):
+        ctx.score_staged(1, target, 20000)
+    # through the plugin surface: solver(grid='sobol') on a device model = the same on the oracle model
+    gpu = models.make_gp(gp.sn2, gp.rho, gp.ell, gp.bias)
+    gpu.add_data(gp.X, gp.Y)
+    bounds = np.array([[0, 1.0]] * 4)
+    a, r = policies.EI(gpu, bounds, list(gp.X)), policies.EI(gp, bounds, list(gp.X))
+    p3, v3, i3 = a.best_of_sobol(bounds, 4096, 3)
+    rv = r(_lib.sobol_points(4, np.arange(4096), bounds))
+    assert np.array_equal(i3, np.lexsort((np.arange(4096), -rv))[:3]) and rel_err(v3, rv[i3], 1e-9) < TOL
+    xa, fa = solvers.solve_lbfgs(a, bounds, ngrid=4096, grid="sobol")
+    xb, fb = solvers.solve_lbfgs(r, bounds, ngrid=4096, grid="sobol")
+    assert np.allclose(xa, xb, atol=1e-4) and abs(fa - fb) <= 1e-6 * max(1, abs(fb))
+
+
 def test_predict_at_training_points_and_incumbent_target(ctx):
     """policies/simple.py:21: target = max_i mu(x_i); recommenders.py:34-35."""
     gp = synth(500, 4, "se", seed=9)

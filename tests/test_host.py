@@ -170,6 +170,30 @@ def test_batched_multistart_solver_matches_sequential_lbfgs():
     assert s.func is solvers.solve_lbfgs_batched
 
 
+def test_sobol_grid_host_restatement_and_solver_option():
+    """`grid='sobol'` (the low-discrepancy grid of the TODO at reference lbfgs.py:43-44): the host restatement
+    of the device generator is bit-identical to SciPy's unscrambled sequence, scaled to the box."""
+    from scipy.stats import qmc
+    for d in (1, 3, 16):
+        ref = qmc.Sobol(d=d, scramble=False).random_base2(9)
+        assert np.array_equal(_lib.sobol_points(d, np.arange(512)), ref)
+        assert np.array_equal(_lib.sobol_points(d, [7, 300, 511]), ref[[7, 300, 511]])
+    b = np.array([[-5, 10.0], [0, 15]])
+    pts = _lib.sobol_points(2, np.arange(64), b)
+    assert np.all(pts >= b[:, 0]) and np.all(pts <= b[:, 1])
+    assert np.allclose(pts, b[:, 0] + 15.0 * qmc.Sobol(d=2, scramble=False).random_base2(6))
+
+    def f(X, grad=False):
+        X = np.array(X, ndmin=2)
+        v = -np.sum((X - np.array([2.0, 3.0])) ** 2, axis=1)
+        return (v, -2 * (X - np.array([2.0, 3.0]))) if grad else v
+    for solve in (solvers.solve_lbfgs, solvers.solve_lbfgs_batched):
+        x, fx = solve(f, b, ngrid=256, grid="sobol")
+        assert np.allclose(x, [2.0, 3.0], atol=1e-5) and abs(fx) < 1e-9
+        with pytest.raises(ValueError):
+            solve(f, b, ngrid=16, grid="halton")
+
+
 def test_policies_match_reference_formulas_on_oracle_model():
     rng = np.random.RandomState(0)
     gp = GPOracle(1e-4, 1.3, [0.3, 0.4], 0.1, "se")
