@@ -2,6 +2,8 @@
 // reference bayesopt.py:114,258,269): Gram matrix K = k(X,X) + sn2 I, blocked
 // right-looking Cholesky (64-wide panels, FP64 DMMA trailing update), blocked
 // recursive triangular inverse W = L^-1, and alpha / beta / log-det.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "dgemm.cuh"
 
@@ -58,42 +60,104 @@ int bo_linalg_gram(bo_ctx *ctx, int kernel, int n, int np, int dp, int S, const 
 // ---------------------------------------------------------------------------
 typedef DTile<64, 64, 32, 16, 3, true> T64NT8;       // 256-thread variant for the fused panel step
 
-// Register-resident factorisation of a 64 x 64 diagonal block and of its inverse by one CTA of
-// 256 threads.  Thread (ty, tx) owns a[ty + 16 ai][tx + 16 b] and x[...] (x starts as the identity)
-// in registers for the whole factorisation; per column only the pivot column of `a` and the pivot
-// row of `x` are broadcast through double-buffered shared memory (one barrier per column).
-// Columns stay unscaled (a[i][j] = L[i][j] sqrt(d_j)), so the multiplier m_ij = a[i][j] / d_j
-// serves both the trailing update a[i][k] -= m_ij a[k][j] and the forward substitution
-// x[i][c] -= m_ij x[j][c]; rows of x are scaled by 1 / L[i][i] at the end.
-// `ra` holds the (already updated) block on entry; L goes to Ab, the inverse to Db.
+// Register-resident factorisation of a 64 x 64 diagonal block by one CTA of 256 threads, followed by the
+// inversion of the factor (needed by the panel solve and by W = L^-1).
+//
+// Factor: thread (ty, tx) owns a[ty + 16 ai][tx + 16 b] in registers for the whole factorisation; per
+// column only the pivot column is broadcast through double-buffered shared memory (one barrier per
+// column).  Columns stay unscaled (a[i][j] = L[i][j] sqrt(d_j)) so the multiplier is m_ij = a[i][j] / d_j
+// with 1 / d_j from MUFU.RCP64H + two Newton steps (the column loop is the serial chain of the whole
+// Cholesky: tools/latency.py measures 67 cycles for the smem -> barrier -> smem round trip, 75-80 for
+// rsqrt / __drcp_rn, 9 per dependent DFMA); the columns are scaled by 1 / sqrt(d_j) at the end.
+//
+// Inverse: NOT carried through the column loop (that doubled its instruction count and the loop is
+// issue-bound) but built afterwards in shared memory by recursive doubling over block sizes 1, 2, .. 32:
+//     X = [[X11, 0], [-X22 L21 X11, X22]]
+// all 32 / b pairs of a level in parallel, two barriers per level, ~87 k FMA in total.
 struct PotrfSmem {
     double colbuf[2][64];
-    double rowbuf[2][64];
-    double rs[64];
+    double dj[64];              // pivots d_j
+    double rs[64];              // 1 / sqrt(d_j) = 1 / L_jj
     int bad;
 };
+#define PF_LD 65                // leading dimension of the 64 x 64 shared-memory tiles (conflict-free columns)
+#define PF_TILE (64 * PF_LD)
 
-// (A split arrive / wait mbarrier version that publishes the next pivot column before finishing the
-//  rank-1 update was measured and is slower: the loop is bound by instruction issue -- ~170 SASS
-//  instructions per column per warp, two warps per scheduler -- not by the barrier: tools/latency.py
-//  gives 67 cycles for the smem -> __syncthreads -> smem round trip, 113 for the mbarrier one.)
-__device__ __forceinline__ void potrf64_regs(double (&ra)[4][4], PotrfSmem &sm, double *Ab, int ld, double *Db,
-                                             int *info, int kblk) {
+__device__ __forceinline__ double pf_rcp(double d) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+    double e = fma(-d, y, 1.0);
+    y = fma(y, e, y);
+    e = fma(-d, y, 1.0);
+    return fma(y, e, y);
+}
+
+// One level of the recursive-doubling inverse: for each of the 32 / B pairs of B x B diagonal blocks
+// (rows r0 .. r0 + 2B), T = L21 X11 then X21 = -X22 T.  A thread owns column ci of one pair and R = max(1, B / 8)
+// rows of it, so the R dot products share the loads of the X11 / T column and run as independent chains.
+template <int B>
+__device__ __forceinline__ void pf_invert_level(const double *Ls, double *Xs, double *Ts) {
+    constexpr int R = B >= 8 ? B / 8 : 1;                 // rows per thread
+    constexpr int NT = 32 * B / R;                        // active threads (32 B outputs per level)
+    constexpr int RS = B / R;                             // row stride between a thread's rows
+    const int tid = threadIdx.x;
+    const int ci = tid & (B - 1);
+    const int rr = (tid / B) % RS;                        // first row of this thread inside the block
+    const int q = tid / (B * RS);                         // pair
+    const int r0 = q * 2 * B;
+    const bool on = tid < NT;
+    if (on) {
+        double acc[R];
+#pragma unroll
+        for (int m = 0; m < R; ++m) acc[m] = 0.0;
+        const double *x11 = Xs + r0 * PF_LD + r0 + ci;
+        const double *l21 = Ls + (r0 + B + rr) * PF_LD + r0;
+        // (X11 is lower triangular, so terms t < ci are zero: fixed bounds keep the loop fully unrolled and
+        //  every load independent of the lane)
+#pragma unroll
+        for (int t = 0; t < B; ++t) {
+            const double x = x11[t * PF_LD];
+#pragma unroll
+            for (int m = 0; m < R; ++m) acc[m] = fma(l21[m * RS * PF_LD + t], x, acc[m]);
+        }
+#pragma unroll
+        for (int m = 0; m < R; ++m) Ts[(r0 + B + rr + m * RS) * 33 + ci] = acc[m];
+    }
+    __syncthreads();
+    if (on) {
+        double acc[R];
+#pragma unroll
+        for (int m = 0; m < R; ++m) acc[m] = 0.0;
+        const double *tt = Ts + (r0 + B) * 33 + ci;
+        const double *x22 = Xs + (r0 + B + rr) * PF_LD + r0 + B;
+        // X22 is lower triangular: beyond the diagonal its entries are zero
+#pragma unroll
+        for (int t = 0; t < B; ++t) {
+            const double tv = tt[t * 33];
+#pragma unroll
+            for (int m = 0; m < R; ++m) acc[m] = fma(x22[m * RS * PF_LD + t], tv, acc[m]);
+        }
+#pragma unroll
+        for (int m = 0; m < R; ++m) Xs[(r0 + B + rr + m * RS) * PF_LD + r0 + ci] = -acc[m];
+    }
+    __syncthreads();
+}
+
+// `ra` holds the (already updated) block on entry; L goes to Ab (global) and Ls (shared), the inverse to Db.
+// Ls, Xs: PF_TILE doubles each; Ts: 64 x 33 doubles.
+__device__ __forceinline__ void potrf64_regs(double (&ra)[4][4], PotrfSmem &sm, double *Ls, double *Xs, double *Ts,
+                                             double *Ab, int ld, double *Db, int *info, int kblk) {
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-    double rx[4][4];
     if (tid == 0) sm.bad = 0;
 #pragma unroll
     for (int ai = 0; ai < 4; ++ai)
 #pragma unroll
-        for (int b = 0; b < 4; ++b) {
-            const int i = ty + 16 * ai, k = tx + 16 * b;
-            if (k > i) ra[ai][b] = 0.0;
-            rx[ai][b] = (i == k) ? 1.0 : 0.0;
-        }
+        for (int b = 0; b < 4; ++b)
+            if (tx + 16 * b > ty + 16 * ai) ra[ai][b] = 0.0;
     int p = 0;
     const bool tx_le_ty = tx <= ty;
     // The column loop is unrolled over the 16-column block jb so that which register tiles take
-    // part in a step (rows below the pivot, columns right of / up to it) is known at compile time;
+    // part in a step (rows below the pivot, columns right of it) is known at compile time;
     // only the comparisons against jl inside the pivot's own tile remain at run time.
 #pragma unroll
     for (int jb = 0; jb < 4; ++jb) {
@@ -104,51 +168,54 @@ __device__ __forceinline__ void potrf64_regs(double (&ra)[4][4], PotrfSmem &sm, 
 #pragma unroll
                 for (int ai = jb; ai < 4; ++ai) sm.colbuf[p][ty + 16 * ai] = ra[ai][jb];
             }
-            if (ty == jl) {            // owners of row j of x (columns <= j)
-#pragma unroll
-                for (int b = 0; b <= jb; ++b) sm.rowbuf[p][tx + 16 * b] = rx[jb][b];
-            }
             __syncthreads();
             const double d = sm.colbuf[p][j];
-            const double r = rsqrt(d);
-            const double r2 = r * r;
+            const double r2 = pf_rcp(d);
             if (tid == 0) {
-                sm.rs[j] = r;
+                sm.dj[j] = d;
                 if (!(d > 0.0) && sm.bad == 0) sm.bad = j + 1;
             }
             const bool tx_gt_jl = tx > jl, ty_gt_jl = ty > jl;
+            double cc[4];
+#pragma unroll
+            for (int b = jb; b < 4; ++b) cc[b] = sm.colbuf[p][tx + 16 * b];
 #pragma unroll
             for (int ai = jb; ai < 4; ++ai) {
                 const bool row_on = (ai > jb) || ty_gt_jl;          // i > j
                 if (!row_on) continue;
                 const double mij = sm.colbuf[p][ty + 16 * ai] * r2;
 #pragma unroll
-                for (int b = 0; b < 4; ++b) {
-                    // trailing update: j < k <= i
-                    if (b >= jb && b <= ai) {
-                        const bool k_gt_j = (b > jb) || tx_gt_jl;
-                        const bool k_le_i = (b < ai) || tx_le_ty;
-                        if (k_gt_j && k_le_i) ra[ai][b] = fma(-mij, sm.colbuf[p][tx + 16 * b], ra[ai][b]);
-                    }
-                    // forward substitution on the identity: k <= j
-                    if (b <= jb) {
-                        const bool k_le_j = (b < jb) || !tx_gt_jl;
-                        if (k_le_j) rx[ai][b] = fma(-mij, sm.rowbuf[p][tx + 16 * b], rx[ai][b]);
-                    }
+                for (int b = jb; b <= ai; ++b) {                    // trailing update: j < k <= i
+                    const bool k_gt_j = (b > jb) || tx_gt_jl;
+                    const bool k_le_i = (b < ai) || tx_le_ty;
+                    if (k_gt_j && k_le_i) ra[ai][b] = fma(-mij, cc[b], ra[ai][b]);
                 }
             }
             p ^= 1;
         }
     }
     __syncthreads();
+    if (tid < 64) sm.rs[tid] = rsqrt(sm.dj[tid]);
+    __syncthreads();
+    // L = a diag(rs): to global, and to shared memory for the inversion; X starts as diag(1 / L_ii)
 #pragma unroll
     for (int ai = 0; ai < 4; ++ai)
 #pragma unroll
         for (int b = 0; b < 4; ++b) {
             const int i = ty + 16 * ai, k = tx + 16 * b;
-            Ab[(int64_t)i * ld + k] = (k <= i) ? ra[ai][b] * sm.rs[k] : 0.0;      // diag: d / sqrt(d)
-            Db[i * 64 + k] = (k <= i) ? rx[ai][b] * sm.rs[i] : 0.0;
+            const double l = (k <= i) ? ra[ai][b] * sm.rs[k] : 0.0;      // diag: d / sqrt(d)
+            Ab[(int64_t)i * ld + k] = l;
+            Ls[i * PF_LD + k] = l;
+            Xs[i * PF_LD + k] = (i == k) ? sm.rs[i] : 0.0;
         }
+    __syncthreads();
+    pf_invert_level<1>(Ls, Xs, Ts);
+    pf_invert_level<2>(Ls, Xs, Ts);
+    pf_invert_level<4>(Ls, Xs, Ts);
+    pf_invert_level<8>(Ls, Xs, Ts);
+    pf_invert_level<16>(Ls, Xs, Ts);
+    pf_invert_level<32>(Ls, Xs, Ts);
+    for (int e = tid; e < 4096; e += 256) Db[e] = Xs[(e >> 6) * PF_LD + (e & 63)];
     if (tid == 0 && sm.bad != 0) atomicCAS(info, 0, kblk * 64 + sm.bad);
 }
 
@@ -169,7 +236,8 @@ chol_step_kernel(double *A, int ld, int64_t strideA, int c, double *dinv, int64_
     const bool has_prev = c > 0;
     if (blockIdx.x == 0) {
         PotrfSmem &sm = *reinterpret_cast<PotrfSmem *>(smem);
-        double *P = smem + (sizeof(PotrfSmem) + 7) / 8;           // [64][65] copy of L_{c,c-1}
+        double *P = smem + (sizeof(PotrfSmem) + 7) / 8;           // [64][65] copy of L_{c,c-1}, later the factor
+        double *Xs = P + PF_TILE, *Ts = Xs + PF_TILE;
         const int tx = tid & 15, ty = tid >> 4;
         double *Ab = Az + (int64_t)c * 64 * (ld + 1);
         double ra[4][4];
@@ -179,22 +247,24 @@ chol_step_kernel(double *A, int ld, int64_t strideA, int c, double *dinv, int64_
             for (int b = 0; b < 4; ++b) ra[ai][b] = Ab[(int64_t)(ty + 16 * ai) * ld + tx + 16 * b];
         if (has_prev) {
             const double *Lp = Az + (int64_t)c * 64 * ld + (int64_t)(c - 1) * 64;
-            for (int e = tid; e < 4096; e += 256) P[(e >> 6) * 65 + (e & 63)] = Lp[(int64_t)(e >> 6) * ld + (e & 63)];
+            for (int e = tid; e < 4096; e += 256) P[(e >> 6) * PF_LD + (e & 63)] = Lp[(int64_t)(e >> 6) * ld + (e & 63)];
             __syncthreads();
-#pragma unroll 4
+            // only the register tiles that touch the lower triangle (b <= ai) are needed
+#pragma unroll 8
             for (int k = 0; k < 64; ++k) {
                 double pa[4], pb[4];
 #pragma unroll
-                for (int ai = 0; ai < 4; ++ai) pa[ai] = P[(ty + 16 * ai) * 65 + k];
+                for (int ai = 0; ai < 4; ++ai) pa[ai] = P[(ty + 16 * ai) * PF_LD + k];
 #pragma unroll
-                for (int b = 0; b < 4; ++b) pb[b] = P[(tx + 16 * b) * 65 + k];
+                for (int b = 0; b < 4; ++b) pb[b] = P[(tx + 16 * b) * PF_LD + k];
 #pragma unroll
                 for (int ai = 0; ai < 4; ++ai)
 #pragma unroll
-                    for (int b = 0; b < 4; ++b) ra[ai][b] = fma(-pa[ai], pb[b], ra[ai][b]);
+                    for (int b = 0; b <= ai; ++b) ra[ai][b] = fma(-pa[ai], pb[b], ra[ai][b]);
             }
+            __syncthreads();                                      // P is reused for the factor below
         }
-        potrf64_regs(ra, sm, Ab, ld, Db, info + blockIdx.z, c);
+        potrf64_regs(ra, sm, P, Xs, Ts, Ab, ld, Db, info + blockIdx.z, c);
         __threadfence();
         __syncthreads();
         if (tid == 0) asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(flag), "r"(1) : "memory");
@@ -236,6 +306,7 @@ chol_step_kernel(double *A, int ld, int64_t strideA, int c, double *dinv, int64_
         } while (v == 0);
     }
     __syncthreads();
+
 #pragma unroll
     for (int mi = 0; mi < T::MI; ++mi)
 #pragma unroll
@@ -250,7 +321,8 @@ chol_step_kernel(double *A, int ld, int64_t strideA, int c, double *dinv, int64_
         }
 }
 
-#define CHOL_STEP_SMEM (T64NT8::SMEM_BYTES > (int)(sizeof(PotrfSmem) + 8 + 64 * 65 * 8) ? T64NT8::SMEM_BYTES : (int)(sizeof(PotrfSmem) + 8 + 64 * 65 * 8))
+#define CHOL_DIAG_SMEM ((int)(sizeof(PotrfSmem) + 8 + (2 * PF_TILE + 64 * 33) * 8))
+#define CHOL_STEP_SMEM (T64NT8::SMEM_BYTES > CHOL_DIAG_SMEM ? T64NT8::SMEM_BYTES : CHOL_DIAG_SMEM)
 
 
 // Lower-triangular tile enumeration for the trailing update.
