@@ -148,9 +148,20 @@ def our_arm(args):
         raise SystemExit("launch with torchrun --nproc-per-node %d for --gpus %d" % (args.gpus, args.gpus))
     torch.cuda.set_device(local)
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"       # keep NCCL's version banner off stdout: ONE JSON line
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # ONE JSON line on stdout: NCCL prints its version banner there when the communicator comes up
+        # (NCCL_DEBUG=VERSION/WARN), so file descriptor 1 points at stderr until the first collective is done
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            warm = torch.zeros(1, device="cuda")
+            dist.all_reduce(warm)
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
     spec = WORKLOADS[args.workload]
     n, d, M, S = spec["n"], spec["d"], (args.candidates or spec["M"]), spec["S"]
     X, y, ell, rho, sn2, bias = make_problem(spec)
