@@ -246,23 +246,32 @@ chol_step_kernel(double *A, int ld, int64_t strideA, int c, double *dinv, int64_
 #pragma unroll
             for (int b = 0; b < 4; ++b) ra[ai][b] = Ab[(int64_t)(ty + 16 * ai) * ld + tx + 16 * b];
         if (has_prev) {
+            // D = A_cc - L_{c,c-1} L_{c,c-1}^T on the FP64 tensor cores (half the shared-memory traffic of a DFMA
+            // register tile), then through shared memory from the MMA fragment layout into the (ty, tx) layout
+            typedef T64NT8 T;
             const double *Lp = Az + (int64_t)c * 64 * ld + (int64_t)(c - 1) * 64;
-            for (int e = tid; e < 4096; e += 256) P[(e >> 6) * PF_LD + (e & 63)] = Lp[(int64_t)(e >> 6) * ld + (e & 63)];
+            const int warp = tid >> 5, lane = tid & 31;
+            const int wm = warp / T::WARPS_N, wn = warp % T::WARPS_N, g = lane >> 2, t = lane & 3;
+            double acc[T::MI][T::NI][2];
+#pragma unroll
+            for (int mi = 0; mi < T::MI; ++mi)
+#pragma unroll
+                for (int ni = 0; ni < T::NI; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+            T::mainloop(acc, Lp, ld, Lp, ld, 0, 64, smem);           // ends with a barrier: smem is free again
+#pragma unroll
+            for (int mi = 0; mi < T::MI; ++mi)
+#pragma unroll
+                for (int ni = 0; ni < T::NI; ++ni) {
+                    const int r = wm * T::WM + mi * 8 + g, cc = wn * T::WN + ni * 8 + 2 * t;
+                    Xs[r * PF_LD + cc] = acc[mi][ni][0];
+                    Xs[r * PF_LD + cc + 1] = acc[mi][ni][1];
+                }
             __syncthreads();
-            // only the register tiles that touch the lower triangle (b <= ai) are needed
-#pragma unroll 8
-            for (int k = 0; k < 64; ++k) {
-                double pa[4], pb[4];
 #pragma unroll
-                for (int ai = 0; ai < 4; ++ai) pa[ai] = P[(ty + 16 * ai) * PF_LD + k];
+            for (int ai = 0; ai < 4; ++ai)
 #pragma unroll
-                for (int b = 0; b < 4; ++b) pb[b] = P[(tx + 16 * b) * PF_LD + k];
-#pragma unroll
-                for (int ai = 0; ai < 4; ++ai)
-#pragma unroll
-                    for (int b = 0; b <= ai; ++b) ra[ai][b] = fma(-pa[ai], pb[b], ra[ai][b]);
-            }
-            __syncthreads();                                      // P is reused for the factor below
+                for (int b = 0; b < 4; ++b) ra[ai][b] -= Xs[(ty + 16 * ai) * PF_LD + tx + 16 * b];
+            __syncthreads();                                      // Xs is rebuilt by the inversion below
         }
         potrf64_regs(ra, sm, P, Xs, Ts, Ab, ld, Db, info + blockIdx.z, c);
         __threadfence();
