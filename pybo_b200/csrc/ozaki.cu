@@ -1046,6 +1046,9 @@ __constant__ double OZ_COS_C[8] = {4.779477332387385e-14, -1.1470745597729725e-1
 __constant__ double OZ_SIN_C[7] = {-7.647163731819816e-13, 1.6059043836821613e-10, -2.505210838544172e-08, 2.7557319223985893e-06,
                                    -0.0001984126984126984, 0.008333333333333333, -0.16666666666666666};
 
+// SKIP leading Taylor terms are dropped when the digits carry 32 bits or fewer (<= 4 slices): cos to r^12
+// (truncation 4e-13), sin to r^11 (7e-12) against a digit quantum of 2^-32 / 127.
+template <int SKIP>
 __device__ __forceinline__ void oz_cos4(const double (&a)[4], double (&out)[4]) {
     double r[4], r2[4], pc[4], ps[4];
     int q[4];
@@ -1057,16 +1060,16 @@ __device__ __forceinline__ void oz_cos4(const double (&a)[4], double (&out)[4]) 
         r[e] = fma(-qd, 1.5707963267948966, a[e]);
         r[e] = fma(-qd, 6.123233995736766e-17, r[e]);
         r2[e] = r[e] * r[e];
-        pc[e] = OZ_COS_C[0];
-        ps[e] = OZ_SIN_C[0];
+        pc[e] = OZ_COS_C[SKIP];
+        ps[e] = OZ_SIN_C[SKIP];
     }
 #pragma unroll
-    for (int c = 1; c < 8; ++c) {
+    for (int c = SKIP + 1; c < 8; ++c) {
 #pragma unroll
         for (int e = 0; e < 4; ++e) pc[e] = fma(pc[e], r2[e], OZ_COS_C[c]);
     }
 #pragma unroll
-    for (int c = 1; c < 7; ++c) {
+    for (int c = SKIP + 1; c < 7; ++c) {
 #pragma unroll
         for (int e = 0; e < 4; ++e) ps[e] = fma(ps[e], r2[e], OZ_SIN_C[c]);
     }
@@ -1134,7 +1137,7 @@ oz_cosine_slices_kernel(int m, int mp, int d, const double *__restrict__ Wp, con
                         a[e] = fma(x[k + 1], w2.y, a[e]);
                     }
                 }
-                oz_cos4(a, cv);
+                oz_cos4<(S <= 4 ? 2 : 0)>(a, cv);
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                     const int i = 4 * q4 + e;
