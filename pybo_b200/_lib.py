@@ -383,7 +383,7 @@ class Context(object):
         """Measured FP64 roof in TFLOP/s: kind 'dmma' (tensor core) or 'dfma'; or dependent-issue
         latencies in cycles: 'lat_dfma', 'lat_rcp', 'lat_rsqrt', 'lat_syncthreads', 'lat_mbarrier', 'lat_dmma'."""
         kinds = {"dmma": 0, "dfma": 1, "lat_dfma": 2, "lat_rcp": 3, "lat_rsqrt": 4, "lat_syncthreads": 5,
-                 "lat_mbarrier": 6, "lat_dmma": 7}
+                 "lat_mbarrier": 6, "lat_dmma": 7, "dmma_dfma_mix": 8}
         v = C.c_double()
         self._check(self._lib.bo_microbench(self._h, kinds[kind], int(iters), C.byref(v)))
         return v.value

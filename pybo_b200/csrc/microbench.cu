@@ -34,6 +34,32 @@ __global__ void __launch_bounds__(256) dfma_peak_kernel(int iters, double *sink)
     if (s == 123.456) sink[0] = s;
 }
 
+// DMMA and DFMA issued from the same warps, independent accumulators: if the two run on separate pipes the
+// combined rate approaches the sum of the two roofs (kind 8; reported as TFLOP/s of both together).
+__global__ void __launch_bounds__(256) dmma_dfma_mix_kernel(int iters, double *sink) {
+    double c[8][2], f[16];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) c[i][0] = c[i][1] = 0.0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) f[i] = threadIdx.x * 1e-9 + i;
+    double a = 1.0 + threadIdx.x * 1e-9, b = 1.0 - threadIdx.x * 1e-9;
+    const double fa = 1.0000001, fb = 1e-9;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            dmma884(c[i][0], c[i][1], a, b);
+            f[2 * i] = fma(f[2 * i], fa, fb);
+            f[2 * i + 1] = fma(f[2 * i + 1], fa, fb);
+        }
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += c[i][0] + c[i][1];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += f[i];
+    if (s == 123.456) sink[0] = s;
+}
+
 // Dependent-issue latencies (cycles per operation, one warp / one CTA, clock64 around a dependent
 // chain): the serial chain of the Cholesky diagonal-block kernel is made of exactly these.
 //   kind 2: DFMA   3: 1/x (__drcp_rn)   4: rsqrt(double)   5: smem write -> __syncthreads -> read (256 threads)
@@ -93,7 +119,7 @@ __global__ void __launch_bounds__(256) latency_kernel(int kind, int iters, doubl
 extern "C" int bo_microbench(bo_ctx *ctx, int kind, int iters, double *tflops) {
     if (!ctx || !tflops) return BO_ERR_ARG;
     BO_CUDA(ctx, cudaSetDevice(ctx->device));
-    if (kind >= 2) {
+    if (kind >= 2 && kind != 8) {
         double *out = nullptr, h[2] = {0.0, 0.0};
         BO_CUDA(ctx, cudaMalloc(&out, 2 * sizeof(double)));
         ctx->launches++;
@@ -116,6 +142,7 @@ extern "C" int bo_microbench(bo_ctx *ctx, int kind, int iters, double *tflops) {
         cudaEventRecord(e0, ctx->stream);
         ctx->launches++;
         if (kind == 0) dmma_peak_kernel<<<blocks, threads, 0, ctx->stream>>>(iters, sink);
+        else if (kind == 8) dmma_dfma_mix_kernel<<<blocks, threads, 0, ctx->stream>>>(iters, sink);
         else dfma_peak_kernel<<<blocks, threads, 0, ctx->stream>>>(iters, sink);
         cudaEventRecord(e1, ctx->stream);
         cudaError_t e = cudaStreamSynchronize(ctx->stream);
@@ -127,7 +154,9 @@ extern "C" int bo_microbench(bo_ctx *ctx, int kind, int iters, double *tflops) {
         cudaEventElapsedTime(&ms, e0, e1);
         // DMMA m8n8k4: 8*8*4 MACs per warp instruction; DFMA: 32 MACs per warp instruction
         const double warps = (double)blocks * threads / 32.0;
-        const double macs = warps * (double)iters * 16.0 * (kind == 0 ? 256.0 : 32.0);
+        // kind 8: 8 DMMA (256 MACs) + 16 DFMA (32 MACs) per iteration
+        const double macs = kind == 8 ? warps * (double)iters * (8.0 * 256.0 + 16.0 * 32.0)
+                                      : warps * (double)iters * 16.0 * (kind == 0 ? 256.0 : 32.0);
         const double tf = 2.0 * macs / (ms * 1e-3) / 1e12;
         if (rep > 0 && tf > best) best = tf;
     }
