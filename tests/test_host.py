@@ -27,6 +27,21 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, name), name
 
 
+def test_header_is_plain_c(tmp_path):
+    """The boundary is a C ABI: include/bo_b200.h must compile as C99 (no C++ or torch types)."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    src = tmp_path / "hdr.c"
+    src.write_text('#include "%s"\nint main(void) { bo_ctx *c = 0; (void)c; return BO_OK; }\n'
+                   % os.path.join(ROOT, "include", "bo_b200.h"))
+    res = subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-c", str(src), "-o",
+                          str(tmp_path / "hdr.o")], capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+
+
 def test_no_cpu_fallback_without_cuda():
     import torch
     if torch.cuda.is_available():
