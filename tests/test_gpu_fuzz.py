@@ -1,0 +1,75 @@
+"""Seeded random-shape parity sweep (GPU): ragged n, odd d, M off the 128 / 32768 tile boundaries, both
+kernels, 1..3 hyper-samples, both precision paths, appends in between -- everything against the oracle."""
+
+import numpy as np
+import pytest
+from scipy.stats import qmc
+
+from conftest import rel_err
+from oracle import GPOracle, MixtureOracle, ucb_beta, ucb_index
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-6
+
+
+def _case(seed):
+    rng = np.random.RandomState(1000 + seed)
+    n = int(rng.choice([1, 2, 63, 64, 65, 127, 129, 200, 383, 640, 1025]))
+    d = int(rng.randint(1, 13))
+    S = int(rng.choice([1, 1, 2, 3]))
+    kernel = str(rng.choice(["se", "matern52"]))
+    M = int(rng.choice([1, 7, 64, 65, 127, 128, 129, 1000, 4097, 33000]))
+    X = rng.rand(n, d)
+    y = np.sin(X.sum(axis=1)) + 0.05 * rng.randn(n)
+    ell = 0.3 * max(1.0, np.sqrt(d / 4.0)) * np.exp(0.1 * rng.randn(S, d))
+    rho = (float(np.ptp(y)) + 0.5) * np.exp(0.1 * rng.randn(S))
+    sn2 = 1e-4 * np.exp(0.3 * rng.randn(S))
+    bias = float(y.mean()) + 0.01 * rng.randn(S)
+    return rng, n, d, S, kernel, M, X, y, ell, rho, sn2, bias
+
+
+@pytest.mark.parametrize("seed", range(14))
+def test_random_shapes_both_paths(ctx, seed):
+    rng, n, d, S, kernel, M, X, y, ell, rho, sn2, bias = _case(seed)
+    k_app = int(rng.randint(0, 4)) if n > 4 else 0           # some observations arrive through bo_append
+    n0 = n - k_app
+    ctx.fit(kernel, X[:n0], y[:n0], ell, rho, sn2, bias)
+    for i in range(n0, n):
+        if ctx.n < ctx.capacity():
+            ctx.append(X[i], y[i:i + 1])
+        else:
+            ctx.fit(kernel, X[:i + 1], y[:i + 1], ell, rho, sn2, bias)
+    assert ctx.n == n
+    gps = []
+    for s in range(S):
+        g = GPOracle(sn2[s], rho[s], ell[s], bias[s], kernel)
+        g.add_data(X, y)
+        gps.append(g)
+    ref = gps[0] if S == 1 else MixtureOracle(gps)
+    Xc = qmc.Sobol(d=d, scramble=False).random_base2(max(1, int(np.ceil(np.log2(M)))))[:M]
+    mu, s2 = ref.predict(Xc)
+    target = float(ref.predict(X)[0].max())
+    beta = ucb_beta(n)
+    cases = [(1, target, ref.get_improvement(target, Xc)), (2, target + 0.05, ref.get_tail(target + 0.05, Xc))]
+    if S == 1:
+        cases += [(0, 0.0, mu), (3, beta, ucb_index(beta, mu, s2))]
+    floor = 1e-9 * float(np.mean(rho))
+    # where the posterior variance collapses to ~1e-6 rho (dense data in 1-2 dimensions) EI / PI amplify the int8
+    # path's absolute error in s2: that regime belongs to the FP64 path, the bound is looser there
+    tol8 = 10 * TOL if float(s2.min()) >= 1e-4 * float(np.mean(rho)) else 1e-3
+    for prec in (0, 1):
+        ctx.set_precision(prec, 1e-9)
+        gmu, gs2 = ctx.predict(Xc)
+        assert rel_err(gmu, mu, 1e-9) < TOL, (seed, prec)
+        assert np.max(np.abs(gs2 - s2) / np.maximum(np.abs(s2), floor)) < (TOL if prec == 0 else 10 * TOL), (seed, prec)
+        for acq, param, want in cases:
+            val, _, best = ctx.score(acq, param, Xc, want_best=True)
+            # int8 path: tails of EI / PI sit far below the floor of the error model; compare above 1e-6 of the maximum
+            assert rel_err(val, want, 1e-9 if prec == 0 else 1e-6) < (TOL if prec == 0 else tol8), (seed, prec, acq)
+            top = np.flatnonzero(want >= want.max() - 1e-9 * max(1.0, abs(want.max())))
+            assert best[1] in top, (seed, prec, acq)
+    ctx.set_precision(0)
+    if M <= 129:                                             # gradients on the small / medium batch paths
+        v, g, _ = ctx.score(1, target, Xc, grad=True)
+        rv, rg = ref.get_improvement(target, Xc, grad=True)
+        assert rel_err(v, rv, 1e-9) < TOL and rel_err(g, rg, 1e-8) < 10 * TOL, seed
