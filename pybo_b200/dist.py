@@ -133,3 +133,18 @@ class ShardedIndex(object):
             idx, val = np.zeros(0, dtype=np.int64), np.zeros(0)
         val, idx = gather_topk(val, idx, k)
         return idx, val
+
+    def best_of_sobol(self, bounds, M, k, start=0):
+        """Sharded form of `ModelIndex.best_of_sobol`: every rank generates and scores its own contiguous
+        block of points [start, start + M) of the Sobol sequence on its device -- no candidate array exists
+        on any host -- and the per-rank top-k lists (global sequence indices) are merged.  Returns
+        (points (k, d), values (k,), sequence indices (k,)), identical on every rank."""
+        from ._lib import sobol_points
+        lo, hi = shard_range(int(M), self.rank, self.world)
+        if hi > lo:
+            _, val, idx = self.index.best_of_sobol(bounds, hi - lo, k, start=int(start) + lo)
+        else:
+            idx, val = np.zeros(0, dtype=np.int64), np.zeros(0)
+        val, idx = gather_topk(val, idx, k)
+        b = np.array(bounds, dtype=np.float64, ndmin=2)
+        return sobol_points(b.shape[0], idx, b), val, idx

@@ -59,6 +59,21 @@ def _worker(rank, world, port, tmpdir):
         idx, val = bdist.ShardedIndex(FakeIndex()).best_of(X, 5)
         full = -np.sum((X - 0.25) ** 2, axis=1)
         assert np.array_equal(idx, np.argsort(-full)[:5]) and np.allclose(val, full[idx])
+        # device-side Sobol grid, sharded: each rank "scores" only its own block of the sequence
+        from pybo_b200 import _lib
+
+        class FakeSobolIndex(object):
+            def best_of_sobol(self, bounds, M, kk, start=0):
+                pts = _lib.sobol_points(len(bounds), np.arange(start, start + M), bounds)
+                v = -np.sum((pts - 0.6) ** 2, axis=1)
+                o = np.lexsort((np.arange(len(v)), -v))[:kk]
+                return pts[o], v[o], o + start
+        bnd = np.array([[0.0, 1.0], [0.0, 2.0], [-1.0, 1.0]])
+        pts, val, idx = bdist.ShardedIndex(FakeSobolIndex()).best_of_sobol(bnd, 1001, 6, start=3)
+        allp = _lib.sobol_points(3, np.arange(3, 1004), bnd)
+        fullv = -np.sum((allp - 0.6) ** 2, axis=1)
+        want = np.lexsort((np.arange(1001), -fullv))[:6]
+        assert np.array_equal(idx, want + 3) and np.allclose(val, fullv[want]) and np.allclose(pts, allp[want])
         open(os.path.join(tmpdir, "ok%d" % rank), "w").close()
     finally:
         dist.destroy_process_group()
