@@ -298,7 +298,7 @@ oz_kstar_slices_kernel(int kernel, int n, int np, int d, int S, const double *__
     mupart[((int64_t)blockIdx.y * 2 + half) * mcp + m] = kb;
 }
 
-// Fast variant for the SE kernel and S <= 5 slices.  The FP64 pipe limits the slicer, so
+// Fast variant (SE and Matern-5/2 kernels) for S <= 5 slices.  The FP64 pipe limits the slicer, so
 // (i) the scaled squared distance comes from one dot product, D/2 = |xc|^2/2 + |xs|^2/2 - xc.xs
 // (rounding error ~1e-14 relative in kappa, far below the 2^-41 quantum of 6 slices), (ii) exp is
 // an inline exp2 (degree-12 Taylor in ln2*f, |f| <= 1/2, error < 2e-16) whose exponent add also
@@ -340,7 +340,7 @@ __device__ __forceinline__ void oz_cp_async16(void *smem_dst, const void *gmem_s
 // observations.  Observation tiles (scaled coordinates + |xs|^2/2) are prefetched with cp.async
 // into a double buffer; each finished 128 x 64 tile is staged in shared memory as the swizzled
 // operand image and copied out with fully coalesced 16-byte-per-lane stores (8 KB per slice).
-template <int DP, int S>
+template <int DP, int S, bool MATERN>
 __global__ void __launch_bounds__(128)
 oz_kstar_slices_fast_kernel(int n, int np, int d, const double *__restrict__ Xs, const double *__restrict__ XsHalfSq,
                             const double *__restrict__ invell, const double *__restrict__ Xc, int64_t c0, int mc,
@@ -414,6 +414,23 @@ oz_kstar_slices_fast_kernel(int n, int np, int d, const double *__restrict__ Xs,
                     }
                 }
                 // v = 2^(z + 32), z = log2(127 kappa) (dot <= 0 up to rounding; a last-ulp excess rounds away)
+                // Matern-5/2: kappa = (1 + r + r^2 / 3) e^-r, r = sqrt(5 D) = sqrt(-10 dot): the exponential part
+                // goes through the same exp2 and the polynomial factor q multiplies its mantissa below
+                double q[4];
+                if (MATERN) {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const double sa = fabs(dot[e] * -10.0) + 1e-300;          // |5 D| (rounding may leave -1e-15)
+                        double y;
+                        asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(sa));
+                        const double hs = 0.5 * sa;
+                        y = y * fma(-hs, y * y, 1.5);
+                        y = y * fma(-hs, y * y, 1.5);
+                        const double r = sa * y;
+                        q[e] = fma(fma(r, 1.0 / 3.0, 1.0), r, 1.0);
+                        dot[e] = -r;                                           // exponent of e
+                    }
+                }
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                     const double z = fma(dot[e], LOG2E, LOG2_127);
@@ -431,6 +448,7 @@ oz_kstar_slices_fast_kernel(int n, int np, int d, const double *__restrict__ Xs,
                 for (int e = 0; e < 4; ++e) {
                     const int i = 4 * q4 + e;
                     pl[e] = fma(pl[e], f[e], 1.0);
+                    if (MATERN) pl[e] *= q[e];
                     // one predicate (live candidate, real observation, no exponent underflow) -> one select
                     const bool on = (((j0 + jq + e) - jlimit) & (-961 - ki[e])) < 0;
                     double v = __hiloint2double(__double2hiint(pl[e]) + (ki[e] << 20), __double2loint(pl[e]));
@@ -813,7 +831,8 @@ int bo_ozaki_init(bo_ctx *ctx) {
     OZ_ATTR(2); OZ_ATTR(3); OZ_ATTR(4); OZ_ATTR(5); OZ_ATTR(6); OZ_ATTR(7);
 #undef OZ_ATTR
 #undef OZ_ATTR1
-#define OZ_KATTR(DP, SS) BO_CUDA(ctx, cudaFuncSetAttribute(oz_kstar_slices_fast_kernel<DP, SS>, cudaFuncAttributeMaxDynamicSharedMemorySize, SS * OZ_A_SLICE_BYTES))
+#define OZ_KATTR(DP, SS) BO_CUDA(ctx, cudaFuncSetAttribute(oz_kstar_slices_fast_kernel<DP, SS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SS * OZ_A_SLICE_BYTES)); \
+                         BO_CUDA(ctx, cudaFuncSetAttribute(oz_kstar_slices_fast_kernel<DP, SS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SS * OZ_A_SLICE_BYTES))
 #define OZ_KATTR_ALL(DP) OZ_KATTR(DP, 2); OZ_KATTR(DP, 3); OZ_KATTR(DP, 4); OZ_KATTR(DP, 5)
     OZ_KATTR_ALL(2); OZ_KATTR_ALL(4); OZ_KATTR_ALL(8); OZ_KATTR_ALL(16);
 #undef OZ_KATTR_ALL
@@ -924,11 +943,16 @@ template <int DP, int S>
 static void launch_oz_kstar_fast(bo_ctx *ctx, int s, const double *dXc, int64_t c0, int mc, int mcp, int8_t *Kss,
                                  cudaStream_t st) {
     const int ntile = ctx->np / 64;
-    oz_kstar_slices_fast_kernel<DP, S><<<dim3(mcp / 128, (ntile + OZ_KS_TILES - 1) / OZ_KS_TILES), 128,
-                                         S * OZ_A_SLICE_BYTES, st>>>(
-        ctx->n, ctx->np, ctx->d, ctx->dXs + (int64_t)s * ctx->np * ctx->dp, ctx->dXsHalfSq + (int64_t)s * ctx->np,
-        ctx->dInvEll + (int64_t)s * ctx->dp, dXc, c0, mc, mcp, Kss, ctx->dBeta + (int64_t)s * ctx->np,
-        ctx->dOzMu + (size_t)ctx->oz_mu_slot * ctx->ozmu_stride);
+    const dim3 grid(mcp / 128, (ntile + OZ_KS_TILES - 1) / OZ_KS_TILES);
+    const double *xs = ctx->dXs + (int64_t)s * ctx->np * ctx->dp, *hsq = ctx->dXsHalfSq + (int64_t)s * ctx->np;
+    const double *ie = ctx->dInvEll + (int64_t)s * ctx->dp, *beta = ctx->dBeta + (int64_t)s * ctx->np;
+    double *mup = ctx->dOzMu + (size_t)ctx->oz_mu_slot * ctx->ozmu_stride;
+    if (ctx->kernel == BO_KERNEL_MATERN52)
+        oz_kstar_slices_fast_kernel<DP, S, true><<<grid, 128, S * OZ_A_SLICE_BYTES, st>>>(ctx->n, ctx->np, ctx->d, xs, hsq, ie, dXc, c0, mc,
+                                                                                   mcp, Kss, beta, mup);
+    else
+        oz_kstar_slices_fast_kernel<DP, S, false><<<grid, 128, S * OZ_A_SLICE_BYTES, st>>>(ctx->n, ctx->np, ctx->d, xs, hsq, ie, dXc, c0,
+                                                                                    mc, mcp, Kss, beta, mup);
     ctx->oz_mu_rows[ctx->oz_mu_slot] = (ntile + OZ_KS_TILES - 1) / OZ_KS_TILES;
 }
 
@@ -936,7 +960,7 @@ template <int DP>
 static int launch_oz_kstar(bo_ctx *ctx, int s, int S, const double *dXc, int64_t c0, int mc, int mcp, int8_t *Kss,
                            cudaStream_t st) {
     BO_LAUNCH_ON(ctx, "oz_kstar_slices_kernel", st);
-    if (ctx->kernel == BO_KERNEL_SE && S >= 2 && S <= 5 && DP <= 16) {
+    if (S >= 2 && S <= 5 && DP <= 16) {
         switch (S) {
             case 2: launch_oz_kstar_fast<DP, 2>(ctx, s, dXc, c0, mc, mcp, Kss, st); break;
             case 3: launch_oz_kstar_fast<DP, 3>(ctx, s, dXc, c0, mc, mcp, Kss, st); break;
