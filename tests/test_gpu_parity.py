@@ -398,6 +398,32 @@ def test_bayesopt_branin_config1_gpu_vs_golden(golden_dir):
     assert info.y.max() > -0.1
 
 
+def test_bayesopt_loop_with_device_grid_batched_refinement_and_appends():
+    """The BO loop (reference bayesopt.py:262-276) with the opt-in fast pieces together: Sobol grid generated and
+    scored on the device, all starts refined in lockstep, `add_data` appending to the device factors in place --
+    against the same loop driven by the oracle model (same grid, same solver), which refits from scratch."""
+    import pybo_b200
+    from pybo_b200 import models
+    bounds = np.array([[-5, 10.0], [0, 15]])
+    ell = 0.25 * (bounds[:, 1] - bounds[:, 0])
+    rng = np.random.RandomState(3)
+    X0 = bounds[:, 0] + (bounds[:, 1] - bounds[:, 0]) * rng.rand(6, 2)
+    Y0 = np.array([_branin(x) for x in X0])
+    solver = ("lbfgs_batched", {"grid": "sobol", "ngrid": 2048})
+    out = []
+    for make in (lambda: models.make_gp(1e-6, 10.0, ell, -5.0), lambda: GPOracle(1e-6, 10.0, ell, -5.0, "se")):
+        m = make()
+        m.add_data(list(X0), list(Y0))
+        xbest, model, info = pybo_b200.solve_bayesopt(_branin, bounds, model=m, niter=8, policy="ei", solver=solver,
+                                                      recommender="incumbent", rng=0)
+        out.append((xbest, model, info))
+    (xa, ma, ia), (xb, mb, ib) = out
+    assert ma.ndata == mb.ndata == 6 + 9
+    assert ma._fit is not None and ma._fit.ctx.n == 15        # factors kept on the device through the appends
+    assert np.allclose(ia.x[:5], ib.x[:5], atol=1e-3) and np.allclose(ia.y[:5], ib.y[:5], atol=1e-3)
+    assert ia.y.max() >= Y0.max() - 1e-9 and np.all(np.isfinite(ia.y))
+
+
 def test_default_model_mcmc_runs():
     import pybo_b200
     bounds = np.array([[-5, 10.0], [0, 15]])
