@@ -72,6 +72,12 @@ int bo_fit_shape(bo_ctx *ctx, int *kernel, int *n, int *d, int *S);
 int bo_fit_info(bo_ctx *ctx, int *info /* S */);
 /* log marginal likelihood of each hyper-sample (what every MCMC step costs) */
 int bo_loglik(bo_ctx *ctx, double *out /* S */);
+/* the same quantity WITHOUT building a scoring state (no W = L^-1, no transpose, no handle state touched):
+ * Gram + Cholesky of the matrix bordered by the residual row, alpha = L^-1 (y - bias) read off the factor.
+ * One likelihood evaluation of the slice sampler behind `MCMC(model, n=10, burn=100)` (bayesopt.py:108-115).
+ * Returns BO_ERR_NOT_PD when a factorisation fails. */
+int bo_loglik_fit(bo_ctx *ctx, int kernel, int n, int d, int S, const double *X, const double *y,
+                  const double *ell, const double *rho, const double *sn2, const double *bias, double *out /* S */);
 /* factor read-back, for parity tests: which = 0 L, 1 W=L^-1, 2 alpha, 3 beta */
 int bo_get_factor(bo_ctx *ctx, int s, int which, double *out);
 
@@ -105,21 +111,46 @@ int bo_fit_capacity(bo_ctx *ctx, int *capacity);
 int bo_score(bo_ctx *ctx, int acq, double param, int64_t M, const double *Xc,
              int flags, double *out_val, double *out_grad, double *best_val,
              int64_t *best_idx);
+/* The same pass with the incumbent left on the device: *record points at one 16-byte record
+ * {int64 bits of the double value, int64 index + index_offset} in the handle, written on the handle's stream
+ * -- nothing about the arg max is copied to the host.  A multi-GPU caller all-gathers the records of its ranks
+ * (NCCL, on bo_stream()) and hands the gathered buffer to bo_incumbent_merge.  (solvers/lbfgs.py:50-51 across
+ * candidate shards.) */
+int bo_score_incumbent(bo_ctx *ctx, int acq, double param, int64_t M, const double *Xc, int flags,
+                       double *out_val, int64_t index_offset, void **record);
+/* records: count x k packed records (device); val/idx (k, host): per slot the maximum value and the lowest
+ * index attaining it over the `count` contributions; NaN never wins.  One kernel + one read-back. */
+int bo_incumbent_merge(bo_ctx *ctx, const void *records, int count, int k, double *val, int64_t *idx);
 /* model.predict(X, grad) (simple.py:21,64; recommenders.py:22,24,34):
  * mu, s2 (M) and optionally dmu, ds2 (M x d); any output may be NULL. */
 int bo_predict(bo_ctx *ctx, int64_t M, const double *Xc, int flags, double *mu,
                double *s2, double *dmu, double *ds2);
 /* top-k of the values of the last bo_score call, descending, ties by lowest
- * index: replaces `argsort(finit)[::-1][:nbest]` (solvers/lbfgs.py:51). */
+ * index: replaces `argsort(finit)[::-1][:nbest]` (solvers/lbfgs.py:51).  NaN values never
+ * rank; when fewer than k values are comparable the tail is returned as idx = -1, val = NaN. */
 int bo_topk(bo_ctx *ctx, int k, int64_t *idx, double *val);
 /* choose the precision path of the scoring contraction (default BO_PREC_F64).
  * For BO_PREC_OZAKI, 0 < tol < 2 is the target absolute error of the entries of
- * V = L^-1 k relative to sqrt(rho); the library picks the number of 7-bit int8
- * slices (and whether the first dropped pair group is accumulated as well) from its
- * error model.  tol >= 2 pins the level: slices = floor(tol) (2..8), extra group iff the
- * fractional part is >= 0.5 (e.g. 5.5).  Gradient requests and batches of <= 64 points
- * always run on the FP64 path. */
+ * V = L^-1 k relative to sqrt(rho); the library picks the number of balanced base-256
+ * int8 slices (digits in [-128, 127]) and whether the first dropped pair group is
+ * accumulated as well from its error model.  tol >= 2 pins the level: slices = floor(tol)
+ * (2..7), extra group iff the fractional part is >= 0.5 (e.g. 5.5).  Gradient requests and
+ * batches of <= 64 points always run on the FP64 path. */
 int bo_set_precision(bo_ctx *ctx, int prec, double tol);
+/* FP64 rescue pass of the int8-slice path (on by default).  Every candidate carries an a-priori
+ * bound on the error the slice truncation leaves in its acquisition value (bo_predict: in s2);
+ * candidates whose bound exceeds tol * max(|value|, floor_rel * max|value|) are re-scored on the
+ * FP64 path inside the same call, so the int8 path meets `tol` wherever the FP64 path does.
+ * Defaults: tol = 2.5e-7 (4x inside the 1e-6 parity bar), floor_rel = 1e-12.  A pass that has
+ * to rescue more than a quarter of its candidates sends the following passes on this fit
+ * straight to the FP64 path. */
+int bo_set_rescue(bo_ctx *ctx, int on, double tol, double floor_rel);
+/* what the last bo_score / bo_predict call did: int8_path = 1 if it ran the int8-slice
+ * contraction, how many of its `total` candidates the rescue pass re-scored in FP64 */
+int bo_rescue_info(bo_ctx *ctx, int *int8_path, int64_t *flagged, int64_t *total);
+/* the a-priori error model behind the rescue pass, for the level currently selected: on the int8 path
+ * |s2 - s2_exact| <= errk[s] * sqrt(q rho_s), q = rho_s - s2, for hyper-sample s (errk: S values) */
+int bo_ozaki_error_bound(bo_ctx *ctx, double *errk);
 /* current path and, for BO_PREC_OZAKI after a scoring call, the level in use encoded as
  * 2 * slices + extra (extra = the digit pairs of group g = slices are accumulated too) */
 int bo_precision_info(bo_ctx *ctx, int *prec, int *slices);
@@ -133,11 +164,26 @@ int bo_precision_info(bo_ctx *ctx, int *prec, int *slices);
 int bo_thompson_set(bo_ctx *ctx, int ndraw, int nW, int m, int d, const double *W,
                     const double *b, const double *theta, const double *scale,
                     const double *bias);
+/* Build the draws on the device -- the work `model.sample_f(n, rng)` does before its `.get` is evaluated
+ * (policies/simple.py:48): for a GP with data X (n x d), y (n), signal variance rho, noise sn2 and constant
+ * mean `bias`, and m random Fourier features phi(x) = sqrt(2 rho / m) cos(W x + b),
+ *   theta_r = A^-1 Phi^T (y - bias) + sqrt(sn2) L^-T eps_r,   A = Phi^T Phi + sn2 I = L L^T,  Phi = phi(X),
+ * i.e. theta_r ~ N(A^-1 Phi^T r, sn2 A^-1), then installs them as bo_thompson_set would (scale_r = sqrt(2 rho / m),
+ * bias_r = bias).  W: nW x m x d, b: nW x m (nW == 1: one basis shared by all draws; nW == ndraw: one basis per
+ * draw, i.e. ndraw independent sample_f calls), noise: ndraw x m standard normals from the caller's random stream.
+ * theta_out (ndraw x m, host) may be NULL.  BO_ERR_NOT_PD if a feature system fails to factor. */
+int bo_thompson_build(bo_ctx *ctx, int n, int d, const double *X, const double *y, double rho, double sn2,
+                      double bias, int ndraw, int nW, int m, const double *W, const double *b,
+                      const double *noise, double *theta_out);
 /* out (ndraw x M) / out_grad (ndraw x M x d) may be NULL; best_* (ndraw, host)
  * may be NULL.  flags: BO_PTR_DEVICE if Xc/out/out_grad are device pointers. */
 int bo_thompson_eval(bo_ctx *ctx, int64_t M, const double *Xc, int flags,
                      double *out, double *out_grad, double *best_val,
                      int64_t *best_idx);
+
+/* per-draw arg max over M candidates left on the device as ndraw packed records (see bo_score_incumbent) */
+int bo_thompson_incumbents(bo_ctx *ctx, int64_t M, const double *Xc, int flags, int64_t index_offset,
+                           void **records, int *ndraw);
 
 /* ---- stand-alone pieces (metric "Cholesky GB/s", parity tests) ----------- */
 /* In-place lower Cholesky of `batch` n x n matrices (only the lower triangle

@@ -18,6 +18,8 @@ from .gp_oracle import (  # noqa: F401
     GPOracle,
     MixtureOracle,
     FourierSampleOracle,
+    thompson_batch_oracle,
+    predict_fast,
     kernel_matrix,
     kernel_gradx,
     ucb_beta,

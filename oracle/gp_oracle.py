@@ -341,3 +341,62 @@ class FourierSampleOracle(object):
         return F, G
 
     __call__ = get
+
+
+def thompson_batch_oracle(gp, m, ndraw, rng=None, shared_basis=True):
+    """ndraw weight-space posterior draws (the batched form of `sample_f`, BASELINE config 4).
+    Returns (W, b, theta, scale): W (nW, m, d), b (nW, m), theta (ndraw, m); nW = 1 with a shared basis
+    (RNG order: spectrum, phases, then randn(ndraw, m)), else nW = ndraw with the RNG order of ndraw
+    successive FourierSampleOracle constructions."""
+    rng = rng if isinstance(rng, np.random.RandomState) else np.random.RandomState(rng)
+    scale = np.sqrt(2.0 * gp.rho / m)
+    resid = gp.Y - gp.bias
+
+    def solve(W, b, noise):                       # noise: (R, m)
+        Phi = scale * np.cos(gp.X @ W.T + b)
+        A = Phi.T @ Phi
+        A[np.diag_indices_from(A)] += gp.sn2
+        L = sla.cholesky(A, lower=True)
+        mean = sla.cho_solve((L, True), Phi.T @ resid)
+        return mean[None, :] + np.sqrt(gp.sn2) * sla.solve_triangular(L, noise.T, lower=True, trans=1).T
+
+    if shared_basis:
+        W = sample_spectrum(gp.kernel, gp.ell, m, rng)
+        b = rng.rand(m) * 2.0 * np.pi
+        theta = solve(W, b, rng.randn(ndraw, m))
+        return W[None], b[None], theta, scale
+    Ws, bs, th = [], [], []
+    for _ in range(ndraw):
+        W = sample_spectrum(gp.kernel, gp.ell, m, rng)
+        b = rng.rand(m) * 2.0 * np.pi
+        th.append(solve(W, b, rng.randn(1, m))[0])
+        Ws.append(W)
+        bs.append(b)
+    return np.array(Ws), np.array(bs), np.array(th), scale
+
+
+# ----------------------------------------------------------------------------
+# CPU-baseline variant of the scoring pass (bench.py only): identical algebra, but the scaled squared
+# distance goes through one dgemm (|a|^2 + |b|^2 - 2 a.b) instead of the (M, n, d) broadcast, and the
+# triangular solve / reductions stay in LAPACK / BLAS -- the fastest honest NumPy/SciPy form of the
+# reference path, so that the GPU/CPU ratio is not inflated by a slow distance kernel.  The checker
+# (`GPOracle.predict`) keeps the cancellation-free differences.
+# ----------------------------------------------------------------------------
+
+def predict_fast(gp, X):
+    X = _as2d(X)
+    A = gp.X / gp.ell
+    B = X / gp.ell
+    D = (A * A).sum(axis=1)[:, None] + (B * B).sum(axis=1)[None, :] - 2.0 * (A @ B.T)
+    np.maximum(D, 0.0, out=D)
+    if gp.kernel == "se":
+        np.multiply(D, -0.5, out=D)
+        np.exp(D, out=D)
+        D *= gp.rho
+    else:
+        r = np.sqrt(5.0 * D)
+        D = gp.rho * (1.0 + r + r * r / 3.0) * np.exp(-r)
+    V = sla.solve_triangular(gp.L, D, lower=True, overwrite_b=True, check_finite=False)
+    mu = gp.bias + gp.alpha @ V
+    s2 = gp.rho - np.einsum("ij,ij->j", V, V)
+    return mu, s2

@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIBPATH = os.path.join(LIBDIR, "libbo_b200.so")
-SOURCES = ["api.cu", "linalg.cu", "score.cu", "thompson.cu", "microbench.cu", "ozaki.cu", "append.cu"]
+SOURCES = ["api.cu", "linalg.cu", "score.cu", "thompson.cu", "thompson_build.cu", "microbench.cu", "ozaki.cu", "append.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",

@@ -26,6 +26,8 @@ EXPORTS = [
     "bo_cholesky", "bo_gram",
     "bo_profile_enable", "bo_profile_reset", "bo_profile_count", "bo_profile_get",
     "bo_launch_count", "bo_microbench", "bo_ozaki_debug", "bo_append", "bo_fit_capacity", "bo_candidates_sobol",
+    "bo_set_rescue", "bo_rescue_info", "bo_ozaki_error_bound", "bo_loglik_fit",
+    "bo_thompson_build", "bo_score_incumbent", "bo_incumbent_merge", "bo_thompson_incumbents",
 ]
 
 
@@ -72,6 +74,14 @@ def _declare(lib):
         "bo_append": (i, [vp, i, vp, vp]),
         "bo_fit_capacity": (i, [vp, vp]),
         "bo_candidates_sobol": (i, [vp, i, i, vp, vp, vp, i64, i64, vp, i]),
+        "bo_set_rescue": (i, [vp, i, d, d]),
+        "bo_rescue_info": (i, [vp, _ip, _lp, _lp]),
+        "bo_ozaki_error_bound": (i, [vp, vp]),
+        "bo_loglik_fit": (i, [vp, i, i, i, i, vp, vp, vp, vp, vp, vp, vp]),
+        "bo_thompson_build": (i, [vp, i, i, vp, vp, d, d, d, i, i, i, vp, vp, vp, vp]),
+        "bo_score_incumbent": (i, [vp, i, d, i64, vp, i, vp, i64, C.POINTER(vp)]),
+        "bo_incumbent_merge": (i, [vp, vp, i, i, vp, vp]),
+        "bo_thompson_incumbents": (i, [vp, i64, vp, i, i64, C.POINTER(vp), _ip]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
@@ -226,6 +236,22 @@ class Context(object):
         self._check(self._lib.bo_loglik(self._h, _ptr(out)))
         return out
 
+    def loglik_fit(self, kernel, X, y, ell, rho, sn2, bias):
+        """Log marginal likelihood of S hyper-samples from Gram + Cholesky alone (bo_loglik_fit): the fitted state
+        of the handle, if any, is not touched."""
+        X = f64(X, 2)
+        y = f64(y, 1)
+        ell = f64(ell, 2)
+        rho, sn2, bias = f64(rho), f64(sn2), f64(bias)
+        n, d = X.shape
+        S = ell.shape[0]
+        if ell.shape[1] != d or len(rho) != S or len(sn2) != S or len(bias) != S or len(y) != n:
+            raise ValueError("inconsistent fit shapes")
+        out = np.empty(S)
+        self._check(self._lib.bo_loglik_fit(self._h, KERNEL_IDS[kernel], n, d, S, _ptr(X), _ptr(y), _ptr(ell),
+                                            _ptr(rho), _ptr(sn2), _ptr(bias), _ptr(out)))
+        return out
+
     def factor(self, which, s=0):
         code = {"L": 0, "W": 1, "alpha": 2, "beta": 3}[which]
         out = np.empty((self.n, self.n) if code < 2 else (self.n,))
@@ -253,6 +279,33 @@ class Context(object):
                                        _ptr(val_ptr), _ptr(grad_ptr),
                                        C.byref(bv) if want_best else None, C.byref(bi) if want_best else None))
         return (bv.value, bi.value) if want_best else None
+
+    # -- incumbents that stay on the device (cross-rank exchange) -------------------------------
+    def score_incumbent(self, acq, param, M, xc, offset=0, val_ptr=None, flags=PTR_DEVICE):
+        """Score and leave the (value, index + offset) record on the device; returns its address.
+        `xc`: device address (flags=PTR_DEVICE), host array (PTR_HOST) or None (PTR_STAGED)."""
+        rec = C.c_void_p()
+        if flags == PTR_HOST:
+            xc = f64(xc, 2)
+        self._check(self._lib.bo_score_incumbent(self._h, int(acq), float(param), int(M), _ptr(xc), int(flags),
+                                                 _ptr(val_ptr), int(offset), C.byref(rec)))
+        return rec.value
+
+    def thompson_incumbents(self, M, xc, offset=0, flags=PTR_DEVICE):
+        """Per-draw arg max left on the device as ndraw records; returns (address, ndraw)."""
+        rec, nd = C.c_void_p(), C.c_int()
+        if flags == PTR_HOST:
+            xc = f64(xc, 2)
+        self._check(self._lib.bo_thompson_incumbents(self._h, int(M), _ptr(xc), int(flags), int(offset),
+                                                     C.byref(rec), C.byref(nd)))
+        return rec.value, nd.value
+
+    def incumbent_merge(self, records_ptr, count, k):
+        """(values (k,), indices (k,)) merged from count x k device records."""
+        val = np.empty(k)
+        idx = np.empty(k, dtype=np.int64)
+        self._check(self._lib.bo_incumbent_merge(self._h, _ptr(records_ptr), int(count), int(k), _ptr(val), _ptr(idx)))
+        return val, idx
 
     # -- device-side candidate grid ---------------------------------------------------
     def sobol(self, d, start, M, bounds=None, out="host"):
@@ -289,10 +342,29 @@ class Context(object):
         return (mu, s2, dmu, ds2) if grad else (mu, s2)
 
     def topk(self, k):
+        """(indices, values) of the k best values of the last `score`, descending, lowest index first among ties;
+        shorter than k when fewer values are comparable (NaN never ranks)."""
         idx = np.empty(k, dtype=np.int64)
         val = np.empty(k)
         self._check(self._lib.bo_topk(self._h, int(k), _ptr(idx), _ptr(val)))
-        return idx, val
+        keep = idx >= 0
+        return idx[keep], val[keep]
+
+    def set_rescue(self, on=True, tol=2.5e-7, floor_rel=1e-12):
+        """FP64 rescue pass of the int8-slice path (bo_set_rescue)."""
+        self._check(self._lib.bo_set_rescue(self._h, 1 if on else 0, float(tol), float(floor_rel)))
+
+    def error_bound(self):
+        """errk (S,): on the int8 path |s2 - s2_exact| <= errk[s] sqrt((rho_s - s2) rho_s) at the selected level."""
+        out = np.empty(self.S)
+        self._check(self._lib.bo_ozaki_error_bound(self._h, _ptr(out)))
+        return out
+
+    def rescue_info(self):
+        """(ran_int8_path, candidates re-scored in FP64, candidates) of the last score / predict call."""
+        path, flagged, total = C.c_int(), C.c_int64(), C.c_int64()
+        self._check(self._lib.bo_rescue_info(self._h, C.byref(path), C.byref(flagged), C.byref(total)))
+        return bool(path.value), flagged.value, total.value
 
     def set_precision(self, prec, tol=1e-9):
         self._check(self._lib.bo_set_precision(self._h, int(prec), float(tol)))
@@ -316,6 +388,25 @@ class Context(object):
         self.th_shape = (ndraw, m, d)
         self._check(self._lib.bo_thompson_set(self._h, ndraw, nW, m, d, _ptr(W), _ptr(b), _ptr(theta),
                                               _ptr(scale), _ptr(bias)))
+
+    def thompson_build(self, X, y, rho, sn2, bias, W, b, noise):
+        """Build weight-space posterior draws on the device (bo_thompson_build) and install them for
+        `thompson_eval`; returns theta (ndraw, m)."""
+        X = f64(X, 2)
+        y = f64(y, 1)
+        W = f64(W, 3)
+        b = f64(b, 2)
+        noise = f64(noise, 2)
+        n, d = X.shape
+        nW, m, dw = W.shape
+        ndraw = noise.shape[0]
+        if dw != d or b.shape != (nW, m) or noise.shape[1] != m or len(y) != n or nW not in (1, ndraw):
+            raise ValueError("inconsistent Thompson build shapes")
+        theta = np.empty((ndraw, m))
+        self._check(self._lib.bo_thompson_build(self._h, n, d, _ptr(X), _ptr(y), float(rho), float(sn2), float(bias),
+                                                ndraw, nW, m, _ptr(W), _ptr(b), _ptr(noise), _ptr(theta)))
+        self.th_shape = (ndraw, m, d)
+        return theta
 
     def thompson_eval(self, X, grad=False, want_values=True, want_best=False):
         X = f64(X, 2)

@@ -47,6 +47,17 @@ __global__ void zero_upper_kernel(double *A, int n, int64_t ld, int64_t stride) 
     if (i < n && j < n && j > i) A[boff + (int64_t)i * ld + j] = 0.0;
 }
 
+// Xs[s][i][k] = X[i][k] / ell_s[k] for i < n, k < d; zero elsewhere (rows up to np, columns up to dp)
+__global__ void scale_x_kernel(const double *__restrict__ X, const double *__restrict__ invell, int n, int np, int d,
+                               int dp, int S, double *__restrict__ Xs) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= (int64_t)S * np * dp) return;
+    const int k = (int)(e % dp);
+    const int i = (int)((e / dp) % np);
+    const int s = (int)(e / ((int64_t)dp * np));
+    Xs[e] = (i < n && k < d) ? X[(int64_t)i * d + k] * invell[(int64_t)s * dp + k] : 0.0;
+}
+
 __global__ void loglik_kernel(const double *alpha, const double *logdet, int n, int np, double *out) {
     __shared__ double red[32];
     const int s = blockIdx.x;
@@ -99,6 +110,7 @@ extern "C" int bo_create(int device, bo_ctx **out) {
     if (rc == BO_OK) rc = bo_score_init(ctx);
     if (rc == BO_OK) rc = bo_ozaki_init(ctx);
     if (rc == BO_OK) rc = bo_thompson_init(ctx);
+    if (rc == BO_OK) rc = bo_thompson_build_init(ctx);
     if (rc != BO_OK) {
         fprintf(stderr, "bo_create: %s\n", ctx->err);
         cudaStreamDestroy(ctx->stream);
@@ -115,10 +127,15 @@ static void free_all(bo_ctx *ctx) {
                        &ctx->dKs, &ctx->dV, &ctx->dU, &ctx->dQpart, &ctx->dPpart, &ctx->dMuS,
                        &ctx->dS2S, &ctx->dDmuS, &ctx->dDs2S, &ctx->dGpart, &ctx->dXc, &ctx->dVal,
                        &ctx->dGradOut, &ctx->dBlkVal, &ctx->th.W, &ctx->th.b, &ctx->th.theta,
-                       &ctx->th.scale, &ctx->th.bias, &ctx->th.dBestVal, &ctx->th.thetaT, &ctx->dOzQ, &ctx->dXsHalfSq, &ctx->dCholDinv, &ctx->dOzMu, &ctx->dAppend, &ctx->dSobol};
+                       &ctx->th.scale, &ctx->th.bias, &ctx->th.dBestVal, &ctx->th.thetaT, &ctx->dOzQ, &ctx->dXsHalfSq, &ctx->dCholDinv, &ctx->dOzMu, &ctx->dAppend, &ctx->dSobol,
+                       &ctx->dMerged, &ctx->dPredict, &ctx->dLoglik, &ctx->dErrEst, &ctx->dErrK, &ctx->dRescue, &ctx->dLLK, &ctx->dLLSmall,
+                       &ctx->th.build};
     for (auto p : ptrs)
         if (*p) { cudaFree(*p); *p = nullptr; }
     if (ctx->dInfo) { cudaFree(ctx->dInfo); ctx->dInfo = nullptr; }
+    if (ctx->dFlagList) { cudaFree(ctx->dFlagList); ctx->dFlagList = nullptr; }
+    if (ctx->dIncumbent) { cudaFree(ctx->dIncumbent); ctx->dIncumbent = nullptr; }
+    if (ctx->dFlagBits) { cudaFree(ctx->dFlagBits); ctx->dFlagBits = nullptr; }
     if (ctx->dAppendInfo) { cudaFree(ctx->dAppendInfo); ctx->dAppendInfo = nullptr; }
     if (ctx->dWs) { cudaFree(ctx->dWs); ctx->dWs = nullptr; }
     if (ctx->dCholInfo) { cudaFree(ctx->dCholInfo); ctx->dCholInfo = nullptr; }
@@ -207,6 +224,7 @@ extern "C" int bo_fit(bo_ctx *ctx, int kernel, int n, int d, int S, const double
     }
     ctx->fitted = false;
     ctx->oz_ready = false;
+    ctx->oz_demoted = false;
     ctx->last_val_valid = false;
     const int np = bo_round_up(n, BO_PAD), dp = padded_dim(d), nblk64 = np / 64;
     const size_t mat = (size_t)S * np * np;
@@ -241,25 +259,27 @@ extern "C" int bo_fit(bo_ctx *ctx, int kernel, int n, int d, int S, const double
     ctx->h_ell.assign(ell, ell + (size_t)S * d);
     ctx->h_info.assign(S, 0);
 
-    // scaled, zero-padded observation coordinates per hyper-sample
-    std::vector<double> xs((size_t)S * np * dp, 0.0), inv((size_t)S * dp, 0.0);
-    for (int s = 0; s < S; ++s) {
+    // inverse lengthscales (zero padded); the scaled, zero-padded coordinates Xs[s][i][k] = X[i][k] / ell_s[k] are
+    // built on the device.  The host buffers are pageable: cudaMemcpyAsync returns once they are staged, so no
+    // synchronisation is needed before they go out of scope.
+    std::vector<double> inv((size_t)S * dp, 0.0);
+    for (int s = 0; s < S; ++s)
         for (int k = 0; k < d; ++k) inv[(size_t)s * dp + k] = 1.0 / ell[s * d + k];
-        for (int i = 0; i < n; ++i)
-            for (int k = 0; k < d; ++k)
-                xs[((size_t)s * np + i) * dp + k] = X[(size_t)i * d + k] * inv[(size_t)s * dp + k];
-    }
     cudaStream_t st = ctx->stream;
     BO_CUDA(ctx, cudaMemcpyAsync(ctx->dX, X, sizeof(double) * n * d, cudaMemcpyHostToDevice, st));
     BO_CUDA(ctx, cudaMemcpyAsync(ctx->dY, y, sizeof(double) * n, cudaMemcpyHostToDevice, st));
-    BO_CUDA(ctx, cudaMemcpyAsync(ctx->dXs, xs.data(), sizeof(double) * xs.size(), cudaMemcpyHostToDevice, st));
     BO_CUDA(ctx, cudaMemcpyAsync(ctx->dInvEll, inv.data(), sizeof(double) * inv.size(), cudaMemcpyHostToDevice, st));
     BO_CUDA(ctx, cudaMemcpyAsync(ctx->dRho, rho, sizeof(double) * S, cudaMemcpyHostToDevice, st));
     BO_CUDA(ctx, cudaMemcpyAsync(ctx->dSn2, sn2, sizeof(double) * S, cudaMemcpyHostToDevice, st));
     BO_CUDA(ctx, cudaMemcpyAsync(ctx->dBias, bias, sizeof(double) * S, cudaMemcpyHostToDevice, st));
-    BO_CUDA(ctx, cudaStreamSynchronize(st));   // host staging vectors go out of scope below
+    {
+        BO_LAUNCH(ctx, "scale_x_kernel");
+        const int64_t tot = (int64_t)S * np * dp;
+        scale_x_kernel<<<(int)((tot + 255) / 256), 256, 0, st>>>(ctx->dX, ctx->dInvEll, n, np, d, dp, S, ctx->dXs);
+        BO_CHECK_LAUNCH(ctx);
+    }
 
-    BO_TRY(bo_linalg_gram(ctx, kernel, n, np, dp, S, ctx->dXs, ctx->dRho, ctx->dSn2, ctx->dL));
+    BO_TRY(bo_linalg_gram(ctx, kernel, n, np, dp, S, ctx->dXs, ctx->dRho, ctx->dSn2, ctx->dL, 0, nullptr, nullptr));
     BO_TRY(bo_linalg_cholesky(ctx, np, S, ctx->dL, ctx->dDinv, ctx->dInfo));
     BO_CUDA(ctx, cudaMemcpyAsync(ctx->h_info.data(), ctx->dInfo, sizeof(int) * S, cudaMemcpyDeviceToHost, st));
     BO_CUDA(ctx, cudaStreamSynchronize(st));
@@ -269,8 +289,7 @@ extern "C" int bo_fit(bo_ctx *ctx, int kernel, int n, int d, int S, const double
                               s, ctx->h_info[s]);
     BO_TRY(bo_linalg_trtri(ctx, np, S, ctx->dL, ctx->dDinv, ctx->dW, ctx->dWT /* scratch */));
     BO_TRY(bo_linalg_transpose(ctx, np, S, ctx->dW, ctx->dWT));
-    BO_TRY(bo_linalg_finish_fit(ctx));
-    BO_CUDA(ctx, cudaStreamSynchronize(st));
+    BO_TRY(bo_linalg_finish_fit(ctx));          // (stream ordered: the first call that reads results synchronises)
 
     int64_t chunk = ((int64_t)1 << 25) / np / 128 * 128;
     ctx->chunk = std::min<int64_t>(16384, std::max<int64_t>(1024, chunk));
@@ -297,16 +316,77 @@ extern "C" int bo_fit_info(bo_ctx *ctx, int *info) {
 extern "C" int bo_loglik(bo_ctx *ctx, double *out) {
     BO_ENTER(ctx);
     if (!ctx->fitted) return bo_set_err(ctx, BO_ERR_STATE, "bo_loglik before bo_fit");
-    double *dOut = nullptr;
-    BO_CUDA(ctx, cudaMalloc(&dOut, sizeof(double) * ctx->S));
+    BO_TRY(bo_reserve(ctx, &ctx->dLoglik, &ctx->loglik_capacity, (size_t)ctx->S));
     {
         BO_LAUNCH(ctx, "loglik_kernel");
-        loglik_kernel<<<ctx->S, 256, 0, ctx->stream>>>(ctx->dAlpha, ctx->dLogdet, ctx->n, ctx->np, dOut);
+        loglik_kernel<<<ctx->S, 256, 0, ctx->stream>>>(ctx->dAlpha, ctx->dLogdet, ctx->n, ctx->np, ctx->dLoglik);
+        BO_CHECK_LAUNCH(ctx);
     }
-    cudaError_t e = cudaMemcpyAsync(out, dOut, sizeof(double) * ctx->S, cudaMemcpyDeviceToHost, ctx->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-    cudaFree(dOut);
-    if (e != cudaSuccess) return bo_set_err(ctx, BO_ERR_CUDA, "bo_loglik: %s", cudaGetErrorString(e));
+    BO_CUDA(ctx, cudaMemcpyAsync(out, ctx->dLoglik, sizeof(double) * ctx->S, cudaMemcpyDeviceToHost, ctx->stream));
+    BO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return BO_OK;
+}
+
+// Log marginal likelihood of S hyper-samples WITHOUT building a scoring state: Gram + Cholesky only.  The
+// residual r_s = y - bias_s rides through the factorisation as one extra row of the padded matrix,
+//     [[K_s, .], [r_s^T, c]] = [[L, 0], [alpha^T, .]] [[L, 0], [alpha^T, .]]^T,   alpha = L^-1 r_s,
+// (c = 1 + 2 |r|^2 / sn2 >= 1 + |alpha|^2 keeps the last pivot positive), so alpha needs no triangular solve,
+// no W = L^-1, no transpose.  One likelihood evaluation of the hyper-parameter sampler (bayesopt.py:108-115).
+extern "C" int bo_loglik_fit(bo_ctx *ctx, int kernel, int n, int d, int S, const double *X, const double *y,
+                             const double *ell, const double *rho, const double *sn2, const double *bias, double *out) {
+    BO_ENTER(ctx);
+    if (kernel != BO_KERNEL_SE && kernel != BO_KERNEL_MATERN52)
+        return bo_set_err(ctx, BO_ERR_ARG, "unknown kernel id %d", kernel);
+    if (n < 1 || d < 1 || d > BO_MAX_D || S < 1 || !X || !y || !ell || !rho || !sn2 || !bias || !out)
+        return bo_set_err(ctx, BO_ERR_ARG, "bo_loglik_fit: bad shape n=%d d=%d S=%d (d <= %d)", n, d, S, BO_MAX_D);
+    for (int s = 0; s < S; ++s) {
+        if (!(rho[s] > 0.0) || !(sn2[s] >= 0.0)) return bo_set_err(ctx, BO_ERR_ARG, "bo_loglik_fit: rho must be > 0, sn2 >= 0");
+        for (int k = 0; k < d; ++k)
+            if (!(ell[s * d + k] > 0.0)) return bo_set_err(ctx, BO_ERR_ARG, "bo_loglik_fit: ell must be > 0");
+    }
+    const int np = bo_round_up(n + 1, 64), dp = padded_dim(d), nblk = np / 64;
+    // small inputs in one host block -> one copy: [X n*d | inv S*dp | rho S | sn2 S | ann S | aug S*np]
+    const size_t oX = 0, oInv = oX + (size_t)n * d, oRho = oInv + (size_t)S * dp, oSn = oRho + S, oAnn = oSn + S,
+                 oAug = oAnn + S, oXs = oAug + (size_t)S * np, total = oXs + (size_t)S * np * dp;
+    std::vector<double> h(oXs, 0.0);
+    std::copy(X, X + (size_t)n * d, h.begin() + oX);
+    for (int s = 0; s < S; ++s) {
+        for (int k = 0; k < d; ++k) h[oInv + (size_t)s * dp + k] = 1.0 / ell[s * d + k];
+        h[oRho + s] = rho[s];
+        h[oSn + s] = sn2[s];
+        double rr = 0.0;
+        for (int i = 0; i < n; ++i) {
+            const double r = y[i] - bias[s];
+            h[oAug + (size_t)s * np + i] = r;
+            rr += r * r;
+        }
+        const double c = 1.0 + 2.0 * rr / (sn2[s] > 1e-300 ? sn2[s] : 1e-300);
+        h[oAnn + s] = c < 1e300 ? c : 1e300;
+    }
+    BO_TRY(bo_reserve(ctx, &ctx->dLLSmall, &ctx->llsmall_capacity, total));
+    BO_TRY(bo_reserve(ctx, &ctx->dLLK, &ctx->llk_capacity, (size_t)S * np * np));
+    BO_TRY(bo_reserve(ctx, &ctx->dCholDinv, &ctx->choldinv_capacity, (size_t)S * nblk * 4096));
+    BO_TRY(bo_reserve(ctx, &ctx->dCholInfo, &ctx->cholinfo_capacity, (size_t)S));
+    BO_TRY(bo_reserve(ctx, &ctx->dLoglik, &ctx->loglik_capacity, (size_t)S));
+    cudaStream_t st = ctx->stream;
+    double *ds = ctx->dLLSmall;
+    BO_CUDA(ctx, cudaMemcpyAsync(ds, h.data(), sizeof(double) * oXs, cudaMemcpyHostToDevice, st));
+    {
+        BO_LAUNCH(ctx, "scale_x_kernel");
+        const int64_t tot = (int64_t)S * np * dp;
+        scale_x_kernel<<<(int)((tot + 255) / 256), 256, 0, st>>>(ds + oX, ds + oInv, n, np, d, dp, S, ds + oXs);
+        BO_CHECK_LAUNCH(ctx);
+    }
+    BO_TRY(bo_linalg_gram(ctx, kernel, n, np, dp, S, ds + oXs, ds + oRho, ds + oSn, ctx->dLLK, 0, ds + oAug, ds + oAnn));
+    BO_TRY(bo_linalg_cholesky(ctx, np, S, ctx->dLLK, ctx->dCholDinv, ctx->dCholInfo));
+    BO_TRY(bo_linalg_loglik_aug(ctx, ctx->dLLK, n, np, S, ctx->dLoglik));
+    std::vector<int> info(S, 0);
+    BO_CUDA(ctx, cudaMemcpyAsync(info.data(), ctx->dCholInfo, sizeof(int) * S, cudaMemcpyDeviceToHost, st));
+    BO_CUDA(ctx, cudaMemcpyAsync(out, ctx->dLoglik, sizeof(double) * S, cudaMemcpyDeviceToHost, st));
+    BO_CUDA(ctx, cudaStreamSynchronize(st));
+    for (int s = 0; s < S; ++s)
+        if (info[s] != 0 && info[s] <= n)
+            return bo_set_err(ctx, BO_ERR_NOT_PD, "bo_loglik_fit: hyper-sample %d, leading minor %d is not positive definite", s, info[s]);
     return BO_OK;
 }
 
@@ -425,9 +505,9 @@ static int stage_candidates(bo_ctx *ctx, int64_t M, const double *Xc, int flags,
     return BO_OK;
 }
 
-extern "C" int bo_score(bo_ctx *ctx, int acq, double param, int64_t M, const double *Xc, int flags,
-                        double *out_val, double *out_grad, double *best_val, int64_t *best_idx) {
-    BO_ENTER(ctx);
+// what == 0: plain bo_score; what == 1: bo_score_incumbent (arg max stays on the device, no read-back)
+static int score_impl(bo_ctx *ctx, int acq, double param, int64_t M, const double *Xc, int flags, double *out_val,
+                      double *out_grad, double *best_val, int64_t *best_idx, bool device_best) {
     if (!ctx->fitted) return bo_set_err(ctx, BO_ERR_STATE, "bo_score before bo_fit");
     if (acq < BO_ACQ_MEAN || acq > BO_ACQ_UCB) return bo_set_err(ctx, BO_ERR_ARG, "unknown acquisition id %d", acq);
     if (M <= 0 || (!Xc && !(flags & BO_PTR_STAGED))) return bo_set_err(ctx, BO_ERR_ARG, "bo_score: need M > 0 candidates");
@@ -448,11 +528,14 @@ extern "C" int bo_score(bo_ctx *ctx, int acq, double param, int64_t M, const dou
             rq.dGrad = ctx->dGradOut;
         }
     }
-    rq.want_best = (best_val != nullptr) || (best_idx != nullptr);
+    const bool fetch_best = (best_val != nullptr) || (best_idx != nullptr);
+    rq.want_best = fetch_best || device_best;
+    ctx->best_valid = false;
     BO_TRY(bo_score_run(ctx, rq));
     ctx->last_val_ptr = rq.dVal;
     ctx->last_M = M;
     ctx->last_val_valid = true;
+    ctx->best_valid = rq.want_best;
     cudaStream_t st = ctx->stream;
     if (!dev && out_val)
         BO_CUDA(ctx, cudaMemcpyAsync(out_val, rq.dVal, sizeof(double) * M, cudaMemcpyDeviceToHost, st));
@@ -460,13 +543,113 @@ extern "C" int bo_score(bo_ctx *ctx, int acq, double param, int64_t M, const dou
         BO_CUDA(ctx, cudaMemcpyAsync(out_grad, rq.dGrad, sizeof(double) * M * ctx->d, cudaMemcpyDeviceToHost, st));
     double bv = 0.0;
     int64_t bi = -1;
-    if (rq.want_best) {
+    if (fetch_best) {
         BO_CUDA(ctx, cudaMemcpyAsync(&bv, ctx->dBlkVal + ctx->blk_capacity - 1, sizeof(double), cudaMemcpyDeviceToHost, st));
         BO_CUDA(ctx, cudaMemcpyAsync(&bi, ctx->dBlkIdx + ctx->blk_capacity - 1, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
     }
-    if (!dev || rq.want_best) BO_CUDA(ctx, cudaStreamSynchronize(st));
+    // host candidates / outputs are only borrowed for the duration of the call
+    if ((!dev && !(flags & BO_PTR_STAGED)) || (!dev && (out_val || out_grad)) || fetch_best) BO_CUDA(ctx, cudaStreamSynchronize(st));
     if (best_val) *best_val = bv;
     if (best_idx) *best_idx = (bi == INT64_MAX) ? 0 : bi;
+    return BO_OK;
+}
+
+extern "C" int bo_score(bo_ctx *ctx, int acq, double param, int64_t M, const double *Xc, int flags,
+                        double *out_val, double *out_grad, double *best_val, int64_t *best_idx) {
+    BO_ENTER(ctx);
+    return score_impl(ctx, acq, param, M, Xc, flags, out_val, out_grad, best_val, best_idx, false);
+}
+
+// ---------------------------------------------------------------------------
+// incumbents that stay on the device: packed 16-byte records {value bits, global index} for the
+// cross-rank exchange (the collective follows the scoring kernels on the same stream)
+// ---------------------------------------------------------------------------
+__global__ void incumbent_pack_kernel(const double *__restrict__ val, const int64_t *__restrict__ idx, int k,
+                                      int64_t offset, int64_t *__restrict__ rec) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= k) return;
+    const double v = val[i];
+    const int64_t ix = idx[i];
+    const bool none = (ix == INT64_MAX) || (v != v);
+    rec[2 * i] = __double_as_longlong(none ? -INFINITY : v);
+    rec[2 * i + 1] = none ? INT64_MAX : ix + offset;
+}
+
+// recs: [count][k] records; out[k]: max value, lowest index among equal values (NaN never wins)
+__global__ void incumbent_merge_kernel(const int64_t *__restrict__ recs, int count, int k, double *__restrict__ oval,
+                                       int64_t *__restrict__ oidx) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= k) return;
+    double bv = -INFINITY;
+    int64_t bi = INT64_MAX;
+    for (int r = 0; r < count; ++r) {
+        const double v = __longlong_as_double(recs[((int64_t)r * k + i) * 2]);
+        const int64_t ix = recs[((int64_t)r * k + i) * 2 + 1];
+        if (v != v) continue;
+        if (v > bv || (v == bv && ix < bi)) { bv = v; bi = ix; }
+    }
+    oval[i] = bv;
+    oidx[i] = bi;
+}
+
+extern "C" int bo_score_incumbent(bo_ctx *ctx, int acq, double param, int64_t M, const double *Xc, int flags,
+                                  double *out_val, int64_t index_offset, void **record) {
+    BO_ENTER(ctx);
+    if (!record) return BO_ERR_ARG;
+    BO_TRY(score_impl(ctx, acq, param, M, Xc, flags, out_val, nullptr, nullptr, nullptr, true));
+    BO_TRY(bo_reserve(ctx, &ctx->dIncumbent, &ctx->incumbent_capacity, (size_t)2));
+    {
+        BO_LAUNCH(ctx, "incumbent_pack_kernel");
+        incumbent_pack_kernel<<<1, 32, 0, ctx->stream>>>(ctx->dBlkVal + ctx->blk_capacity - 1,
+                                                        ctx->dBlkIdx + ctx->blk_capacity - 1, 1, index_offset, ctx->dIncumbent);
+        BO_CHECK_LAUNCH(ctx);
+    }
+    *record = ctx->dIncumbent;
+    return BO_OK;
+}
+
+extern "C" int bo_thompson_incumbents(bo_ctx *ctx, int64_t M, const double *Xc, int flags, int64_t index_offset,
+                                      void **records, int *ndraw) {
+    BO_ENTER(ctx);
+    bo_thompson_state &th = ctx->th;
+    if (!records) return BO_ERR_ARG;
+    if (th.ndraw == 0) return bo_set_err(ctx, BO_ERR_STATE, "bo_thompson_incumbents before bo_thompson_set / bo_thompson_build");
+    if (M <= 0 || !Xc) return bo_set_err(ctx, BO_ERR_ARG, "bo_thompson_incumbents: need M > 0 points");
+    const double *dXc = Xc;
+    if (!(flags & BO_PTR_DEVICE)) {
+        BO_TRY(bo_reserve(ctx, &ctx->dXc, &ctx->xc_capacity, (size_t)M * th.d));
+        BO_CUDA(ctx, cudaMemcpyAsync(ctx->dXc, Xc, sizeof(double) * M * th.d, cudaMemcpyHostToDevice, ctx->stream));
+        dXc = ctx->dXc;
+        ctx->staged_M = 0;
+    }
+    BO_TRY(bo_thompson_run(ctx, M, dXc, nullptr, nullptr, th.dBestVal, th.dBestIdx));
+    ctx->last_val_valid = false;
+    BO_TRY(bo_reserve(ctx, &ctx->dIncumbent, &ctx->incumbent_capacity, (size_t)2 * th.ndraw));
+    {
+        BO_LAUNCH(ctx, "incumbent_pack_kernel");
+        incumbent_pack_kernel<<<(th.ndraw + 127) / 128, 128, 0, ctx->stream>>>(th.dBestVal, th.dBestIdx, th.ndraw, index_offset,
+                                                                              ctx->dIncumbent);
+        BO_CHECK_LAUNCH(ctx);
+    }
+    *records = ctx->dIncumbent;
+    if (ndraw) *ndraw = th.ndraw;
+    return BO_OK;
+}
+
+extern "C" int bo_incumbent_merge(bo_ctx *ctx, const void *records, int count, int k, double *val, int64_t *idx) {
+    BO_ENTER(ctx);
+    if (!records || count < 1 || k < 1 || !val || !idx) return bo_set_err(ctx, BO_ERR_ARG, "bo_incumbent_merge: bad arguments");
+    BO_TRY(bo_reserve(ctx, &ctx->dMerged, &ctx->merged_capacity, (size_t)2 * k));
+    double *ov = ctx->dMerged;
+    int64_t *oi = reinterpret_cast<int64_t *>(ctx->dMerged + k);
+    {
+        BO_LAUNCH(ctx, "incumbent_merge_kernel");
+        incumbent_merge_kernel<<<(k + 127) / 128, 128, 0, ctx->stream>>>(static_cast<const int64_t *>(records), count, k, ov, oi);
+        BO_CHECK_LAUNCH(ctx);
+    }
+    BO_CUDA(ctx, cudaMemcpyAsync(val, ov, sizeof(double) * k, cudaMemcpyDeviceToHost, ctx->stream));
+    BO_CUDA(ctx, cudaMemcpyAsync(idx, oi, sizeof(int64_t) * k, cudaMemcpyDeviceToHost, ctx->stream));
+    BO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return BO_OK;
 }
 
@@ -480,14 +663,16 @@ extern "C" int bo_predict(bo_ctx *ctx, int64_t M, const double *Xc, int flags, d
     ScoreRequest rq;
     rq.mode = 1; rq.M = M;
     BO_TRY(stage_candidates(ctx, M, Xc, flags, &rq.dXc));
-    double *scratch = nullptr;
     if (dev) {
         rq.dMu = mu; rq.dS2 = s2; rq.dDmu = dmu; rq.dDs2 = ds2;
     } else {
-        BO_CUDA(ctx, cudaMalloc(&scratch, sizeof(double) * M * (2 + 2 * (size_t)d)));
+        // staging lives in the handle (no malloc / free, hence no device-wide sync, per L-BFGS callback)
+        const bool g = dmu || ds2;
+        BO_TRY(bo_reserve(ctx, &ctx->dPredict, &ctx->predict_capacity, (size_t)M * (2 + (g ? 2 * (size_t)d : 0))));
+        double *scratch = ctx->dPredict;
         rq.dMu = scratch;
         rq.dS2 = scratch + M;
-        if (dmu || ds2) {
+        if (g) {
             rq.dDmu = scratch + 2 * M;
             rq.dDs2 = scratch + 2 * M + M * d;
         }
@@ -502,10 +687,6 @@ extern "C" int bo_predict(bo_ctx *ctx, int64_t M, const double *Xc, int flags, d
         if (ds2 && e == cudaSuccess) e = cudaMemcpyAsync(ds2, rq.dDs2, sizeof(double) * M * d, cudaMemcpyDeviceToHost, st);
         if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     }
-    if (scratch) {
-        cudaStreamSynchronize(ctx->stream);
-        cudaFree(scratch);
-    }
     if (rc != BO_OK) return rc;
     if (e != cudaSuccess) return bo_set_err(ctx, BO_ERR_CUDA, "bo_predict: %s", cudaGetErrorString(e));
     return BO_OK;
@@ -518,6 +699,9 @@ extern "C" int bo_topk(bo_ctx *ctx, int k, int64_t *idx, double *val) {
     if (k > ctx->last_M) k = (int)ctx->last_M;
     std::vector<double> hv(k);
     BO_TRY(bo_topk_run(ctx, ctx->last_val_ptr, ctx->last_M, k, hv.data(), idx));
+    // fewer than k finite (non-NaN) values: the tail is marked idx = -1, val = NaN (callers truncate there)
+    for (int j = 0; j < k; ++j)
+        if (idx[j] == INT64_MAX || idx[j] < 0) { idx[j] = -1; hv[j] = NAN; }
     if (val) std::copy(hv.begin(), hv.end(), val);
     return BO_OK;
 }
@@ -526,9 +710,38 @@ extern "C" int bo_set_precision(bo_ctx *ctx, int prec, double tol) {
     if (!ctx) return BO_ERR_ARG;
     if (prec != BO_PREC_F64 && prec != BO_PREC_OZAKI) return bo_set_err(ctx, BO_ERR_ARG, "unknown precision path %d", prec);
     if (prec == BO_PREC_OZAKI && !(tol > 0.0)) return bo_set_err(ctx, BO_ERR_ARG, "bo_set_precision: tol must be > 0");
+    if (ctx->prec != prec || ctx->prec_tol != tol) ctx->oz_demoted = false;
     ctx->prec = prec;
-    ctx->prec_tol = tol;
-    ctx->oz_ready = false;
+    ctx->prec_tol = tol;         // (the W slice planes stay valid: bo_ozaki_prepare re-slices only when the level changes)
+    return BO_OK;
+}
+
+extern "C" int bo_set_rescue(bo_ctx *ctx, int on, double tol, double floor_rel) {
+    if (!ctx) return BO_ERR_ARG;
+    if (on && (!(tol > 0.0) || !(floor_rel >= 0.0))) return bo_set_err(ctx, BO_ERR_ARG, "bo_set_rescue: tol must be > 0, floor >= 0");
+    ctx->oz_rescue = on != 0;
+    if (on) { ctx->oz_rescue_tol = tol; ctx->oz_rescue_floor = floor_rel; }
+    ctx->oz_demoted = false;
+    return BO_OK;
+}
+
+extern "C" int bo_ozaki_error_bound(bo_ctx *ctx, double *errk) {
+    BO_ENTER(ctx);
+    if (!errk) return BO_ERR_ARG;
+    if (!ctx->fitted || ctx->prec != BO_PREC_OZAKI) return bo_set_err(ctx, BO_ERR_STATE, "bo_ozaki_error_bound: fit and select BO_PREC_OZAKI first");
+    const int S = bo_ozaki_choose_slices(ctx, ctx->prec_tol);
+    if (S < 1) return BO_ERR_CUDA;
+    BO_TRY(bo_ozaki_prepare(ctx, S));
+    BO_TRY(bo_ozaki_error_scale(ctx, S));
+    for (int s = 0; s < ctx->S; ++s) errk[s] = ctx->h_errk[s];
+    return BO_OK;
+}
+
+extern "C" int bo_rescue_info(bo_ctx *ctx, int *int8_path, int64_t *flagged, int64_t *total) {
+    if (!ctx) return BO_ERR_ARG;
+    if (int8_path) *int8_path = ctx->oz_last_path;
+    if (flagged) *flagged = ctx->oz_last_flagged;
+    if (total) *total = ctx->oz_last_total;
     return BO_OK;
 }
 
@@ -706,7 +919,7 @@ extern "C" int bo_gram(bo_ctx *ctx, int kernel, int n, int d, const double *X, c
     if (e == cudaSuccess) e = cudaMemcpyAsync(dXs, xs.data(), sizeof(double) * xs.size(), cudaMemcpyHostToDevice, st);
     if (e == cudaSuccess) e = cudaMemcpyAsync(dHyp, hyp, sizeof(hyp), cudaMemcpyHostToDevice, st);
     int rc = BO_OK;
-    if (e == cudaSuccess) rc = bo_linalg_gram(ctx, kernel, n, np, dp, 1, dXs, dHyp, dHyp + 1, dK);
+    if (e == cudaSuccess) rc = bo_linalg_gram(ctx, kernel, n, np, dp, 1, dXs, dHyp, dHyp + 1, dK, 1, nullptr, nullptr);
     if (e == cudaSuccess && rc == BO_OK)
         e = cudaMemcpy2DAsync(K, sizeof(double) * n, dK, sizeof(double) * np, sizeof(double) * n, n,
                               dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st);

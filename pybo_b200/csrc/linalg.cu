@@ -21,35 +21,140 @@ __device__ __forceinline__ double kern_from_sqdist(int kernel, double D, double 
     return rho * (1.0 + r + r * r * (1.0 / 3.0)) * exp(-r);
 }
 
-__global__ void gram_kernel(int kernel, int n, int np, int dp, const double *__restrict__ Xs,
-                            const double *__restrict__ rho, const double *__restrict__ sn2,
-                            double *__restrict__ K) {
+// One CTA = one 64 x 64 tile of the LOWER triangle (tile row ti >= tile column tj; upper tiles are produced by
+// mirroring, never recomputed).  The 2 x 64 scaled points are staged in shared memory k-major, so a thread reads its
+// four row points as broadcasts and its four column points as two 16-byte loads; thread (ty, tx) owns rows
+// ty + 16 a and columns 4 tx + b and stores 32 contiguous bytes per row (a warp covers two full 512-byte row
+// segments).  With `mirror` the tile also goes through a padded shared-memory transpose and is written to the upper
+// triangle with the same store pattern.  `aug` (optional, S x np): row `n` of the padded matrix receives
+// [aug[0..n), ann] instead of the identity -- the right-hand side rides through the factorisation (bo_loglik_fit).
+template <int DP>
+__global__ void __launch_bounds__(256)
+gram_tile_kernel(int kernel, int n, int np, const double *__restrict__ Xs, const double *__restrict__ rho,
+                 const double *__restrict__ sn2, double *__restrict__ K, int mirror, const double *__restrict__ aug,
+                 const double *__restrict__ ann) {
+    // the point stage (2 x DP x 64 doubles) and the transpose tile (64 x 65) share one buffer: the tile is written
+    // only after every thread has finished reading the points
+    constexpr int STAGE = 2 * DP * 64, TILE = 64 * 65;
+    __shared__ __align__(16) double buf[STAGE > TILE ? STAGE : TILE];
+    double (*xi)[64] = reinterpret_cast<double (*)[64]>(buf);
+    double (*xj)[64] = reinterpret_cast<double (*)[64]>(buf + DP * 64);
+    double (*tile)[65] = reinterpret_cast<double (*)[65]>(buf);
     const int s = blockIdx.z;
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    const int i = blockIdx.y * blockDim.y + threadIdx.y;
-    if (i >= np || j >= np) return;
-    double v;
-    if (i < n && j < n) {
-        const double *xi = Xs + ((int64_t)s * np + i) * dp;
-        const double *xj = Xs + ((int64_t)s * np + j) * dp;
-        double D = 0.0;
-        for (int k = 0; k < dp; ++k) {
-            double t = xi[k] - xj[k];
-            D = fma(t, t, D);
-        }
-        v = kern_from_sqdist(kernel, D, rho[s]);
-        if (i == j) v += sn2[s];
-    } else {
-        v = (i == j) ? 1.0 : 0.0;
+    int x = blockIdx.x;
+    int ti = (int)((sqrt(8.0 * x + 1.0) - 1.0) * 0.5);
+    while ((ti + 1) * (ti + 2) / 2 <= x) ++ti;
+    while (ti * (ti + 1) / 2 > x) --ti;
+    const int tj = x - ti * (ti + 1) / 2;
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const double *Xb = Xs + (int64_t)s * np * DP;
+    for (int e = tid; e < 64 * DP; e += 256) {
+        xi[e % DP][e / DP] = Xb[(int64_t)ti * 64 * DP + e];
+        xj[e % DP][e / DP] = Xb[(int64_t)tj * 64 * DP + e];
     }
-    K[(int64_t)s * np * np + (int64_t)i * np + j] = v;
+    __syncthreads();
+    double D[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) D[a][b] = 0.0;
+#pragma unroll
+    for (int k = 0; k < DP; ++k) {
+        double pi[4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) pi[a] = xi[k][ty + 16 * a];
+        const double2 p01 = *reinterpret_cast<const double2 *>(&xj[k][4 * tx]);
+        const double2 p23 = *reinterpret_cast<const double2 *>(&xj[k][4 * tx + 2]);
+        const double pj[4] = {p01.x, p01.y, p23.x, p23.y};
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                const double t = pi[a] - pj[b];
+                D[a][b] = fma(t, t, D[a][b]);
+            }
+    }
+    const double rh = rho[s], sn = sn2[s];
+    double *Kb = K + (int64_t)s * np * np;
+    const bool offdiag = ti != tj;
+    if (mirror && offdiag) __syncthreads();                    // points consumed: the buffer becomes the tile
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+        const int i = ti * 64 + ty + 16 * a;
+        double v[4];
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const int j = tj * 64 + 4 * tx + b;
+            if (i < n && j < n) {
+                v[b] = kern_from_sqdist(kernel, D[a][b], rh);
+                if (i == j) v[b] += sn;
+            } else if (aug != nullptr && i == n && j <= n) {
+                v[b] = (j < n) ? aug[(int64_t)s * np + j] : ann[s];
+            } else {
+                v[b] = (i == j) ? 1.0 : 0.0;
+            }
+        }
+        double *dst = Kb + (int64_t)i * np + tj * 64 + 4 * tx;
+        *reinterpret_cast<double2 *>(dst) = make_double2(v[0], v[1]);
+        *reinterpret_cast<double2 *>(dst + 2) = make_double2(v[2], v[3]);
+        if (mirror && offdiag) {
+#pragma unroll
+            for (int b = 0; b < 4; ++b) tile[ty + 16 * a][4 * tx + b] = v[b];
+        }
+    }
+    if (mirror && offdiag) {
+        __syncthreads();
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            const int r = ty + 16 * a;                         // row of the mirrored tile = column of the computed one
+            double *dst = Kb + (int64_t)(tj * 64 + r) * np + ti * 64 + 4 * tx;
+            *reinterpret_cast<double2 *>(dst) = make_double2(tile[4 * tx][r], tile[4 * tx + 1][r]);
+            *reinterpret_cast<double2 *>(dst + 2) = make_double2(tile[4 * tx + 2][r], tile[4 * tx + 3][r]);
+        }
+    }
 }
 
+// K_s = k_s(X, X) + sn2_s I on the lower triangle of S padded np x np matrices (np % 64 == 0); `mirror` also fills
+// the upper triangle (the factorisation never reads it).
 int bo_linalg_gram(bo_ctx *ctx, int kernel, int n, int np, int dp, int S, const double *dXs,
-                   const double *rho_dev, const double *sn2_dev, double *K) {
-    dim3 blk(32, 8), grd((np + 31) / 32, (np + 7) / 8, S);
+                   const double *rho_dev, const double *sn2_dev, double *K, int mirror, const double *aug,
+                   const double *ann) {
+    const int T = np / 64;
+    dim3 grd(T * (T + 1) / 2, 1, S);
     BO_LAUNCH(ctx, "gram_kernel");
-    gram_kernel<<<grd, blk, 0, ctx->stream>>>(kernel, n, np, dp, dXs, rho_dev, sn2_dev, K);
+    switch (dp) {
+#define GRAM_RUN(DPV) case DPV: gram_tile_kernel<DPV><<<grd, 256, 0, ctx->stream>>>(kernel, n, np, dXs, rho_dev, sn2_dev, K, mirror, aug, ann); break
+        GRAM_RUN(2); GRAM_RUN(4); GRAM_RUN(8); GRAM_RUN(16); GRAM_RUN(32);
+#undef GRAM_RUN
+        default: return bo_set_err(ctx, BO_ERR_ARG, "unsupported padded dimension %d", dp);
+    }
+    BO_CHECK_LAUNCH(ctx);
+    return BO_OK;
+}
+
+// log marginal likelihood from an augmented factor: row n of L holds alpha^T = (L^-1 r)^T
+//   ll = -1/2 |alpha|^2 - sum_{i<n} log L_ii - n/2 log(2 pi)
+__global__ void loglik_aug_kernel(const double *__restrict__ L, int n, int np, double *__restrict__ out) {
+    __shared__ double red[32];
+    const double *Ls = L + (int64_t)blockIdx.x * np * np;
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const double a = Ls[(int64_t)n * np + i];
+        acc += -0.5 * a * a - log(Ls[(int64_t)i * (np + 1)]);
+    }
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        double v = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : 0.0;
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (threadIdx.x == 0) out[blockIdx.x] = v - 0.5 * n * 1.8378770664093453;   // log(2 pi)
+    }
+}
+
+int bo_linalg_loglik_aug(bo_ctx *ctx, const double *L, int n, int np, int S, double *out) {
+    BO_LAUNCH(ctx, "loglik_aug_kernel");
+    loglik_aug_kernel<<<S, 256, 0, ctx->stream>>>(L, n, np, out);
     BO_CHECK_LAUNCH(ctx);
     return BO_OK;
 }

@@ -939,6 +939,26 @@ int bo_ozaki_choose_slices(bo_ctx *ctx, double tol) {
     return OZ_MAX_S;
 }
 
+// A-priori bound on the error of s2 = rho - |v|^2 on this path, used by the rescue pass (score.cu run_oz):
+//     |ds2| <= errK * sqrt(q rho),  q = rho - s2 = |v|^2,  errK = OZ_ERR_SAFETY * est(level)
+// with est(level) the model above (8 sqrt(np) 2^emax sqrt(rho) 256^-S, / 32 with the extra pair group).  ds2 = 2 v . dv
+// with independent zero-mean entry errors dv_i, hence the sqrt(q) factor.  Calibration (tools/oz_calib.py, nine shapes
+// x six levels x 73 k candidates incl. 8 k placed on top of observations): max |ds2| / (est sqrt(q rho)) = 0.85,
+// median 0.03 -- the factor 2 leaves > 2.3x on the worst case seen (profiles/r2_oz_calib.txt).
+#define OZ_ERR_SAFETY 2.0
+int bo_ozaki_error_scale(bo_ctx *ctx, int S) {
+    const int ns = ctx->S;
+    ctx->h_errk.assign(ns, 0.0);
+    for (int s = 0; s < ns; ++s) {
+        const double est = 8.0 * sqrt((double)ctx->np) * ldexp(1.0, ctx->h_emax[s]) * sqrt(ctx->h_rho[s]) * ldexp(1.0, -8 * S) /
+                           (ctx->oz_extra ? 32.0 : 1.0);
+        ctx->h_errk[s] = OZ_ERR_SAFETY * est;
+    }
+    BO_TRY(bo_reserve(ctx, &ctx->dErrK, &ctx->errk_capacity, (size_t)ns));
+    BO_CUDA(ctx, cudaMemcpyAsync(ctx->dErrK, ctx->h_errk.data(), sizeof(double) * ns, cudaMemcpyHostToDevice, ctx->stream));
+    return BO_OK;
+}
+
 template <int DP, int S>
 static void launch_oz_kstar_fast(bo_ctx *ctx, int s, const double *dXc, int64_t c0, int mc, int mcp, int8_t *Kss,
                                  cudaStream_t st) {

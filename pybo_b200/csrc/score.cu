@@ -339,6 +339,12 @@ struct AcqParams {
     double *blkval;
     int64_t *blkidx;
     int64_t blk0;
+    // int8-slice path only: a-priori bound on the absolute error of s2_s is  errK[s] * sqrt(q_s rho_s),
+    // q_s = rho_s - s2_s (ozaki.cu, bo_ozaki_error_scale); errest[c0 + m] receives the first-order bound on the
+    // absolute error of this candidate's output (mode 0: the acquisition value, mode 1: s2), +inf where the
+    // first-order estimate itself is not trustworthy (s2_s < 16 x its own error bound)
+    const double *rhoS, *errK;
+    double *errest;
 };
 
 __device__ __forceinline__ bool better(double v, int64_t i, double bv, int64_t bi) {
@@ -354,16 +360,24 @@ __global__ void __launch_bounds__(256) acq_kernel(AcqParams p) {
         const double invS = 1.0 / S;
         const bool want_grad = (p.mode == 0) ? (p.out_grad != nullptr) : (p.out_dmu != nullptr || p.out_ds2 != nullptr);
         const int64_t gi = p.c0 + m;
+        double eacc = 0.0;                  // error bound accumulator (int8-slice path)
         if (p.mode == 0 && (p.acq == BO_ACQ_EI || p.acq == BO_ACQ_PI)) {
             // mean over hyper-samples of the per-sample EI / PI at the common target
             double acc = 0.0;
             for (int s = 0; s < S; ++s) {
                 const double mu = p.muS[(int64_t)s * p.mcp + m];
-                const double s2 = fmax(p.s2S[(int64_t)s * p.mcp + m], S2_FLOOR);
+                const double s2r = p.s2S[(int64_t)s * p.mcp + m];
+                const double s2 = fmax(s2r, S2_FLOOR);
                 const double sd = sqrt(s2), dl = mu - p.param, z = dl / sd;
                 const double cdf = 0.5 * erfc(-z * M_SQRT1_2);
                 const double pdf = INV_SQRT_2PI * exp(-0.5 * z * z);
                 acc += (p.acq == BO_ACQ_EI) ? (dl * cdf + sd * pdf) : cdf;
+                if (p.errest) {
+                    // |dEI/ds2| = pdf / (2 sd),  |dPI/ds2| = pdf |z| / (2 s2)
+                    const double E = p.errK[s] * sqrt(fmax(p.rhoS[s] - s2r, 0.0) * p.rhoS[s]);
+                    const double sens = (p.acq == BO_ACQ_EI) ? 0.5 * pdf / sd : 0.5 * pdf * fabs(z) / s2;
+                    eacc += (s2r < 16.0 * E) ? INFINITY : sens * E;
+                }
             }
             val = acc * invS;
             if (want_grad) {
@@ -391,17 +405,27 @@ __global__ void __launch_bounds__(256) acq_kernel(AcqParams p) {
             double s2b = 0.0;
             for (int s = 0; s < S; ++s) {
                 const double dm = p.muS[(int64_t)s * p.mcp + m] - mub;
-                s2b += p.s2S[(int64_t)s * p.mcp + m] + dm * dm;
+                const double s2r = p.s2S[(int64_t)s * p.mcp + m];
+                s2b += s2r + dm * dm;
+                if (p.errest) {
+                    const double E = p.errK[s] * sqrt(fmax(p.rhoS[s] - s2r, 0.0) * p.rhoS[s]);
+                    eacc += (p.mode == 0 && p.acq == BO_ACQ_UCB && s2r < 16.0 * E) ? INFINITY : E;
+                }
             }
             s2b *= invS;
+            // rho - |v|^2 can round below zero next to an observation (sn2 ~ 1e-6 rho): the variance handed back
+            // is clamped at 0 and the UCB square roots see a tiny positive floor instead of NaN / Inf
+            const double s2c = fmax(s2b, S2_FLOOR);
             if (p.mode == 1) {
                 if (p.out_mu) p.out_mu[gi] = mub;
-                if (p.out_s2) p.out_s2[gi] = s2b;
+                if (p.out_s2) p.out_s2[gi] = fmax(s2b, 0.0);
                 val = mub;
             } else if (p.acq == BO_ACQ_MEAN) {
                 val = mub;
+                eacc = 0.0;                                  // the mean never goes through the int8 contraction
             } else {   // UCB, reference policies/simple.py:72
-                val = mub + sqrt(p.param * s2b);
+                val = mub + sqrt(p.param * s2c);
+                eacc *= 0.5 * sqrt(p.param / s2c);           // |dUCB/ds2b| x error of s2b (invS applied below)
             }
             if (want_grad) {
                 for (int k = 0; k < d; ++k) {
@@ -421,12 +445,13 @@ __global__ void __launch_bounds__(256) acq_kernel(AcqParams p) {
                     } else if (p.acq == BO_ACQ_MEAN) {
                         p.out_grad[gi * d + k] = dmb;
                     } else {   // simple.py:69-70
-                        p.out_grad[gi * d + k] = dmb + 0.5 * sqrt(p.param / s2b) * dsb;
+                        p.out_grad[gi * d + k] = dmb + 0.5 * sqrt(p.param / s2c) * dsb;
                     }
                 }
             }
         }
         if (p.mode == 0 && p.out_val) p.out_val[gi] = val;
+        if (p.errest) p.errest[gi] = eacc * invS;
     }
     if (p.blkval == nullptr) return;
     // block arg max, ties to the lowest index, NaN never wins
@@ -512,6 +537,121 @@ topk_pass_kernel(const double *__restrict__ vals, int64_t M, const double *__res
 }
 
 // ---------------------------------------------------------------------------
+// rescue pass of the int8-slice path (kernels): candidates whose a-priori error bound exceeds the
+// acquisition tolerance are compacted, re-scored on the FP64 path and scattered back.
+// ---------------------------------------------------------------------------
+// flagged <=> !(errest <= tol * max(|x|, floor)), floor = floor_abs + floor_rel * |*gmax| (NaN flags too)
+__global__ void oz_flag_kernel(int64_t M, const double *__restrict__ x, const double *__restrict__ errest, double tol,
+                               double floor_abs, double floor_rel, const double *__restrict__ gmax,
+                               int *__restrict__ list, int *__restrict__ count) {
+    const double gm = gmax ? fabs(gmax[0]) : 0.0;
+    const double floor = floor_abs + ((gm == gm && gm < INFINITY) ? floor_rel * gm : 0.0);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < M; i += (int64_t)gridDim.x * blockDim.x) {
+        const double e = errest[i];
+        if (e == 0.0) continue;
+        const double thr = tol * fmax(fabs(x[i]), floor);
+        if (!(e <= thr)) list[atomicAdd(count, 1)] = (int)i;
+    }
+}
+
+// the flagged list is sorted so the compact batch (and with it every FP64 tile) does not depend on the
+// order in which the atomics landed: bitonic sort in one block for small lists, else a rank-by-count pass
+__global__ void oz_sort_small_kernel(int *__restrict__ list, int count) {
+    extern __shared__ int sl[];
+    int np2 = 1;
+    while (np2 < count) np2 <<= 1;
+    for (int i = threadIdx.x; i < np2; i += blockDim.x) sl[i] = i < count ? list[i] : 0x7fffffff;
+    __syncthreads();
+    for (int k = 2; k <= np2; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < np2; i += blockDim.x) {
+                const int l = i ^ j;
+                if (l > i) {
+                    const int a = sl[i], b = sl[l];
+                    const bool up = (i & k) == 0;
+                    if ((a > b) == up) { sl[i] = b; sl[l] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    for (int i = threadIdx.x; i < count; i += blockDim.x) list[i] = sl[i];
+}
+
+// large lists: mark flags in a bitmap, then compact in index order (block prefix over 64-bit words)
+__global__ void oz_mark_kernel(const int *__restrict__ list, int count, unsigned long long *__restrict__ bits) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) atomicOr(bits + (list[i] >> 6), 1ull << (list[i] & 63));
+}
+__global__ void oz_wordcount_kernel(const unsigned long long *__restrict__ bits, int nwords, int *__restrict__ blocksum) {
+    __shared__ int red[32];
+    const int w = blockIdx.x * 1024 + threadIdx.x;
+    int c = w < nwords ? __popcll(bits[w]) : 0;
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        int v = red[threadIdx.x];
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (threadIdx.x == 0) blocksum[blockIdx.x] = v;
+    }
+}
+__global__ void oz_compact_kernel(const unsigned long long *__restrict__ bits, int nwords, const int *__restrict__ blocksum,
+                                  int *__restrict__ list) {
+    __shared__ int wsum[32];
+    __shared__ int base_s;
+    const int w = blockIdx.x * 1024 + threadIdx.x;
+    const unsigned long long word = w < nwords ? bits[w] : 0ull;
+    const int c = __popcll(word);
+    if (threadIdx.x == 0) {
+        int b = 0;
+        for (int i = 0; i < (int)blockIdx.x; ++i) b += blocksum[i];
+        base_s = b;
+    }
+    // inclusive scan of c over the block
+    int v = c;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v += t;
+    }
+    if (lane == 31) wsum[wid] = v;
+    __syncthreads();
+    if (wid == 0) {
+        int t = wsum[lane];
+        for (int o = 1; o < 32; o <<= 1) {
+            const int u = __shfl_up_sync(0xffffffffu, t, o);
+            if (lane >= o) t += u;
+        }
+        wsum[lane] = t;
+    }
+    __syncthreads();
+    int pos = base_s + v - c + (wid ? wsum[wid - 1] : 0);
+    unsigned long long rem = word;
+    while (rem) {
+        const int b = __ffsll((long long)rem) - 1;
+        list[pos++] = w * 64 + b;
+        rem &= rem - 1;
+    }
+}
+
+__global__ void oz_gather_rows_kernel(const double *__restrict__ Xc, int d, const int *__restrict__ list, int count,
+                                      double *__restrict__ out) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= (int64_t)count * d) return;
+    const int i = (int)(e / d), k = (int)(e - (int64_t)i * d);
+    out[e] = Xc[(int64_t)list[i] * d + k];
+}
+
+__global__ void oz_scatter_kernel(const int *__restrict__ list, int count, const double *__restrict__ a,
+                                  double *__restrict__ outa, const double *__restrict__ b, double *__restrict__ outb) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const int g = list[i];
+    if (outa) outa[g] = a[i];
+    if (outb) outb[g] = b[i];
+}
+
+// ---------------------------------------------------------------------------
 // host orchestration
 // ---------------------------------------------------------------------------
 int bo_score_init(bo_ctx *ctx) {
@@ -553,135 +693,80 @@ static int launch_grad_partial(bo_ctx *ctx, int s, const double *dXc, int64_t c0
         }                                                                     \
     } while (0)
 
-int bo_score_run(bo_ctx *ctx, const ScoreRequest &rq) {
-    if (!ctx->fitted) return bo_set_err(ctx, BO_ERR_STATE, "bo_score/bo_predict before bo_fit");
+// gradient / small-batch scratch: every buffer has its own capacity (a refit with another n, S or d changes
+// their sizes independently of np * cap)
+static int reserve_v(bo_ctx *ctx, size_t n_v) {
+    BO_TRY(bo_reserve(ctx, &ctx->dV, &ctx->v_capacity, n_v));
+    return BO_OK;
+}
+static int reserve_grad(bo_ctx *ctx, size_t n_v, size_t cap, int S, int d, int dp) {
+    BO_TRY(bo_reserve(ctx, &ctx->dV, &ctx->v_capacity, n_v));
+    BO_TRY(bo_reserve(ctx, &ctx->dU, &ctx->u_capacity, n_v));
+    BO_TRY(bo_reserve(ctx, &ctx->dGpart, &ctx->gpart_capacity, (size_t)GRAD_SLICES * cap * 2 * dp));
+    BO_TRY(bo_reserve(ctx, &ctx->dDmuS, &ctx->dmus_capacity, (size_t)S * cap * d));
+    BO_TRY(bo_reserve(ctx, &ctx->dDs2S, &ctx->ds2s_capacity, (size_t)S * cap * d));
+    return BO_OK;
+}
+
+static int reserve_moments(bo_ctx *ctx, int nblk, int64_t cap, int S) {
+    const size_t need = (size_t)nblk * cap;
+    if (ctx->mom_capacity < need || !ctx->dQpart) {
+        size_t c1 = ctx->mom_capacity, c2 = ctx->mom_capacity;
+        BO_TRY(bo_reserve(ctx, &ctx->dQpart, &c1, need));
+        BO_TRY(bo_reserve(ctx, &ctx->dPpart, &c2, need));
+        ctx->mom_capacity = need;
+    }
+    const size_t needm = (size_t)S * cap;
+    if (ctx->gm_capacity < needm || !ctx->dMuS) {
+        size_t c1 = ctx->gm_capacity, c2 = ctx->gm_capacity;
+        BO_TRY(bo_reserve(ctx, &ctx->dMuS, &c1, needm));
+        BO_TRY(bo_reserve(ctx, &ctx->dS2S, &c2, needm));
+        ctx->gm_capacity = needm;
+    }
+    return BO_OK;
+}
+
+static int reserve_blocks(bo_ctx *ctx, size_t need) {
+    if (ctx->blk_capacity < need || !ctx->dBlkVal) {
+        size_t c1 = ctx->blk_capacity, c2 = ctx->blk_capacity;
+        BO_TRY(bo_reserve(ctx, &ctx->dBlkVal, &c1, need));
+        BO_TRY(bo_reserve(ctx, &ctx->dBlkIdx, &c2, need));
+        ctx->blk_capacity = need;
+    }
+    return BO_OK;
+}
+
+#define ARGMAX_PASS_BLOCKS 592
+
+// (max, first arg max) of a device array into the tail record dBlkVal/dBlkIdx[blk_capacity - 1]
+static int final_argmax_over(bo_ctx *ctx, const double *vals, int64_t M) {
+    const int nb = (int)((M + 255) / 256 < ARGMAX_PASS_BLOCKS ? (M + 255) / 256 : ARGMAX_PASS_BLOCKS);
+    {
+        BO_LAUNCH(ctx, "topk_pass_kernel");
+        topk_pass_kernel<<<nb, 256, 0, ctx->stream>>>(vals, M, nullptr, nullptr, 1, ctx->dBlkVal, ctx->dBlkIdx);
+        BO_CHECK_LAUNCH(ctx);
+    }
+    BO_LAUNCH(ctx, "argmax_final_kernel");
+    argmax_final_kernel<<<1, 1024, 0, ctx->stream>>>(ctx->dBlkVal, ctx->dBlkIdx, nb, ctx->dBlkVal + ctx->blk_capacity - 1,
+                                                    ctx->dBlkIdx + ctx->blk_capacity - 1);
+    BO_CHECK_LAUNCH(ctx);
+    return BO_OK;
+}
+
+// FP64 path: K* (SIMT) -> V = W K* (DMMA) -> moments -> [gradients] -> acquisition, chunk by chunk
+static int run_fp64(bo_ctx *ctx, const ScoreRequest &rq) {
     const int np = ctx->np, S = ctx->S, d = ctx->d, dp = ctx->dp, nblk = np / 128;
     const bool grad = (rq.mode == 0) ? (rq.dGrad != nullptr) : (rq.dDmu != nullptr || rq.dDs2 != nullptr);
     const int64_t M = rq.M;
-    if (M <= 0) return bo_set_err(ctx, BO_ERR_ARG, "M must be positive");
-    // int8-slice path for value-only passes when selected; gradients stay on the FP64 path
-    // (tiny batches stay on the exact FP64 GEMV/GEMM path: nothing to gain from the tensor pipe there)
-    const bool oz = (ctx->prec == BO_PREC_OZAKI) && !grad && rq.M > 64;
-    int oz_S = 0;
-    if (oz) {
-        oz_S = bo_ozaki_choose_slices(ctx, ctx->prec_tol);
-        if (oz_S < 1) return BO_ERR_CUDA;
-        BO_TRY(bo_ozaki_prepare(ctx, oz_S));
-    }
-    const int64_t chunk = oz ? (int64_t)256 * 128 : ctx->chunk;
+    const int64_t chunk = ctx->chunk;
     const int64_t cap = bo_round_up64(M < chunk ? M : chunk, 128);
-
-    if (!oz) BO_TRY(bo_reserve(ctx, &ctx->dKs, &ctx->ks_capacity, (size_t)np * cap));
-    {
-        size_t need = (size_t)nblk * cap;
-        if (ctx->mom_capacity < need || !ctx->dQpart) {
-            size_t c1 = ctx->mom_capacity, c2 = ctx->mom_capacity;
-            BO_TRY(bo_reserve(ctx, &ctx->dQpart, &c1, need));
-            BO_TRY(bo_reserve(ctx, &ctx->dPpart, &c2, need));
-            ctx->mom_capacity = need;
-        }
-        size_t needm = (size_t)S * cap;
-        if (ctx->gm_capacity < needm || !ctx->dMuS) {
-            size_t c1 = ctx->gm_capacity, c2 = ctx->gm_capacity;
-            BO_TRY(bo_reserve(ctx, &ctx->dMuS, &c1, needm));
-            BO_TRY(bo_reserve(ctx, &ctx->dS2S, &c2, needm));
-            ctx->gm_capacity = needm;
-        }
-    }
-    if (grad) {
-        size_t need = (size_t)np * cap;
-        if (ctx->grad_capacity < need || !ctx->dV) {
-            size_t c1 = ctx->grad_capacity, c2 = ctx->grad_capacity, c3 = 0, c4 = 0, c5 = 0;
-            BO_TRY(bo_reserve(ctx, &ctx->dV, &c1, need));
-            BO_TRY(bo_reserve(ctx, &ctx->dU, &c2, need));
-            if (ctx->dGpart) { cudaFree(ctx->dGpart); ctx->dGpart = nullptr; }
-            if (ctx->dDmuS) { cudaFree(ctx->dDmuS); ctx->dDmuS = nullptr; }
-            if (ctx->dDs2S) { cudaFree(ctx->dDs2S); ctx->dDs2S = nullptr; }
-            BO_TRY(bo_reserve(ctx, &ctx->dGpart, &c3, (size_t)GRAD_SLICES * cap * 2 * dp));
-            BO_TRY(bo_reserve(ctx, &ctx->dDmuS, &c4, (size_t)S * cap * d));
-            BO_TRY(bo_reserve(ctx, &ctx->dDs2S, &c5, (size_t)S * cap * d));
-            ctx->grad_capacity = need;
-        }
-    }
+    BO_TRY(bo_reserve(ctx, &ctx->dKs, &ctx->ks_capacity, (size_t)np * cap));
+    BO_TRY(reserve_moments(ctx, nblk, cap, S));
+    if (grad) BO_TRY(reserve_grad(ctx, (size_t)np * cap, (size_t)cap, S, d, dp));
+    else if (M <= 16) BO_TRY(reserve_v(ctx, (size_t)np * cap));
     const int64_t nchunks = (M + chunk - 1) / chunk;
     const int64_t nblocks_total = nchunks * ((chunk + 255) / 256);
-    if (rq.want_best) {
-        size_t c1 = ctx->blk_capacity, c2 = ctx->blk_capacity;
-        if (ctx->blk_capacity < (size_t)nblocks_total + 8 || !ctx->dBlkVal) {
-            BO_TRY(bo_reserve(ctx, &ctx->dBlkVal, &c1, (size_t)nblocks_total + 8));
-            BO_TRY(bo_reserve(ctx, &ctx->dBlkIdx, &c2, (size_t)nblocks_total + 8));
-            ctx->blk_capacity = (size_t)nblocks_total + 8;
-        }
-    }
-
-    if (oz) {
-        // Software pipeline over work items (chunk, hyper-sample): the operand slicer of item w+1
-        // runs on the low-priority side stream while the tcgen05 contraction of item w runs on
-        // the main stream (different pipes: FP64/ALU vs tensor).  Two slice buffers.
-        const int64_t nchunk = (M + chunk - 1) / chunk;
-        const int64_t nitems = nchunk * S;
-        BO_TRY(bo_ozaki_reserve(ctx, oz_S, (int)cap, nitems > 1 ? 2 : 1));
-        auto item = [&](int64_t w, int64_t &c0, int &mc, int &mcp, int &s) {
-            c0 = (w / S) * chunk;
-            s = (int)(w % S);
-            mc = (int)((M - c0) < chunk ? (M - c0) : chunk);
-            mcp = bo_round_up(mc, 128);
-        };
-        int64_t c0; int mc, mcp, s;
-        // Overlap is opt-in (BO_OZ_OVERLAP=1): on a power-capped B200 the two kernels only slow each
-        // other down (measured: contraction 2.77 -> 3.56 ms per chunk), so by default both stages
-        // run back to back on the main stream.
-        static const bool overlap = getenv("BO_OZ_OVERLAP") && atoi(getenv("BO_OZ_OVERLAP")) != 0;
-        cudaStream_t side = overlap ? ctx->stream2 : ctx->stream;
-        // candidates staged on the main stream must be visible to the side stream
-        BO_CUDA(ctx, cudaEventRecord(ctx->ev_consumed[0], ctx->stream));
-        BO_CUDA(ctx, cudaStreamWaitEvent(side, ctx->ev_consumed[0], 0));
-        item(0, c0, mc, mcp, s);
-        BO_TRY(bo_ozaki_slice(ctx, s, oz_S, rq.dXc, c0, mc, mcp, 0, side));
-        BO_CUDA(ctx, cudaEventRecord(ctx->ev_sliced[0], side));
-        int64_t blk0 = 0;
-        for (int64_t w = 0; w < nitems; ++w) {
-            const int buf = (int)(w & 1);
-            item(w, c0, mc, mcp, s);
-            BO_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_sliced[buf], 0));
-            BO_TRY(bo_ozaki_contract(ctx, s, oz_S, mcp, buf, ctx->dMuS + (int64_t)s * mcp, ctx->dS2S + (int64_t)s * mcp, nullptr));
-            BO_CUDA(ctx, cudaEventRecord(ctx->ev_consumed[buf], ctx->stream));
-            if (w + 1 < nitems) {
-                int64_t c1; int mc1, mcp1, s1;
-                item(w + 1, c1, mc1, mcp1, s1);
-                const int nbuf = (int)((w + 1) & 1);
-                if (w >= 1) BO_CUDA(ctx, cudaStreamWaitEvent(side, ctx->ev_consumed[nbuf], 0));
-                BO_TRY(bo_ozaki_slice(ctx, s1, oz_S, rq.dXc, c1, mc1, mcp1, nbuf, side));
-                BO_CUDA(ctx, cudaEventRecord(ctx->ev_sliced[nbuf], side));
-            }
-            if (s == S - 1) {
-                AcqParams ap = {};
-                ap.mode = rq.mode; ap.acq = rq.acq; ap.param = rq.param;
-                ap.S = S; ap.d = d; ap.mc = mc; ap.mcp = mcp; ap.c0 = c0;
-                ap.muS = ctx->dMuS; ap.s2S = ctx->dS2S; ap.dmuS = nullptr; ap.ds2S = nullptr;
-                ap.out_val = rq.dVal; ap.out_grad = nullptr;
-                ap.out_mu = rq.dMu; ap.out_s2 = rq.dS2; ap.out_dmu = nullptr; ap.out_ds2 = nullptr;
-                ap.blkval = rq.want_best ? ctx->dBlkVal : nullptr;
-                ap.blkidx = rq.want_best ? ctx->dBlkIdx : nullptr;
-                ap.blk0 = blk0;
-                const int nb = (mc + 255) / 256;
-                {
-                    BO_LAUNCH(ctx, "acq_kernel");
-                    acq_kernel<<<nb, 256, 0, ctx->stream>>>(ap);
-                    BO_CHECK_LAUNCH(ctx);
-                }
-                blk0 += nb;
-            }
-        }
-        if (rq.want_best) {
-            BO_LAUNCH(ctx, "argmax_final_kernel");
-            argmax_final_kernel<<<1, 1024, 0, ctx->stream>>>(ctx->dBlkVal, ctx->dBlkIdx, blk0,
-                                                            ctx->dBlkVal + ctx->blk_capacity - 1,
-                                                            ctx->dBlkIdx + ctx->blk_capacity - 1);
-            BO_CHECK_LAUNCH(ctx);
-        }
-        return BO_OK;
-    }
+    if (rq.want_best) BO_TRY(reserve_blocks(ctx, (size_t)(nblocks_total > ARGMAX_PASS_BLOCKS ? nblocks_total : ARGMAX_PASS_BLOCKS) + 8));
 
     int64_t blk0 = 0;
     for (int64_t c0 = 0; c0 < M; c0 += chunk) {
@@ -692,19 +777,6 @@ int bo_score_run(bo_ctx *ctx, const ScoreRequest &rq) {
             if (mc <= 16) {
                 // small batch: triangular GEMVs (V, and U = W^T V for gradients) instead of tiled GEMMs
                 const int MC = mc <= 1 ? 1 : (mc <= 2 ? 2 : (mc <= 4 ? 4 : (mc <= 8 ? 8 : 16)));
-                size_t need = (size_t)np * mcp;
-                if (ctx->grad_capacity < need || !ctx->dV) {
-                    size_t c1 = ctx->grad_capacity, c2 = ctx->grad_capacity, c3 = 0, c4 = 0, c5 = 0;
-                    BO_TRY(bo_reserve(ctx, &ctx->dV, &c1, need));
-                    BO_TRY(bo_reserve(ctx, &ctx->dU, &c2, need));
-                    if (ctx->dGpart) { cudaFree(ctx->dGpart); ctx->dGpart = nullptr; }
-                    if (ctx->dDmuS) { cudaFree(ctx->dDmuS); ctx->dDmuS = nullptr; }
-                    if (ctx->dDs2S) { cudaFree(ctx->dDs2S); ctx->dDs2S = nullptr; }
-                    BO_TRY(bo_reserve(ctx, &ctx->dGpart, &c3, (size_t)GRAD_SLICES * cap * 2 * dp));
-                    BO_TRY(bo_reserve(ctx, &ctx->dDmuS, &c4, (size_t)S * cap * d));
-                    BO_TRY(bo_reserve(ctx, &ctx->dDs2S, &c5, (size_t)S * cap * d));
-                    ctx->grad_capacity = need;
-                }
                 const double *Wm = ctx->dW + (int64_t)s * np * np, *WTm = ctx->dWT + (int64_t)s * np * np;
                 {
                     BO_LAUNCH(ctx, "trimv_small_kernel");
@@ -809,6 +881,183 @@ int bo_score_run(bo_ctx *ctx, const ScoreRequest &rq) {
     }
     return BO_OK;
 }
+
+// int8-slice path: slices -> tcgen05 contraction -> moments -> acquisition + error bound, chunk by chunk;
+// then the FP64 rescue of the candidates whose bound exceeds the tolerance.
+static int run_oz(bo_ctx *ctx, const ScoreRequest &rq, int oz_S) {
+    const int np = ctx->np, S = ctx->S, d = ctx->d;
+    const int64_t M = rq.M;
+    const int64_t chunk = (int64_t)256 * 128;
+    const int64_t cap = bo_round_up64(M < chunk ? M : chunk, 128);
+    BO_TRY(reserve_moments(ctx, np / 128, cap, S));
+    // what the rescue pass looks at: mode 0 -> the acquisition value (not for the mean, which never goes through
+    // the int8 contraction); mode 1 -> s2
+    const bool rescue = ctx->oz_rescue && ((rq.mode == 0) ? (rq.acq != BO_ACQ_MEAN) : (rq.dS2 != nullptr));
+    const bool need_best = rq.want_best || (rescue && rq.mode == 0);
+    const int64_t nchunk = (M + chunk - 1) / chunk;
+    const int64_t nblocks_total = nchunk * ((chunk + 255) / 256);
+    if (need_best) BO_TRY(reserve_blocks(ctx, (size_t)(nblocks_total > ARGMAX_PASS_BLOCKS ? nblocks_total : ARGMAX_PASS_BLOCKS) + 8));
+    if (rescue) {
+        BO_TRY(bo_reserve(ctx, &ctx->dErrEst, &ctx->errest_capacity, (size_t)M));
+        BO_TRY(bo_reserve(ctx, &ctx->dFlagList, &ctx->flaglist_capacity, (size_t)M + 1));
+        BO_TRY(bo_ozaki_error_scale(ctx, oz_S));
+    }
+
+    // Software pipeline over work items (chunk, hyper-sample): the operand slicer of item w+1
+    // runs on the low-priority side stream while the tcgen05 contraction of item w runs on
+    // the main stream (different pipes: FP64/ALU vs tensor).  Two slice buffers.
+    const int64_t nitems = nchunk * S;
+    BO_TRY(bo_ozaki_reserve(ctx, oz_S, (int)cap, nitems > 1 ? 2 : 1));
+    auto item = [&](int64_t w, int64_t &c0, int &mc, int &mcp, int &s) {
+        c0 = (w / S) * chunk;
+        s = (int)(w % S);
+        mc = (int)((M - c0) < chunk ? (M - c0) : chunk);
+        mcp = bo_round_up(mc, 128);
+    };
+    int64_t c0; int mc, mcp, s;
+    // Overlap is opt-in (BO_OZ_OVERLAP=1): on a power-capped B200 the two kernels only slow each
+    // other down (measured: contraction 2.77 -> 3.56 ms per chunk), so by default both stages
+    // run back to back on the main stream.
+    static const bool overlap = getenv("BO_OZ_OVERLAP") && atoi(getenv("BO_OZ_OVERLAP")) != 0;
+    cudaStream_t side = overlap ? ctx->stream2 : ctx->stream;
+    // candidates staged on the main stream must be visible to the side stream
+    BO_CUDA(ctx, cudaEventRecord(ctx->ev_consumed[0], ctx->stream));
+    BO_CUDA(ctx, cudaStreamWaitEvent(side, ctx->ev_consumed[0], 0));
+    item(0, c0, mc, mcp, s);
+    BO_TRY(bo_ozaki_slice(ctx, s, oz_S, rq.dXc, c0, mc, mcp, 0, side));
+    BO_CUDA(ctx, cudaEventRecord(ctx->ev_sliced[0], side));
+    int64_t blk0 = 0;
+    for (int64_t w = 0; w < nitems; ++w) {
+        const int buf = (int)(w & 1);
+        item(w, c0, mc, mcp, s);
+        BO_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_sliced[buf], 0));
+        BO_TRY(bo_ozaki_contract(ctx, s, oz_S, mcp, buf, ctx->dMuS + (int64_t)s * mcp, ctx->dS2S + (int64_t)s * mcp, nullptr));
+        BO_CUDA(ctx, cudaEventRecord(ctx->ev_consumed[buf], ctx->stream));
+        if (w + 1 < nitems) {
+            int64_t c1; int mc1, mcp1, s1;
+            item(w + 1, c1, mc1, mcp1, s1);
+            const int nbuf = (int)((w + 1) & 1);
+            if (w >= 1) BO_CUDA(ctx, cudaStreamWaitEvent(side, ctx->ev_consumed[nbuf], 0));
+            BO_TRY(bo_ozaki_slice(ctx, s1, oz_S, rq.dXc, c1, mc1, mcp1, nbuf, side));
+            BO_CUDA(ctx, cudaEventRecord(ctx->ev_sliced[nbuf], side));
+        }
+        if (s == S - 1) {
+            AcqParams ap = {};
+            ap.mode = rq.mode; ap.acq = rq.acq; ap.param = rq.param;
+            ap.S = S; ap.d = d; ap.mc = mc; ap.mcp = mcp; ap.c0 = c0;
+            ap.muS = ctx->dMuS; ap.s2S = ctx->dS2S; ap.dmuS = nullptr; ap.ds2S = nullptr;
+            ap.out_val = rq.dVal; ap.out_grad = nullptr;
+            ap.out_mu = rq.dMu; ap.out_s2 = rq.dS2; ap.out_dmu = nullptr; ap.out_ds2 = nullptr;
+            ap.blkval = need_best ? ctx->dBlkVal : nullptr;
+            ap.blkidx = need_best ? ctx->dBlkIdx : nullptr;
+            ap.blk0 = blk0;
+            if (rescue) { ap.rhoS = ctx->dRho; ap.errK = ctx->dErrK; ap.errest = ctx->dErrEst; }
+            const int nb = (mc + 255) / 256;
+            {
+                BO_LAUNCH(ctx, "acq_kernel");
+                acq_kernel<<<nb, 256, 0, ctx->stream>>>(ap);
+                BO_CHECK_LAUNCH(ctx);
+            }
+            blk0 += nb;
+        }
+    }
+    double *gmax = ctx->dBlkVal ? ctx->dBlkVal + ctx->blk_capacity - 1 : nullptr;
+    if (need_best) {
+        BO_LAUNCH(ctx, "argmax_final_kernel");
+        argmax_final_kernel<<<1, 1024, 0, ctx->stream>>>(ctx->dBlkVal, ctx->dBlkIdx, blk0, gmax,
+                                                        ctx->dBlkIdx + ctx->blk_capacity - 1);
+        BO_CHECK_LAUNCH(ctx);
+    }
+    ctx->oz_last_total = M;
+    ctx->oz_last_flagged = 0;
+    if (!rescue) return BO_OK;
+
+    // ---- rescue: flag, compact (sorted), re-score in FP64, scatter ----
+    int *count_dev = ctx->dFlagList + M;
+    BO_CUDA(ctx, cudaMemsetAsync(count_dev, 0, sizeof(int), ctx->stream));
+    {
+        double floor_abs = 0.0;
+        if (rq.mode == 1) {                                // s2: floor 1e-9 * mean rho (the parity metric's floor)
+            for (int i = 0; i < S; ++i) floor_abs += ctx->h_rho[i];
+            floor_abs *= 1e-9 / S;
+        }
+        BO_LAUNCH(ctx, "oz_flag_kernel");
+        const int nb = (int)((M + 255) / 256 < 1184 ? (M + 255) / 256 : 1184);
+        oz_flag_kernel<<<nb, 256, 0, ctx->stream>>>(M, rq.mode == 0 ? rq.dVal : rq.dS2, ctx->dErrEst, ctx->oz_rescue_tol,
+                                                    floor_abs, rq.mode == 0 ? ctx->oz_rescue_floor : 0.0,
+                                                    rq.mode == 0 ? gmax : nullptr, ctx->dFlagList, count_dev);
+        BO_CHECK_LAUNCH(ctx);
+    }
+    int count = 0;
+    BO_CUDA(ctx, cudaMemcpyAsync(&count, count_dev, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    BO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->oz_last_flagged = count;
+    if (count == 0) return BO_OK;
+    if (count <= 8192) {
+        int np2 = 1;
+        while (np2 < count) np2 <<= 1;
+        BO_LAUNCH(ctx, "oz_sort_small_kernel");
+        oz_sort_small_kernel<<<1, 1024, np2 * sizeof(int), ctx->stream>>>(ctx->dFlagList, count);
+        BO_CHECK_LAUNCH(ctx);
+    } else {
+        const int nwords = (int)((M + 63) / 64), nwb = (nwords + 1023) / 1024;
+        BO_TRY(bo_reserve(ctx, &ctx->dFlagBits, &ctx->flagbits_capacity, (size_t)nwords + (size_t)(nwb + 1) / 2 + 1));
+        int *blocksum = reinterpret_cast<int *>(ctx->dFlagBits + nwords);
+        BO_CUDA(ctx, cudaMemsetAsync(ctx->dFlagBits, 0, sizeof(unsigned long long) * nwords, ctx->stream));
+        ctx->launches += 3;
+        oz_mark_kernel<<<(count + 255) / 256, 256, 0, ctx->stream>>>(ctx->dFlagList, count, ctx->dFlagBits);
+        oz_wordcount_kernel<<<nwb, 1024, 0, ctx->stream>>>(ctx->dFlagBits, nwords, blocksum);
+        oz_compact_kernel<<<nwb, 1024, 0, ctx->stream>>>(ctx->dFlagBits, nwords, blocksum, ctx->dFlagList);
+        BO_CHECK_LAUNCH(ctx);
+    }
+    const size_t per = (size_t)d + 2;
+    BO_TRY(bo_reserve(ctx, &ctx->dRescue, &ctx->rescue_capacity, (size_t)count * per));
+    double *xr = ctx->dRescue, *ra = xr + (size_t)count * d, *rb = ra + count;
+    {
+        BO_LAUNCH(ctx, "oz_gather_rows_kernel");
+        oz_gather_rows_kernel<<<(int)(((int64_t)count * d + 255) / 256), 256, 0, ctx->stream>>>(rq.dXc, d, ctx->dFlagList, count, xr);
+        BO_CHECK_LAUNCH(ctx);
+    }
+    ScoreRequest r2;
+    r2.mode = rq.mode; r2.acq = rq.acq; r2.param = rq.param; r2.M = count; r2.dXc = xr;
+    if (rq.mode == 0) r2.dVal = ra;
+    else { r2.dMu = ra; r2.dS2 = rb; }
+    r2.want_best = false;
+    BO_TRY(run_fp64(ctx, r2));
+    {
+        BO_LAUNCH(ctx, "oz_scatter_kernel");
+        if (rq.mode == 0)
+            oz_scatter_kernel<<<(count + 255) / 256, 256, 0, ctx->stream>>>(ctx->dFlagList, count, ra, rq.dVal, nullptr, nullptr);
+        else
+            oz_scatter_kernel<<<(count + 255) / 256, 256, 0, ctx->stream>>>(ctx->dFlagList, count, ra, rq.dMu, rb, rq.dS2);
+        BO_CHECK_LAUNCH(ctx);
+    }
+    if (rq.want_best) BO_TRY(final_argmax_over(ctx, rq.dVal, M));
+    // a fit where the int8 path hands most of its work to the rescue (posterior variance collapsed over the
+    // whole candidate set, e.g. n = 1024 in d = 4) is an FP64 problem: later passes go there directly
+    if (M >= 4096 && (double)count > ctx->oz_demote_frac * (double)M) ctx->oz_demoted = true;
+    return BO_OK;
+}
+
+int bo_score_run(bo_ctx *ctx, const ScoreRequest &rq) {
+    if (!ctx->fitted) return bo_set_err(ctx, BO_ERR_STATE, "bo_score/bo_predict before bo_fit");
+    const bool grad = (rq.mode == 0) ? (rq.dGrad != nullptr) : (rq.dDmu != nullptr || rq.dDs2 != nullptr);
+    if (rq.M <= 0) return bo_set_err(ctx, BO_ERR_ARG, "M must be positive");
+    // int8-slice path for value-only passes when selected; gradients stay on the FP64 path
+    // (tiny batches stay on the exact FP64 GEMV/GEMM path: nothing to gain from the tensor pipe there)
+    const bool oz = (ctx->prec == BO_PREC_OZAKI) && !grad && rq.M > 64 && !ctx->oz_demoted;
+    ctx->oz_last_path = oz ? 1 : 0;
+    if (!oz) {
+        ctx->oz_last_total = rq.M;
+        ctx->oz_last_flagged = 0;
+        return run_fp64(ctx, rq);
+    }
+    const int oz_S = bo_ozaki_choose_slices(ctx, ctx->prec_tol);
+    if (oz_S < 1) return BO_ERR_CUDA;
+    BO_TRY(bo_ozaki_prepare(ctx, oz_S));
+    return run_oz(ctx, rq, oz_S);
+}
+
 
 // top-k of a device-resident value array; results land in dBlkVal/dBlkIdx tail
 int bo_topk_run(bo_ctx *ctx, const double *vals, int64_t M, int k, double *h_val, int64_t *h_idx) {

@@ -8,10 +8,9 @@ of libbo_b200.so.  All numerics for data-bearing models run on the device;
 without the CUDA library these classes raise `BackendError`.
 """
 
-import sys
+import weakref
 
 import numpy as np
-import scipy.linalg as sla
 
 from . import _lib
 from .utils import rstate
@@ -65,12 +64,19 @@ class _Param(object):
     """One named hyper-parameter block with an optional prior."""
 
     def __init__(self, owner, attr, positive):
-        self._owner, self._attr, self.positive = owner, attr, positive
+        # weak back-reference: a model and its parameter blocks must not form a cycle, so that dropping the last
+        # reference to a `model.copy()` (a policy's private copy) releases its share of the fitted handle at once
+        self._owner, self._attr, self.positive = weakref.ref(owner), attr, positive
         self.prior = None
 
     @property
     def value(self):
-        return getattr(self._owner, self._attr)
+        return getattr(self._owner(), self._attr)
+
+    def __getstate__(self):
+        state = dict(self.__dict__)
+        state["_owner"] = None               # re-linked by the owner's __setstate__
+        return state
 
     def set_prior(self, name, *args):
         self.prior = None if name is None else _Prior(name, *args)
@@ -88,6 +94,8 @@ class _Fit(object):
     def __init__(self, kernel, X, Y, ell, rho, sn2, bias, device=None):
         self.ctx = _lib.Context(device)
         self.ctx.fit(kernel, X, Y, ell, rho, sn2, bias)
+        self.owners = 0                      # models currently holding this handle (`_Base._hold` / `_drop`)
+        self.applied = ("fp64", None)        # precision path last written into the handle
 
 
 class _Base(object):
@@ -105,15 +113,38 @@ class _Base(object):
         `predict` at fewer than 65 points always use FP64."""
         if path not in ("fp64", "int8"):
             raise ValueError("precision path must be 'fp64' or 'int8'")
+        # per-model state, written into the (possibly shared) handle right before each device call: setting the
+        # precision of one copy never changes the arithmetic of another model sharing the handle
         self._precision = (path, float(tol))
-        if self._fit is not None:
-            self._fit.ctx.set_precision(1 if path == "int8" else 0, float(tol))
         return self
+
+    _fit = None
 
     def _init_data(self, d):
         self._X = np.zeros((0, d))
         self._Y = np.zeros((0,))
+        self._drop()
+
+    # -- ownership of the shared fitted handle ---------------------------------------------------------
+    def _hold(self, fit):
+        """Take a share of `fit` (or of nothing)."""
+        self._drop()
+        if fit is not None:
+            fit.owners += 1
+        self._fit = fit
+
+    def _drop(self):
+        fit = self.__dict__.get("_fit")
+        if fit is not None:
+            fit.owners -= 1
         self._fit = None
+        return fit
+
+    def __del__(self):
+        try:
+            self._drop()
+        except Exception:
+            pass
 
     # hyper-sample view: (ell[S,d], rho[S], sn2[S], bias[S])
     def _hypers(self):
@@ -144,11 +175,10 @@ class _Base(object):
         (no `copy()` still shares it) and the handle has room, the new rows of L, W, alpha, beta are
         appended on the device in O(n^2) per point (bo_append) instead of refactorising; otherwise
         the handle is dropped and the next use refits."""
-        fit = self._fit
-        self._fit = None
+        fit = self._drop()
         if fit is None or not self.incremental or len(Y) == 0 or len(Y) > 8:
             return
-        if sys.getrefcount(fit) > 2:            # `fit` here + the getrefcount argument: anyone else shares it
+        if fit.owners > 0:                      # a `copy()` still shares the handle: never mutate it
             return
         try:
             if fit.ctx.n + len(Y) > fit.ctx.capacity():
@@ -156,16 +186,18 @@ class _Base(object):
             fit.ctx.append(X, Y)
         except (np.linalg.LinAlgError, _lib.BackendError):
             return
-        self._fit = fit
+        self._hold(fit)
 
     def _ensure_fit(self):
         if self._fit is None:
             ell, rho, sn2, bias = self._hypers()
-            self._fit = _Fit(self.kernel, self._X, self._Y, ell, rho, sn2, bias, self.device)
+            self._hold(_Fit(self.kernel, self._X, self._Y, ell, rho, sn2, bias, self.device))
+        fit = self._fit
+        if fit.applied != self._precision:
             path, tol = self._precision
-            if path == "int8":
-                self._fit.ctx.set_precision(1, tol)
-        return self._fit.ctx
+            fit.ctx.set_precision(1 if path == "int8" else 0, tol)
+            fit.applied = self._precision
+        return fit.ctx
 
     # pickling / checkpointing (reference bayesopt.py:39-55): device state is rebuilt lazily
     def __getstate__(self):
@@ -236,7 +268,8 @@ class GP(_Base):
 
     def copy(self):
         new = GP(self.sn2, self.rho, self.ell, self.bias, self.kernel, self.device)
-        new._X, new._Y, new._fit = self._X, self._Y, self._fit
+        new._X, new._Y = self._X, self._Y
+        new._hold(self._fit)
         new._precision = self._precision
         for k, p in self.params.items():
             new.params[k].prior = p.prior
@@ -245,7 +278,7 @@ class GP(_Base):
     def __setstate__(self, state):
         self.__dict__.update(state)
         for p in self.params.values():
-            p._owner = self
+            p._owner = weakref.ref(self)
 
     # hyper-parameter vector in the unconstrained space used by the sampler
     def get_theta(self):
@@ -256,7 +289,7 @@ class GP(_Base):
         self.sn2, self.rho = float(np.exp(theta[0])), float(np.exp(theta[1]))
         self.ell = np.exp(np.asarray(theta[2:2 + d], dtype=float))
         self.bias = float(theta[2 + d])
-        self._fit = None
+        self._drop()
 
     def logprior(self):
         """log prior + log |Jacobian| of the log transform of the positive blocks."""
@@ -322,7 +355,6 @@ class MCMC(_Base):
         self.device = model.device
         self._n = int(n)
         self._X, self._Y = model._X.copy(), model._Y.copy()
-        self._fit = None
         self._sampler_ctx = None
         self._thetas = None
         if burn > 0:
@@ -346,7 +378,8 @@ class MCMC(_Base):
 
     def _logpost(self, theta):
         """log hyper-posterior at `theta`: host-side priors + the device log marginal
-        likelihood (one Gram + Cholesky per call, on a handle kept for the sampler)."""
+        likelihood (bo_loglik_fit: Gram + Cholesky of the matrix bordered by the residual row -- no W = L^-1, no
+        transpose, no scoring state -- on a handle kept for the sampler)."""
         gp = self._proto
         try:
             with np.errstate(over="raise", invalid="raise"):
@@ -359,8 +392,7 @@ class MCMC(_Base):
             if getattr(self, "_sampler_ctx", None) is None:
                 self._sampler_ctx = _lib.Context(self.device)
             ctx = self._sampler_ctx
-            ctx.fit(self.kernel, self._X, self._Y, gp.ell[None, :], [gp.rho], [gp.sn2], [gp.bias])
-            ll = float(ctx.loglik()[0])
+            ll = float(ctx.loglik_fit(self.kernel, self._X, self._Y, gp.ell[None, :], [gp.rho], [gp.sn2], [gp.bias])[0])
         except (np.linalg.LinAlgError, FloatingPointError, OverflowError, ValueError):
             return -np.inf
         val = lp + ll
@@ -376,8 +408,8 @@ class MCMC(_Base):
             theta, lp = _slice_sample(self._logpost, theta, lp, self._rng)
             out.append(theta.copy())
         self._thetas = np.array(out[-self._n:])
-        self._proto._fit = None
-        self._fit = None
+        self._proto._drop()
+        self._drop()
 
     def _hypers(self):
         th = self._thetas
@@ -390,14 +422,17 @@ class MCMC(_Base):
     def add_data(self, X, Y, resample=True):
         resample = resample and self._proto is not None and any(p.prior is not None for p in self._proto.params.values())
         if resample:
-            self._fit = None            # new hyper-samples follow: nothing to append to
+            self._drop()                # new hyper-samples follow: nothing to append to
         _Base.add_data(self, X, Y)
         if resample:
             self._resample(self._n)
 
     def copy(self):
         new = MCMC.__new__(MCMC)
-        new.__dict__.update(self.__dict__)
+        state = dict(self.__dict__)
+        fit = state.pop("_fit", None)
+        new.__dict__.update(state)
+        new._hold(fit)
         new._proto = self._proto.copy()
         new._thetas = self._thetas.copy()
         return new
@@ -422,19 +457,12 @@ def _spectrum(kernel, ell, m, rng):
     return W
 
 
-def _weight_posterior(Phi, resid, sn2, noise):
-    """theta ~ N(A^-1 Phi^T r, sn2 A^-1),  A = Phi^T Phi + sn2 I."""
-    A = Phi.T @ Phi
-    A[np.diag_indices_from(A)] += sn2
-    L = sla.cholesky(A, lower=True)
-    mean = sla.cho_solve((L, True), Phi.T @ resid)
-    return mean + np.sqrt(sn2) * sla.solve_triangular(L, noise, lower=True, trans=1)
-
-
 class FourierSample(object):
     """f(x) = bias + sqrt(2 rho / m) cos(W x + b) . theta; `.get(X, grad)` is the
-    Thompson index (reference policies/simple.py:48).  The draw is built once on
-    the host (m x m solve); evaluation over candidate batches runs on the GPU."""
+    Thompson index (reference policies/simple.py:48).  The spectral points, phases and the
+    standard-normal vector come from `rng` (NumPy stream, in this order); the feature system
+    Phi^T Phi + sn2 I, its Cholesky factor and the two solves behind theta run on the device
+    (bo_thompson_build), as does every evaluation."""
 
     def __init__(self, gp, m, rng=None):
         rng = rstate(rng)
@@ -444,12 +472,15 @@ class FourierSample(object):
         self.W = _spectrum(gp.kernel, gp.ell, self.m, rng)
         self.b = rng.rand(self.m) * 2.0 * np.pi
         self.device = gp.device
-        if gp.ndata > 0:
-            Phi = self.scale * np.cos(gp._X @ self.W.T + self.b)
-            self.theta = _weight_posterior(Phi, gp._Y - gp.bias, gp.sn2, rng.randn(self.m))
-        else:
-            self.theta = rng.randn(self.m)
         self._ctx = None
+        noise = rng.randn(self.m)
+        if gp.ndata > 0:
+            ctx = _lib.Context(self.device)
+            self.theta = ctx.thompson_build(gp._X, gp._Y, gp.rho, gp.sn2, gp.bias, self.W[None], self.b[None],
+                                            noise[None])[0]
+            self._ctx = ctx
+        else:
+            self.theta = noise
 
     def _context(self):
         if self._ctx is None:
@@ -477,53 +508,70 @@ class FourierSample(object):
 
 
 class ThompsonBatch(object):
-    """ndraw posterior draws sharing one random-feature basis (BASELINE config 4:
-    256 draws x 1M candidates).  Each draw has its own theta; the basis (W, b) is
-    common, so evaluation is one dense (M x m) x (m x ndraw) contraction."""
+    """ndraw posterior draws evaluated together (BASELINE config 4: 256 draws x 1M candidates).
 
-    def __init__(self, gp, m, ndraw, rng=None):
+    shared_basis=True (default): one random-feature basis (W, b) for all draws, each draw its own theta, so
+    evaluation is one dense (M x m) x (m x ndraw) contraction (FP64 tensor cores, or int8 slices on tcgen05).
+    shared_basis=False: every draw has its own basis, drawn from `rng` in the order ndraw successive
+    `model.sample_f(m, rng)` calls would use -- the literal batched form of policies/simple.py:48.
+    Either way the feature systems are built and solved on the device (bo_thompson_build)."""
+
+    def __init__(self, gp, m, ndraw, rng=None, shared_basis=True):
         rng = rstate(rng)
         self.m, self.ndraw = int(m), int(ndraw)
+        self.shared_basis = bool(shared_basis)
         self.bias = float(gp.bias)
         self.scale = float(np.sqrt(2.0 * gp.rho / self.m))
-        self.W = _spectrum(gp.kernel, gp.ell, self.m, rng)
-        self.b = rng.rand(self.m) * 2.0 * np.pi
         self.device = gp.device
-        noise = rng.randn(self.ndraw, self.m)
+        if self.shared_basis:
+            self.W = _spectrum(gp.kernel, gp.ell, self.m, rng)[None]
+            self.b = (rng.rand(self.m) * 2.0 * np.pi)[None]
+            noise = rng.randn(self.ndraw, self.m)
+        else:
+            W, b, noise = [], [], []
+            for _ in range(self.ndraw):
+                W.append(_spectrum(gp.kernel, gp.ell, self.m, rng))
+                b.append(rng.rand(self.m) * 2.0 * np.pi)
+                noise.append(rng.randn(self.m))
+            self.W, self.b, noise = np.array(W), np.array(b), np.array(noise)
+        self._ctx = None
         if gp.ndata > 0:
-            Phi = self.scale * np.cos(gp._X @ self.W.T + self.b)
-            A = Phi.T @ Phi
-            A[np.diag_indices_from(A)] += gp.sn2
-            L = sla.cholesky(A, lower=True)
-            mean = sla.cho_solve((L, True), Phi.T @ (gp._Y - gp.bias))
-            self.theta = mean[None, :] + np.sqrt(gp.sn2) * sla.solve_triangular(L, noise.T, lower=True, trans=1).T
+            ctx = _lib.Context(self.device)
+            self.theta = ctx.thompson_build(gp._X, gp._Y, gp.rho, gp.sn2, gp.bias, self.W, self.b, noise)
+            self._ctx = ctx
+            self._applied = ("fp64", None)
         else:
             self.theta = noise
-        self._ctx = None
 
     _precision = ("fp64", 1e-9)
+    _applied = ("fp64", None)
 
     def set_precision(self, path="fp64", tol=1e-8):
         """'fp64': FP64 tensor-core contraction with on-the-fly cosine features (default); 'int8': the
-        features and Theta are cut into balanced base-256 int8 slices and contracted on tcgen05 (batches of
-        >= 1024 candidates; `tol` is the target error relative to a draw's own scale, >= 2 pins the level)."""
+        features and Theta are cut into balanced base-256 int8 slices and contracted on tcgen05 (shared basis,
+        batches of >= 1024 candidates; `tol` is the target error relative to a draw's own scale, >= 2 pins the level)."""
         if path not in ("fp64", "int8"):
             raise ValueError("precision path must be 'fp64' or 'int8'")
         self._precision = (path, float(tol))
-        if self._ctx is not None:
-            self._ctx.set_precision(1 if path == "int8" else 0, float(tol))
         return self
 
     def _context(self):
         if self._ctx is None:
             ctx = _lib.Context(self.device)
-            ctx.thompson_set(self.W[None], self.b[None], self.theta,
+            ctx.thompson_set(self.W, self.b, self.theta,
                              np.full(self.ndraw, self.scale), np.full(self.ndraw, self.bias))
-            path, tol = self._precision
-            if path == "int8":
-                ctx.set_precision(1, tol)
             self._ctx = ctx
+            self._applied = ("fp64", None)
+        if self._applied != self._precision:
+            path, tol = self._precision
+            self._ctx.set_precision(1 if path == "int8" else 0, tol)
+            self._applied = self._precision
         return self._ctx
+
+    def __getstate__(self):
+        state = dict(self.__dict__)
+        state["_ctx"] = None
+        return state
 
     def get(self, X):
         X = np.array(X, dtype=np.float64, ndmin=2)

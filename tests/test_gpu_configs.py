@@ -11,6 +11,11 @@ from oracle import GPOracle, MixtureOracle, ucb_beta, ucb_index
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-6
+# config 2 only: floor of the relative-error metric as a fraction of max|ref|.  n=1024 points in d=4 with ell = 0.25 and
+# sn2 = 1e-6 give cond(K) ~ 1e9 and s2/rho down to 2e-6; z = (mu - t)/s reaches -200 there, and EI below 1e-9 of its
+# maximum amplifies the O(1e-13 rho) disagreement in s2 that two LAPACK builds already show.  Every other config and
+# test uses the SURVEY 8c(7) floor of 1e-12 max|ref| (conftest.rel_err default).
+FLOOR2 = 1e-9
 
 
 def problem(n, d, seed=0):
@@ -22,7 +27,9 @@ def problem(n, d, seed=0):
 
 def test_config2_rbf_n1024_d4_ei(ctx):
     """RBF GP n=1024 d=4, EI (ill-conditioned regime: s2/rho down to 1e-6): FP64 path vs oracle on
-    50k Sobol candidates; the int8 path's error model must pick a deeper level here and still agree."""
+    50k Sobol candidates.  The int8 path picks a deeper level here, its rescue pass re-scores in FP64 every
+    candidate whose error bound exceeds the tolerance (most of them in this regime), so it meets the same
+    1e-6 as the FP64 path -- and, having rescued more than a quarter, hands later passes to FP64 altogether."""
     rng, X, y, rho, bias = problem(1024, 4)
     gp = GPOracle(1e-6, rho, 0.25 * np.ones(4), bias, "se")
     gp.add_data(X, y)
@@ -31,13 +38,19 @@ def test_config2_rbf_n1024_d4_ei(ctx):
     target = float(gp.predict(X)[0].max())
     ref = gp.get_improvement(target, Xc)
     val, _, best = ctx.score(1, target, Xc, want_best=True)
-    assert rel_err(val, ref, 1e-9) < TOL and best[1] == int(np.argmax(ref))
+    assert rel_err(val, ref, FLOOR2) < TOL and best[1] == int(np.argmax(ref))
     ctx.set_precision(1, 1e-8)
     v8, _, b8 = ctx.score(1, target, Xc, want_best=True)
     _, slices, extra = ctx.precision_info()
     assert 2 * slices + extra > 10                                # deeper than the headline's (5, no extra): 2^e sqrt(rho) ~ 300 here
+    ran8, rescued, total = ctx.rescue_info()
+    assert ran8 and total == len(Xc) and rescued > 0.25 * total   # variance collapsed over most of the box
     assert b8[1] == best[1]
-    assert rel_err(v8, ref, 1e-6) < 1e-4                          # loose: this regime belongs to the FP64 path
+    assert rel_err(v8, ref, FLOOR2) < TOL                         # same bar as the FP64 path
+    assert rel_err(v8, val) < TOL
+    v8b, _, _ = ctx.score(1, target, Xc[:5000])
+    assert not ctx.rescue_info()[0]                               # demoted: this fit now scores in FP64
+    assert np.array_equal(v8b, val[:5000])
 
 
 def test_config3_matern_n4096_d8_ucb(ctx):
@@ -68,7 +81,7 @@ def test_config4_thompson_n4096_d16_256_draws(ctx):
     tb = models.ThompsonBatch(gp, m=512, ndraw=256, rng=7)
     Xc = qmc.Sobol(d=16, scramble=False).random_base2(15)[:20001]
     F = tb.get(Xc)                                                # (256, M)
-    ref = tb.bias + (tb.scale * np.cos(Xc @ tb.W.T + tb.b)) @ tb.theta.T
+    ref = tb.bias + (tb.scale * np.cos(Xc @ tb.W[0].T + tb.b[0])) @ tb.theta.T
     assert rel_err(F, ref.T, 1e-9) < TOL
     bv, bi = tb.argmax(Xc)
     assert np.array_equal(bi, np.argmax(ref, axis=0)) and np.allclose(bv, ref.max(axis=0), rtol=1e-9)

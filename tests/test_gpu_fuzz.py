@@ -10,6 +10,7 @@ from oracle import GPOracle, MixtureOracle, ucb_beta, ucb_index
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-6
+FLOOR = 1e-9       # floor of the relative-error metric as a fraction of max|ref|
 
 
 def _case(seed):
@@ -54,18 +55,17 @@ def test_random_shapes_both_paths(ctx, seed):
     if S == 1:
         cases += [(0, 0.0, mu), (3, beta, ucb_index(beta, mu, s2))]
     floor = 1e-9 * float(np.mean(rho))
-    # where the posterior variance collapses to ~1e-6 rho (dense data in 1-2 dimensions) EI / PI amplify the int8
-    # path's absolute error in s2: that regime belongs to the FP64 path, the bound is looser there
-    tol8 = 10 * TOL if float(s2.min()) >= 1e-4 * float(np.mean(rho)) else 1e-3
+    # Both precision paths are held to the same bar (north_star: 1e-6 relative): the int8 path's rescue pass re-scores
+    # in FP64 every candidate whose a-priori error bound exceeds 2.5e-7 of max(|value|, 1e-12 max|value|), so where the
+    # posterior variance collapses (dense data in 1-2 dimensions) it simply does more of its work in FP64.
     for prec in (0, 1):
         ctx.set_precision(prec, 1e-9)
         gmu, gs2 = ctx.predict(Xc)
         assert rel_err(gmu, mu, 1e-9) < TOL, (seed, prec)
-        assert np.max(np.abs(gs2 - s2) / np.maximum(np.abs(s2), floor)) < (TOL if prec == 0 else 10 * TOL), (seed, prec)
+        assert np.max(np.abs(gs2 - s2) / np.maximum(np.abs(s2), floor)) < TOL, (seed, prec)
         for acq, param, want in cases:
             val, _, best = ctx.score(acq, param, Xc, want_best=True)
-            # int8 path: tails of EI / PI sit far below the floor of the error model; compare above 1e-6 of the maximum
-            assert rel_err(val, want, 1e-9 if prec == 0 else 1e-6) < (TOL if prec == 0 else tol8), (seed, prec, acq)
+            assert rel_err(val, want, FLOOR) < TOL, (seed, prec, acq, rel_err(val, want, FLOOR))
             top = np.flatnonzero(want >= want.max() - 1e-9 * max(1.0, abs(want.max())))
             assert best[1] in top, (seed, prec, acq)
     ctx.set_precision(0)

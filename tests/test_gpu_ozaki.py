@@ -108,6 +108,7 @@ def test_ozaki_slice_count_follows_tolerance(ctx):
     Xc = qmc.Sobol(d=8, scramble=False).random_base2(9)
     mu, s2 = gp.predict(Xc)
     errs = []
+    ctx.set_rescue(False)                           # raw slice error: no FP64 rescue of the candidates it flags
     for S in (3, 4, 5, 6):
         ctx.set_precision(1, float(S))              # tol >= 2 pins the slice count
         gmu, gs2 = ctx.predict(Xc)
@@ -130,11 +131,11 @@ def test_full_size_headline_shape_int8_vs_fp64_and_oracle(ctx):
     val, _, best = ctx.score(1, target, Xc, want_best=True)
     top8 = ctx.topk(10)
     assert ctx.precision_info() == (1, 5, False)
-    assert rel_err(val, f64val, 1e-9) < 2e-7            # measured: 4.9e-8 over 2^20 candidates
+    assert rel_err(val, f64val) < 2.5e-7                # measured: 4.9e-8 over 2^20 candidates; floor 1e-12 max
     assert best[1] == f64best[1] and np.array_equal(top8[0], top64[0])
     sl = slice(32700, 32900)
     ref = gp.get_improvement(target, Xc[sl])
-    assert rel_err(val[sl], ref, 1e-9) < 1e-6
+    assert rel_err(val[sl], ref) < 1e-6
     # the mean never goes through the int8 contraction
     mu, s2 = ctx.predict(Xc[:5000])
     rmu, rs2 = gp.predict(Xc[:5000])
@@ -147,7 +148,8 @@ def test_full_size_headline_shape_int8_vs_fp64_and_oracle(ctx):
     ctx.set_precision(1, 4.5)
     fast, _, fbest = ctx.score(1, target, Xc, want_best=True)
     assert ctx.precision_info() == (1, 4, True) and fbest[1] == f64best[1]
-    assert rel_err(fast, f64val, 1e-9) < 1e-6           # measured: 4.2e-7 over 2^20 candidates
+    assert rel_err(fast, f64val) < 2.5e-7               # 4.2e-7 before the rescue pass; its flagged candidates are FP64 now
+    assert ctx.rescue_info()[1] > 0
 
 
 @pytest.mark.parametrize("d,m,ndraw,M", [(2, 128, 7, 1500), (16, 500, 300, 4097), (8, 1024, 256, 40000), (5, 33, 64, 1024)])
@@ -161,7 +163,7 @@ def test_thompson_batch_int8_path(d, m, ndraw, M):
     mine.add_data(gp.X, gp.Y)
     tb = models.ThompsonBatch(mine, m=m, ndraw=ndraw, rng=5)
     Xc = qmc.Sobol(d=d, scramble=False).random_base2(int(np.ceil(np.log2(M))))[:M]
-    ref = (tb.bias + (tb.scale * np.cos(Xc @ tb.W.T + tb.b)) @ tb.theta.T).T
+    ref = (tb.bias + (tb.scale * np.cos(Xc @ tb.W[0].T + tb.b[0])) @ tb.theta.T).T
     F64 = tb.get(Xc)
     bv64, bi64 = tb.argmax(Xc)
     tb.set_precision("int8", 1e-8)

@@ -1,0 +1,50 @@
+"""Small end-to-end exercise of every kernel family, for compute-sanitizer (memcheck / racecheck / synccheck):
+fit (Gram, Cholesky step kernel with its inter-CTA flags, trtri), FP64 scoring + gradients, the int8-slice
+tcgen05/TMA/TMEM path, top-k, device Sobol grid, incremental append, batched stand-alone Cholesky, Thompson on
+both paths.  Shapes are small: the sanitizer slows kernels 10-100x."""
+import sys
+
+import numpy as np
+
+sys.path.insert(0, '.')
+from scipy.stats import qmc
+from pybo_b200 import _lib, models
+
+rng = np.random.RandomState(0)
+n, d, M = 300, 3, 1500
+X = rng.rand(n, d)
+y = np.sin(X.sum(1)) + 0.01 * rng.randn(n)
+rho, bias = float(np.ptp(y)), float(y.mean())
+ctx = _lib.Context(0)
+ctx.fit("se", X[:-2], y[:-2], 0.3 * np.ones((2, d)), [rho, 1.1 * rho], [1e-4, 2e-4], [bias, bias])
+ctx.append(X[-2:], y[-2:])
+Xc = qmc.Sobol(d=d, scramble=False).random_base2(11)[:M]
+mu, s2 = ctx.predict(Xc)
+target = float(ctx.predict(X)[0].max())
+v0, _, b0 = ctx.score(1, target, Xc, want_best=True)
+vg, g, _ = ctx.score(1, target, Xc[:5], grad=True)
+vg, g, _ = ctx.score(2, target, Xc[:100], grad=True)
+idx, val = ctx.topk(10)
+ctx.set_precision(1, 1e-8)
+v8, _, b8 = ctx.score(1, target, Xc, want_best=True)
+ctx.set_precision(1, 4.5)
+v8b, _, _ = ctx.score(3, 2.0, Xc, want_best=True)
+ctx.set_precision(0)
+ctx.sobol(d, 0, 1024, out="staged")
+ctx.score_staged(1, target, 1024)
+print("loglik", ctx.loglik())
+A = rng.randn(2, 200, 200)
+A = A @ A.transpose(0, 2, 1) + 200 * np.eye(200)
+L = ctx.cholesky(A)
+print("chol err", np.abs(L - np.linalg.cholesky(A)).max())
+K = ctx.gram("matern52", X, 0.3 * np.ones(d), rho, 1e-4)
+gp = models.make_gp(1e-4, rho, 0.3 * np.ones(d), bias)
+gp.add_data(X, y)
+tb = models.ThompsonBatch(gp, m=128, ndraw=64, rng=1)
+F = tb.get(Xc)
+tb.set_precision("int8", 1e-8)
+F8 = tb.get(Xc)
+bv, bi = tb.argmax(Xc)
+fs = gp.sample_f(50, rng=2)
+fv, fg = fs.get(Xc[:7], grad=True)
+print("ok", b0, b8, float(np.abs(v8 - v0).max()), float(np.abs(F8 - F).max()))
