@@ -142,6 +142,7 @@ def test_rescue_pass_reports_and_repairs(ctx):
     assert rel_err(mu, rmu, 1e-9) < TOL
     assert np.max(np.abs(s2 - rs2) / np.maximum(np.abs(rs2), 1e-9 * rho)) < TOL
     # at the training points everything is flagged (s2 ~ sn2): the incumbent target is an FP64 quantity
+    ctx.set_rescue(True)                                          # (re-arm: a pass that rescued > 25 % demotes the fit to FP64)
     mu_d, s2_d = ctx.predict(X)
     assert ctx.rescue_info()[1] == len(X)
     assert rel_err(mu_d, gp.predict(X)[0], 1e-9) < TOL
@@ -220,9 +221,9 @@ def test_precision_is_per_model_state():
     a = models.make_gp(1e-4, rho, 0.3 * np.ones(3), bias)
     a.add_data(X, y)
     Xc = qmc.Sobol(d=3, scramble=False).random_base2(12)
+    va = a.get_improvement(0.1, Xc)                                # fits lazily; copies taken from here on share the handle
     b = a.copy()
-    assert b._fit is None or b._fit is a._fit
-    va = a.get_improvement(0.1, Xc)
+    assert b._fit is a._fit
     b.set_precision("int8", 3.0)                                  # deliberately coarse
     b._ensure_fit().set_rescue(False)
     vb = b.get_improvement(0.1, Xc)

@@ -32,7 +32,19 @@ v8b, _, _ = ctx.score(3, 2.0, Xc, want_best=True)
 ctx.set_precision(0)
 ctx.sobol(d, 0, 1024, out="staged")
 ctx.score_staged(1, target, 1024)
-print("loglik", ctx.loglik())
+print("loglik", ctx.loglik(), ctx.loglik_fit("se", X, y, 0.3 * np.ones((2, d)), [rho, 1.1 * rho], [1e-4, 2e-4], [bias, bias]))
+# rescue pass of the int8 path (coarse level so that candidates are flagged), large-list compaction, incumbent records
+ctx.set_precision(1, 4.0)
+vr, _, br = ctx.score(1, target, Xc, want_best=True)
+print("rescue", ctx.rescue_info())
+Xbig = qmc.Sobol(d=d, scramble=False).random_base2(14)
+ctx.set_rescue(True, 1e-12, 1e-12)
+ctx.score(2, target, Xbig, want_best=True)
+print("rescue (everything flagged)", ctx.rescue_info())
+ctx.set_rescue(True)
+ctx.set_precision(0)
+rec = ctx.score_incumbent(1, target, len(Xc), Xc, offset=5, flags=0)
+print("incumbent", ctx.incumbent_merge(rec, 1, 1))
 A = rng.randn(2, 200, 200)
 A = A @ A.transpose(0, 2, 1) + 200 * np.eye(200)
 L = ctx.cholesky(A)
@@ -45,6 +57,8 @@ F = tb.get(Xc)
 tb.set_precision("int8", 1e-8)
 F8 = tb.get(Xc)
 bv, bi = tb.argmax(Xc)
+tp = models.ThompsonBatch(gp, m=40, ndraw=6, rng=3, shared_basis=False)      # one feature system per draw, built on the device
+print("per-draw bases", tp.argmax(Xc)[1])
 fs = gp.sample_f(50, rng=2)
 fv, fg = fs.get(Xc[:7], grad=True)
 print("ok", b0, b8, float(np.abs(v8 - v0).max()), float(np.abs(F8 - F).max()))
