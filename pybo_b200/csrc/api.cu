@@ -169,6 +169,7 @@ extern "C" int bo_destroy(bo_ctx *ctx) {
     cudaStreamSynchronize(ctx->stream);
     if (ctx->stream2) cudaStreamSynchronize(ctx->stream2);
     prof_drain(ctx);
+    bo_linalg_drop_graphs(ctx);
     free_all(ctx);
     for (int i = 0; i < 2; ++i) {
         if (ctx->ev_sliced[i]) cudaEventDestroy(ctx->ev_sliced[i]);

@@ -42,6 +42,15 @@ struct bo_thompson_state {
     size_t build_capacity = 0;
 };
 
+struct bo_chol_graph {
+    double *A = nullptr, *dinv = nullptr;
+    int *info = nullptr, *flags = nullptr;
+    int np = 0, batch = 0;
+    int64_t launches = 0;
+    uint64_t stamp = 0;
+    cudaGraphExec_t exec = nullptr;
+};
+
 struct bo_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -74,6 +83,10 @@ struct bo_ctx {
     int *dCholInfo = nullptr;
     int *dCholFlags = nullptr;     // per (matrix, panel) 'diagonal block factored' flags of the fused step kernel
     size_t cholflags_capacity = 0;
+    std::vector<bo_chol_graph> chol_graphs;    // captured factorisation patterns (linalg.cu bo_linalg_cholesky)
+    std::vector<bo_chol_graph> chol_seen;      // patterns requested once so far (captured when they come back)
+    uint64_t chol_graph_clock = 0;
+    int chol_flow_grid = 0;                    // co-resident CTAs of the persistent factorisation kernel (0: unavailable)
     size_t choldinv_capacity = 0, cholinfo_capacity = 0;
     std::vector<double> h_rho, h_sn2, h_bias, h_ell;
     std::vector<int> h_info;
@@ -244,6 +257,7 @@ int bo_linalg_trtri(bo_ctx *ctx, int np, int batch, const double *L, const doubl
 int bo_linalg_transpose(bo_ctx *ctx, int np, int batch, const double *A, double *AT);
 int bo_linalg_finish_fit(bo_ctx *ctx);
 int bo_linalg_init(bo_ctx *ctx);
+void bo_linalg_drop_graphs(bo_ctx *ctx);
 int bo_score_init(bo_ctx *ctx);
 int bo_ozaki_init(bo_ctx *ctx);
 int bo_thompson_init(bo_ctx *ctx);

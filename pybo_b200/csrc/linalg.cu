@@ -330,16 +330,24 @@ __device__ __forceinline__ void potrf64_regs(double (&ra)[4][4], PotrfSmem &sm, 
 //                up -- L_ic = R Dinv_c^T.
 // The column update of the tiles below the diagonal overlaps the factorisation of the diagonal block;
 // CTA 0 never waits and is dispatched before the CTAs that wait for it, so the spin cannot deadlock.
+// mode 0: fused (above); mode 1: diagonal CTA only (grid.x = 1); mode 2: panel CTAs only, launched after mode 1 in
+// stream order (grid.x = nblk - c - 1, no flag to wait for, the smaller GEMM-only shared-memory footprint).  The split
+// form is used when many matrices are factored at once: CTAs that spin on the flag while the diagonal block is being
+// factored hold shared memory that the trailing updates of the other matrices could be using.
 __global__ void __launch_bounds__(256)
 chol_step_kernel(double *A, int ld, int64_t strideA, int c, double *dinv, int64_t strideD, int *info, int *flags,
-                 int nblk) {
+                 int nblk, int mode, int kprev) {
     extern __shared__ __align__(16) double smem[];
     const int tid = threadIdx.x;
     double *Az = A + blockIdx.z * strideA;
     double *Db = dinv + blockIdx.z * strideD + (int64_t)c * 4096;
     int *flag = flags + blockIdx.z * nblk + c;
-    const bool has_prev = c > 0;
-    if (blockIdx.x == 0) {
+    // kprev: width of the finished columns directly left of block column c that still have to be applied to it
+    // (0, 64 or 128: trailing updates run per PAIR of panels, see chol_enqueue)
+    const bool has_prev = kprev > 0;
+    const int64_t cprev = (int64_t)c * 64 - kprev;
+    const int bx = (mode == 2) ? (int)blockIdx.x + 1 : (int)blockIdx.x;
+    if (bx == 0) {
         PotrfSmem &sm = *reinterpret_cast<PotrfSmem *>(smem);
         double *P = smem + (sizeof(PotrfSmem) + 7) / 8;           // [64][65] copy of L_{c,c-1}, later the factor
         double *Xs = P + PF_TILE, *Ts = Xs + PF_TILE;
@@ -354,7 +362,7 @@ chol_step_kernel(double *A, int ld, int64_t strideA, int c, double *dinv, int64_
             // D = A_cc - L_{c,c-1} L_{c,c-1}^T on the FP64 tensor cores (half the shared-memory traffic of a DFMA
             // register tile), then through shared memory from the MMA fragment layout into the (ty, tx) layout
             typedef T64NT8 T;
-            const double *Lp = Az + (int64_t)c * 64 * ld + (int64_t)(c - 1) * 64;
+            const double *Lp = Az + (int64_t)c * 64 * ld + cprev;
             const int warp = tid >> 5, lane = tid & 31;
             const int wm = warp / T::WARPS_N, wn = warp % T::WARPS_N, g = lane >> 2, t = lane & 3;
             double acc[T::MI][T::NI][2];
@@ -362,7 +370,7 @@ chol_step_kernel(double *A, int ld, int64_t strideA, int c, double *dinv, int64_
             for (int mi = 0; mi < T::MI; ++mi)
 #pragma unroll
                 for (int ni = 0; ni < T::NI; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
-            T::mainloop(acc, Lp, ld, Lp, ld, 0, 64, smem);           // ends with a barrier: smem is free again
+            T::mainloop(acc, Lp, ld, Lp, ld, 0, kprev, smem);        // ends with a barrier: smem is free again
 #pragma unroll
             for (int mi = 0; mi < T::MI; ++mi)
 #pragma unroll
@@ -385,7 +393,7 @@ chol_step_kernel(double *A, int ld, int64_t strideA, int c, double *dinv, int64_
         return;
     }
     typedef T64NT8 T;
-    const int i = c + blockIdx.x;
+    const int i = c + bx;
     double *C = Az + (int64_t)i * 64 * ld + (int64_t)c * 64;
     const int warp = tid >> 5, lane = tid & 31;
     const int wm = warp / T::WARPS_N, wn = warp % T::WARPS_N;
@@ -396,9 +404,9 @@ chol_step_kernel(double *A, int ld, int64_t strideA, int c, double *dinv, int64_
         for (int mi = 0; mi < T::MI; ++mi)
 #pragma unroll
             for (int ni = 0; ni < T::NI; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
-        const double *Li = Az + (int64_t)i * 64 * ld + (int64_t)(c - 1) * 64;
-        const double *Lc = Az + (int64_t)c * 64 * ld + (int64_t)(c - 1) * 64;
-        T::mainloop(acc, Li, ld, Lc, ld, 0, 64, smem);
+        const double *Li = Az + (int64_t)i * 64 * ld + cprev;
+        const double *Lc = Az + (int64_t)c * 64 * ld + cprev;
+        T::mainloop(acc, Li, ld, Lc, ld, 0, kprev, smem);
 #pragma unroll
         for (int mi = 0; mi < T::MI; ++mi)
 #pragma unroll
@@ -413,13 +421,15 @@ chol_step_kernel(double *A, int ld, int64_t strideA, int c, double *dinv, int64_
         __threadfence();             // the tile is re-read below through cp.async (L2)
         __syncthreads();
     }
-    if (tid == 0) {
-        int v;
-        do {
-            asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
-        } while (v == 0);
+    if (mode == 0) {
+        if (tid == 0) {
+            int v;
+            do {
+                asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+            } while (v == 0);
+        }
+        __syncthreads();
     }
-    __syncthreads();
 
 #pragma unroll
     for (int mi = 0; mi < T::MI; ++mi)
@@ -435,14 +445,198 @@ chol_step_kernel(double *A, int ld, int64_t strideA, int c, double *dinv, int64_
         }
 }
 
+// ---------------------------------------------------------------------------
+// Single-matrix factorisation as ONE persistent cooperative kernel (dataflow over 64 x 64 tiles).
+//
+// The launch-per-step pipeline above spends a third of every step on kernel boundaries (drain of the slowest panel
+// CTA, launch, cross-stream event) and synchronises whole kernels where single tiles depend on each other.  Here every
+// CTA is resident for the whole factorisation and tiles are handed over through release / acquire flags in global
+// memory:
+//   solved[r][c]   (c <  r)  tile L_rc is final;   solved[c][c]  the diagonal block c is factored and Dinv_c stored
+//   applied[i][j]            number of panel PAIRS (2q, 2q+1) the update workers have applied to tile (i, j)
+// Row CTA r (blockIdx.x = r < nblk) owns block row r of the panel chain: for c = 0 .. r-1 it applies panel c-1 to its
+// tile (r, c), multiplies by Dinv_c^T as soon as that exists, and at c = r factors the diagonal block -- the same
+// arithmetic, in the same order, as chol_step_kernel.  While it waits for Dinv_c at an odd c it already applies panel
+// c-1 to its tile in column c+1, so that every tile meets its own step with only ONE panel (K = 64) left to apply.
+// All other CTAs -- and the row CTAs once their row is done -- are update workers: they draw trailing-update tasks
+// (pair p, tile (i, j), i >= j >= 2p + 3:  C_ij -= L_i,pair L_j,pair^T, K = 128) from one atomic counter, in an order
+// (pair, column, row) that is a topological order of the dependency graph and serves the columns the chain needs next
+// first.  Cooperative launch guarantees that every CTA is resident, so a waiting CTA always waits for a running one.
+// ---------------------------------------------------------------------------
+struct CholFlowParams {
+    double *A;
+    int ld, nblk;
+    double *dinv;
+    int *info;
+    int *solved, *applied, *next;
+};
+
+__device__ __forceinline__ int flow_ld_acquire(const int *p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void flow_wait(const int *flag, int v) {
+    if (threadIdx.x == 0) {
+        while (flow_ld_acquire(flag) < v) __nanosleep(64);
+    }
+    __syncthreads();
+}
+// every thread's global writes first (fence), then one release store
+__device__ __forceinline__ void flow_signal(int *flag, int v) {
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(flag), "r"(v) : "memory");
+}
+
+// SUB: C -= A B^T (C is read into the accumulators, negated, while the operand stages are in flight); else C = A B^T.
+// A: 64 rows (lda), B: 64 rows stored [n][k] (ldb); K a multiple of 16.  Ends with every thread's stores issued.
+template <bool SUB>
+__device__ __forceinline__ void flow_gemm(double *C, int ldc, const double *Ap, int lda, const double *Bp, int ldb, int K,
+                                          double *smem) {
+    typedef T64NT8 T;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int wm = warp / T::WARPS_N, wn = warp % T::WARPS_N;
+    const int g = lane >> 2, t = lane & 3;
+    double acc[T::MI][T::NI][2];
+#pragma unroll
+    for (int mi = 0; mi < T::MI; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < T::NI; ++ni) {
+            if (SUB) {
+                const int r = wm * T::WM + mi * 8 + g, c = wn * T::WN + ni * 8 + 2 * t;
+                // (L2 load: the tile may have been written by another SM since this SM last cached it)
+                const double2 v = __ldcg(reinterpret_cast<const double2 *>(&C[(int64_t)r * ldc + c]));
+                acc[mi][ni][0] = -v.x;
+                acc[mi][ni][1] = -v.y;
+            } else {
+                acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+            }
+        }
+    T::mainloop(acc, Ap, lda, Bp, ldb, 0, K, smem);
+    const double sg = SUB ? -1.0 : 1.0;
+#pragma unroll
+    for (int mi = 0; mi < T::MI; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < T::NI; ++ni) {
+            const int r = wm * T::WM + mi * 8 + g, c = wn * T::WN + ni * 8 + 2 * t;
+            *reinterpret_cast<double2 *>(&C[(int64_t)r * ldc + c]) = make_double2(sg * acc[mi][ni][0], sg * acc[mi][ni][1]);
+        }
+}
+
+__device__ __forceinline__ int flow_napp(int c) { return c >= 3 ? (c - 3) / 2 + 1 : 0; }
+
+__global__ void __launch_bounds__(256)
+chol_flow_kernel(CholFlowParams p) {
+    extern __shared__ __align__(16) double smem[];
+    __shared__ int s_task[4];
+    const int tid = threadIdx.x, nblk = p.nblk, ld = p.ld;
+    double *Az = p.A;
+    if ((int)blockIdx.x < nblk) {
+        // ===================== row CTA: block row r of the panel chain =====================
+        const int r = blockIdx.x;
+        double *row = Az + (int64_t)r * 64 * ld;
+        for (int c = 0; c < r; ++c) {
+            double *Trc = row + (int64_t)c * 64;
+            flow_wait(p.applied + (int64_t)r * nblk + c, flow_napp(c));
+            if (c >= 1) {                                   // panel c-1 onto this tile
+                flow_wait(p.solved + (int64_t)c * nblk + (c - 1), 1);
+                flow_gemm<true>(Trc, ld, row + (int64_t)(c - 1) * 64, ld, Az + (int64_t)c * 64 * ld + (int64_t)(c - 1) * 64, ld, 64, smem);
+            }
+            if ((c & 1) && c + 1 <= r) {                    // idle until Dinv_c exists: panel c-1 onto the tile in column c+1
+                flow_wait(p.applied + (int64_t)r * nblk + c + 1, flow_napp(c + 1));
+                if (c + 1 < r) flow_wait(p.solved + (int64_t)(c + 1) * nblk + (c - 1), 1);
+                flow_gemm<true>(row + (int64_t)(c + 1) * 64, ld, row + (int64_t)(c - 1) * 64, ld,
+                                Az + (int64_t)(c + 1) * 64 * ld + (int64_t)(c - 1) * 64, ld, 64, smem);
+            }
+            __threadfence();                                // the tile is re-read below through cp.async (L2)
+            flow_wait(p.solved + (int64_t)c * nblk + c, 1); // Dinv_c (also the barrier behind the fence)
+            flow_gemm<false>(Trc, ld, Trc, ld, p.dinv + (int64_t)c * 4096, 64, 64, smem);
+            flow_signal(p.solved + (int64_t)r * nblk + c, 1);
+        }
+        {   // diagonal block r
+            PotrfSmem &sm = *reinterpret_cast<PotrfSmem *>(smem);
+            double *P = smem + (sizeof(PotrfSmem) + 7) / 8;
+            double *Xs = P + PF_TILE, *Ts = Xs + PF_TILE;
+            const int tx = tid & 15, ty = tid >> 4;
+            double *Ab = row + (int64_t)r * 64;
+            flow_wait(p.applied + (int64_t)r * nblk + r, flow_napp(r));
+            double ra[4][4];
+#pragma unroll
+            for (int ai = 0; ai < 4; ++ai)
+#pragma unroll
+                for (int b = 0; b < 4; ++b) ra[ai][b] = __ldcg(&Ab[(int64_t)(ty + 16 * ai) * ld + tx + 16 * b]);
+            if (r >= 1) {
+                typedef T64NT8 T;
+                const double *Lp = row + (int64_t)(r - 1) * 64;
+                const int warp = tid >> 5, lane = tid & 31;
+                const int wm = warp / T::WARPS_N, wn = warp % T::WARPS_N, g = lane >> 2, t = lane & 3;
+                double acc[T::MI][T::NI][2];
+#pragma unroll
+                for (int mi = 0; mi < T::MI; ++mi)
+#pragma unroll
+                    for (int ni = 0; ni < T::NI; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+                T::mainloop(acc, Lp, ld, Lp, ld, 0, 64, smem);           // ends with a barrier: smem is free again
+#pragma unroll
+                for (int mi = 0; mi < T::MI; ++mi)
+#pragma unroll
+                    for (int ni = 0; ni < T::NI; ++ni) {
+                        const int rr = wm * T::WM + mi * 8 + g, cc = wn * T::WN + ni * 8 + 2 * t;
+                        Xs[rr * PF_LD + cc] = acc[mi][ni][0];
+                        Xs[rr * PF_LD + cc + 1] = acc[mi][ni][1];
+                    }
+                __syncthreads();
+#pragma unroll
+                for (int ai = 0; ai < 4; ++ai)
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) ra[ai][b] -= Xs[(ty + 16 * ai) * PF_LD + tx + 16 * b];
+                __syncthreads();
+            }
+            potrf64_regs(ra, sm, P, Xs, Ts, Ab, ld, p.dinv + (int64_t)r * 4096, p.info, r);
+            flow_signal(p.solved + (int64_t)r * nblk + r, 1);
+        }
+    }
+    // ===================== update worker =====================
+    for (;;) {
+        __syncthreads();                                    // s_task of the previous round fully consumed
+        if (tid == 0) {
+            const int t = atomicAdd(p.next, 1);
+            // task t -> (pair q, tile (i, j)): pairs in order, inside a pair column by column
+            int q = 0, rem = t, T = nblk - 3;
+            while (T > 0 && rem >= T * (T + 1) / 2) { rem -= T * (T + 1) / 2; T -= 2; ++q; }
+            if (T <= 0) {
+                s_task[0] = -1;
+            } else {
+                int jj = 0;
+                while (rem >= T - jj) { rem -= T - jj; ++jj; }
+                s_task[0] = q;
+                s_task[1] = 2 * q + 3 + jj + rem;           // i
+                s_task[2] = 2 * q + 3 + jj;                 // j
+            }
+        }
+        __syncthreads();
+        const int q = s_task[0], i = s_task[1], j = s_task[2];
+        if (q < 0) break;
+        flow_wait(p.solved + (int64_t)i * nblk + 2 * q + 1, 1);          // row i of the pair (its even panel came first)
+        if (j != i) flow_wait(p.solved + (int64_t)j * nblk + 2 * q + 1, 1);
+        flow_wait(p.applied + (int64_t)i * nblk + j, q);                 // earlier pairs on this tile
+        flow_gemm<true>(Az + (int64_t)i * 64 * ld + (int64_t)j * 64, ld, Az + (int64_t)i * 64 * ld + (int64_t)(2 * q) * 64, ld,
+                        Az + (int64_t)j * 64 * ld + (int64_t)(2 * q) * 64, ld, 128, smem);
+        flow_signal(p.applied + (int64_t)i * nblk + j, q + 1);
+    }
+}
+
 #define CHOL_DIAG_SMEM ((int)(sizeof(PotrfSmem) + 8 + (2 * PF_TILE + 64 * 33) * 8))
 #define CHOL_STEP_SMEM (T64NT8::SMEM_BYTES > CHOL_DIAG_SMEM ? T64NT8::SMEM_BYTES : CHOL_DIAG_SMEM)
 
 
-// Lower-triangular tile enumeration for the trailing update.
+// Trailing update, one 64 x 64 tile of the lower triangle per CTA: C -= P_m P_n^T (K = 64 or 128 panel columns).  The accumulators start as
+// -C: the tile is fetched from global memory straight into registers while the operand stages are still in flight, and
+// the result is written back negated, so the read of C is off the tail of the kernel (a launch of this kernel is
+// latency-bound in the second half of the factorisation, where the triangle holds fewer tiles than the chip has SMs).
 template <class T>
 __global__ void __launch_bounds__(T::NTHREADS)
-syrk_tri_kernel(double *A22, const double *P, int ld, int64_t strideA, int ntile) {
+syrk_tri_kernel(double *A22, const double *P, int ld, int64_t strideA, int K) {
     extern __shared__ __align__(16) double smem[];
     // linear index -> (tm >= tn)
     int x = blockIdx.x;
@@ -450,31 +644,31 @@ syrk_tri_kernel(double *A22, const double *P, int ld, int64_t strideA, int ntile
     while ((tm + 1) * (tm + 2) / 2 <= x) ++tm;
     while (tm * (tm + 1) / 2 > x) --tm;
     int tn = x - tm * (tm + 1) / 2;
-    (void)ntile;
     const double *Pb = P + blockIdx.z * strideA;
     double *Cb = A22 + blockIdx.z * strideA;
     const double *Ap = Pb + (int64_t)tm * T::BM * ld;
     const double *Bp = Pb + (int64_t)tn * T::BN * ld;
     double *C = Cb + (int64_t)tm * T::BM * ld + (int64_t)tn * T::BN;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int wm = warp / T::WARPS_N, wn = warp % T::WARPS_N;
+    const int g = lane >> 2, t = lane & 3;
     double acc[T::MI][T::NI][2];
 #pragma unroll
     for (int mi = 0; mi < T::MI; ++mi)
 #pragma unroll
-        for (int ni = 0; ni < T::NI; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
-    T::mainloop(acc, Ap, ld, Bp, ld, 0, BO_NB, smem);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int wm = warp / T::WARPS_N, wn = warp % T::WARPS_N;
-    const int g = lane >> 2, t = lane & 3;
+        for (int ni = 0; ni < T::NI; ++ni) {
+            const int r = wm * T::WM + mi * 8 + g, c = wn * T::WN + ni * 8 + 2 * t;
+            const double2 v = *reinterpret_cast<const double2 *>(&C[(int64_t)r * ld + c]);
+            acc[mi][ni][0] = -v.x;
+            acc[mi][ni][1] = -v.y;
+        }
+    T::mainloop(acc, Ap, ld, Bp, ld, 0, K, smem);
 #pragma unroll
     for (int mi = 0; mi < T::MI; ++mi)
 #pragma unroll
         for (int ni = 0; ni < T::NI; ++ni) {
             int r = wm * T::WM + mi * 8 + g, c = wn * T::WN + ni * 8 + 2 * t;
-            double2 *dst = reinterpret_cast<double2 *>(&C[(int64_t)r * ld + c]);
-            double2 v = *dst;
-            v.x -= acc[mi][ni][0];
-            v.y -= acc[mi][ni][1];
-            *dst = v;
+            *reinterpret_cast<double2 *>(&C[(int64_t)r * ld + c]) = make_double2(-acc[mi][ni][0], -acc[mi][ni][1]);
         }
 }
 
@@ -488,47 +682,162 @@ static int set_smem(bo_ctx *ctx, K kernel, int bytes) {
 // Right-looking with a one-panel lookahead: step c (chol_step_kernel, main high-priority stream)
 // applies panel c-1 to block column c, factors the diagonal block and solves the panel in one
 // launch, while the rest of the trailing update of panel c-1 (columns > c) runs on the side stream.
-int bo_linalg_cholesky(bo_ctx *ctx, int np, int batch, double *A, double *dinv, int *dInfo) {
+static int chol_enqueue(bo_ctx *ctx, int np, int batch, double *A, double *dinv, int *dInfo) {
     const int nblk = np / BO_NB;
     const int64_t strideA = (int64_t)np * np, strideD = (int64_t)nblk * 4096;
     cudaStream_t main = ctx->stream, side = ctx->stream2;
-    BO_TRY(bo_reserve(ctx, &ctx->dCholFlags, &ctx->cholflags_capacity, (size_t)batch * nblk));
     BO_CUDA(ctx, cudaMemsetAsync(dInfo, 0, sizeof(int) * batch, main));
     BO_CUDA(ctx, cudaMemsetAsync(ctx->dCholFlags, 0, sizeof(int) * batch * nblk, main));
-    auto step = [&](int c) -> int {
-        BO_LAUNCH(ctx, "chol_step_kernel");
-        chol_step_kernel<<<dim3(nblk - c, 1, batch), 256, CHOL_STEP_SMEM, main>>>(A, np, strideA, c, dinv, strideD, dInfo,
-                                                                                  ctx->dCholFlags, nblk);
-        BO_CHECK_LAUNCH(ctx);
+    // many matrices at once: diagonal and panel as two launches (no CTA spins on the flag); see chol_step_kernel
+    const bool split = (int64_t)batch * nblk > 2 * (int64_t)ctx->sm_count;
+    auto step = [&](int c, int kprev) -> int {
+        if (!split) {
+            BO_LAUNCH(ctx, "chol_step_kernel");
+            chol_step_kernel<<<dim3(nblk - c, 1, batch), 256, CHOL_STEP_SMEM, main>>>(A, np, strideA, c, dinv, strideD, dInfo,
+                                                                                      ctx->dCholFlags, nblk, 0, kprev);
+            BO_CHECK_LAUNCH(ctx);
+            return BO_OK;
+        }
+        {
+            BO_LAUNCH(ctx, "chol_diag_kernel");
+            chol_step_kernel<<<dim3(1, 1, batch), 256, CHOL_STEP_SMEM, main>>>(A, np, strideA, c, dinv, strideD, dInfo,
+                                                                               ctx->dCholFlags, nblk, 1, kprev);
+            BO_CHECK_LAUNCH(ctx);
+        }
+        if (nblk - c - 1 > 0) {
+            BO_LAUNCH(ctx, "chol_panel_kernel");
+            chol_step_kernel<<<dim3(nblk - c - 1, 1, batch), 256, T64NT8::SMEM_BYTES, main>>>(A, np, strideA, c, dinv, strideD, dInfo,
+                                                                                             ctx->dCholFlags, nblk, 2, kprev);
+            BO_CHECK_LAUNCH(ctx);
+        }
         return BO_OK;
     };
-    auto rest = [&](int k) -> int {          // A_ij -= L_ik L_jk^T for i >= j >= k+2 (side stream)
-        const int T = nblk - k - 2;
+    // Trailing updates run per PAIR of panels (K = 128): a 64 x 64 tile of C is read and written once per 128 panel
+    // columns instead of once per 64 -- the update is bound by L2 traffic (C in, C out, two operand tiles per 0.5 MFLOP
+    // at K = 64), not by the FP64 tensor pipe.  Pair p = panels (2p, 2p+1):
+    //   step(2p)   applies pair p-1 to block column 2p itself         (kprev = 128, nothing to wait for)
+    //   step(2p+1) applies panel 2p to block column 2p+1 itself       (kprev = 64) after rest(p-1) has finished with it
+    //   rest(p)    A_ij -= L_i,pair L_j,pair^T for i >= j >= 2p+3     (side stream, after step(2p+1))
+    auto rest = [&](int p) -> int {
+        const int j0 = 2 * p + 3, T = nblk - j0;
         if (T <= 0) return BO_OK;
-        double *panel = A + (int64_t)(k + 2) * BO_NB * np + (int64_t)k * BO_NB;
-        double *A22 = A + (int64_t)(k + 2) * BO_NB * (np + 1);
-        const int ntile = T * (T + 1) / 2;
+        double *panel = A + (int64_t)j0 * BO_NB * np + (int64_t)(2 * p) * BO_NB;
+        double *A22 = A + (int64_t)j0 * BO_NB * (np + 1);
         BO_LAUNCH_ON(ctx, "chol_syrk_kernel", side);
-        syrk_tri_kernel<T64NT><<<dim3(ntile, 1, batch), T64NT::NTHREADS, T64NT::SMEM_BYTES, side>>>(
-            A22, panel, np, strideA, ntile);
+        syrk_tri_kernel<T64NT><<<dim3(T * (T + 1) / 2, 1, batch), T64NT::NTHREADS, T64NT::SMEM_BYTES, side>>>(
+            A22, panel, np, strideA, 2 * BO_NB);
         BO_CHECK_LAUNCH(ctx);
         return BO_OK;
     };
-    // the side stream must see everything queued on the main stream so far (the input matrix)
+    if (nblk <= 2) {
+        BO_TRY(step(0, 0));
+        if (nblk == 2) BO_TRY(step(1, BO_NB));
+        return BO_OK;
+    }
+    // fork: the side stream must see everything queued on the main stream so far (the input matrix)
     BO_CUDA(ctx, cudaEventRecord(ctx->ev_consumed[0], main));
     BO_CUDA(ctx, cudaStreamWaitEvent(side, ctx->ev_consumed[0], 0));
-    BO_TRY(step(0));
-    BO_CUDA(ctx, cudaEventRecord(ctx->ev_sliced[0], main));               // panel 0 ready
-    for (int k = 0; k + 1 < nblk; ++k) {
-        const int e = k & 1;
-        BO_CUDA(ctx, cudaStreamWaitEvent(side, ctx->ev_sliced[e], 0));    // panel k
-        BO_TRY(rest(k));
-        BO_CUDA(ctx, cudaEventRecord(ctx->ev_consumed[e], side));          // rest(k) done
-        if (k >= 1) BO_CUDA(ctx, cudaStreamWaitEvent(main, ctx->ev_consumed[e ^ 1], 0));   // rest(k-1) touched column k+1
-        BO_TRY(step(k + 1));
-        BO_CUDA(ctx, cudaEventRecord(ctx->ev_sliced[e ^ 1], main));       // panel k+1 ready
+    const int npair = (nblk + 1) / 2;
+    for (int p = 0; p < npair; ++p) {
+        const int e = p & 1;
+        BO_TRY(step(2 * p, p > 0 ? 2 * BO_NB : 0));
+        if (2 * p + 1 < nblk) {
+            if (p >= 1) BO_CUDA(ctx, cudaStreamWaitEvent(main, ctx->ev_consumed[e ^ 1], 0));   // rest(p-1) done with column 2p+1
+            BO_TRY(step(2 * p + 1, BO_NB));
+        }
+        BO_CUDA(ctx, cudaEventRecord(ctx->ev_sliced[e], main));            // pair p complete
+        BO_CUDA(ctx, cudaStreamWaitEvent(side, ctx->ev_sliced[e], 0));
+        BO_TRY(rest(p));
+        BO_CUDA(ctx, cudaEventRecord(ctx->ev_consumed[e], side));          // rest(p) done
     }
-    if (nblk > 1) BO_CUDA(ctx, cudaStreamWaitEvent(main, ctx->ev_consumed[(nblk - 2) & 1], 0));
+    BO_CUDA(ctx, cudaStreamWaitEvent(main, ctx->ev_consumed[(npair - 1) & 1], 0));   // join
+    return BO_OK;
+}
+
+// The factorisation is a fixed pattern of ~3 nblk launches and ~4 nblk event edges across two streams; issued one by one
+// the host spends longer queueing them than the device needs to run the serial chain.  The whole pattern is therefore
+// captured once per (matrix address, size, batch) into a CUDA graph and replayed (a handle refactors the same buffers
+// on every bo_fit / bo_loglik_fit); the event profiler needs real launches, so profiling runs bypass the graph.
+void bo_linalg_drop_graphs(bo_ctx *ctx) {
+    for (auto &g : ctx->chol_graphs)
+        if (g.exec) cudaGraphExecDestroy(g.exec);
+    ctx->chol_graphs.clear();
+}
+
+// one matrix: the persistent dataflow kernel (chol_flow_kernel)
+static int chol_flow(bo_ctx *ctx, int np, double *A, double *dinv, int *dInfo, int grid) {
+    const int nblk = np / BO_NB;
+    const size_t nflags = 2 * (size_t)nblk * nblk + 8;
+    BO_TRY(bo_reserve(ctx, &ctx->dCholFlags, &ctx->cholflags_capacity, nflags));
+    BO_CUDA(ctx, cudaMemsetAsync(dInfo, 0, sizeof(int), ctx->stream));
+    BO_CUDA(ctx, cudaMemsetAsync(ctx->dCholFlags, 0, sizeof(int) * nflags, ctx->stream));
+    CholFlowParams prm;
+    prm.A = A; prm.ld = np; prm.nblk = nblk; prm.dinv = dinv; prm.info = dInfo;
+    prm.solved = ctx->dCholFlags;
+    prm.applied = ctx->dCholFlags + (size_t)nblk * nblk;
+    prm.next = ctx->dCholFlags + 2 * (size_t)nblk * nblk;
+    void *args[] = {&prm};
+    BO_LAUNCH(ctx, "chol_flow_kernel");
+    BO_CUDA(ctx, cudaLaunchCooperativeKernel((const void *)chol_flow_kernel, dim3(grid), dim3(256), args, CHOL_STEP_SMEM, ctx->stream));
+    return BO_OK;
+}
+
+int bo_linalg_cholesky(bo_ctx *ctx, int np, int batch, double *A, double *dinv, int *dInfo) {
+    const int nblk = np / BO_NB;
+    static const bool use_flow = !(getenv("BO_CHOL_FLOW") && atoi(getenv("BO_CHOL_FLOW")) == 0);
+    // (measured: 2.07 vs 2.2 ms at n = 4096; at n <= 2048 the chain of 45 k cycles per diagonal block dominates either
+    //  way and the launch-per-step form, replayed as a graph, is a few per cent ahead)
+    if (use_flow && batch == 1 && nblk >= 48 && ctx->chol_flow_grid >= nblk + 16)
+        return chol_flow(ctx, np, A, dinv, dInfo, ctx->chol_flow_grid);
+    BO_TRY(bo_reserve(ctx, &ctx->dCholFlags, &ctx->cholflags_capacity, (size_t)batch * nblk));
+    static const bool use_graph = !(getenv("BO_CHOL_GRAPH") && atoi(getenv("BO_CHOL_GRAPH")) == 0);
+    // (measured: the replayed graph wins 7 % at n <= 2048, loses 7 % at n = 4096 where the chain is bound by the device)
+    if (!use_graph || ctx->prof_on || nblk < 3 || nblk > 32 || batch > 16) return chol_enqueue(ctx, np, batch, A, dinv, dInfo);
+    for (auto &g : ctx->chol_graphs)
+        if (g.A == A && g.dinv == dinv && g.info == dInfo && g.flags == ctx->dCholFlags && g.np == np && g.batch == batch) {
+            g.stamp = ++ctx->chol_graph_clock;
+            ctx->launches += g.launches;
+            BO_CUDA(ctx, cudaGraphLaunch(g.exec, ctx->stream));
+            return BO_OK;
+        }
+    // capture only a pattern that comes back (one-shot callers hand in a fresh scratch matrix every time)
+    {
+        bool seen = false;
+        for (auto &k : ctx->chol_seen) seen = seen || (k.A == A && k.dinv == dinv && k.info == dInfo && k.np == np && k.batch == batch);
+        if (!seen) {
+            bo_chol_graph k;
+            k.A = A; k.dinv = dinv; k.info = dInfo; k.np = np; k.batch = batch;
+            if (ctx->chol_seen.size() >= 8) ctx->chol_seen.erase(ctx->chol_seen.begin());
+            ctx->chol_seen.push_back(k);
+            return chol_enqueue(ctx, np, batch, A, dinv, dInfo);
+        }
+    }
+    const int64_t l0 = ctx->launches;
+    BO_CUDA(ctx, cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+    const int rc = chol_enqueue(ctx, np, batch, A, dinv, dInfo);
+    cudaGraph_t graph = nullptr;
+    const cudaError_t e = cudaStreamEndCapture(ctx->stream, &graph);
+    if (rc != BO_OK) {
+        if (graph) cudaGraphDestroy(graph);
+        return rc;
+    }
+    if (e != cudaSuccess) return bo_set_err(ctx, BO_ERR_CUDA, "Cholesky graph capture failed: %s", cudaGetErrorString(e));
+    bo_chol_graph g;
+    g.A = A; g.dinv = dinv; g.info = dInfo; g.flags = ctx->dCholFlags; g.np = np; g.batch = batch;
+    g.launches = ctx->launches - l0;
+    g.stamp = ++ctx->chol_graph_clock;
+    const cudaError_t ei = cudaGraphInstantiate(&g.exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ei != cudaSuccess) return bo_set_err(ctx, BO_ERR_CUDA, "Cholesky graph instantiation failed: %s", cudaGetErrorString(ei));
+    if (ctx->chol_graphs.size() >= 4) {          // keep the four most recently used patterns
+        size_t old = 0;
+        for (size_t i = 1; i < ctx->chol_graphs.size(); ++i)
+            if (ctx->chol_graphs[i].stamp < ctx->chol_graphs[old].stamp) old = i;
+        cudaGraphExecDestroy(ctx->chol_graphs[old].exec);
+        ctx->chol_graphs.erase(ctx->chol_graphs.begin() + old);
+    }
+    ctx->chol_graphs.push_back(g);
+    BO_CUDA(ctx, cudaGraphLaunch(g.exec, ctx->stream));
     return BO_OK;
 }
 
@@ -728,6 +1037,13 @@ int bo_linalg_finish_fit(bo_ctx *ctx) {
 int bo_linalg_init(bo_ctx *ctx) {
     BO_TRY(set_smem(ctx, dgemm_kernel<T64NT>, T64NT::SMEM_BYTES));
     BO_TRY(set_smem(ctx, chol_step_kernel, CHOL_STEP_SMEM));
+    BO_TRY(set_smem(ctx, chol_flow_kernel, CHOL_STEP_SMEM));
+    {
+        int per_sm = 0, coop = 0;
+        BO_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, chol_flow_kernel, 256, CHOL_STEP_SMEM));
+        BO_CUDA(ctx, cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, ctx->device));
+        ctx->chol_flow_grid = coop ? per_sm * ctx->sm_count : 0;
+    }
     BO_TRY(set_smem(ctx, syrk_tri_kernel<T64NT>, T64NT::SMEM_BYTES));
     BO_TRY(set_smem(ctx, trtri_node_kernel<0>, T64NN::SMEM_BYTES));
     BO_TRY(set_smem(ctx, trtri_node_kernel<1>, T64NN::SMEM_BYTES));

@@ -331,17 +331,63 @@ __device__ __forceinline__ double oz_exp2_scaled(double z, int shift) {
 }
 
 #define OZ_KS_TILES 4      // observation tiles (of 64) per block
+#define OZ_KS_THREADS 256  // two threads per candidate: each covers 32 of a tile's 64 observations
+
+// 2^(i / 128), i = 0 .. 127, correctly rounded
+__constant__ double OZ_EXP2_TAB[128] = {
+    1.0, 1.0054299011128027, 1.0108892860517005, 1.016378314910953,
+    1.0218971486541166, 1.0274459491187637, 1.0330248790212284, 1.0386341019613787,
+    1.0442737824274138, 1.0499440858006872, 1.0556451783605572, 1.061377227289262,
+    1.0671404006768237, 1.0729348675259756, 1.0787607977571199, 1.0846183622133092,
+    1.0905077326652577, 1.0964290818163769, 1.102382583307841, 1.1083684117236787,
+    1.1143867425958924, 1.1204377524096067, 1.1265216186082418, 1.1326385195987192,
+    1.1387886347566916, 1.1449721444318042, 1.1511892299529827, 1.1574400736337511,
+    1.1637248587775775, 1.1700437696832502, 1.1763969916502812, 1.182784710984341,
+    1.189207115002721, 1.1956643920398273, 1.202156731452703, 1.2086843236265816,
+    1.215247359980469, 1.2218460329727576, 1.22848053610687, 1.2351510639369334,
+    1.241857812073484, 1.2486009771892048, 1.255380757024691, 1.2621973503942507,
+    1.2690509571917332, 1.275941778396392, 1.2828700160787783, 1.2898358734066657,
+    1.2968395546510096, 1.3038812651919358, 1.3109612115247644, 1.318079601266064,
+    1.3252366431597413, 1.3324325470831615, 1.339667524053303, 1.3469417862329458,
+    1.3542555469368927, 1.3616090206382248, 1.3690024229745905, 1.3764359707545302,
+    1.383909881963832, 1.3914243757719262, 1.3989796725383112, 1.4065759938190154,
+    1.4142135623730951, 1.4218926021691656, 1.42961333839197, 1.4373759974489824,
+    1.4451808069770467, 1.4530279958490526, 1.460917794180647, 1.4688504333369818,
+    1.4768261459394993, 1.4848451658727524, 1.4929077282912648, 1.5010140696264256,
+    1.5091644275934228, 1.5173590411982147, 1.5255981507445384, 1.533881997840956,
+    1.5422108254079407, 1.550584877685, 1.559004400237837, 1.567469639965553,
+    1.5759808451078865, 1.5845382652524937, 1.593142151342267, 1.6017927556826934,
+    1.6104903319492543, 1.6192351351948637, 1.6280274218573478, 1.6368674497669644,
+    1.645755478153965, 1.6546917676561943, 1.6636765803267364, 1.6727101796415966,
+    1.681792830507429, 1.6909247992693053, 1.7001063537185235, 1.709337763100463,
+    1.718619298122478, 1.7279512309618377, 1.7373338352737062, 1.746767386199169,
+    1.7562521603732995, 1.7657884359332727, 1.7753764925265212, 1.785016611318935,
+    1.7947090750031072, 1.804454167806624, 1.8142521755003989, 1.8241033854070534,
+    1.8340080864093424, 1.843966568958626, 1.8539791250833855, 1.864046048397789,
+    1.8741676341103, 1.8843441790323345, 1.8945759815869656, 1.9048633418176741,
+    1.9152065613971474, 1.925605943636125, 1.9360617934922943, 1.9465744175792332,
+    1.9571441241754002, 1.9677712232331759, 1.978456026387951, 1.9891988469672663};
+// ln2^j / j!, j = 5 .. 1: 2^r for |r| <= 2^-8 to 5.5e-19 (relative)
+#define OZ_P5 0.0013333558146428443
+#define OZ_P4 0.009618129107628477
+#define OZ_P3 0.05550410866482158
+#define OZ_P2 0.24022650695910072
+#define OZ_P1 0.6931471805599453
 
 __device__ __forceinline__ void oz_cp_async16(void *smem_dst, const void *gmem_src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src));
 }
 
-// block: one candidate tile (128 candidates, one per thread) x up to OZ_KS_TILES k blocks of 64
-// observations.  Observation tiles (scaled coordinates + |xs|^2/2) are prefetched with cp.async
-// into a double buffer; each finished 128 x 64 tile is staged in shared memory as the swizzled
-// operand image and copied out with fully coalesced 16-byte-per-lane stores (8 KB per slice).
+// block: one candidate tile (128 candidates) x up to OZ_KS_TILES k blocks of 64 observations; thread = (candidate,
+// half of the k block), 256 threads so that three blocks (24 warps) fit an SM -- with one thread per candidate
+// (round 1) only 15 warps were resident and the kernel sat at 52 % of the FP64 pipe waiting on its own latency.
+// Observation tiles (scaled coordinates + |xs|^2/2) are prefetched with cp.async into a double buffer; each finished
+// 128 x 64 tile is staged in shared memory as the swizzled operand image and copied out with fully coalesced
+// 16-byte-per-lane stores (8 KB per slice).
+// exp2: z = k + i/128 + r with |r| <= 2^-8 (rint(128 z) is read from the low mantissa word of z + 1.5 * 2^45),
+// 2^z = 2^k T[i] P5(r): a shared-memory table look-up and 5 FMAs instead of the 12-term Horner chain.
 template <int DP, int S, bool MATERN>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(OZ_KS_THREADS, 3)
 oz_kstar_slices_fast_kernel(int n, int np, int d, const double *__restrict__ Xs, const double *__restrict__ XsHalfSq,
                             const double *__restrict__ invell, const double *__restrict__ Xc, int64_t c0, int mc,
                             int mcp, int8_t *__restrict__ Ks, const double *__restrict__ beta,
@@ -349,20 +395,23 @@ oz_kstar_slices_fast_kernel(int n, int np, int d, const double *__restrict__ Xs,
     __shared__ __align__(16) double xs[2][64][DP];
     __shared__ __align__(16) double hb[2][64];
     __shared__ __align__(16) double bt[2][64];                      // beta of the tile
+    __shared__ double tab[128];
     extern __shared__ __align__(16) uint8_t oz_stage[];          // [S][128 rows][64 B]
     const int tid = threadIdx.x;
+    const int row = tid & 127, half = tid >> 7;
     const int nkb = np / 64, ntiles = mcp / 128;
     const int t0 = blockIdx.y * OZ_KS_TILES;
     const int t1 = (t0 + OZ_KS_TILES < nkb) ? t0 + OZ_KS_TILES : nkb;
     auto prefetch = [&](int tile, int buf) {
         const double *src = Xs + (int64_t)tile * 64 * DP;
-        for (int e = tid; e < 64 * DP / 2; e += 128) oz_cp_async16(&xs[buf][0][0] + 2 * e, src + 2 * e);
+        for (int e = tid; e < 64 * DP / 2; e += OZ_KS_THREADS) oz_cp_async16(&xs[buf][0][0] + 2 * e, src + 2 * e);
         if (tid < 32) oz_cp_async16(&hb[buf][0] + 2 * tid, XsHalfSq + (int64_t)tile * 64 + 2 * tid);
         else if (tid < 64) oz_cp_async16(&bt[buf][0] + 2 * (tid - 32), beta + (int64_t)tile * 64 + 2 * (tid - 32));
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
     prefetch(t0, 0);
-    const int m = blockIdx.x * 128 + tid;
+    if (tid < 128) tab[tid] = OZ_EXP2_TAB[tid];
+    const int m = blockIdx.x * 128 + row;
     const bool live = m < mc;
     double xc[DP], ha = 0.0;
 #pragma unroll
@@ -373,10 +422,11 @@ oz_kstar_slices_fast_kernel(int n, int np, int d, const double *__restrict__ Xs,
     ha *= 0.5;
     constexpr double LOG2E = 1.4426950408889634;
     constexpr double LOG2_127 = 6.988684686772166;      // kappa * 127 * 2^32 = 2^(log2 kappa + LOG2_127 + 32)
+    constexpr double MAGIC45 = 52776558133248.0;        // 1.5 * 2^45: ulp = 2^-7
     static_assert(S >= 2 && S <= 5, "fast slicer handles 2..5 slices");
-    const int swz = (tid >> 1) & 3;
+    const int swz = (row >> 1) & 3;
     const int jlimit = live ? n : 0;      // observations j < jlimit contribute for this thread's candidate
-    double kb = 0.0;                 // sum_j 127 * 2^32 kappa_j beta_j over this block's observations (FP64)
+    double kb = 0.0;                 // sum_j 127 * 2^32 kappa_j beta_j over this thread's observations (FP64)
     for (int tile = t0; tile < t1; ++tile) {
         const int buf = (tile - t0) & 1;
         if (tile + 1 < t1) {
@@ -388,20 +438,20 @@ oz_kstar_slices_fast_kernel(int n, int np, int d, const double *__restrict__ Xs,
         __syncthreads();        // tile data landed; previous copy-out has finished reading the stage
         const int j0 = tile * 64;
 #pragma unroll 1
-        for (int sub = 0; sub < 4; ++sub) {
+        for (int sb = 0; sb < 2; ++sb) {
+            const int sub = 2 * half + sb;
             const int jj0 = sub * 16;
             // X = rint(kappa * 127 * 2^32) < 2^39 as a 5-byte integer; the bytes of X + 0x8080808080,
             // each XOR 0x80, are its balanced base-256 digits (slice s = byte 4 - s): the low word is
             // transposed to slice-major words with byte permutes, the top digit sits in the high word.
             uint32_t wlow[16], wtop[4];
-            // four elements in lockstep: the distance dot products and the exp2 Horner chains of the
-            // four are independent, so the FP64 pipe always has work in flight (a single chain per
-            // thread left it waiting on its own latency 55 % of the time)
+            // four elements in lockstep: the distance dot products and the exp2 chains of the
+            // four are independent, so the FP64 pipe always has work in flight
 #pragma unroll
             for (int q4 = 0; q4 < 4; ++q4) {
                 const int jq = jj0 + 4 * q4;
-                double dot[4], f[4], pl[4];
-                int ki[4];
+                double dot[4], r[4], pl[4];
+                int ki[4], ti[4];
 #pragma unroll
                 for (int e = 0; e < 4; ++e) dot[e] = -ha - hb[buf][jq + e];
 #pragma unroll
@@ -426,28 +476,34 @@ oz_kstar_slices_fast_kernel(int n, int np, int d, const double *__restrict__ Xs,
                         const double hs = 0.5 * sa;
                         y = y * fma(-hs, y * y, 1.5);
                         y = y * fma(-hs, y * y, 1.5);
-                        const double r = sa * y;
-                        q[e] = fma(fma(r, 1.0 / 3.0, 1.0), r, 1.0);
-                        dot[e] = -r;                                           // exponent of e
+                        const double rr = sa * y;
+                        q[e] = fma(fma(rr, 1.0 / 3.0, 1.0), rr, 1.0);
+                        dot[e] = -rr;                                          // exponent of e
                     }
                 }
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                     const double z = fma(dot[e], LOG2E, LOG2_127);
-                    const double zz = z + 6755399441055744.0;          // 1.5 * 2^52: low word = rint(z)
-                    ki[e] = __double2loint(zz) + 32;
-                    f[e] = z - (zz - 6755399441055744.0);              // [-0.5, 0.5]
-                    pl[e] = OZ_EXP2_C[0];
+                    const double zz = z + MAGIC45;                      // low word = rint(128 z)
+                    const int n128 = __double2loint(zz);
+                    ki[e] = (n128 >> 7) + 32;
+                    ti[e] = n128 & 127;
+                    r[e] = z - (zz - MAGIC45);                          // [-2^-8, 2^-8]
+                    pl[e] = OZ_P5;
                 }
 #pragma unroll
-                for (int c = 1; c < 12; ++c) {
+                for (int e = 0; e < 4; ++e) pl[e] = fma(pl[e], r[e], OZ_P4);
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) pl[e] = fma(pl[e], f[e], OZ_EXP2_C[c]);
-                }
+                for (int e = 0; e < 4; ++e) pl[e] = fma(pl[e], r[e], OZ_P3);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) pl[e] = fma(pl[e], r[e], OZ_P2);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) pl[e] = fma(pl[e], r[e], OZ_P1);
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                     const int i = 4 * q4 + e;
-                    pl[e] = fma(pl[e], f[e], 1.0);
+                    const double t = tab[ti[e]];
+                    pl[e] = fma(pl[e] * r[e], t, t);                    // T[i] (1 + r P(r))
                     if (MATERN) pl[e] *= q[e];
                     // one predicate (live candidate, real observation, no exponent underflow) -> one select
                     const bool on = (((j0 + jq + e) - jlimit) & (-961 - ki[e])) < 0;
@@ -463,7 +519,7 @@ oz_kstar_slices_fast_kernel(int n, int np, int d, const double *__restrict__ Xs,
                     else wtop[q4] |= top << (8 * e);
                 }
             }
-            uint8_t *o0 = oz_stage + tid * 64 + ((sub ^ swz) << 4);
+            uint8_t *o0 = oz_stage + row * 64 + ((sub ^ swz) << 4);
             *reinterpret_cast<uint4 *>(o0) = make_uint4(wtop[0], wtop[1], wtop[2], wtop[3]);
 #pragma unroll
             for (int s = 1; s < S; ++s) {
@@ -485,12 +541,12 @@ oz_kstar_slices_fast_kernel(int n, int np, int d, const double *__restrict__ Xs,
             uint4 *dst = reinterpret_cast<uint4 *>(Ks + oz_kss_block(s, blockIdx.x, tile, ntiles, nkb));
             const uint4 *src = reinterpret_cast<const uint4 *>(oz_stage + s * OZ_A_SLICE_BYTES);
 #pragma unroll
-            for (int e = 0; e < OZ_A_SLICE_BYTES / 16 / 128; ++e) dst[e * 128 + tid] = src[e * 128 + tid];
+            for (int e = 0; e < OZ_A_SLICE_BYTES / 16 / OZ_KS_THREADS; ++e) dst[e * OZ_KS_THREADS + tid] = src[e * OZ_KS_THREADS + tid];
         }
     }
     // the posterior mean needs no contraction with W: mu = bias + rho * kappa . beta (beta = K^-1 r);
-    // per-block partials, summed in a fixed order by oz_moments_kernel
-    mupart[(int64_t)blockIdx.y * mcp + m] = kb * (1.0 / 545460846592.0);      // 127 * 2^32
+    // per-(block, half) partials, summed in a fixed order by oz_moments_kernel
+    mupart[((int64_t)blockIdx.y * 2 + half) * mcp + m] = kb * (1.0 / 545460846592.0);      // 127 * 2^32
 }
 
 // |xs_j|^2 / 2 per observation (once per fit)
@@ -968,12 +1024,12 @@ static void launch_oz_kstar_fast(bo_ctx *ctx, int s, const double *dXc, int64_t 
     const double *ie = ctx->dInvEll + (int64_t)s * ctx->dp, *beta = ctx->dBeta + (int64_t)s * ctx->np;
     double *mup = ctx->dOzMu + (size_t)ctx->oz_mu_slot * ctx->ozmu_stride;
     if (ctx->kernel == BO_KERNEL_MATERN52)
-        oz_kstar_slices_fast_kernel<DP, S, true><<<grid, 128, S * OZ_A_SLICE_BYTES, st>>>(ctx->n, ctx->np, ctx->d, xs, hsq, ie, dXc, c0, mc,
+        oz_kstar_slices_fast_kernel<DP, S, true><<<grid, OZ_KS_THREADS, S * OZ_A_SLICE_BYTES, st>>>(ctx->n, ctx->np, ctx->d, xs, hsq, ie, dXc, c0, mc,
                                                                                    mcp, Kss, beta, mup);
     else
-        oz_kstar_slices_fast_kernel<DP, S, false><<<grid, 128, S * OZ_A_SLICE_BYTES, st>>>(ctx->n, ctx->np, ctx->d, xs, hsq, ie, dXc, c0,
+        oz_kstar_slices_fast_kernel<DP, S, false><<<grid, OZ_KS_THREADS, S * OZ_A_SLICE_BYTES, st>>>(ctx->n, ctx->np, ctx->d, xs, hsq, ie, dXc, c0,
                                                                                     mc, mcp, Kss, beta, mup);
-    ctx->oz_mu_rows[ctx->oz_mu_slot] = (ntile + OZ_KS_TILES - 1) / OZ_KS_TILES;
+    ctx->oz_mu_rows[ctx->oz_mu_slot] = 2 * ((ntile + OZ_KS_TILES - 1) / OZ_KS_TILES);
 }
 
 template <int DP>
