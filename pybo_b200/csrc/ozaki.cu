@@ -386,7 +386,7 @@ __device__ __forceinline__ void oz_cp_async16(void *smem_dst, const void *gmem_s
 // 16-byte-per-lane stores (8 KB per slice).
 // exp2: z = k + i/128 + r with |r| <= 2^-8 (rint(128 z) is read from the low mantissa word of z + 1.5 * 2^45),
 // 2^z = 2^k T[i] P5(r): a shared-memory table look-up and 5 FMAs instead of the 12-term Horner chain.
-template <int DP, int S, bool MATERN>
+template <int DP, int S, bool MATERN, bool TAB>
 __global__ void __launch_bounds__(OZ_KS_THREADS, 3)
 oz_kstar_slices_fast_kernel(int n, int np, int d, const double *__restrict__ Xs, const double *__restrict__ XsHalfSq,
                             const double *__restrict__ invell, const double *__restrict__ Xc, int64_t c0, int mc,
@@ -410,7 +410,7 @@ oz_kstar_slices_fast_kernel(int n, int np, int d, const double *__restrict__ Xs,
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
     prefetch(t0, 0);
-    if (tid < 128) tab[tid] = OZ_EXP2_TAB[tid];
+    if (TAB && tid < 128) tab[tid] = OZ_EXP2_TAB[tid];
     const int m = blockIdx.x * 128 + row;
     const bool live = m < mc;
     double xc[DP], ha = 0.0;
@@ -481,29 +481,50 @@ oz_kstar_slices_fast_kernel(int n, int np, int d, const double *__restrict__ Xs,
                         dot[e] = -rr;                                          // exponent of e
                     }
                 }
+                if (TAB) {
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const double z = fma(dot[e], LOG2E, LOG2_127);
-                    const double zz = z + MAGIC45;                      // low word = rint(128 z)
-                    const int n128 = __double2loint(zz);
-                    ki[e] = (n128 >> 7) + 32;
-                    ti[e] = n128 & 127;
-                    r[e] = z - (zz - MAGIC45);                          // [-2^-8, 2^-8]
-                    pl[e] = OZ_P5;
+                    for (int e = 0; e < 4; ++e) {
+                        const double z = fma(dot[e], LOG2E, LOG2_127);
+                        const double zz = z + MAGIC45;                      // low word = rint(128 z)
+                        const int n128 = __double2loint(zz);
+                        ki[e] = (n128 >> 7) + 32;
+                        ti[e] = n128 & 127;
+                        r[e] = z - (zz - MAGIC45);                          // [-2^-8, 2^-8]
+                        pl[e] = OZ_P5;
+                    }
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) pl[e] = fma(pl[e], r[e], OZ_P4);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) pl[e] = fma(pl[e], r[e], OZ_P3);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) pl[e] = fma(pl[e], r[e], OZ_P2);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) pl[e] = fma(pl[e], r[e], OZ_P1);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const double t = tab[ti[e]];
+                        pl[e] = fma(pl[e] * r[e], t, t);                    // T[i] (1 + r P(r))
+                    }
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const double z = fma(dot[e], LOG2E, LOG2_127);
+                        const double zz = z + 6755399441055744.0;          // 1.5 * 2^52: low word = rint(z)
+                        ki[e] = __double2loint(zz) + 32;
+                        r[e] = z - (zz - 6755399441055744.0);              // [-0.5, 0.5]
+                        pl[e] = OZ_EXP2_C[0];
+                    }
+#pragma unroll
+                    for (int c = 1; c < 12; ++c) {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) pl[e] = fma(pl[e], r[e], OZ_EXP2_C[c]);
+                    }
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) pl[e] = fma(pl[e], r[e], 1.0);
                 }
-#pragma unroll
-                for (int e = 0; e < 4; ++e) pl[e] = fma(pl[e], r[e], OZ_P4);
-#pragma unroll
-                for (int e = 0; e < 4; ++e) pl[e] = fma(pl[e], r[e], OZ_P3);
-#pragma unroll
-                for (int e = 0; e < 4; ++e) pl[e] = fma(pl[e], r[e], OZ_P2);
-#pragma unroll
-                for (int e = 0; e < 4; ++e) pl[e] = fma(pl[e], r[e], OZ_P1);
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                     const int i = 4 * q4 + e;
-                    const double t = tab[ti[e]];
-                    pl[e] = fma(pl[e] * r[e], t, t);                    // T[i] (1 + r P(r))
                     if (MATERN) pl[e] *= q[e];
                     // one predicate (live candidate, real observation, no exponent underflow) -> one select
                     const bool on = (((j0 + jq + e) - jlimit) & (-961 - ki[e])) < 0;
@@ -887,8 +908,10 @@ int bo_ozaki_init(bo_ctx *ctx) {
     OZ_ATTR(2); OZ_ATTR(3); OZ_ATTR(4); OZ_ATTR(5); OZ_ATTR(6); OZ_ATTR(7);
 #undef OZ_ATTR
 #undef OZ_ATTR1
-#define OZ_KATTR(DP, SS) BO_CUDA(ctx, cudaFuncSetAttribute(oz_kstar_slices_fast_kernel<DP, SS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SS * OZ_A_SLICE_BYTES)); \
-                         BO_CUDA(ctx, cudaFuncSetAttribute(oz_kstar_slices_fast_kernel<DP, SS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SS * OZ_A_SLICE_BYTES))
+#define OZ_KATTR(DP, SS) BO_CUDA(ctx, cudaFuncSetAttribute(oz_kstar_slices_fast_kernel<DP, SS, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SS * OZ_A_SLICE_BYTES)); \
+                         BO_CUDA(ctx, cudaFuncSetAttribute(oz_kstar_slices_fast_kernel<DP, SS, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SS * OZ_A_SLICE_BYTES)); \
+                         BO_CUDA(ctx, cudaFuncSetAttribute(oz_kstar_slices_fast_kernel<DP, SS, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SS * OZ_A_SLICE_BYTES)); \
+                         BO_CUDA(ctx, cudaFuncSetAttribute(oz_kstar_slices_fast_kernel<DP, SS, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SS * OZ_A_SLICE_BYTES))
 #define OZ_KATTR_ALL(DP) OZ_KATTR(DP, 2); OZ_KATTR(DP, 3); OZ_KATTR(DP, 4); OZ_KATTR(DP, 5)
     OZ_KATTR_ALL(2); OZ_KATTR_ALL(4); OZ_KATTR_ALL(8); OZ_KATTR_ALL(16);
 #undef OZ_KATTR_ALL
@@ -1023,12 +1046,15 @@ static void launch_oz_kstar_fast(bo_ctx *ctx, int s, const double *dXc, int64_t 
     const double *xs = ctx->dXs + (int64_t)s * ctx->np * ctx->dp, *hsq = ctx->dXsHalfSq + (int64_t)s * ctx->np;
     const double *ie = ctx->dInvEll + (int64_t)s * ctx->dp, *beta = ctx->dBeta + (int64_t)s * ctx->np;
     double *mup = ctx->dOzMu + (size_t)ctx->oz_mu_slot * ctx->ozmu_stride;
-    if (ctx->kernel == BO_KERNEL_MATERN52)
-        oz_kstar_slices_fast_kernel<DP, S, true><<<grid, OZ_KS_THREADS, S * OZ_A_SLICE_BYTES, st>>>(ctx->n, ctx->np, ctx->d, xs, hsq, ie, dXc, c0, mc,
-                                                                                   mcp, Kss, beta, mup);
-    else
-        oz_kstar_slices_fast_kernel<DP, S, false><<<grid, OZ_KS_THREADS, S * OZ_A_SLICE_BYTES, st>>>(ctx->n, ctx->np, ctx->d, xs, hsq, ie, dXc, c0,
-                                                                                    mc, mcp, Kss, beta, mup);
+    // exp2 through the 128-entry table (5 FMAs + one conflict-prone shared-memory look-up) or the 12-term Horner chain:
+    // measured 0.436 vs 0.460 ms per 32768 x 4096 chunk (the kernel is bound by shared-memory wavefronts and the FP64
+    // pipe at about the same level either way); BO_OZ_EXP2_TABLE=0 selects the polynomial
+    static const bool tab = !(getenv("BO_OZ_EXP2_TABLE") && atoi(getenv("BO_OZ_EXP2_TABLE")) == 0);
+#define OZ_KS_RUN(MAT, TB) oz_kstar_slices_fast_kernel<DP, S, MAT, TB><<<grid, OZ_KS_THREADS, S * OZ_A_SLICE_BYTES, st>>>( \
+        ctx->n, ctx->np, ctx->d, xs, hsq, ie, dXc, c0, mc, mcp, Kss, beta, mup)
+    if (ctx->kernel == BO_KERNEL_MATERN52) { if (tab) OZ_KS_RUN(true, true); else OZ_KS_RUN(true, false); }
+    else { if (tab) OZ_KS_RUN(false, true); else OZ_KS_RUN(false, false); }
+#undef OZ_KS_RUN
     ctx->oz_mu_rows[ctx->oz_mu_slot] = 2 * ((ntile + OZ_KS_TILES - 1) / OZ_KS_TILES);
 }
 

@@ -1,12 +1,19 @@
 """Summarise gpurun_out ncu artefacts into profiles/ (launch shares + key counters)."""
 import collections
 import csv
+import json
+import os
 import subprocess
 import sys
 
-tag, kern = sys.argv[1], sys.argv[2]           # e.g. r1_fp64 score_gemm
+import json
+import os
+
+tag, kern = sys.argv[1], sys.argv[2]           # e.g. r2_int8 oz_score oz_kstar
 kerns = sys.argv[2:]
-rows = [r for r in csv.reader(open('gpurun_out/launches.csv')) if len(r) > 5]
+# library kernel name + bench workload a capture stands for (profiles/traffic.json feeds bench.py's roofline.traffic)
+TRAFFIC_KEYS = {"oz_score": ("rbf_n4096_d8_ei", "oz_score_kernel"), "score_gemm": ("rbf_n4096_d8_ei", "score_gemm_kernel")}
+rows = [r for r in csv.reader(open('gpurun_out/launches.csv' if os.path.exists('gpurun_out/launches.csv') else 'profiles/%s_launches.csv' % tag)) if len(r) > 5]
 hdr = rows[0]
 ki, vi, ui = hdr.index('Kernel Name'), hdr.index('Metric Value'), hdr.index('Metric Unit')
 agg = collections.OrderedDict()
@@ -19,7 +26,8 @@ for r in rows[1:]:
 tot = sum(a[1] for a in agg.values())
 out = ["# ncu --metrics gpu__time_duration.sum --clock-control none over a short bench.py run",
        "# (cold-cache, serialised launches: compare SHARES, not absolutes)", "kernel,launches,total_us,share"]
-STEP = ('kstar', 'score_gemm', 'moments', 'acq_kernel', 'argmax_final', 'oz_score', 'oz_kstar', 'oz_moments')
+STEP = ('kstar', 'score_gemm', 'moments', 'acq_kernel', 'argmax_final', 'oz_score', 'oz_kstar', 'oz_moments', 'oz_flag', 'oz_sort',
+        'oz_gather', 'oz_scatter', 'topk_pass', 'incumbent_')
 step_tot = sum(t for k, (c, t) in agg.items() if any(s in k for s in STEP))
 out[2] = "kernel,launches,total_us,share_of_all,share_of_scoring_step"
 for k, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
@@ -39,7 +47,10 @@ want = ['Kernel Name', 'gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__
         'launch__registers_per_thread', 'launch__grid_size', 'launch__block_size', 'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum',
         'sm__issue_active.avg.pct_of_peak_sustained_elapsed', 'sm__cycles_elapsed.max', 'smsp__inst_executed.sum']
 for kern in kerns:
-    raw = subprocess.run(['ncu', '-i', 'gpurun_out/prof_%s.ncu-rep' % kern, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
+    if os.path.exists('gpurun_out/prof_%s_raw.csv' % kern):
+        raw = open('gpurun_out/prof_%s_raw.csv' % kern).read()
+    else:
+        raw = subprocess.run(['ncu', '-i', 'gpurun_out/prof_%s.ncu-rep' % kern, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
     rr = list(csv.reader(raw.splitlines()))
     h, u, v = rr[0], rr[1], rr[2]
     lines = ["# ncu --set full --clock-control none -k regex:%s, first captured launch (bench.py --candidates 65536)" % kern, ""]
@@ -48,3 +59,15 @@ for kern in kerns:
             i = h.index(k); lines.append("%s = %s %s" % (k, v[i], u[i]))
     open('profiles/%s_%s_ncu.txt' % (tag, kern), 'w').write("\n".join(lines) + "\n")
     print("\n".join(lines))
+    if kern in TRAFFIC_KEYS and 'dram__bytes_read.sum' in h:
+        def to_bytes(name):
+            i = h.index(name)
+            mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[u[i]]
+            return float(v[i].replace(',', '')) * mult
+        path = 'profiles/traffic.json'
+        t = json.load(open(path)) if os.path.exists(path) else {}
+        wl, name = TRAFFIC_KEYS[kern]
+        t.setdefault(wl, {})[name] = dict(dram_bytes=to_bytes('dram__bytes_read.sum') + to_bytes('dram__bytes_write.sum'),
+                                          dram_read=to_bytes('dram__bytes_read.sum'), dram_write=to_bytes('dram__bytes_write.sum'),
+                                          source='profiles/%s_%s_ncu.txt (ncu --set full, one launch = 32768 candidates)' % (tag, kern))
+        json.dump(t, open(path, 'w'), indent=1)
