@@ -38,6 +38,9 @@ static int ctx_padded_dim(int d) {
 #define OZ_A_SLICE_BYTES (OZ_BM * OZ_BK)   // 8192
 #define OZ_B_SLICE_BYTES (OZ_BN * OZ_BK)   // 4096
 #define OZ_THREADS 192   // warp 0: TMA producer, warp 1: MMA issuer, warps 2-5: epilogue
+#define OZ_ROW_SMEM 8192      // MODE 1: row scale + bias of up to 512 draws
+#define OZ_ARG_LD 129         // MODE 1: leading dimension (doubles) of the 64 x 128 arg-max transpose buffer
+#define OZ_ARG_SMEM (64 * OZ_ARG_LD * 8)
 
 // ---------------------------------------------------------------------------
 // PTX wrappers
@@ -333,41 +336,16 @@ __device__ __forceinline__ double oz_exp2_scaled(double z, int shift) {
 #define OZ_KS_TILES 4      // observation tiles (of 64) per block
 #define OZ_KS_THREADS 256  // two threads per candidate: each covers 32 of a tile's 64 observations
 
-// 2^(i / 128), i = 0 .. 127, correctly rounded
-__constant__ double OZ_EXP2_TAB[128] = {
-    1.0, 1.0054299011128027, 1.0108892860517005, 1.016378314910953,
-    1.0218971486541166, 1.0274459491187637, 1.0330248790212284, 1.0386341019613787,
-    1.0442737824274138, 1.0499440858006872, 1.0556451783605572, 1.061377227289262,
-    1.0671404006768237, 1.0729348675259756, 1.0787607977571199, 1.0846183622133092,
-    1.0905077326652577, 1.0964290818163769, 1.102382583307841, 1.1083684117236787,
-    1.1143867425958924, 1.1204377524096067, 1.1265216186082418, 1.1326385195987192,
-    1.1387886347566916, 1.1449721444318042, 1.1511892299529827, 1.1574400736337511,
-    1.1637248587775775, 1.1700437696832502, 1.1763969916502812, 1.182784710984341,
-    1.189207115002721, 1.1956643920398273, 1.202156731452703, 1.2086843236265816,
-    1.215247359980469, 1.2218460329727576, 1.22848053610687, 1.2351510639369334,
-    1.241857812073484, 1.2486009771892048, 1.255380757024691, 1.2621973503942507,
-    1.2690509571917332, 1.275941778396392, 1.2828700160787783, 1.2898358734066657,
-    1.2968395546510096, 1.3038812651919358, 1.3109612115247644, 1.318079601266064,
-    1.3252366431597413, 1.3324325470831615, 1.339667524053303, 1.3469417862329458,
-    1.3542555469368927, 1.3616090206382248, 1.3690024229745905, 1.3764359707545302,
-    1.383909881963832, 1.3914243757719262, 1.3989796725383112, 1.4065759938190154,
-    1.4142135623730951, 1.4218926021691656, 1.42961333839197, 1.4373759974489824,
-    1.4451808069770467, 1.4530279958490526, 1.460917794180647, 1.4688504333369818,
-    1.4768261459394993, 1.4848451658727524, 1.4929077282912648, 1.5010140696264256,
-    1.5091644275934228, 1.5173590411982147, 1.5255981507445384, 1.533881997840956,
-    1.5422108254079407, 1.550584877685, 1.559004400237837, 1.567469639965553,
-    1.5759808451078865, 1.5845382652524937, 1.593142151342267, 1.6017927556826934,
-    1.6104903319492543, 1.6192351351948637, 1.6280274218573478, 1.6368674497669644,
-    1.645755478153965, 1.6546917676561943, 1.6636765803267364, 1.6727101796415966,
-    1.681792830507429, 1.6909247992693053, 1.7001063537185235, 1.709337763100463,
-    1.718619298122478, 1.7279512309618377, 1.7373338352737062, 1.746767386199169,
-    1.7562521603732995, 1.7657884359332727, 1.7753764925265212, 1.785016611318935,
-    1.7947090750031072, 1.804454167806624, 1.8142521755003989, 1.8241033854070534,
-    1.8340080864093424, 1.843966568958626, 1.8539791250833855, 1.864046048397789,
-    1.8741676341103, 1.8843441790323345, 1.8945759815869656, 1.9048633418176741,
-    1.9152065613971474, 1.925605943636125, 1.9360617934922943, 1.9465744175792332,
-    1.9571441241754002, 1.9677712232331759, 1.978456026387951, 1.9891988469672663};
-// ln2^j / j!, j = 5 .. 1: 2^r for |r| <= 2^-8 to 5.5e-19 (relative)
+// 2^(i / 16), i = 0 .. 15, correctly rounded.  Sixteen doubles fill exactly one 128-byte row of shared memory: two
+// lanes reading different entries hit different banks, two lanes reading the same entry are a broadcast, so the
+// look-up is free of bank conflicts whatever the indices are (a 128-entry table cost 15.6 M conflicts per launch).
+__constant__ double OZ_EXP2_TAB[16] = {
+    1.0, 1.0442737824274138, 1.0905077326652577, 1.1387886347566916, 1.189207115002721, 1.241857812073484,
+    1.2968395546510096, 1.3542555469368927, 1.4142135623730951, 1.4768261459394993, 1.5422108254079407,
+    1.6104903319492543, 1.681792830507429, 1.7562521603732995, 1.8340080864093424, 1.9152065613971474};
+// ln2^j / j!, j = 7 .. 1: (2^r - 1) / r for |r| <= 2^-5 to 1.2e-18 (relative to 2^r)
+#define OZ_P7 1.5252733804059841e-05
+#define OZ_P6 0.0001540353039338161
 #define OZ_P5 0.0013333558146428443
 #define OZ_P4 0.009618129107628477
 #define OZ_P3 0.05550410866482158
@@ -384,8 +362,8 @@ __device__ __forceinline__ void oz_cp_async16(void *smem_dst, const void *gmem_s
 // Observation tiles (scaled coordinates + |xs|^2/2) are prefetched with cp.async into a double buffer; each finished
 // 128 x 64 tile is staged in shared memory as the swizzled operand image and copied out with fully coalesced
 // 16-byte-per-lane stores (8 KB per slice).
-// exp2: z = k + i/128 + r with |r| <= 2^-8 (rint(128 z) is read from the low mantissa word of z + 1.5 * 2^45),
-// 2^z = 2^k T[i] P5(r): a shared-memory table look-up and 5 FMAs instead of the 12-term Horner chain.
+// exp2: z = k + i/16 + r with |r| <= 2^-5 (rint(16 z) is read from the low mantissa word of z + 1.5 * 2^48),
+// 2^z = 2^k T[i] (1 + r P6(r)): a conflict-free shared-memory look-up and 8 FMAs instead of the 12-term Horner chain.
 template <int DP, int S, bool MATERN, bool TAB>
 __global__ void __launch_bounds__(OZ_KS_THREADS, 3)
 oz_kstar_slices_fast_kernel(int n, int np, int d, const double *__restrict__ Xs, const double *__restrict__ XsHalfSq,
@@ -395,7 +373,7 @@ oz_kstar_slices_fast_kernel(int n, int np, int d, const double *__restrict__ Xs,
     __shared__ __align__(16) double xs[2][64][DP];
     __shared__ __align__(16) double hb[2][64];
     __shared__ __align__(16) double bt[2][64];                      // beta of the tile
-    __shared__ double tab[128];
+    __shared__ __align__(128) double tab[16];
     extern __shared__ __align__(16) uint8_t oz_stage[];          // [S][128 rows][64 B]
     const int tid = threadIdx.x;
     const int row = tid & 127, half = tid >> 7;
@@ -410,7 +388,7 @@ oz_kstar_slices_fast_kernel(int n, int np, int d, const double *__restrict__ Xs,
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
     prefetch(t0, 0);
-    if (TAB && tid < 128) tab[tid] = OZ_EXP2_TAB[tid];
+    if (TAB && tid < 16) tab[tid] = OZ_EXP2_TAB[tid];
     const int m = blockIdx.x * 128 + row;
     const bool live = m < mc;
     double xc[DP], ha = 0.0;
@@ -422,7 +400,7 @@ oz_kstar_slices_fast_kernel(int n, int np, int d, const double *__restrict__ Xs,
     ha *= 0.5;
     constexpr double LOG2E = 1.4426950408889634;
     constexpr double LOG2_127 = 6.988684686772166;      // kappa * 127 * 2^32 = 2^(log2 kappa + LOG2_127 + 32)
-    constexpr double MAGIC45 = 52776558133248.0;        // 1.5 * 2^45: ulp = 2^-7
+    constexpr double MAGIC48 = 422212465065984.0;       // 1.5 * 2^48: ulp = 2^-4
     static_assert(S >= 2 && S <= 5, "fast slicer handles 2..5 slices");
     const int swz = (row >> 1) & 3;
     const int jlimit = live ? n : 0;      // observations j < jlimit contribute for this thread's candidate
@@ -485,13 +463,17 @@ oz_kstar_slices_fast_kernel(int n, int np, int d, const double *__restrict__ Xs,
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
                         const double z = fma(dot[e], LOG2E, LOG2_127);
-                        const double zz = z + MAGIC45;                      // low word = rint(128 z)
-                        const int n128 = __double2loint(zz);
-                        ki[e] = (n128 >> 7) + 32;
-                        ti[e] = n128 & 127;
-                        r[e] = z - (zz - MAGIC45);                          // [-2^-8, 2^-8]
-                        pl[e] = OZ_P5;
+                        const double zz = z + MAGIC48;                      // low word = rint(16 z)
+                        const int n16 = __double2loint(zz);
+                        ki[e] = (n16 >> 4) + 32;
+                        ti[e] = n16 & 15;
+                        r[e] = z - (zz - MAGIC48);                          // [-2^-5, 2^-5]
+                        pl[e] = OZ_P7;
                     }
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) pl[e] = fma(pl[e], r[e], OZ_P6);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) pl[e] = fma(pl[e], r[e], OZ_P5);
 #pragma unroll
                     for (int e = 0; e < 4; ++e) pl[e] = fma(pl[e], r[e], OZ_P4);
 #pragma unroll
@@ -635,6 +617,7 @@ oz_score_kernel(const __grid_constant__ CUtensorMap tmapB, OzParams p) {
     // bars[0..nst): full, [nst..2nst): empty, then tmem_full[2], tmem_empty[2]
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * nst + 4);
     double *row_sm = reinterpret_cast<double *>(bars + 2 * nst + 6);      // MODE 1: [2][nrb * 64] row scale, row bias
+    double *argT = row_sm + OZ_ROW_SMEM / 8;                               // MODE 1: [64][OZ_ARG_LD] arg-max transpose
     const uint32_t bar0 = smem_u32(bars);
     auto full_bar = [&](int s) { return bar0 + 8u * s; };
     auto empty_bar = [&](int s) { return bar0 + 8u * (nst + s); };
@@ -795,45 +778,38 @@ oz_score_kernel(const __grid_constant__ CUtensorMap tmapB, OzParams p) {
                     if (p.out && cand_live && rowb + c < p.nrows_live) p.out[(int64_t)(rowb + c) * p.out_ld + p.c0 + cand] = vcol[c];
                 }
                 if (p.blkval) {
-                    // Per-draw first arg max over the warp's 32 consecutive candidates as a butterfly that
-                    // halves the column set every round (a lane keeps the half selected by its lane bit and
-                    // hands the other half to its partner): 62 exchanges per lane instead of 64 x 5, and every
-                    // lane ends up owning two draws.  NaN never wins; ties go to the lower candidate.
-                    int bi[64];
+                    // Per-draw first arg max over the tile's 128 candidates.  Round 1 ran a register butterfly per warp
+                    // (62 exchanges of a double and an int per lane, 250 registers): ncu showed the epilogue, not the
+                    // tensor pipe, pacing the kernel (39 % of the int8 roof).  Now the four epilogue warps transpose the
+                    // tile through shared memory -- thread (candidate) writes its 64 draw values, then thread (draw, half)
+                    // scans 64 candidates in index order -- and one shuffle joins the halves.  NaN never wins; ties go to
+                    // the lower candidate (strict > in scan order).
+                    const int pos = quarter * 32 + lane;
 #pragma unroll
                     for (int c = 0; c < 64; ++c) {
                         const bool ok = cand_live && vcol[c] == vcol[c];
-                        bi[c] = ok ? cand : 0x7fffffff;
-                        if (!ok) vcol[c] = -INFINITY;
+                        argT[c * OZ_ARG_LD + pos] = ok ? vcol[c] : -INFINITY;
                     }
-#pragma unroll
-                    for (int rd = 0; rd < 5; ++rd) {
-                        const int o = 16 >> rd, half = 32 >> rd;
-                        const bool up = (lane & o) != 0;
-#pragma unroll
-                        for (int j = 0; j < half; ++j) {
-                            const double sv = up ? vcol[j] : vcol[j + half];
-                            const int si = up ? bi[j] : bi[j + half];
-                            const double kv = up ? vcol[j + half] : vcol[j];
-                            const int ki = up ? bi[j + half] : bi[j];
-                            const double ov = __shfl_xor_sync(0xffffffffu, sv, o);
-                            const int oi = __shfl_xor_sync(0xffffffffu, si, o);
-                            const bool take = ov > kv || (ov == kv && oi < ki);
-                            vcol[j] = take ? ov : kv;
-                            bi[j] = take ? oi : ki;
-                        }
+                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                    const int cc = pos >> 1, hh = pos & 1;
+                    const double *col = argT + cc * OZ_ARG_LD + hh * 64;
+                    double bv = -INFINITY;
+                    int bi = 0x7fffffff;
+#pragma unroll 16
+                    for (int i = 0; i < 64; ++i) {
+                        const double v = col[i];
+                        if (v > bv) { bv = v; bi = hh * 64 + i; }
                     }
-                    const int colb = 32 * ((lane >> 4) & 1) + 16 * ((lane >> 3) & 1) + 8 * ((lane >> 2) & 1) +
-                                     4 * ((lane >> 1) & 1) + 2 * (lane & 1);
-#pragma unroll
-                    for (int j = 0; j < 2; ++j) {
-                        const int row = rowb + colb + j;
-                        if (row < p.nrows_live) {
-                            const int64_t o = (int64_t)row * p.blk_ld + p.blk0 + un.tile * 4 + quarter;
-                            p.blkval[o] = vcol[j];
-                            p.blkidx[o] = bi[j] == 0x7fffffff ? INT64_MAX : p.c0 + bi[j];
-                        }
+                    const double ov = __shfl_xor_sync(0xffffffffu, bv, 1);
+                    const int oi = __shfl_xor_sync(0xffffffffu, bi, 1);
+                    if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+                    const int row = rowb + cc;
+                    if (hh == 0 && row < p.nrows_live) {
+                        const int64_t o = (int64_t)row * p.blk_ld + p.blk0 + un.tile;
+                        p.blkval[o] = bv;
+                        p.blkidx[o] = bi == 0x7fffffff ? INT64_MAX : p.c0 + (int64_t)un.tile * OZ_BM + bi;
                     }
+                    asm volatile("bar.sync 1, 128;" ::: "memory");      // the transpose buffer is free again
                 }
             }
         }
@@ -897,15 +873,26 @@ static int oz_stage_count(int S) {
     int n = (200 * 1024) / stage;
     return n > 4 ? 4 : (n < 2 ? 2 : n);
 }
-#define OZ_ROW_SMEM 8192      // MODE 1: row scale + bias of up to 512 draws
 static size_t oz_smem_bytes(int S) {
     return (size_t)oz_stage_count(S) * S * (OZ_A_SLICE_BYTES + OZ_B_SLICE_BYTES) + 1024 + 256;
 }
+// MODE 1 (Thompson) also holds the row scale / bias and the arg-max transpose buffer: fewer ring stages
+static int oz_stage_count_m1(int S) {
+    const int stage = S * (OZ_A_SLICE_BYTES + OZ_B_SLICE_BYTES);
+    int n = (227 * 1024 - 1280 - OZ_ROW_SMEM - OZ_ARG_SMEM) / stage;
+    return n > 4 ? 4 : (n < 2 ? 2 : n);
+}
+static size_t oz_smem_bytes_m1(int S) {
+    return (size_t)oz_stage_count_m1(S) * S * (OZ_A_SLICE_BYTES + OZ_B_SLICE_BYTES) + 1024 + 256 + OZ_ROW_SMEM + OZ_ARG_SMEM;
+}
 
 int bo_ozaki_init(bo_ctx *ctx) {
-#define OZ_ATTR1(SS, EE, MM) BO_CUDA(ctx, cudaFuncSetAttribute(oz_score_kernel<SS, EE, MM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)oz_smem_bytes(SS) + MM * OZ_ROW_SMEM))
-#define OZ_ATTR(SS) OZ_ATTR1(SS, 0, 0); OZ_ATTR1(SS, 1, 0); OZ_ATTR1(SS, 0, 1); OZ_ATTR1(SS, 1, 1)
+#define OZ_ATTR1(SS, EE, MM) BO_CUDA(ctx, cudaFuncSetAttribute(oz_score_kernel<SS, EE, MM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(MM ? oz_smem_bytes_m1(SS) : oz_smem_bytes(SS))))
+#define OZ_ATTR(SS) OZ_ATTR1(SS, 0, 0); OZ_ATTR1(SS, 1, 0)
+#define OZ_ATTR_M1(SS) OZ_ATTR1(SS, 0, 1); OZ_ATTR1(SS, 1, 1)
     OZ_ATTR(2); OZ_ATTR(3); OZ_ATTR(4); OZ_ATTR(5); OZ_ATTR(6); OZ_ATTR(7);
+    OZ_ATTR_M1(3); OZ_ATTR_M1(4); OZ_ATTR_M1(5);          // the Thompson path runs 3..5 slices
+#undef OZ_ATTR_M1
 #undef OZ_ATTR
 #undef OZ_ATTR1
 #define OZ_KATTR(DP, SS) BO_CUDA(ctx, cudaFuncSetAttribute(oz_kstar_slices_fast_kernel<DP, SS, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SS * OZ_A_SLICE_BYTES)); \
@@ -1046,9 +1033,7 @@ static void launch_oz_kstar_fast(bo_ctx *ctx, int s, const double *dXc, int64_t 
     const double *xs = ctx->dXs + (int64_t)s * ctx->np * ctx->dp, *hsq = ctx->dXsHalfSq + (int64_t)s * ctx->np;
     const double *ie = ctx->dInvEll + (int64_t)s * ctx->dp, *beta = ctx->dBeta + (int64_t)s * ctx->np;
     double *mup = ctx->dOzMu + (size_t)ctx->oz_mu_slot * ctx->ozmu_stride;
-    // exp2 through the 128-entry table (5 FMAs + one conflict-prone shared-memory look-up) or the 12-term Horner chain:
-    // measured 0.436 vs 0.460 ms per 32768 x 4096 chunk (the kernel is bound by shared-memory wavefronts and the FP64
-    // pipe at about the same level either way); BO_OZ_EXP2_TABLE=0 selects the polynomial
+    // exp2 through the 16-entry table or the 12-term Horner chain (BO_OZ_EXP2_TABLE=0)
     static const bool tab = !(getenv("BO_OZ_EXP2_TABLE") && atoi(getenv("BO_OZ_EXP2_TABLE")) == 0);
 #define OZ_KS_RUN(MAT, TB) oz_kstar_slices_fast_kernel<DP, S, MAT, TB><<<grid, OZ_KS_THREADS, S * OZ_A_SLICE_BYTES, st>>>( \
         ctx->n, ctx->np, ctx->d, xs, hsq, ie, dXc, c0, mc, mcp, Kss, beta, mup)
@@ -1392,11 +1377,11 @@ static int th_oz_prepare(bo_ctx *ctx, int S) {
     return BO_OK;
 }
 
-// 32-candidate blocks the int8 path reports per draw for M candidates
+// 128-candidate tiles the int8 path reports per draw for M candidates
 int64_t bo_thompson_ozaki_blocks(int64_t M) {
     const int64_t chunk = 256 * 128;
     const int64_t full = M / chunk, rem = M - full * chunk;
-    return full * (chunk / 32) + bo_round_up64(rem, 128) / 32;
+    return full * (chunk / OZ_BM) + bo_round_up64(rem, OZ_BM) / OZ_BM;
 }
 
 bool bo_thompson_ozaki_usable(bo_ctx *ctx, int64_t M) {
@@ -1432,7 +1417,7 @@ int bo_thompson_ozaki_run(bo_ctx *ctx, int64_t M, const double *dXc, double *dOu
         }
         OzParams p = {};
         p.nrb = ndp / OZ_BN; p.nkb = mp / OZ_BK; p.full_k = 1;
-        p.S = S; p.nstages = oz_stage_count(S); p.ntiles = mcp / OZ_BM; p.mcp = mcp;
+        p.S = S; p.nstages = oz_stage_count_m1(S); p.ntiles = mcp / OZ_BM; p.mcp = mcp;
         p.nacc = (2 * (S + extra) * OZ_BN <= 512) ? 2 : 1;
         p.tiles_per_group = 64;
         p.rowscale = th.ozRowScale; p.rowbias = th.ozRowBias; p.kss = th.ozPhi;
@@ -1443,15 +1428,15 @@ int bo_thompson_ozaki_run(bo_ctx *ctx, int64_t M, const double *dXc, double *dOu
         {
             BO_LAUNCH(ctx, "oz_thompson_kernel");
             switch (S) {
-#define OZ_TRUN(SS) case SS: if (extra) oz_score_kernel<SS, 1, 1><<<grid, OZ_THREADS, oz_smem_bytes(SS) + OZ_ROW_SMEM, ctx->stream>>>(tmB, p); \
-                          else oz_score_kernel<SS, 0, 1><<<grid, OZ_THREADS, oz_smem_bytes(SS) + OZ_ROW_SMEM, ctx->stream>>>(tmB, p); break
+#define OZ_TRUN(SS) case SS: if (extra) oz_score_kernel<SS, 1, 1><<<grid, OZ_THREADS, oz_smem_bytes_m1(SS), ctx->stream>>>(tmB, p); \
+                          else oz_score_kernel<SS, 0, 1><<<grid, OZ_THREADS, oz_smem_bytes_m1(SS), ctx->stream>>>(tmB, p); break
                 OZ_TRUN(3); OZ_TRUN(4); OZ_TRUN(5);
 #undef OZ_TRUN
                 default: return bo_set_err(ctx, BO_ERR_ARG, "Thompson int8 path handles 3..5 slices, got %d", S);
             }
             BO_CHECK_LAUNCH(ctx);
         }
-        blk0 += mcp / 32;
+        blk0 += mcp / OZ_BM;
     }
     return BO_OK;
 }
