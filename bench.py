@@ -47,6 +47,19 @@ PARITY_TOL = 1e-6          # north_star: outputs within 1e-6 relative
 PARITY_FLOOR = 1e-12       # ... with the SURVEY 8c(7) floor of 1e-12 max|ref|
 
 
+def workload_config(name, spec, M, world):
+    """The `config` object both arms print (identical keys and values, so the driver can match the two lines)."""
+    n, d = spec["n"], spec["d"]
+    cfg = dict(workload=name, kernel=spec["kernel"], n=n, d=d, acq=spec["acq"], hyper_samples=spec["S"], candidates_per_gpu=int(M),
+               candidates="unscrambled Sobol, contiguous block per rank",
+               l2="inputs exceed L2: W factor %.0f MB + cross-kernel scratch >= %.0f MB + candidates %.0f MB per pass"
+                  % (n * n * 8 / 1e6, n * 8192 * 8 / 1e6, M * d * 8 / 1e6),
+               parallelism="dp%d candidate shards" % world)
+    if spec["acq"] == "thompson":
+        cfg.update(draws=spec["ndraw"], features=spec["m"], basis="shared by all draws")
+    return cfg
+
+
 def flop_per_eval(n, d):
     """F(n,d) = n^2 + n(3d+2) + 4n + 30 flop per acquisition evaluation."""
     return n * n + n * (3 * d + 2) + 4 * n + 30
@@ -528,13 +541,10 @@ def our_arm(args):
     line = dict(metric="acq_evals_per_sec", value=value, unit="evals/s", n_gpus=world, steps=args.steps,
                 warmup=args.warmup, ms_per_step=dev_ms / args.steps, higher_is_better=True, scaling="weak",
                 vs_baseline=None, dtype=dtype, data="synthetic",
-                config=dict(workload=args.workload, kernel=spec["kernel"], n=n, d=d, acq=spec["acq"],
-                            hyper_samples=S, candidates_per_gpu=M, candidates="unscrambled Sobol, contiguous block per rank",
-                            precision=level,
-                            l2="inputs exceed L2: W factor %.0f MB + cross-kernel scratch >= %.0f MB + candidates %.0f MB per pass"
-                            % (n * n * 8 / 1e6, n * 8192 * 8 / 1e6, M * d * 8 / 1e6), parallelism="dp%d candidate shards" % world,
-                            incumbent_exchange="packed device record -> NCCL all-gather on the library's stream -> device merge"
-                            if world > 1 else "device record -> merge kernel -> one 16-byte read-back"),
+                config=workload_config(args.workload, spec, M, world),
+                path=dict(precision=level,
+                          incumbent_exchange="packed device record -> NCCL all-gather on the library's stream -> device merge"
+                          if world > 1 else "device record -> merge kernel -> one 16-byte read-back"),
                 clocks=clocks,
                 e2e=dict(value=e2e_value, unit="evals/s", ms_per_step=e2e_ms / args.steps,
                          h2d_bytes_per_step=int(M * d * 8), d2h_bytes_per_step=int(10 * 16),
@@ -616,9 +626,8 @@ def thompson_arm(h, args):
                 ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
                 dtype="int8 slices of cosine features and Theta on tcgen05, f64 reassembly" if path == "int8" else "f64",
                 data="synthetic",
-                config=dict(workload=args.workload, n=w.n, d=w.d, draws=w.ndraw, features=w.m, basis="shared by all draws",
-                            candidates_per_gpu=w.M, parallelism="dp%d candidate shards" % h.world,
-                            draws_built="on the device from the same seed on every rank (bo_thompson_build, %.3f s)" % w.build_s),
+                config=workload_config(args.workload, w.spec, w.M, h.world),
+                path=dict(draws_built="on the device from the same seed on every rank (bo_thompson_build, %.3f s)" % w.build_s),
                 clocks=clocks,
                 e2e=dict(value=w.ndraw * w.M * h.world * args.steps / (e2e_ms * 1e-3), unit="draw-evals/s", ms_per_step=e2e_ms / args.steps,
                          h2d_bytes_per_step=int(w.M * w.d * 8), d2h_bytes_per_step=int(w.ndraw * 16)),
@@ -861,8 +870,7 @@ def reference_arm(args):
     line = dict(impl="reference", metric="acq_evals_per_sec", value=value, unit="evals/s", n_gpus=args.gpus,
                 steps=args.steps, warmup=args.warmup, ms_per_step=(time.perf_counter() - t0) * 1e3 / max(1, args.steps),
                 higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64", data="synthetic",
-                config=dict(workload=args.workload, kernel=spec["kernel"], n=spec["n"], d=spec["d"], acq=spec["acq"],
-                            hyper_samples=spec["S"], candidates_per_gpu=spec["M"]),
+                config=workload_config(args.workload, spec, args.candidates or spec["M"], args.gpus),
                 cpu_baseline=res, e2e=dict(value=value, unit="evals/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
                 gpu_launches=0)
     print(json.dumps(line))
@@ -898,8 +906,7 @@ def reference_arm_thompson(args, spec):
     line = dict(impl="reference", metric="thompson_draw_evals_per_sec", value=value, unit="draw-evals/s", n_gpus=args.gpus, steps=args.steps,
                 warmup=args.warmup, ms_per_step=(time.perf_counter() - t0) * 1e3 / max(1, args.steps), higher_is_better=True,
                 scaling="weak", vs_baseline=None, dtype="f64", data="synthetic",
-                config=dict(workload=args.workload, n=spec["n"], d=spec["d"], draws=spec["ndraw"], features=spec["m"],
-                            candidates_per_gpu=spec["M"]),
+                config=workload_config(args.workload, spec, args.candidates or spec["M"], args.gpus),
                 cpu_baseline=res, e2e=dict(value=value, unit="draw-evals/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
     print(json.dumps(line))
 

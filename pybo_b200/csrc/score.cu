@@ -894,6 +894,8 @@ static int run_oz(bo_ctx *ctx, const ScoreRequest &rq, int oz_S) {
     // the int8 contraction); mode 1 -> s2
     const bool rescue = ctx->oz_rescue && ((rq.mode == 0) ? (rq.acq != BO_ACQ_MEAN) : (rq.dS2 != nullptr));
     const bool need_best = rq.want_best || (rescue && rq.mode == 0);
+    if (rescue && M > (int64_t)0x7fffffff)
+        return bo_set_err(ctx, BO_ERR_ARG, "int8 path: at most 2^31 - 1 candidates per call (the rescue list holds 32-bit indices)");
     const int64_t nchunk = (M + chunk - 1) / chunk;
     const int64_t nblocks_total = nchunk * ((chunk + 255) / 256);
     if (need_best) BO_TRY(reserve_blocks(ctx, (size_t)(nblocks_total > ARGMAX_PASS_BLOCKS ? nblocks_total : ARGMAX_PASS_BLOCKS) + 8));
