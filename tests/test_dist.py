@@ -74,6 +74,30 @@ def _worker(rank, world, port, tmpdir):
         fullv = -np.sum((allp - 0.6) ** 2, axis=1)
         want = np.lexsort((np.arange(1001), -fullv))[:6]
         assert np.array_equal(idx, want + 3) and np.allclose(val, fullv[want]) and np.allclose(pts, allp[want])
+        # Thompson batch across ranks (BASELINE config 4): per-draw arg max of each rank's block, exchanged as packed
+        # records.  A stand-in for the device handle exercises the same host logic (CPU process group: the records are
+        # merged locally and go through the host-staged reduction).
+        draws = np.random.RandomState(2).randn(7, 1003)
+        draws[3, [10, 700]] = 11.0                             # a tie across the two shards: the lower index wins
+
+        class FakeCtx(object):
+            device, stream = 0, 0
+
+            def thompson_incumbents(self, M, xc, offset=0, flags=1):
+                blk = draws[:, offset:offset + M]
+                self.rec = (blk.max(axis=1), blk.argmax(axis=1) + offset)
+                return 12345, draws.shape[0]
+
+            def incumbent_merge(self, ptr, count, k):
+                assert ptr == 12345 and count == 1 and k == draws.shape[0]
+                return self.rec
+
+        class FakeBatch(object):
+            def _context(self):
+                return FakeCtx()
+        st = bdist.ShardedThompson(FakeBatch())
+        gv, gi = st.argmax(np.zeros((draws.shape[1], 3)))
+        assert np.array_equal(gi, draws.argmax(axis=1)) and np.array_equal(gv, draws.max(axis=1)) and gi[3] == 10
         open(os.path.join(tmpdir, "ok%d" % rank), "w").close()
     finally:
         dist.destroy_process_group()
