@@ -38,9 +38,11 @@ static int ctx_padded_dim(int d) {
 #define OZ_A_SLICE_BYTES (OZ_BM * OZ_BK)   // 8192
 #define OZ_B_SLICE_BYTES (OZ_BN * OZ_BK)   // 4096
 #define OZ_THREADS 192   // warp 0: TMA producer, warp 1: MMA issuer, warps 2-5: epilogue
+#define OZ_THREADS_M1 320   // MODE 1 (Thompson): eight epilogue warps, two per TMEM lane quarter, 32 draw columns each
 #define OZ_ROW_SMEM 8192      // MODE 1: row scale + bias of up to 512 draws
-#define OZ_ARG_LD 129         // MODE 1: leading dimension (doubles) of the 64 x 128 arg-max transpose buffer
-#define OZ_ARG_SMEM (64 * OZ_ARG_LD * 8)
+#define OZ_ARG_LD 137         // MODE 1: leading dimension (doubles) of the 16 x 128 arg-max transpose buffer; candidate p sits at
+                              // p + (p >> 4) so that the eight 16-candidate parts of a column start in different banks
+#define OZ_ARG_SMEM (2 * 16 * OZ_ARG_LD * 8)
 
 // ---------------------------------------------------------------------------
 // PTX wrappers
@@ -602,7 +604,7 @@ __device__ __forceinline__ OzUnit oz_decode(int u, int nb, int T, int ntiles) {
 // MODE 0: scoring (B = slices of the triangular W, k range cut at the diagonal, epilogue reduces |v|^2);
 // MODE 1: Thompson draws (B = slices of Theta, full k range, epilogue writes values / per-draw arg max).
 template <int S, int EXTRA, int MODE>
-__global__ void __launch_bounds__(OZ_THREADS, 1)
+__global__ void __launch_bounds__(MODE == 1 ? OZ_THREADS_M1 : OZ_THREADS, 1)
 oz_score_kernel(const __grid_constant__ CUtensorMap tmapB, OzParams p) {
     extern __shared__ uint8_t oz_smem_raw[];
     // 1024-byte aligned operand ring
@@ -617,7 +619,7 @@ oz_score_kernel(const __grid_constant__ CUtensorMap tmapB, OzParams p) {
     // bars[0..nst): full, [nst..2nst): empty, then tmem_full[2], tmem_empty[2]
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * nst + 4);
     double *row_sm = reinterpret_cast<double *>(bars + 2 * nst + 6);      // MODE 1: [2][nrb * 64] row scale, row bias
-    double *argT = row_sm + OZ_ROW_SMEM / 8;                               // MODE 1: [64][OZ_ARG_LD] arg-max transpose
+    double *argT = row_sm + OZ_ROW_SMEM / 8;                               // MODE 1: [16][OZ_ARG_LD] arg-max transpose
     const uint32_t bar0 = smem_u32(bars);
     auto full_bar = [&](int s) { return bar0 + 8u * s; };
     auto empty_bar = [&](int s) { return bar0 + 8u * (nst + s); };
@@ -636,13 +638,13 @@ oz_score_kernel(const __grid_constant__ CUtensorMap tmapB, OzParams p) {
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(tmem_full(a), 1);
-            mbar_init(tmem_empty(a), 4);
+            mbar_init(tmem_empty(a), MODE == 1 ? 8 : 4);       // one arrival per epilogue warp
         }
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 512);
     if (MODE == 1) {
-        for (int i = threadIdx.x; i < p.nrb * OZ_BN; i += OZ_THREADS) {
+        for (int i = threadIdx.x; i < p.nrb * OZ_BN; i += (int)blockDim.x) {
             row_sm[i] = p.rowscale[i];
             row_sm[p.nrb * OZ_BN + i] = p.rowbias[i];
         }
@@ -700,6 +702,10 @@ oz_score_kernel(const __grid_constant__ CUtensorMap tmapB, OzParams p) {
     } else {
         // ===================== epilogue: one candidate per thread =====================
         const int quarter = warp & 3;                          // TMEM lane quarter this warp may access
+        // MODE 1: the per-draw work of a unit (reassembly of 64 columns, scale / bias, arg max) was latency-bound on ONE
+        // warp per scheduler (ncu: 8.7 cycles per issued instruction, 0.17 IPC) and paced the kernel at 45 % of the tensor
+        // pipe; two warps share each lane quarter and take 32 columns each.
+        const int ehalf = (MODE == 1) ? ((warp - 2) >> 2) : 0;
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int u = blockIdx.x; u < nunits; u += gridDim.x) {
@@ -755,13 +761,13 @@ oz_score_kernel(const __grid_constant__ CUtensorMap tmapB, OzParams p) {
                 const int64_t o = (int64_t)un.rb * p.mcp + (int64_t)un.tile * OZ_BM + quarter * 32 + lane;
                 p.qpart[o] = q;
             } else {
-                // drain all 64 columns into registers first so the accumulators go back to the MMA warp
+                // drain this warp's 32 columns into registers first so the accumulators go back to the MMA warp
                 // before the stores and the per-draw arg max
-                double vcol[64];
+                double vcol[32];
 #pragma unroll
-                for (int cb = 0; cb < 4; ++cb) {
+                for (int cb = 0; cb < 2; ++cb) {
                     double v16[16];
-                    reassemble(cb * 16, v16);
+                    reassemble((ehalf * 2 + cb) * 16, v16);
 #pragma unroll
                     for (int i = 0; i < 16; ++i) vcol[cb * 16 + i] = v16[i];
                 }
@@ -771,45 +777,53 @@ oz_score_kernel(const __grid_constant__ CUtensorMap tmapB, OzParams p) {
                 if (++acc == nacc) { acc = 0; acc_phase ^= 1; }
                 const int cand = un.tile * OZ_BM + quarter * 32 + lane;
                 const bool cand_live = cand < p.mc;
-                const int rowb = un.rb * OZ_BN;
+                const int rowb = un.rb * OZ_BN + ehalf * 32;
 #pragma unroll
-                for (int c = 0; c < 64; ++c) {
+                for (int c = 0; c < 32; ++c) {
                     vcol[c] = fma(vcol[c], row_sm[rowb + c], row_sm[p.nrb * OZ_BN + rowb + c]);
                     if (p.out && cand_live && rowb + c < p.nrows_live) p.out[(int64_t)(rowb + c) * p.out_ld + p.c0 + cand] = vcol[c];
                 }
                 if (p.blkval) {
                     // Per-draw first arg max over the tile's 128 candidates.  Round 1 ran a register butterfly per warp
                     // (62 exchanges of a double and an int per lane, 250 registers): ncu showed the epilogue, not the
-                    // tensor pipe, pacing the kernel (39 % of the int8 roof).  Now the four epilogue warps transpose the
-                    // tile through shared memory -- thread (candidate) writes its 64 draw values, then thread (draw, half)
-                    // scans 64 candidates in index order -- and one shuffle joins the halves.  NaN never wins; ties go to
-                    // the lower candidate (strict > in scan order).
+                    // tensor pipe, pacing the kernel (39 % of the int8 roof).  Now each half of the epilogue warps
+                    // transposes its 32 draws through shared memory, 16 draws per round: thread (candidate) writes its
+                    // values, then thread (draw, 16-candidate part) scans in index order and three shuffles join the
+                    // eight parts.  NaN never wins; ties go to the lower candidate (strict > in scan order).
                     const int pos = quarter * 32 + lane;
+                    const int cc = pos >> 3, part = pos & 7;            // scan role: draw cc of the round, candidates 16 part ..
+                    double *argH = argT + ehalf * 16 * OZ_ARG_LD;       // each half of the epilogue warps has its own buffer ...
+                    const int barid = 1 + ehalf;                        // ... and its own named barrier (4 warps)
 #pragma unroll
-                    for (int c = 0; c < 64; ++c) {
-                        const bool ok = cand_live && vcol[c] == vcol[c];
-                        argT[c * OZ_ARG_LD + pos] = ok ? vcol[c] : -INFINITY;
+                    for (int rd = 0; rd < 2; ++rd) {
+#pragma unroll
+                        for (int c = 0; c < 16; ++c) {
+                            const double v = vcol[rd * 16 + c];
+                            argH[c * OZ_ARG_LD + pos + (pos >> 4)] = (cand_live && v == v) ? v : -INFINITY;
+                        }
+                        asm volatile("bar.sync %0, 128;" ::"r"(barid) : "memory");
+                        const double *col = argH + cc * OZ_ARG_LD + part * 17;
+                        double bv = -INFINITY;
+                        int bi = 0x7fffffff;
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            const double v = col[i];
+                            if (v > bv) { bv = v; bi = part * 16 + i; }
+                        }
+#pragma unroll
+                        for (int o = 1; o < 8; o <<= 1) {               // join the eight parts of a draw (adjacent lanes)
+                            const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+                            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                            if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+                        }
+                        const int row = rowb + rd * 16 + cc;
+                        if (part == 0 && row < p.nrows_live) {
+                            const int64_t o = (int64_t)row * p.blk_ld + p.blk0 + un.tile;
+                            p.blkval[o] = bv;
+                            p.blkidx[o] = bi == 0x7fffffff ? INT64_MAX : p.c0 + (int64_t)un.tile * OZ_BM + bi;
+                        }
+                        asm volatile("bar.sync %0, 128;" ::"r"(barid) : "memory");  // the transpose buffer is free again
                     }
-                    asm volatile("bar.sync 1, 128;" ::: "memory");
-                    const int cc = pos >> 1, hh = pos & 1;
-                    const double *col = argT + cc * OZ_ARG_LD + hh * 64;
-                    double bv = -INFINITY;
-                    int bi = 0x7fffffff;
-#pragma unroll 16
-                    for (int i = 0; i < 64; ++i) {
-                        const double v = col[i];
-                        if (v > bv) { bv = v; bi = hh * 64 + i; }
-                    }
-                    const double ov = __shfl_xor_sync(0xffffffffu, bv, 1);
-                    const int oi = __shfl_xor_sync(0xffffffffu, bi, 1);
-                    if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
-                    const int row = rowb + cc;
-                    if (hh == 0 && row < p.nrows_live) {
-                        const int64_t o = (int64_t)row * p.blk_ld + p.blk0 + un.tile;
-                        p.blkval[o] = bv;
-                        p.blkidx[o] = bi == 0x7fffffff ? INT64_MAX : p.c0 + (int64_t)un.tile * OZ_BM + bi;
-                    }
-                    asm volatile("bar.sync 1, 128;" ::: "memory");      // the transpose buffer is free again
                 }
             }
         }
@@ -1428,8 +1442,8 @@ int bo_thompson_ozaki_run(bo_ctx *ctx, int64_t M, const double *dXc, double *dOu
         {
             BO_LAUNCH(ctx, "oz_thompson_kernel");
             switch (S) {
-#define OZ_TRUN(SS) case SS: if (extra) oz_score_kernel<SS, 1, 1><<<grid, OZ_THREADS, oz_smem_bytes_m1(SS), ctx->stream>>>(tmB, p); \
-                          else oz_score_kernel<SS, 0, 1><<<grid, OZ_THREADS, oz_smem_bytes_m1(SS), ctx->stream>>>(tmB, p); break
+#define OZ_TRUN(SS) case SS: if (extra) oz_score_kernel<SS, 1, 1><<<grid, OZ_THREADS_M1, oz_smem_bytes_m1(SS), ctx->stream>>>(tmB, p); \
+                          else oz_score_kernel<SS, 0, 1><<<grid, OZ_THREADS_M1, oz_smem_bytes_m1(SS), ctx->stream>>>(tmB, p); break
                 OZ_TRUN(3); OZ_TRUN(4); OZ_TRUN(5);
 #undef OZ_TRUN
                 default: return bo_set_err(ctx, BO_ERR_ARG, "Thompson int8 path handles 3..5 slices, got %d", S);
