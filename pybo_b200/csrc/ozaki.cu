@@ -37,8 +37,8 @@ static int ctx_padded_dim(int d) {
 #define OZ_DIGIT_BIAS7 0x0080808080808080ll   // 128 in each of the 7 digit bytes
 #define OZ_A_SLICE_BYTES (OZ_BM * OZ_BK)   // 8192
 #define OZ_B_SLICE_BYTES (OZ_BN * OZ_BK)   // 4096
-#define OZ_THREADS 192   // warp 0: TMA producer, warp 1: MMA issuer, warps 2-5: epilogue
-#define OZ_THREADS_M1 320   // MODE 1 (Thompson): eight epilogue warps, two per TMEM lane quarter, 32 draw columns each
+#define OZ_THREADS 320   // warp 0: TMA producer, warp 1: MMA issuer, warps 2-9: epilogue (two per TMEM lane quarter)
+#define OZ_THREADS_M1 OZ_THREADS
 #define OZ_ROW_SMEM 8192      // MODE 1: row scale + bias of up to 512 draws
 #define OZ_ARG_LD 137         // MODE 1: leading dimension (doubles) of the 16 x 128 arg-max transpose buffer; candidate p sits at
                               // p + (p >> 4) so that the eight 16-candidate parts of a column start in different banks
@@ -604,7 +604,7 @@ __device__ __forceinline__ OzUnit oz_decode(int u, int nb, int T, int ntiles) {
 // MODE 0: scoring (B = slices of the triangular W, k range cut at the diagonal, epilogue reduces |v|^2);
 // MODE 1: Thompson draws (B = slices of Theta, full k range, epilogue writes values / per-draw arg max).
 template <int S, int EXTRA, int MODE>
-__global__ void __launch_bounds__(MODE == 1 ? OZ_THREADS_M1 : OZ_THREADS, 1)
+__global__ void __launch_bounds__(OZ_THREADS, 1)
 oz_score_kernel(const __grid_constant__ CUtensorMap tmapB, OzParams p) {
     extern __shared__ uint8_t oz_smem_raw[];
     // 1024-byte aligned operand ring
@@ -638,7 +638,7 @@ oz_score_kernel(const __grid_constant__ CUtensorMap tmapB, OzParams p) {
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(tmem_full(a), 1);
-            mbar_init(tmem_empty(a), MODE == 1 ? 8 : 4);       // one arrival per epilogue warp
+            mbar_init(tmem_empty(a), 8);                       // one arrival per epilogue warp
         }
         fence_barrier_init();
     }
@@ -702,10 +702,10 @@ oz_score_kernel(const __grid_constant__ CUtensorMap tmapB, OzParams p) {
     } else {
         // ===================== epilogue: one candidate per thread =====================
         const int quarter = warp & 3;                          // TMEM lane quarter this warp may access
-        // MODE 1: the per-draw work of a unit (reassembly of 64 columns, scale / bias, arg max) was latency-bound on ONE
-        // warp per scheduler (ncu: 8.7 cycles per issued instruction, 0.17 IPC) and paced the kernel at 45 % of the tensor
-        // pipe; two warps share each lane quarter and take 32 columns each.
-        const int ehalf = (MODE == 1) ? ((warp - 2) >> 2) : 0;
+        // Eight epilogue warps, two per lane quarter, 32 of the unit's 64 columns each: with one warp per scheduler the
+        // epilogue was latency-bound (ncu: 8.7 cycles per issued instruction, 0.17 IPC); in MODE 1 it paced the kernel at
+        // 45 % of the tensor pipe, in MODE 0 at 5 slices (a single accumulator set) it held the set for a fifth of the time.
+        const int ehalf = (warp - 2) >> 2;
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int u = blockIdx.x; u < nunits; u += gridDim.x) {
@@ -743,22 +743,63 @@ oz_score_kernel(const __grid_constant__ CUtensorMap tmapB, OzParams p) {
                 }
             };
             if (MODE == 0) {
-#pragma unroll 1
-                for (int c0 = 0; c0 < OZ_BN; c0 += 16) {
-                    double v16[16];
-                    reassemble(c0, v16);
-                    const int row0 = un.rb * OZ_BN + c0;
+                const int cbase = ehalf * 32;                  // this warp's 32 of the unit's 64 rows of W
+                if (NG <= 5) {
+                    // Drain first, compute later: the warp's NG x 32 accumulators go to registers, the TMEM set goes back
+                    // to the MMA warp at once, and the reassembly / reduction runs while the next unit's MMAs are already
+                    // issuing.  (At 5 slices only ONE accumulator set fits TMEM, so every cycle the set is held after
+                    // the last MMA of a unit is a cycle the tensor pipe idles: with the in-place epilogue of round 1 --
+                    // one warp per scheduler, 8.7 cycles per dependent instruction -- that was a fifth of the kernel.)
+                    int32_t r[NG][2][16];
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        const double vv = v16[i] * __ldg(p.rowscale + row0 + i);
+                    for (int g = 0; g < NG; ++g) {
+                        tmem_ld16(lane_base + (uint32_t)(g * OZ_BN + cbase), r[g][0]);
+                        tmem_ld16(lane_base + (uint32_t)(g * OZ_BN + cbase + 16), r[g][1]);
+                    }
+                    tmem_ld_wait();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(tmem_empty(acc));
+                    if (p.dbg && un.tile == 0) {
+#pragma unroll
+                        for (int g = 0; g < NG; ++g) {
+                            int32_t *o = p.dbg + (((int64_t)un.rb * NG + g) * 128 + quarter * 32 + lane) * 64 + cbase;
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) o[i] = r[g][i >> 4][i & 15];
+                        }
+                    }
+                    const int row0 = un.rb * OZ_BN + cbase;
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        constexpr int GI = G < 4 ? G : 4;
+                        long long a = (long long)r[0][i >> 4][i & 15];
+#pragma unroll
+                        for (int g = 1; g <= GI; ++g) a = a * 256 + (long long)r[g][i >> 4][i & 15];
+                        double v = (double)a;
+#pragma unroll
+                        for (int g = GI + 1; g <= G; ++g) v = fma(v, 256.0, (double)r[g][i >> 4][i & 15]);
+                        const double vv = v * (1.0 / (double)(1ull << (8 * G))) * __ldg(p.rowscale + row0 + i);
                         q = fma(vv, vv, q);
                     }
+                } else {
+#pragma unroll 1
+                    for (int c0 = cbase; c0 < cbase + 32; c0 += 16) {
+                        double v16[16];
+                        reassemble(c0, v16);
+                        const int row0 = un.rb * OZ_BN + c0;
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            const double vv = v16[i] * __ldg(p.rowscale + row0 + i);
+                            q = fma(vv, vv, q);
+                        }
+                    }
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(tmem_empty(acc));
                 }
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(tmem_empty(acc));
                 if (++acc == nacc) { acc = 0; acc_phase ^= 1; }
-                const int64_t o = (int64_t)un.rb * p.mcp + (int64_t)un.tile * OZ_BM + quarter * 32 + lane;
+                // two partial sums per (row block, candidate): one per half of the epilogue warps
+                const int64_t o = ((int64_t)un.rb * 2 + ehalf) * p.mcp + (int64_t)un.tile * OZ_BM + quarter * 32 + lane;
                 p.qpart[o] = q;
             } else {
                 // drain this warp's 32 columns into registers first so the accumulators go back to the MMA warp
@@ -1113,7 +1154,7 @@ int bo_ozaki_contract(bo_ctx *ctx, int s, int S, int mcp, int buf, double *mu, d
     BO_TRY(make_tmap(ctx, &tmB, ctx->dWs + (size_t)s * S * np * np, np, np, S, OZ_BN));
     const int nb = np / OZ_BN;
     {
-        size_t need = (size_t)nb * mcp;
+        size_t need = (size_t)2 * nb * mcp;              // two partial sums per row block (one per half of the epilogue warps)
         BO_TRY(bo_reserve(ctx, &ctx->dOzQ, &ctx->ozpart_capacity, need));
     }
     OzParams p = {};
@@ -1149,7 +1190,7 @@ int bo_ozaki_contract(bo_ctx *ctx, int s, int S, int mcp, int buf, double *mu, d
     {
         BO_LAUNCH(ctx, "oz_moments_kernel");
         oz_moments_kernel<<<(mcp + 255) / 256, 256, 0, ctx->stream>>>(
-            nb, ctx->oz_mu_rows[buf], mcp, ctx->dOzQ, ctx->dOzMu + (size_t)buf * ctx->ozmu_stride, ctx->h_rho[s],
+            2 * nb, ctx->oz_mu_rows[buf], mcp, ctx->dOzQ, ctx->dOzMu + (size_t)buf * ctx->ozmu_stride, ctx->h_rho[s],
             ctx->h_bias[s], mu, s2);
         BO_CHECK_LAUNCH(ctx);
     }
