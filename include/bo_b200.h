@@ -148,6 +148,10 @@ int bo_set_rescue(bo_ctx *ctx, int on, double tol, double floor_rel);
 /* what the last bo_score / bo_predict call did: int8_path = 1 if it ran the int8-slice
  * contraction, how many of its `total` candidates the rescue pass re-scored in FP64 */
 int bo_rescue_info(bo_ctx *ctx, int *int8_path, int64_t *flagged, int64_t *total);
+/* tuning knobs that do not change results.  "oz_cluster": CTAs per thread-block cluster of the int8 scoring
+ * contraction (1, 2 or 4; 0 = library default): the CTAs of a cluster work on the same candidate tile and adjacent row
+ * blocks of W and fetch the K* slice tile once, by TMA multicast. */
+int bo_set_option(bo_ctx *ctx, const char *key, double value);
 /* the a-priori error model behind the rescue pass, for the level currently selected: on the int8 path
  * |s2 - s2_exact| <= errk[s] * sqrt(q rho_s), q = rho_s - s2, for hyper-sample s (errk: S values) */
 int bo_ozaki_error_bound(bo_ctx *ctx, double *errk);

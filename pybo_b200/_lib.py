@@ -27,7 +27,7 @@ EXPORTS = [
     "bo_profile_enable", "bo_profile_reset", "bo_profile_count", "bo_profile_get",
     "bo_launch_count", "bo_microbench", "bo_ozaki_debug", "bo_append", "bo_fit_capacity", "bo_candidates_sobol",
     "bo_set_rescue", "bo_rescue_info", "bo_ozaki_error_bound", "bo_loglik_fit",
-    "bo_thompson_build", "bo_score_incumbent", "bo_incumbent_merge", "bo_thompson_incumbents",
+    "bo_thompson_build", "bo_score_incumbent", "bo_incumbent_merge", "bo_thompson_incumbents", "bo_set_option",
 ]
 
 
@@ -80,6 +80,7 @@ def _declare(lib):
         "bo_loglik_fit": (i, [vp, i, i, i, i, vp, vp, vp, vp, vp, vp, vp]),
         "bo_thompson_build": (i, [vp, i, i, vp, vp, d, d, d, i, i, i, vp, vp, vp, vp]),
         "bo_score_incumbent": (i, [vp, i, d, i64, vp, i, vp, i64, C.POINTER(vp)]),
+        "bo_set_option": (i, [vp, C.c_char_p, d]),
         "bo_incumbent_merge": (i, [vp, vp, i, i, vp, vp]),
         "bo_thompson_incumbents": (i, [vp, i64, vp, i, i64, C.POINTER(vp), _ip]),
     }
@@ -349,6 +350,10 @@ class Context(object):
         self._check(self._lib.bo_topk(self._h, int(k), _ptr(idx), _ptr(val)))
         keep = idx >= 0
         return idx[keep], val[keep]
+
+    def set_option(self, key, value):
+        """Tuning knobs that do not change results (bo_set_option), e.g. ("oz_cluster", 2)."""
+        self._check(self._lib.bo_set_option(self._h, key.encode(), float(value)))
 
     def set_rescue(self, on=True, tol=2.5e-7, floor_rel=1e-12):
         """FP64 rescue pass of the int8-slice path (bo_set_rescue)."""

@@ -726,6 +726,17 @@ extern "C" int bo_set_rescue(bo_ctx *ctx, int on, double tol, double floor_rel) 
     return BO_OK;
 }
 
+extern "C" int bo_set_option(bo_ctx *ctx, const char *key, double value) {
+    if (!ctx || !key) return BO_ERR_ARG;
+    if (strcmp(key, "oz_cluster") == 0) {
+        const int v = (int)value;
+        if (v != 0 && v != 1 && v != 2 && v != 4) return bo_set_err(ctx, BO_ERR_ARG, "oz_cluster must be 0 (default), 1, 2 or 4");
+        ctx->oz_cluster = v;
+        return BO_OK;
+    }
+    return bo_set_err(ctx, BO_ERR_ARG, "bo_set_option: unknown key '%s'", key);
+}
+
 extern "C" int bo_ozaki_error_bound(bo_ctx *ctx, double *errk) {
     BO_ENTER(ctx);
     if (!errk) return BO_ERR_ARG;

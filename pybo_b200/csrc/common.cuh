@@ -157,6 +157,7 @@ struct bo_ctx {
     int oz_mu_slot = 0, oz_mu_rows[2] = {0, 0};
     // FP64 rescue pass of the int8-slice path (score.cu run_oz): per-candidate a-priori error bound -> flag list
     // -> compact FP64 re-score -> scatter
+    int oz_cluster = 0;                 // CTAs per cluster of the scoring contraction (0: library default)
     bool oz_rescue = true;
     double oz_rescue_tol = 2.5e-7;      // flag when the bound exceeds tol * max(|value|, floor * max |value|)
     double oz_rescue_floor = 1e-12;

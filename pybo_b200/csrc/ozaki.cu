@@ -37,6 +37,7 @@ static int ctx_padded_dim(int d) {
 #define OZ_DIGIT_BIAS7 0x0080808080808080ll   // 128 in each of the 7 digit bytes
 #define OZ_A_SLICE_BYTES (OZ_BM * OZ_BK)   // 8192
 #define OZ_B_SLICE_BYTES (OZ_BN * OZ_BK)   // 4096
+#define OZ_DEFAULT_CLUSTER 1   // CTAs per cluster of the scoring contraction (BO_OZ_CLUSTER overrides)
 #define OZ_THREADS 320   // warp 0: TMA producer, warp 1: MMA issuer, warps 2-9: epilogue (two per TMEM lane quarter)
 #define OZ_THREADS_M1 OZ_THREADS
 #define OZ_ROW_SMEM 8192      // MODE 1: row scale + bias of up to 512 draws
@@ -98,6 +99,22 @@ __host__ __device__ __forceinline__ size_t oz_kss_offset(int s, int m, int j, in
     return oz_kss_block(s, m >> 7, j >> 6, ntiles, nkb) + (size_t)r * 64 + (size_t)((c ^ ((r >> 1) & 3)) << 4) + (j & 15);
 }
 
+// 1-D bulk copy multicast to the CTAs of the cluster in `mask`: the bytes land at the same CTA-relative offset in each
+// destination CTA and complete_tx is signalled on the mbarrier at the same offset in each of them
+__device__ __forceinline__ void bulk_load_multicast(uint32_t smem_dst, const void *gsrc, uint32_t bytes, uint32_t bar, uint16_t mask) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
+                 ::"r"(smem_dst), "l"(gsrc), "r"(bytes), "r"(bar), "h"(mask) : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
 __device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -119,6 +136,11 @@ __device__ __forceinline__ void umma_i8(uint32_t tmem_c, uint64_t adesc, uint64_
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// the same arrival delivered to the barrier at this offset in every CTA of `mask`
+__device__ __forceinline__ void umma_commit_multicast(uint32_t bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"(mask) : "memory");
 }
 // 32 lanes x 16 consecutive 32-bit columns
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, int32_t (&r)[16]) {
@@ -603,7 +625,14 @@ __device__ __forceinline__ OzUnit oz_decode(int u, int nb, int T, int ntiles) {
 
 // MODE 0: scoring (B = slices of the triangular W, k range cut at the diagonal, epilogue reduces |v|^2);
 // MODE 1: Thompson draws (B = slices of Theta, full k range, epilogue writes values / per-draw arg max).
-template <int S, int EXTRA, int MODE>
+// CL > 1 (MODE 0): thread-block clusters of CL CTAs work on the SAME candidate tile and CL adjacent row blocks of W.
+// The K* slice tile of a k block -- two thirds of a stage's bytes -- is fetched ONCE per cluster: CTA r loads the slices
+// s = r (mod CL) and multicasts them into the shared memory of all CL CTAs; every CTA loads its own W slices.  A stage may
+// be refilled only when every CTA of the cluster has consumed it, so each MMA thread commits its stage release to the
+// `empty` barrier of ALL CTAs (count CL).  The CL row blocks have k ranges that differ by up to CL - 1 blocks: the
+// CTAs with the shorter range step through those stages without loads or MMAs, so the rings stay in lockstep; the k
+// blocks past the shortest range are loaded privately by the CTAs that need them.
+template <int S, int EXTRA, int MODE, int CL>
 __global__ void __launch_bounds__(OZ_THREADS, 1)
 oz_score_kernel(const __grid_constant__ CUtensorMap tmapB, OzParams p) {
     extern __shared__ uint8_t oz_smem_raw[];
@@ -627,14 +656,18 @@ oz_score_kernel(const __grid_constant__ CUtensorMap tmapB, OzParams p) {
     auto tmem_empty = [&](int a) { return bar0 + 8u * (2 * nst + 2 + a); };
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int nb = p.nrb;
+    static_assert(CL == 1 || MODE == 0, "clusters are wired for the scoring mode only");
+    const int crank = (CL > 1) ? (int)cluster_ctarank() : 0;
+    constexpr uint16_t cmask = (uint16_t)((1u << CL) - 1u);
+    const int nb = p.nrb / CL;                   // row-block groups (CL adjacent row blocks each)
     const int nunits = p.ntiles * nb;
+    const int ucta = (int)blockIdx.x / CL, ustride = (int)gridDim.x / CL;   // unit walk of this cluster
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmapB);
         for (int s = 0; s < nst; ++s) {
             mbar_init(full_bar(s), 1);
-            mbar_init(empty_bar(s), 1);
+            mbar_init(empty_bar(s), CL);
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(tmem_full(a), 1);
@@ -652,6 +685,7 @@ oz_score_kernel(const __grid_constant__ CUtensorMap tmapB, OzParams p) {
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    if (CL > 1) cluster_sync_all();              // every CTA's barriers exist before anyone multicasts into them
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
@@ -659,18 +693,29 @@ oz_score_kernel(const __grid_constant__ CUtensorMap tmapB, OzParams p) {
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int u = blockIdx.x; u < nunits; u += gridDim.x) {
+            for (int u = ucta; u < nunits; u += ustride) {
                 const OzUnit un = oz_decode(u, nb, p.tiles_per_group, p.ntiles);
-                const int klast = (MODE == 1 || p.full_k) ? p.nkb - 1 : un.rb;
+                const int rb = un.rb * CL + crank;                          // this CTA's row block
+                const int kown = (MODE == 1 || p.full_k) ? p.nkb - 1 : rb;  // last k block this CTA needs
+                const int kshared = (MODE == 1 || p.full_k) ? p.nkb - 1 : un.rb * CL;   // ... every CTA of the cluster needs
+                const int klast = (MODE == 1 || p.full_k) ? p.nkb - 1 : un.rb * CL + CL - 1;
                 for (int kb = 0; kb <= klast; ++kb) {
                     mbar_wait(empty_bar(stage), phase ^ 1);
+                    if (kb > kown) {                                        // not mine: keep the ring in step
+                        mbar_arrive(full_bar(stage));
+                        if (++stage == nst) { stage = 0; phase ^= 1; }
+                        continue;
+                    }
                     mbar_expect_tx(full_bar(stage), stage_bytes);
                     const uint32_t sA = base + stage * stage_bytes;
                     const uint32_t sB = sA + S * OZ_A_SLICE_BYTES;
+                    const bool shared = CL > 1 && kb <= kshared;
                     for (int s = 0; s < S; ++s) {
-                        bulk_load(sA + s * OZ_A_SLICE_BYTES, p.kss + oz_kss_block(s, un.tile, kb, p.ntiles, p.nkb),
-                                  OZ_A_SLICE_BYTES, full_bar(stage));
-                        tma_load_3d(sB + s * OZ_B_SLICE_BYTES, &tmapB, kb * OZ_BK, un.rb * OZ_BN, s, full_bar(stage));
+                        const int8_t *src = p.kss + oz_kss_block(s, un.tile, kb, p.ntiles, p.nkb);
+                        if (!shared) bulk_load(sA + s * OZ_A_SLICE_BYTES, src, OZ_A_SLICE_BYTES, full_bar(stage));
+                        else if (s % CL == crank)
+                            bulk_load_multicast(sA + s * OZ_A_SLICE_BYTES, src, OZ_A_SLICE_BYTES, full_bar(stage), cmask);
+                        tma_load_3d(sB + s * OZ_B_SLICE_BYTES, &tmapB, kb * OZ_BK, rb * OZ_BN, s, full_bar(stage));
                     }
                     if (++stage == nst) { stage = 0; phase ^= 1; }
                 }
@@ -681,18 +726,21 @@ oz_score_kernel(const __grid_constant__ CUtensorMap tmapB, OzParams p) {
         if (lane == 0) {
             int stage = 0, acc = 0;
             uint32_t phase = 0, acc_phase = 0;
-            for (int u = blockIdx.x; u < nunits; u += gridDim.x) {
+            for (int u = ucta; u < nunits; u += ustride) {
                 const OzUnit un = oz_decode(u, nb, p.tiles_per_group, p.ntiles);
                 mbar_wait(tmem_empty(acc), acc_phase ^ 1);    // epilogue has drained this accumulator set
                 tc_fence_after();
                 const uint32_t tacc = tmem_base + (uint32_t)(acc * NG * OZ_BN);
-                const int klast = (MODE == 1 || p.full_k) ? p.nkb - 1 : un.rb;
+                const int kown = (MODE == 1 || p.full_k) ? p.nkb - 1 : un.rb * CL + crank;
+                const int klast = (MODE == 1 || p.full_k) ? p.nkb - 1 : un.rb * CL + CL - 1;
                 for (int kb = 0; kb <= klast; ++kb) {
                     mbar_wait(full_bar(stage), phase);
                     tc_fence_after();
                     const uint32_t sA = base + stage * stage_bytes;
-                    oz_issue_stage<S, EXTRA>(sA, sA + S * OZ_A_SLICE_BYTES, tacc, kb == 0);
-                    umma_commit(empty_bar(stage));            // smem slot free once these MMAs retire
+                    if (kb <= kown) oz_issue_stage<S, EXTRA>(sA, sA + S * OZ_A_SLICE_BYTES, tacc, kb == 0);
+                    // smem slot free once these MMAs retire -- in every CTA of the cluster that may write into it
+                    if (CL > 1) umma_commit_multicast(empty_bar(stage), cmask);
+                    else umma_commit(empty_bar(stage));
                     if (++stage == nst) { stage = 0; phase ^= 1; }
                 }
                 umma_commit(tmem_full(acc));                  // accumulators of this unit are complete
@@ -708,8 +756,9 @@ oz_score_kernel(const __grid_constant__ CUtensorMap tmapB, OzParams p) {
         const int ehalf = (warp - 2) >> 2;
         int acc = 0;
         uint32_t acc_phase = 0;
-        for (int u = blockIdx.x; u < nunits; u += gridDim.x) {
-            const OzUnit un = oz_decode(u, nb, p.tiles_per_group, p.ntiles);
+        for (int u = ucta; u < nunits; u += ustride) {
+            OzUnit un = oz_decode(u, nb, p.tiles_per_group, p.ntiles);
+            un.rb = un.rb * CL + crank;                        // this CTA's row block
             const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * NG * OZ_BN);
             double q = 0.0;
             mbar_wait(tmem_full(acc), acc_phase);
@@ -871,6 +920,7 @@ oz_score_kernel(const __grid_constant__ CUtensorMap tmapB, OzParams p) {
     }
     tc_fence_before();
     __syncthreads();
+    if (CL > 1) cluster_sync_all();              // nobody leaves while a peer may still multicast into its shared memory
     if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
@@ -942,12 +992,16 @@ static size_t oz_smem_bytes_m1(int S) {
 }
 
 int bo_ozaki_init(bo_ctx *ctx) {
-#define OZ_ATTR1(SS, EE, MM) BO_CUDA(ctx, cudaFuncSetAttribute(oz_score_kernel<SS, EE, MM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(MM ? oz_smem_bytes_m1(SS) : oz_smem_bytes(SS))))
+#define OZ_ATTR1(SS, EE, MM) BO_CUDA(ctx, cudaFuncSetAttribute(oz_score_kernel<SS, EE, MM, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(MM ? oz_smem_bytes_m1(SS) : oz_smem_bytes(SS))))
+#define OZ_ATTR_CL(SS, EE) BO_CUDA(ctx, cudaFuncSetAttribute(oz_score_kernel<SS, EE, 0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)oz_smem_bytes(SS))); \
+                           BO_CUDA(ctx, cudaFuncSetAttribute(oz_score_kernel<SS, EE, 0, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)oz_smem_bytes(SS)))
 #define OZ_ATTR(SS) OZ_ATTR1(SS, 0, 0); OZ_ATTR1(SS, 1, 0)
 #define OZ_ATTR_M1(SS) OZ_ATTR1(SS, 0, 1); OZ_ATTR1(SS, 1, 1)
     OZ_ATTR(2); OZ_ATTR(3); OZ_ATTR(4); OZ_ATTR(5); OZ_ATTR(6); OZ_ATTR(7);
     OZ_ATTR_M1(3); OZ_ATTR_M1(4); OZ_ATTR_M1(5);          // the Thompson path runs 3..5 slices
 #undef OZ_ATTR_M1
+    OZ_ATTR_CL(4, 0); OZ_ATTR_CL(4, 1); OZ_ATTR_CL(5, 0); OZ_ATTR_CL(5, 1);     // cluster variants of the common levels
+#undef OZ_ATTR_CL
 #undef OZ_ATTR
 #undef OZ_ATTR1
 #define OZ_KATTR(DP, SS) BO_CUDA(ctx, cudaFuncSetAttribute(oz_kstar_slices_fast_kernel<DP, SS, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SS * OZ_A_SLICE_BYTES)); \
@@ -1175,15 +1229,53 @@ int bo_ozaki_contract(bo_ctx *ctx, int s, int S, int mcp, int buf, double *mu, d
     p.rowscale = ctx->dRowScale + (size_t)s * np;
     p.qpart = ctx->dOzQ; p.dbg = dbg; p.kss = Kss;
     const int nunits = p.ntiles * nb;
-    const int grid = nunits < ctx->sm_count ? nunits : ctx->sm_count;
+    // Clusters of CL CTAs share the K* tile by TMA multicast (see oz_score_kernel): bo_set_option("oz_cluster", 1 / 2 / 4)
+    // or BO_OZ_CLUSTER.  Measured at the headline shape: CL = 2 cuts the L2 -> SM operand traffic by a third and changes
+    // neither the time (2.73 vs 2.72 ms per launch) nor the clock under the power cap (1687 MHz): the cap is set by the
+    // tensor pipe itself working on random digits, not by operand movement.  CL = 4 is slower (4.87 ms: four rings in
+    // lockstep, 37 clusters).  Default 1.
+    static const int env_cl = getenv("BO_OZ_CLUSTER") ? atoi(getenv("BO_OZ_CLUSTER")) : 0;
+    const int want_cl = ctx->oz_cluster > 0 ? ctx->oz_cluster : (env_cl > 0 ? env_cl : OZ_DEFAULT_CLUSTER);
+    int cl = (S == 4 || S == 5) ? want_cl : 1;
+    while (cl > 1 && (nb % cl != 0 || ctx->sm_count % cl != 0)) cl >>= 1;
+    if (cl != 1 && cl != 2 && cl != 4) cl = 1;
     {
         BO_LAUNCH(ctx, "oz_score_kernel");
-        switch (S) {
-#define OZ_RUN(SS) case SS: if (extra) oz_score_kernel<SS, 1, 0><<<grid, OZ_THREADS, oz_smem_bytes(SS), ctx->stream>>>(tmB, p); \
-                         else oz_score_kernel<SS, 0, 0><<<grid, OZ_THREADS, oz_smem_bytes(SS), ctx->stream>>>(tmB, p); break
-            OZ_RUN(2); OZ_RUN(3); OZ_RUN(4); OZ_RUN(5); OZ_RUN(6); OZ_RUN(7);
+        if (cl == 1) {
+            const int grid = nunits < ctx->sm_count ? nunits : ctx->sm_count;
+            switch (S) {
+#define OZ_RUN(SS) case SS: if (extra) oz_score_kernel<SS, 1, 0, 1><<<grid, OZ_THREADS, oz_smem_bytes(SS), ctx->stream>>>(tmB, p); \
+                         else oz_score_kernel<SS, 0, 0, 1><<<grid, OZ_THREADS, oz_smem_bytes(SS), ctx->stream>>>(tmB, p); break
+                OZ_RUN(2); OZ_RUN(3); OZ_RUN(4); OZ_RUN(5); OZ_RUN(6); OZ_RUN(7);
 #undef OZ_RUN
-            default: return bo_set_err(ctx, BO_ERR_ARG, "int8 path needs 2..7 slices, got %d", S);
+                default: return bo_set_err(ctx, BO_ERR_ARG, "int8 path needs 2..7 slices, got %d", S);
+            }
+        } else {
+            const int ncl_units = nunits / cl;                 // units of a cluster: (tile, group of cl row blocks)
+            int nclusters = ctx->sm_count / cl;
+            if (ncl_units < nclusters) nclusters = ncl_units;
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3((unsigned)(nclusters * cl));
+            cfg.blockDim = dim3(OZ_THREADS);
+            cfg.dynamicSmemBytes = oz_smem_bytes(S);
+            cfg.stream = ctx->stream;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = (unsigned)cl;
+            at[0].val.clusterDim.y = 1;
+            at[0].val.clusterDim.z = 1;
+            cfg.attrs = at;
+            cfg.numAttrs = 1;
+#define OZ_RUN_CL(SS, EE, CC) BO_CUDA(ctx, cudaLaunchKernelEx(&cfg, oz_score_kernel<SS, EE, 0, CC>, tmB, p))
+            if (S == 5 && !extra && cl == 2) OZ_RUN_CL(5, 0, 2);
+            else if (S == 5 && !extra && cl == 4) OZ_RUN_CL(5, 0, 4);
+            else if (S == 5 && extra && cl == 2) OZ_RUN_CL(5, 1, 2);
+            else if (S == 5 && extra && cl == 4) OZ_RUN_CL(5, 1, 4);
+            else if (S == 4 && !extra && cl == 2) OZ_RUN_CL(4, 0, 2);
+            else if (S == 4 && !extra && cl == 4) OZ_RUN_CL(4, 0, 4);
+            else if (S == 4 && extra && cl == 2) OZ_RUN_CL(4, 1, 2);
+            else OZ_RUN_CL(4, 1, 4);
+#undef OZ_RUN_CL
         }
         BO_CHECK_LAUNCH(ctx);
     }
@@ -1483,8 +1575,8 @@ int bo_thompson_ozaki_run(bo_ctx *ctx, int64_t M, const double *dXc, double *dOu
         {
             BO_LAUNCH(ctx, "oz_thompson_kernel");
             switch (S) {
-#define OZ_TRUN(SS) case SS: if (extra) oz_score_kernel<SS, 1, 1><<<grid, OZ_THREADS_M1, oz_smem_bytes_m1(SS), ctx->stream>>>(tmB, p); \
-                          else oz_score_kernel<SS, 0, 1><<<grid, OZ_THREADS_M1, oz_smem_bytes_m1(SS), ctx->stream>>>(tmB, p); break
+#define OZ_TRUN(SS) case SS: if (extra) oz_score_kernel<SS, 1, 1, 1><<<grid, OZ_THREADS_M1, oz_smem_bytes_m1(SS), ctx->stream>>>(tmB, p); \
+                          else oz_score_kernel<SS, 0, 1, 1><<<grid, OZ_THREADS_M1, oz_smem_bytes_m1(SS), ctx->stream>>>(tmB, p); break
                 OZ_TRUN(3); OZ_TRUN(4); OZ_TRUN(5);
 #undef OZ_TRUN
                 default: return bo_set_err(ctx, BO_ERR_ARG, "Thompson int8 path handles 3..5 slices, got %d", S);

@@ -182,3 +182,22 @@ def test_thompson_batch_int8_path(d, m, ndraw, M):
         tb.set_precision("int8", lvl)
         errs.append(np.max(np.abs(tb.get(Xc) - ref)))
     assert errs[0] > errs[1] > errs[2] and errs[0] / errs[1] > 50
+
+
+@pytest.mark.parametrize("cl", [2, 4])
+def test_cluster_multicast_variant_is_bit_identical(ctx, cl):
+    """The thread-block-cluster form of the contraction (K* tile fetched once per cluster by TMA multicast, stage
+    release committed to every CTA of the cluster) computes exactly what the single-CTA form computes."""
+    gp = synth(1024, 8, "se", seed=1)
+    ctx.fit("se", gp.X, gp.Y, gp.ell[None], [gp.rho], [gp.sn2], [gp.bias])
+    Xc = qmc.Sobol(d=8, scramble=False).random_base2(15)[:33000]
+    target = float(gp.predict(gp.X)[0].max())
+    ctx.set_rescue(False)
+    for level in (5.0, 4.5):
+        ctx.set_precision(1, level)
+        ctx.set_option("oz_cluster", 1)
+        base, _, b0 = ctx.score(1, target, Xc, want_best=True)
+        ctx.set_option("oz_cluster", cl)
+        got, _, b1 = ctx.score(1, target, Xc, want_best=True)
+        assert np.array_equal(got, base) and b0 == b1
+    ctx.set_option("oz_cluster", 0)
