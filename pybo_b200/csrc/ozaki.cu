@@ -454,8 +454,15 @@ oz_kstar_slices_fast_kernel(int n, int np, int d, const double *__restrict__ Xs,
                 const int jq = jj0 + 4 * q4;
                 double dot[4], r[4], pl[4];
                 int ki[4], ti[4];
+                // |xs|^2/2 and beta of the four observations as two 16-byte broadcasts each
+                const double2 hb01 = *reinterpret_cast<const double2 *>(&hb[buf][jq]);
+                const double2 hb23 = *reinterpret_cast<const double2 *>(&hb[buf][jq + 2]);
+                const double2 bt01 = *reinterpret_cast<const double2 *>(&bt[buf][jq]);
+                const double2 bt23 = *reinterpret_cast<const double2 *>(&bt[buf][jq + 2]);
+                const double hbv[4] = {hb01.x, hb01.y, hb23.x, hb23.y};
+                const double btv[4] = {bt01.x, bt01.y, bt23.x, bt23.y};
 #pragma unroll
-                for (int e = 0; e < 4; ++e) dot[e] = -ha - hb[buf][jq + e];
+                for (int e = 0; e < 4; ++e) dot[e] = -ha - hbv[e];
 #pragma unroll
                 for (int k = 0; k < DP; k += 2) {
 #pragma unroll
@@ -536,7 +543,7 @@ oz_kstar_slices_fast_kernel(int n, int np, int d, const double *__restrict__ Xs,
                     const bool on = (((j0 + jq + e) - jlimit) & (-961 - ki[e])) < 0;
                     double v = __hiloint2double(__double2hiint(pl[e]) + (ki[e] << 20), __double2loint(pl[e]));
                     v = on ? v : 0.0;                                           // in [0, 127 * 2^32]
-                    kb = fma(v, bt[buf][jq + e], kb);
+                    kb = fma(v, btv[e], kb);
                     const double vv = v + 4503599627370496.0;                   // + 2^52: mantissa = rint(v)
                     const uint32_t lo = (uint32_t)__double2loint(vv) + 0x80808080u;
                     const uint32_t hi = ((uint32_t)__double2hiint(vv) + 0x80u + (lo < 0x80808080u ? 1u : 0u)) & 0xFFu;
