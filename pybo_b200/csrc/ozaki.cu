@@ -544,11 +544,11 @@ oz_kstar_slices_fast_kernel(int n, int np, int d, const double *__restrict__ Xs,
                     double v = __hiloint2double(__double2hiint(pl[e]) + (ki[e] << 20), __double2loint(pl[e]));
                     v = on ? v : 0.0;                                           // in [0, 127 * 2^32]
                     kb = fma(v, btv[e], kb);
-                    const double vv = v + 4503599627370496.0;                   // + 2^52: mantissa = rint(v)
-                    const uint32_t lo = (uint32_t)__double2loint(vv) + 0x80808080u;
-                    const uint32_t hi = ((uint32_t)__double2hiint(vv) + 0x80u + (lo < 0x80808080u ? 1u : 0u)) & 0xFFu;
-                    wlow[i] = lo ^ 0x80808080u;
-                    const uint32_t top = hi ^ 0x80u;
+                    // + 2^52 puts rint(v) into the mantissa; the digit bias 0x8080808080 rides in the same addition
+                    // (exact: the sum stays below 2^53), so the carry between the words costs no integer instruction
+                    const double vv = v + (4503599627370496.0 + 551911719040.0);
+                    wlow[i] = (uint32_t)__double2loint(vv) ^ 0x80808080u;
+                    const uint32_t top = ((uint32_t)__double2hiint(vv) & 0xFFu) ^ 0x80u;
                     if (e == 0) wtop[q4] = top;
                     else wtop[q4] |= top << (8 * e);
                 }

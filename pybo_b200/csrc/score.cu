@@ -887,7 +887,8 @@ static int run_fp64(bo_ctx *ctx, const ScoreRequest &rq) {
 static int run_oz(bo_ctx *ctx, const ScoreRequest &rq, int oz_S) {
     const int np = ctx->np, S = ctx->S, d = ctx->d;
     const int64_t M = rq.M;
-    const int64_t chunk = (int64_t)256 * 128;
+    static const int chunk_tiles = getenv("BO_OZ_CHUNK_TILES") ? atoi(getenv("BO_OZ_CHUNK_TILES")) : 256;
+    const int64_t chunk = (int64_t)(chunk_tiles > 0 ? chunk_tiles : 256) * 128;
     const int64_t cap = bo_round_up64(M < chunk ? M : chunk, 128);
     BO_TRY(reserve_moments(ctx, np / 128, cap, S));
     // what the rescue pass looks at: mode 0 -> the acquisition value (not for the mean, which never goes through
