@@ -60,17 +60,27 @@ __device__ __forceinline__ double ap_row_dot(const double *__restrict__ row, con
     double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
     const int beg = lo & ~1;
     int j = beg + 2 * lane;
-    for (; j + 64 < hi; j += 128) {
+    // 256 elements per round: four independent 16-byte loads of the matrix row per lane in flight (a warp streams its
+    // two rows alone, so the bytes it keeps in flight set the bandwidth it reaches)
+    for (; j + 192 < hi; j += 256) {
         const double2 w0 = *reinterpret_cast<const double2 *>(row + j);
         const double2 w1 = *reinterpret_cast<const double2 *>(row + j + 64);
+        const double2 w2 = *reinterpret_cast<const double2 *>(row + j + 128);
+        const double2 w3 = *reinterpret_cast<const double2 *>(row + j + 192);
         const double2 v0 = *reinterpret_cast<const double2 *>(vec + j);
         const double2 v1 = *reinterpret_cast<const double2 *>(vec + j + 64);
+        const double2 v2 = *reinterpret_cast<const double2 *>(vec + j + 128);
+        const double2 v3 = *reinterpret_cast<const double2 *>(vec + j + 192);
         a0 = fma(j >= lo ? w0.x : 0.0, v0.x, a0);
         a1 = fma(w0.y, v0.y, a1);
         a2 = fma(w1.x, v1.x, a2);
-        a3 = fma(j + 65 < hi ? w1.y : 0.0, v1.y, a3);
+        a3 = fma(w1.y, v1.y, a3);
+        a0 = fma(w2.x, v2.x, a0);
+        a1 = fma(w2.y, v2.y, a1);
+        a2 = fma(w3.x, v3.x, a2);
+        a3 = fma(j + 193 < hi ? w3.y : 0.0, v3.y, a3);
     }
-    if (j < hi) {
+    for (; j < hi; j += 64) {
         const double2 w0 = *reinterpret_cast<const double2 *>(row + j);
         const double2 v0 = *reinterpret_cast<const double2 *>(vec + j);
         a0 = fma(j >= lo ? w0.x : 0.0, v0.x, a0);
@@ -79,24 +89,64 @@ __device__ __forceinline__ double ap_row_dot(const double *__restrict__ row, con
     return ap_warp_sum((a0 + a1) + (a2 + a3));
 }
 
+// The same dot product shared by the AP_ROWS warps of a block: warp w takes the 256-element rounds w, w + AP_ROWS, ...
+// of the row, so a 4096-element row is two dependent load rounds per warp instead of sixteen (one warp streaming a
+// row alone is bound by the latency of its own load rounds: 29 us per product at n = 4096, a third of the HBM roof).
+// Returns the block-wide sum in every thread of warp 0 (red: AP_ROWS doubles of shared memory).
+__device__ __forceinline__ double ap_row_dot_block(const double *__restrict__ row, const double *__restrict__ vec, int lo, int hi,
+                                                   double *red) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int beg = lo & ~1;
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    for (int j0 = beg + 256 * w; j0 < hi; j0 += 256 * AP_ROWS) {
+        const int j = j0 + 2 * lane;
+        double2 wv[4], vv[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            const int jt = j + 64 * t;
+            const bool in = jt < hi;                           // (rows are padded to an even length >= hi)
+            wv[t] = in ? *reinterpret_cast<const double2 *>(row + jt) : make_double2(0.0, 0.0);
+            vv[t] = in ? *reinterpret_cast<const double2 *>(vec + jt) : make_double2(0.0, 0.0);
+        }
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            const int jt = j + 64 * t;
+            const double x = (jt >= lo) ? wv[t].x : 0.0;
+            const double y = (jt + 1 < hi) ? wv[t].y : 0.0;
+            if (t & 1) { a2 = fma(x, vv[t].x, a2); a3 = fma(y, vv[t].y, a3); }
+            else { a0 = fma(x, vv[t].x, a0); a1 = fma(y, vv[t].y, a1); }
+        }
+    }
+    const double part = ap_warp_sum((a0 + a1) + (a2 + a3));
+    __syncthreads();                                           // red is reused between calls
+    if (lane == 0) red[w] = part;
+    __syncthreads();
+    double tot = 0.0;
+    if (w == 0) {
+#pragma unroll
+        for (int i = 0; i < AP_ROWS; ++i) tot += red[i];       // fixed order
+    }
+    return tot;
+}
+
 // lvec[i] = sum_{j <= i} W[i][j] kvec[j] for i < n (coalesced along the rows), lvec[i] = 0 on [n, np).
 // A warp takes rows r and n - 1 - r, so every warp streams n + 1 elements whatever r is.
 __global__ void __launch_bounds__(32 * AP_ROWS)
 append_wk_kernel(const double *__restrict__ W, const double *__restrict__ kvec, int n, int np, double *__restrict__ lvec) {
-    const int r = blockIdx.x * AP_ROWS + (threadIdx.x >> 5);
-    const int lane = threadIdx.x & 31;
+    __shared__ double red[AP_ROWS];
+    const int r = blockIdx.x;                                  // one block per row pair (r, n - 1 - r): n + 1 elements
     const int half = (n + 1) >> 1;
     if (r < half) {
         const int r2 = n - 1 - r;
-        const double d0 = ap_row_dot(W + (int64_t)r * np, kvec, 0, r + 1, lane);
-        if (lane == 0) lvec[r] = d0;
+        const double d0 = ap_row_dot_block(W + (int64_t)r * np, kvec, 0, r + 1, red);
+        if (threadIdx.x == 0) lvec[r] = d0;
         if (r2 != r) {
-            const double d1 = ap_row_dot(W + (int64_t)r2 * np, kvec, 0, r2 + 1, lane);
-            if (lane == 0) lvec[r2] = d1;
+            const double d1 = ap_row_dot_block(W + (int64_t)r2 * np, kvec, 0, r2 + 1, red);
+            if (threadIdx.x == 0) lvec[r2] = d1;
         }
     }
-    // zero the padding once (first block)
-    if (blockIdx.x == 0)
+    // zero the padding once (last block)
+    if (blockIdx.x == gridDim.x - 1)
         for (int i = n + threadIdx.x; i < np; i += blockDim.x) lvec[i] = 0.0;
 }
 
@@ -152,23 +202,25 @@ __global__ void append_pivot_kernel(const double *__restrict__ lvec, double *__r
 __global__ void __launch_bounds__(32 * AP_ROWS)
 append_wrow_kernel(double *__restrict__ W, double *__restrict__ WT, const double *__restrict__ lvec,
                    const double *__restrict__ scal, const int *__restrict__ info, double *__restrict__ beta, int n, int np) {
+    __shared__ double red[AP_ROWS];
     if (*info != 0) return;
-    const int r = blockIdx.x * AP_ROWS + (threadIdx.x >> 5);
-    const int lane = threadIdx.x & 31;
+    const int r = blockIdx.x;                                  // one block per row pair (r, n - 1 - r)
     const double lam_inv = scal[2], a = scal[1];
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-        W[(int64_t)n * np + n] = lam_inv;
-        WT[(int64_t)n * np + n] = lam_inv;
-        beta[n] = a * lam_inv;
-    }
     const int half = (n + 1) >> 1;
-    if (r >= half) return;
+    if (r >= half) {                                           // the extra block closes the diagonal
+        if (threadIdx.x == 0) {
+            W[(int64_t)n * np + n] = lam_inv;
+            WT[(int64_t)n * np + n] = lam_inv;
+            beta[n] = a * lam_inv;
+        }
+        return;
+    }
 #pragma unroll 1
     for (int t = 0; t < 2; ++t) {
         const int j = t == 0 ? r : n - 1 - r;
         if (t == 1 && j == r) break;
-        const double acc = ap_row_dot(WT + (int64_t)j * np, lvec, j, n, lane);
-        if (lane == 0) {
+        const double acc = ap_row_dot_block(WT + (int64_t)j * np, lvec, j, n, red);
+        if (threadIdx.x == 0) {
             const double w = -acc * lam_inv;
             W[(int64_t)n * np + j] = w;
             WT[(int64_t)j * np + n] = w;
@@ -222,7 +274,7 @@ extern "C" int bo_append(bo_ctx *ctx, int m, const double *Xnew, const double *y
             }
             {
                 BO_LAUNCH(ctx, "append_wk_kernel");
-                append_wk_kernel<<<((n + 1) / 2 + AP_ROWS - 1) / AP_ROWS + 1, 32 * AP_ROWS, 0, st>>>(ctx->dW + mo, kvec, n, np, lvec);
+                append_wk_kernel<<<(n + 1) / 2 + 1, 32 * AP_ROWS, 0, st>>>(ctx->dW + mo, kvec, n, np, lvec);
                 BO_CHECK_LAUNCH(ctx);
             }
             {
@@ -234,7 +286,7 @@ extern "C" int bo_append(bo_ctx *ctx, int m, const double *Xnew, const double *y
             }
             {
                 BO_LAUNCH(ctx, "append_wrow_kernel");
-                append_wrow_kernel<<<((n + 1) / 2 + AP_ROWS - 1) / AP_ROWS + 1, 32 * AP_ROWS, 0, st>>>(
+                append_wrow_kernel<<<(n + 1) / 2 + 1, 32 * AP_ROWS, 0, st>>>(
                     ctx->dW + mo, ctx->dWT + mo, lvec, sm + dp, ctx->dAppendInfo + s, ctx->dBeta + (size_t)s * np, n, np);
                 BO_CHECK_LAUNCH(ctx);
             }
