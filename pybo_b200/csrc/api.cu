@@ -597,14 +597,15 @@ extern "C" int bo_score_incumbent(bo_ctx *ctx, int acq, double param, int64_t M,
                                   double *out_val, int64_t index_offset, void **record) {
     BO_ENTER(ctx);
     if (!record) return BO_ERR_ARG;
-    BO_TRY(score_impl(ctx, acq, param, M, Xc, flags, out_val, nullptr, nullptr, nullptr, true));
+    // the record is written by the pass's own final arg-max kernel (fused: no extra launch between the scoring
+    // kernels and the collective that follows on the stream)
     BO_TRY(bo_reserve(ctx, &ctx->dIncumbent, &ctx->incumbent_capacity, (size_t)2));
-    {
-        BO_LAUNCH(ctx, "incumbent_pack_kernel");
-        incumbent_pack_kernel<<<1, 32, 0, ctx->stream>>>(ctx->dBlkVal + ctx->blk_capacity - 1,
-                                                        ctx->dBlkIdx + ctx->blk_capacity - 1, 1, index_offset, ctx->dIncumbent);
-        BO_CHECK_LAUNCH(ctx);
-    }
+    ctx->rec_ptr = ctx->dIncumbent;
+    ctx->rec_offset = index_offset;
+    const int rc = score_impl(ctx, acq, param, M, Xc, flags, out_val, nullptr, nullptr, nullptr, true);
+    ctx->rec_ptr = nullptr;
+    ctx->rec_offset = 0;
+    if (rc != BO_OK) return rc;
     *record = ctx->dIncumbent;
     return BO_OK;
 }

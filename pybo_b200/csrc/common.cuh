@@ -132,6 +132,8 @@ struct bo_ctx {
     double *dMerged = nullptr;       // bo_incumbent_merge result staging
     size_t merged_capacity = 0;
     bool best_valid = false;
+    int64_t *rec_ptr = nullptr;      // when set, the final arg-max kernel of a scoring pass also writes the packed record
+    int64_t rec_offset = 0;
     double *dBlkVal = nullptr;  // per-block argmax staging
     int64_t *dBlkIdx = nullptr;
     size_t blk_capacity = 0;

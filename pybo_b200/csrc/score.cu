@@ -479,7 +479,7 @@ __global__ void __launch_bounds__(256) acq_kernel(AcqParams p) {
 // single block: reduce (val, idx) pairs; writes result[0] = val, ridx[0] = idx
 __global__ void __launch_bounds__(1024)
 argmax_final_kernel(const double *__restrict__ bval, const int64_t *__restrict__ bidx, int64_t nb,
-                    double *__restrict__ rval, int64_t *__restrict__ ridx) {
+                    double *__restrict__ rval, int64_t *__restrict__ ridx, int64_t *__restrict__ rec, int64_t rec_offset) {
     __shared__ double sv[32];
     __shared__ int64_t si[32];
     double bv = -INFINITY;
@@ -499,6 +499,13 @@ argmax_final_kernel(const double *__restrict__ bval, const int64_t *__restrict__
             if (better(sv[w], si[w], bv, bi)) { bv = sv[w]; bi = si[w]; }
         rval[0] = bv;
         ridx[0] = bi;
+        // cross-rank exchange: the packed {value bits, global index} record is written by the same thread, so the
+        // collective can follow this kernel directly on the stream (bo_score_incumbent)
+        if (rec != nullptr) {
+            const bool none = (bi == INT64_MAX) || (bv != bv);
+            rec[0] = __double_as_longlong(none ? -INFINITY : bv);
+            rec[1] = none ? INT64_MAX : bi + rec_offset;
+        }
     }
 }
 
@@ -748,7 +755,7 @@ static int final_argmax_over(bo_ctx *ctx, const double *vals, int64_t M) {
     }
     BO_LAUNCH(ctx, "argmax_final_kernel");
     argmax_final_kernel<<<1, 1024, 0, ctx->stream>>>(ctx->dBlkVal, ctx->dBlkIdx, nb, ctx->dBlkVal + ctx->blk_capacity - 1,
-                                                    ctx->dBlkIdx + ctx->blk_capacity - 1);
+                                                    ctx->dBlkIdx + ctx->blk_capacity - 1, ctx->rec_ptr, ctx->rec_offset);
     BO_CHECK_LAUNCH(ctx);
     return BO_OK;
 }
@@ -876,7 +883,7 @@ static int run_fp64(bo_ctx *ctx, const ScoreRequest &rq) {
         BO_LAUNCH(ctx, "argmax_final_kernel");
         argmax_final_kernel<<<1, 1024, 0, ctx->stream>>>(ctx->dBlkVal, ctx->dBlkIdx, blk0,
                                                         ctx->dBlkVal + ctx->blk_capacity - 1,
-                                                        ctx->dBlkIdx + ctx->blk_capacity - 1);
+                                                        ctx->dBlkIdx + ctx->blk_capacity - 1, ctx->rec_ptr, ctx->rec_offset);
         BO_CHECK_LAUNCH(ctx);
     }
     return BO_OK;
@@ -968,7 +975,7 @@ static int run_oz(bo_ctx *ctx, const ScoreRequest &rq, int oz_S) {
     if (need_best) {
         BO_LAUNCH(ctx, "argmax_final_kernel");
         argmax_final_kernel<<<1, 1024, 0, ctx->stream>>>(ctx->dBlkVal, ctx->dBlkIdx, blk0, gmax,
-                                                        ctx->dBlkIdx + ctx->blk_capacity - 1);
+                                                        ctx->dBlkIdx + ctx->blk_capacity - 1, ctx->rec_ptr, ctx->rec_offset);
         BO_CHECK_LAUNCH(ctx);
     }
     ctx->oz_last_total = M;
@@ -1083,7 +1090,7 @@ int bo_topk_run(bo_ctx *ctx, const double *vals, int64_t M, int k, double *h_val
         }
         {
             BO_LAUNCH(ctx, "argmax_final_kernel");
-            argmax_final_kernel<<<1, 1024, 0, ctx->stream>>>(ctx->dBlkVal, ctx->dBlkIdx, nb, rv + j, ri + j);
+            argmax_final_kernel<<<1, 1024, 0, ctx->stream>>>(ctx->dBlkVal, ctx->dBlkIdx, nb, rv + j, ri + j, nullptr, 0);
             BO_CHECK_LAUNCH(ctx);
         }
     }
