@@ -787,7 +787,8 @@ int bo_linalg_cholesky(bo_ctx *ctx, int np, int batch, double *A, double *dinv, 
     static const bool use_flow = !(getenv("BO_CHOL_FLOW") && atoi(getenv("BO_CHOL_FLOW")) == 0);
     // (measured: 2.07 vs 2.2 ms at n = 4096; at n <= 2048 the chain of 45 k cycles per diagonal block dominates either
     //  way and the launch-per-step form, replayed as a graph, is a few per cent ahead)
-    if (use_flow && batch == 1 && nblk >= 48 && ctx->chol_flow_grid >= nblk + 16)
+    static const int flow_min = getenv("BO_CHOL_FLOW_MIN") ? atoi(getenv("BO_CHOL_FLOW_MIN")) : 48;   // (tests / sanitizer lower it)
+    if (use_flow && batch == 1 && nblk >= flow_min && nblk >= 4 && ctx->chol_flow_grid >= nblk + 16)
         return chol_flow(ctx, np, A, dinv, dInfo, ctx->chol_flow_grid);
     BO_TRY(bo_reserve(ctx, &ctx->dCholFlags, &ctx->cholflags_capacity, (size_t)batch * nblk));
     static const bool use_graph = !(getenv("BO_CHOL_GRAPH") && atoi(getenv("BO_CHOL_GRAPH")) == 0);

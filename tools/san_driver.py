@@ -45,6 +45,10 @@ ctx.set_rescue(True)
 ctx.set_precision(0)
 rec = ctx.score_incumbent(1, target, len(Xc), Xc, offset=5, flags=0)
 print("incumbent", ctx.incumbent_merge(rec, 1, 1))
+A1 = rng.randn(600, 600)
+A1 = A1 @ A1.T + 600 * np.eye(600)
+L1 = ctx.cholesky(A1)                       # one matrix, 10 blocks: the dataflow kernel when BO_CHOL_FLOW_MIN <= 10
+print("chol (single) err", np.abs(L1 - np.linalg.cholesky(A1)).max())
 A = rng.randn(2, 200, 200)
 A = A @ A.transpose(0, 2, 1) + 200 * np.eye(200)
 L = ctx.cholesky(A)
