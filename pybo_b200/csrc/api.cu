@@ -175,6 +175,13 @@ extern "C" int bo_destroy(bo_ctx *ctx) {
         if (ctx->ev_sliced[i]) cudaEventDestroy(ctx->ev_sliced[i]);
         if (ctx->ev_consumed[i]) cudaEventDestroy(ctx->ev_consumed[i]);
     }
+    for (int l = 0; l < BO_CHOL_MAX_LANES - 1; ++l) {
+        for (auto &e : ctx->chol_lane_ev[l])
+            if (e) cudaEventDestroy(e);
+        if (ctx->chol_lane_main[l]) cudaStreamDestroy(ctx->chol_lane_main[l]);
+        if (ctx->chol_lane_side[l]) cudaStreamDestroy(ctx->chol_lane_side[l]);
+    }
+    if (ctx->chol_lane_fork) cudaEventDestroy(ctx->chol_lane_fork);
     if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
     cudaStreamDestroy(ctx->stream);
     delete ctx;

@@ -51,11 +51,15 @@ struct bo_chol_graph {
     cudaGraphExec_t exec = nullptr;
 };
 
+#define BO_CHOL_MAX_LANES 8
+
 struct bo_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t stream2 = nullptr;       // low-priority side stream (operand slicing overlaps the contraction)
     cudaEvent_t ev_sliced[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr};
+    cudaStream_t chol_lane_main[BO_CHOL_MAX_LANES - 1] = {}, chol_lane_side[BO_CHOL_MAX_LANES - 1] = {};   // extra stream pairs of the batched Cholesky (lazy)
+    cudaEvent_t chol_lane_ev[BO_CHOL_MAX_LANES - 1][5] = {}, chol_lane_fork = nullptr;
     char err[512] = {0};
     int sm_count = 0;
     cudaDeviceProp prop;
@@ -86,6 +90,7 @@ struct bo_ctx {
     std::vector<bo_chol_graph> chol_graphs;    // captured factorisation patterns (linalg.cu bo_linalg_cholesky)
     std::vector<bo_chol_graph> chol_seen;      // patterns requested once so far (captured when they come back)
     uint64_t chol_graph_clock = 0;
+    int chol_group = 0;                        // panels per trailing update of the launch-per-step Cholesky (0: default)
     int chol_flow_grid = 0;                    // co-resident CTAs of the persistent factorisation kernel (0: unavailable)
     size_t choldinv_capacity = 0, cholinfo_capacity = 0;
     std::vector<double> h_rho, h_sn2, h_bias, h_ell;

@@ -682,75 +682,121 @@ static int set_smem(bo_ctx *ctx, K kernel, int bytes) {
 // Right-looking with a one-panel lookahead: step c (chol_step_kernel, main high-priority stream)
 // applies panel c-1 to block column c, factors the diagonal block and solves the panel in one
 // launch, while the rest of the trailing update of panel c-1 (columns > c) runs on the side stream.
-static int chol_enqueue(bo_ctx *ctx, int np, int batch, double *A, double *dinv, int *dInfo) {
+struct chol_lane {                 // one (main, side) stream pair and its hand-over events
+    cudaStream_t main, side;
+    cudaEvent_t sliced[2], consumed[2];
+};
+
+static int chol_enqueue_lane(bo_ctx *ctx, const chol_lane &ln, bool split, int np, int batch, double *A, double *dinv,
+                             int *dInfo, int *flags) {
     const int nblk = np / BO_NB;
     const int64_t strideA = (int64_t)np * np, strideD = (int64_t)nblk * 4096;
-    cudaStream_t main = ctx->stream, side = ctx->stream2;
-    BO_CUDA(ctx, cudaMemsetAsync(dInfo, 0, sizeof(int) * batch, main));
-    BO_CUDA(ctx, cudaMemsetAsync(ctx->dCholFlags, 0, sizeof(int) * batch * nblk, main));
-    // many matrices at once: diagonal and panel as two launches (no CTA spins on the flag); see chol_step_kernel
-    const bool split = (int64_t)batch * nblk > 2 * (int64_t)ctx->sm_count;
+    cudaStream_t main = ln.main, side = ln.side;
     auto step = [&](int c, int kprev) -> int {
         if (!split) {
-            BO_LAUNCH(ctx, "chol_step_kernel");
+            BO_LAUNCH_ON(ctx, "chol_step_kernel", main);
             chol_step_kernel<<<dim3(nblk - c, 1, batch), 256, CHOL_STEP_SMEM, main>>>(A, np, strideA, c, dinv, strideD, dInfo,
-                                                                                      ctx->dCholFlags, nblk, 0, kprev);
+                                                                                      flags, nblk, 0, kprev);
             BO_CHECK_LAUNCH(ctx);
             return BO_OK;
         }
         {
-            BO_LAUNCH(ctx, "chol_diag_kernel");
+            BO_LAUNCH_ON(ctx, "chol_diag_kernel", main);
             chol_step_kernel<<<dim3(1, 1, batch), 256, CHOL_STEP_SMEM, main>>>(A, np, strideA, c, dinv, strideD, dInfo,
-                                                                               ctx->dCholFlags, nblk, 1, kprev);
+                                                                               flags, nblk, 1, kprev);
             BO_CHECK_LAUNCH(ctx);
         }
         if (nblk - c - 1 > 0) {
-            BO_LAUNCH(ctx, "chol_panel_kernel");
+            BO_LAUNCH_ON(ctx, "chol_panel_kernel", main);
             chol_step_kernel<<<dim3(nblk - c - 1, 1, batch), 256, T64NT8::SMEM_BYTES, main>>>(A, np, strideA, c, dinv, strideD, dInfo,
-                                                                                             ctx->dCholFlags, nblk, 2, kprev);
+                                                                                             flags, nblk, 2, kprev);
             BO_CHECK_LAUNCH(ctx);
         }
         return BO_OK;
     };
-    // Trailing updates run per PAIR of panels (K = 128): a 64 x 64 tile of C is read and written once per 128 panel
+    // Trailing updates run per GROUP of G panels (K = 64 G): a 64 x 64 tile of C is read and written once per 64 G panel
     // columns instead of once per 64 -- the update is bound by L2 traffic (C in, C out, two operand tiles per 0.5 MFLOP
-    // at K = 64), not by the FP64 tensor pipe.  Pair p = panels (2p, 2p+1):
-    //   step(2p)   applies pair p-1 to block column 2p itself         (kprev = 128, nothing to wait for)
-    //   step(2p+1) applies panel 2p to block column 2p+1 itself       (kprev = 64) after rest(p-1) has finished with it
-    //   rest(p)    A_ij -= L_i,pair L_j,pair^T for i >= j >= 2p+3     (side stream, after step(2p+1))
+    // at K = 64), not by the FP64 tensor pipe.  G = 2 for one matrix (the panel chain is the critical path and its own
+    // pre-update grows with G), G = 4 for many matrices at once (the trailing update is).  Group p = panels [Gp, Gp+G):
+    //   step(Gp)     applies group p-1 to block column Gp itself          (kprev = 64 G, nothing to wait for)
+    //   step(Gp+i)   applies panels Gp..Gp+i-1 to block column Gp+i       (kprev = 64 i) after rest(p-1) is done with it
+    //   rest(p)      A_ij -= L_i,grp L_j,grp^T for i >= j >= G(p+1)+1     (side stream, after the group's last step)
+    const int G = ctx->chol_group > 0 ? ctx->chol_group : (split ? 4 : 2);
     auto rest = [&](int p) -> int {
-        const int j0 = 2 * p + 3, T = nblk - j0;
+        const int j0 = G * (p + 1) + 1, T = nblk - j0;
         if (T <= 0) return BO_OK;
-        double *panel = A + (int64_t)j0 * BO_NB * np + (int64_t)(2 * p) * BO_NB;
+        double *panel = A + (int64_t)j0 * BO_NB * np + (int64_t)(G * p) * BO_NB;
         double *A22 = A + (int64_t)j0 * BO_NB * (np + 1);
         BO_LAUNCH_ON(ctx, "chol_syrk_kernel", side);
         syrk_tri_kernel<T64NT><<<dim3(T * (T + 1) / 2, 1, batch), T64NT::NTHREADS, T64NT::SMEM_BYTES, side>>>(
-            A22, panel, np, strideA, 2 * BO_NB);
+            A22, panel, np, strideA, G * BO_NB);
         BO_CHECK_LAUNCH(ctx);
         return BO_OK;
     };
-    if (nblk <= 2) {
-        BO_TRY(step(0, 0));
-        if (nblk == 2) BO_TRY(step(1, BO_NB));
+    if (nblk <= G) {
+        for (int c = 0; c < nblk; ++c) BO_TRY(step(c, c * BO_NB));
         return BO_OK;
     }
     // fork: the side stream must see everything queued on the main stream so far (the input matrix)
-    BO_CUDA(ctx, cudaEventRecord(ctx->ev_consumed[0], main));
-    BO_CUDA(ctx, cudaStreamWaitEvent(side, ctx->ev_consumed[0], 0));
-    const int npair = (nblk + 1) / 2;
-    for (int p = 0; p < npair; ++p) {
+    BO_CUDA(ctx, cudaEventRecord(ln.consumed[0], main));
+    BO_CUDA(ctx, cudaStreamWaitEvent(side, ln.consumed[0], 0));
+    const int ngrp = (nblk + G - 1) / G;
+    for (int p = 0; p < ngrp; ++p) {
         const int e = p & 1;
-        BO_TRY(step(2 * p, p > 0 ? 2 * BO_NB : 0));
-        if (2 * p + 1 < nblk) {
-            if (p >= 1) BO_CUDA(ctx, cudaStreamWaitEvent(main, ctx->ev_consumed[e ^ 1], 0));   // rest(p-1) done with column 2p+1
-            BO_TRY(step(2 * p + 1, BO_NB));
+        for (int i = 0; i < G && G * p + i < nblk; ++i) {
+            if (i == 1 && p >= 1) BO_CUDA(ctx, cudaStreamWaitEvent(main, ln.consumed[e ^ 1], 0));   // rest(p-1) done
+            BO_TRY(step(G * p + i, i == 0 ? (p > 0 ? G * BO_NB : 0) : i * BO_NB));
         }
-        BO_CUDA(ctx, cudaEventRecord(ctx->ev_sliced[e], main));            // pair p complete
-        BO_CUDA(ctx, cudaStreamWaitEvent(side, ctx->ev_sliced[e], 0));
+        BO_CUDA(ctx, cudaEventRecord(ln.sliced[e], main));            // group p complete
+        BO_CUDA(ctx, cudaStreamWaitEvent(side, ln.sliced[e], 0));
         BO_TRY(rest(p));
-        BO_CUDA(ctx, cudaEventRecord(ctx->ev_consumed[e], side));          // rest(p) done
+        BO_CUDA(ctx, cudaEventRecord(ln.consumed[e], side));          // rest(p) done
     }
-    BO_CUDA(ctx, cudaStreamWaitEvent(main, ctx->ev_consumed[(npair - 1) & 1], 0));   // join
+    BO_CUDA(ctx, cudaStreamWaitEvent(main, ln.consumed[(ngrp - 1) & 1], 0));   // join
+    return BO_OK;
+}
+
+// Many matrices at once are factored as independent sub-batches on their own stream pairs: a sub-batch that sits in
+// its diagonal-block step (one CTA per matrix) leaves the SMs to the others' trailing updates.
+static int chol_enqueue(bo_ctx *ctx, int np, int batch, double *A, double *dinv, int *dInfo) {
+    const int nblk = np / BO_NB;
+    const int64_t strideA = (int64_t)np * np, strideD = (int64_t)nblk * 4096;
+    BO_CUDA(ctx, cudaMemsetAsync(dInfo, 0, sizeof(int) * batch, ctx->stream));
+    BO_CUDA(ctx, cudaMemsetAsync(ctx->dCholFlags, 0, sizeof(int) * batch * nblk, ctx->stream));
+    // many matrices at once: diagonal and panel as two launches (no CTA spins on the flag); see chol_step_kernel
+    const bool split = (int64_t)batch * nblk > 2 * (int64_t)ctx->sm_count;
+    chol_lane l0{ctx->stream, ctx->stream2, {ctx->ev_sliced[0], ctx->ev_sliced[1]}, {ctx->ev_consumed[0], ctx->ev_consumed[1]}};
+    static const int max_lanes = getenv("BO_CHOL_LANES") ? std::min(BO_CHOL_MAX_LANES, std::max(1, atoi(getenv("BO_CHOL_LANES")))) : 2;
+    const int lanes = split ? std::min(max_lanes, batch / 2) : 1;
+    if (lanes <= 1) return chol_enqueue_lane(ctx, l0, split, np, batch, A, dinv, dInfo, ctx->dCholFlags);
+    if (!ctx->chol_lane_fork) {
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        for (int l = 0; l < BO_CHOL_MAX_LANES - 1; ++l) {
+            BO_CUDA(ctx, cudaStreamCreateWithPriority(&ctx->chol_lane_main[l], cudaStreamNonBlocking, hi));
+            BO_CUDA(ctx, cudaStreamCreateWithPriority(&ctx->chol_lane_side[l], cudaStreamNonBlocking, lo));
+            for (int i = 0; i < 5; ++i) BO_CUDA(ctx, cudaEventCreateWithFlags(&ctx->chol_lane_ev[l][i], cudaEventDisableTiming));
+        }
+        BO_CUDA(ctx, cudaEventCreateWithFlags(&ctx->chol_lane_fork, cudaEventDisableTiming));
+    }
+    BO_CUDA(ctx, cudaEventRecord(ctx->chol_lane_fork, ctx->stream));                         // fork
+    int b0 = 0;
+    for (int l = 0; l < lanes; ++l) {
+        const int bl = (batch - b0) / (lanes - l);
+        if (l == lanes - 1) {
+            BO_TRY(chol_enqueue_lane(ctx, l0, split, np, bl, A + b0 * strideA, dinv + b0 * strideD, dInfo + b0,
+                                     ctx->dCholFlags + (int64_t)b0 * nblk));
+        } else {
+            cudaEvent_t *ev = ctx->chol_lane_ev[l];
+            chol_lane ln{ctx->chol_lane_main[l], ctx->chol_lane_side[l], {ev[0], ev[1]}, {ev[2], ev[3]}};
+            BO_CUDA(ctx, cudaStreamWaitEvent(ln.main, ctx->chol_lane_fork, 0));
+            BO_TRY(chol_enqueue_lane(ctx, ln, split, np, bl, A + b0 * strideA, dinv + b0 * strideD, dInfo + b0,
+                                     ctx->dCholFlags + (int64_t)b0 * nblk));
+            BO_CUDA(ctx, cudaEventRecord(ev[4], ln.main));
+        }
+        b0 += bl;
+    }
+    for (int l = 0; l < lanes - 1; ++l) BO_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->chol_lane_ev[l][4], 0));   // join
     return BO_OK;
 }
 
@@ -1044,6 +1090,10 @@ int bo_linalg_init(bo_ctx *ctx) {
         BO_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, chol_flow_kernel, 256, CHOL_STEP_SMEM));
         BO_CUDA(ctx, cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, ctx->device));
         ctx->chol_flow_grid = coop ? per_sm * ctx->sm_count : 0;
+    }
+    if (const char *e = getenv("BO_CHOL_GROUP")) {      // panels per trailing update (A/B knob; 0 = per-shape default)
+        int g = atoi(e);
+        ctx->chol_group = (g >= 1 && g <= 8) ? g : 0;
     }
     BO_TRY(set_smem(ctx, syrk_tri_kernel<T64NT>, T64NT::SMEM_BYTES));
     BO_TRY(set_smem(ctx, trtri_node_kernel<0>, T64NN::SMEM_BYTES));
