@@ -284,12 +284,20 @@ class ScoringWorkload(object):
         return float(v[0]), int(i[0])
 
     def level(self):
-        """What the last pass actually ran: path, slice level, rescue count."""
+        """What the last pass actually ran: path, slice level(s), tiers of the repair."""
         ran8, rescued, total = self.ctx.rescue_info()
-        _, slices, extra = self.ctx.precision_info()
-        return dict(path="int8 slices" if ran8 else "fp64", slices=slices if ran8 else None, extra_group=bool(extra) if ran8 else None,
-                    digit_pairs=(slices * (slices + 1) // 2 + ((slices - 1) if extra else 0)) if ran8 else None,
-                    rescued_fp64=int(rescued), candidates=int(total))
+        if not ran8:
+            return dict(path="fp64", slices=None, extra_group=None, digit_pairs=None, rescued_fp64=0, candidates=int(total))
+        t = self.ctx.tier_info()
+        pairs = lambda lv: lv[0] * (lv[0] + 1) // 2 + ((lv[0] - 1) if lv[1] else 0)
+        slices, extra = t["rest"]
+        out = dict(path="int8 slices", slices=slices, extra_group=extra, digit_pairs=pairs(t["rest"]),
+                   rescued_fp64=int(rescued), candidates=int(total), flagged_by_main_pass=int(t["first_flagged"]))
+        if t["first"] != t["rest"]:
+            out["first_chunk"] = dict(slices=t["first"][0], extra_group=t["first"][1], digit_pairs=pairs(t["first"]))
+        if t["tier2"]:
+            out["flagged_rescored_at"] = dict(slices=t["tier2"][0], extra_group=t["tier2"][1], digit_pairs=pairs(t["tier2"]))
+        return out
 
     def parity(self, m_check=None):
         """In-run parity of the selected path against the FP64 path on the first m_check candidates of this rank's
@@ -448,10 +456,11 @@ def our_arm(args):
         w.set_path("ozaki")
         w.step_device()
 
-    # for the record: the next-cheaper precision level (4 slices + first dropped pair group) with the same rescue pass
+    # for the record: the same pass with the tiers off (every chunk at the level the tolerance selects, flagged
+    # candidates straight to FP64) -- the round-1 / early round-2 configuration
     fast_level = None
-    if args.precision == "ozaki" and args.tol == 1e-8 and not args.quick:
-        w.set_path("ozaki", 4.5)
+    if args.precision == "ozaki" and not args.quick:
+        w.ctx.set_option("oz_tiered", 0)
         for _ in range(2):
             w.step_device()
         fsteps = max(2, args.steps // 4)
@@ -460,9 +469,9 @@ def our_arm(args):
         fpar = w.parity(m_check=1 << 18)
         fast_level = dict(level=fl, value=M * world * fsteps / (fms * 1e-3), unit="evals/s", ms_per_step=fms / fsteps,
                           incumbent_index=finc[1], parity_in_run=fpar,
-                          note="13 digit pairs instead of 15; its rescue pass re-scores several per cent of the candidates in FP64, "
-                               "which costs more than the two saved pairs: not the default")
-        w.set_path("ozaki", args.tol)
+                          note="tiers off (bo_set_option oz_tiered = 0): one level for the whole pass, flagged candidates "
+                               "straight to the FP64 path")
+        w.ctx.set_option("oz_tiered", 1)
         w.step_device()
 
     configs = None
@@ -492,7 +501,12 @@ def our_arm(args):
         nb = npad // 64
         # algorithmic: n^2 (forward-substitution equivalent) + 4n (reductions) flop per candidate
         alg_flop_per_launch = (n * n + 4 * n) * (M * S * args.steps) / max(1, gk["launches"])
-        exec_ops_per_launch = 2.0 * pairs * 64 * 64 * nb * (nb + 1) / 2 * (M * S * args.steps) / max(1, gk["launches"])
+        # executed int8 products: the main pass at its level(s) plus the flagged list re-scored one tier up
+        chunk = 32768
+        first_pairs = level.get("first_chunk", {}).get("digit_pairs", pairs)
+        t2 = level.get("flagged_rescored_at")
+        pair_cands = pairs * max(0, M - chunk) + first_pairs * min(M, chunk) + (t2["digit_pairs"] * level["flagged_by_main_pass"] if t2 else 0)
+        exec_ops_per_launch = 2.0 * 64 * 64 * nb * (nb + 1) / 2 * (pair_cands * S * args.steps) / max(1, gk["launches"])
         avg_ms = gk["total_ms"] / max(1, gk["launches"])
         achieved = alg_flop_per_launch / (avg_ms * 1e-3) / 1e12 if avg_ms > 0 else 0.0
         executed = exec_ops_per_launch / (avg_ms * 1e-3) / 1e12 if avg_ms > 0 else 0.0
@@ -502,7 +516,8 @@ def our_arm(args):
                         frac=achieved / int8_peak, traffic=tr["bytes"] if tr else None, traffic_source=tr["source"] if tr else None,
                         peak_source="int8 tensor roof = 2 x the %s bf16 figure of MEASURED_PEAKS.json (tcgen05 kind::i8 issues at "
                                     "twice the bf16 rate: ncu peak_sustained 16384 vs 8192 op/clk/SM)" % pk["source"],
-                        int8_slices=slices, slice_pairs=pairs, executed_int8_tops=executed,
+                        int8_slices=slices, slice_pairs=pairs, rescored_one_tier_up=level.get("flagged_by_main_pass") if t2 else 0,
+                        executed_int8_tops=executed,
                         frac_executed=executed / int8_peak,
                         note="achieved counts ALGORITHMIC flop (n^2 + 4n per candidate); the emulation executes %d int8 "
                              "products per algorithmic product, so frac_executed is the tensor-pipe utilisation" % pairs,
@@ -535,7 +550,9 @@ def our_arm(args):
 
     if level["path"] != "fp64":
         dtype = ("int8 slices: %d balanced base-256 digits per operand%s, exact int32 accumulation on tcgen05, f64 reassembly; "
-                 "f64 mean; f64 rescue of flagged candidates" % (level["slices"], " + first dropped pair group" if level["extra_group"] else ""))
+                 "f64 mean; candidates whose a-priori error bound exceeds 2.5e-7 re-scored%s in f64"
+                 % (level["slices"], " + first dropped pair group" if level["extra_group"] else "",
+                    " with %d digits, what that cannot certify" % level["flagged_rescored_at"]["slices"] if level.get("flagged_rescored_at") else ""))
     else:
         dtype = "f64"
     line = dict(metric="acq_evals_per_sec", value=value, unit="evals/s", n_gpus=world, steps=args.steps,
@@ -554,7 +571,7 @@ def our_arm(args):
                                      api="policies.ModelIndex.best_of_sobol: Sobol block generated on the device, scored, device top-10"),
                 gpu_launches=int(launches), roofline=roofline, parity_in_run=parity, fp64_path=fp64_path, cpu_baseline=cpu,
                 cholesky=chol, cholesky_batched=chol_b, fit=fit, incremental_refit=append, configs=configs,
-                fit_seconds=w.fit_s, incumbent=dict(value=incumbent[0], index=incumbent[1]), faster_level=fast_level,
+                fit_seconds=w.fit_s, incumbent=dict(value=incumbent[0], index=incumbent[1]), untiered=fast_level,
                 kernels={k: dict(launches=v["launches"], ms=round(v["total_ms"], 3)) for k, v in prof.items()})
     print(json.dumps(line))
     if world > 1:

@@ -143,14 +143,27 @@ int bo_set_precision(bo_ctx *ctx, int prec, double tol);
  * FP64 path inside the same call, so the int8 path meets `tol` wherever the FP64 path does.
  * Defaults: tol = 2.5e-7 (4x inside the 1e-6 parity bar), floor_rel = 1e-12.  A pass that has
  * to rescue more than a quarter of its candidates sends the following passes on this fit
- * straight to the FP64 path. */
+ * straight to the FP64 path.
+ * Tiers (tolerance-selected levels only; a level pinned with tol >= 2 runs exactly as pinned): a flagged list of
+ * >= 4096 candidates is first re-scored on the int8 path one level up and only what that cannot certify goes to FP64.
+ * Since whatever is not certified is re-scored, the level of the main pass only decides the speed: on passes of
+ * >= 4 chunks of 32 768 candidates the first chunk runs one half-level below the selected level, and if at most
+ * 10 % of it is flagged there the rest of the pass does too. */
 int bo_set_rescue(bo_ctx *ctx, int on, double tol, double floor_rel);
 /* what the last bo_score / bo_predict call did: int8_path = 1 if it ran the int8-slice
  * contraction, how many of its `total` candidates the rescue pass re-scored in FP64 */
 int bo_rescue_info(bo_ctx *ctx, int *int8_path, int64_t *flagged, int64_t *total);
+/* the tiers of the last int8 pass.  Levels are coded 2 * slices + extra_group: level_first = candidate chunk 0,
+ * level_rest = the other chunks, level_tier2 = the level the flagged list was re-scored at (0: straight to FP64);
+ * first_flagged = candidates the main pass flagged, fp64_rescored = those that ended on the FP64 path
+ * (= bo_rescue_info's `flagged`).  All zero after a pass on the FP64 path. */
+int bo_tier_info(bo_ctx *ctx, int *level_first, int *level_rest, int *level_tier2, int64_t *first_flagged,
+                 int64_t *fp64_rescored);
 /* tuning knobs that do not change results.  "oz_cluster": CTAs per thread-block cluster of the int8 scoring
  * contraction (1, 2 or 4; 0 = library default): the CTAs of a cluster work on the same candidate tile and adjacent row
- * blocks of W and fetch the K* slice tile once, by TMA multicast. */
+ * blocks of W and fetch the K* slice tile once, by TMA multicast.  "oz_tiered" (0 / 1, default 1), "oz_tier_frac"
+ * (default 0.10), "oz_tier_min" (default 4096): the tiers described at bo_set_rescue (results stay within the rescue
+ * tolerance either way; which tier certified a candidate changes its last digits). */
 int bo_set_option(bo_ctx *ctx, const char *key, double value);
 /* the a-priori error model behind the rescue pass, for the level currently selected: on the int8 path
  * |s2 - s2_exact| <= errk[s] * sqrt(q rho_s), q = rho_s - s2, for hyper-sample s (errk: S values) */

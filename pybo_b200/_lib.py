@@ -27,7 +27,7 @@ EXPORTS = [
     "bo_profile_enable", "bo_profile_reset", "bo_profile_count", "bo_profile_get",
     "bo_launch_count", "bo_microbench", "bo_ozaki_debug", "bo_append", "bo_fit_capacity", "bo_candidates_sobol",
     "bo_set_rescue", "bo_rescue_info", "bo_ozaki_error_bound", "bo_loglik_fit",
-    "bo_thompson_build", "bo_score_incumbent", "bo_incumbent_merge", "bo_thompson_incumbents", "bo_set_option",
+    "bo_thompson_build", "bo_score_incumbent", "bo_incumbent_merge", "bo_thompson_incumbents", "bo_set_option", "bo_tier_info",
 ]
 
 
@@ -76,6 +76,7 @@ def _declare(lib):
         "bo_candidates_sobol": (i, [vp, i, i, vp, vp, vp, i64, i64, vp, i]),
         "bo_set_rescue": (i, [vp, i, d, d]),
         "bo_rescue_info": (i, [vp, _ip, _lp, _lp]),
+        "bo_tier_info": (i, [vp, _ip, _ip, _ip, _lp, _lp]),
         "bo_ozaki_error_bound": (i, [vp, vp]),
         "bo_loglik_fit": (i, [vp, i, i, i, i, vp, vp, vp, vp, vp, vp, vp]),
         "bo_thompson_build": (i, [vp, i, i, vp, vp, d, d, d, i, i, i, vp, vp, vp, vp]),
@@ -370,6 +371,16 @@ class Context(object):
         path, flagged, total = C.c_int(), C.c_int64(), C.c_int64()
         self._check(self._lib.bo_rescue_info(self._h, C.byref(path), C.byref(flagged), C.byref(total)))
         return bool(path.value), flagged.value, total.value
+
+    def tier_info(self):
+        """Tiers of the last int8 pass (bo_tier_info): dict with the levels as (slices, extra_group) pairs --
+        `first` (candidate chunk 0), `rest` (the other chunks), `tier2` (re-score level of the flagged list, None if
+        it went straight to FP64) -- and the counts `first_flagged`, `fp64_rescored`."""
+        a, b, c = C.c_int(), C.c_int(), C.c_int()
+        ff, fr = C.c_int64(), C.c_int64()
+        self._check(self._lib.bo_tier_info(self._h, C.byref(a), C.byref(b), C.byref(c), C.byref(ff), C.byref(fr)))
+        lvl = lambda L: (L >> 1, bool(L & 1)) if L else None
+        return dict(first=lvl(a.value), rest=lvl(b.value), tier2=lvl(c.value), first_flagged=ff.value, fp64_rescored=fr.value)
 
     def set_precision(self, prec, tol=1e-9):
         self._check(self._lib.bo_set_precision(self._h, int(prec), float(tol)))

@@ -128,12 +128,13 @@ static void free_all(bo_ctx *ctx) {
                        &ctx->dS2S, &ctx->dDmuS, &ctx->dDs2S, &ctx->dGpart, &ctx->dXc, &ctx->dVal,
                        &ctx->dGradOut, &ctx->dBlkVal, &ctx->th.W, &ctx->th.b, &ctx->th.theta,
                        &ctx->th.scale, &ctx->th.bias, &ctx->th.dBestVal, &ctx->th.thetaT, &ctx->dOzQ, &ctx->dXsHalfSq, &ctx->dCholDinv, &ctx->dOzMu, &ctx->dAppend, &ctx->dSobol,
-                       &ctx->dMerged, &ctx->dPredict, &ctx->dLoglik, &ctx->dErrEst, &ctx->dErrK, &ctx->dRescue, &ctx->dLLK, &ctx->dLLSmall,
+                       &ctx->dMerged, &ctx->dPredict, &ctx->dLoglik, &ctx->dErrEst, &ctx->dErrK, &ctx->dRescue, &ctx->dErrEst2, &ctx->dRescue2, &ctx->dLLK, &ctx->dLLSmall,
                        &ctx->th.build};
     for (auto p : ptrs)
         if (*p) { cudaFree(*p); *p = nullptr; }
     if (ctx->dInfo) { cudaFree(ctx->dInfo); ctx->dInfo = nullptr; }
     if (ctx->dFlagList) { cudaFree(ctx->dFlagList); ctx->dFlagList = nullptr; }
+    if (ctx->dFlagList2) { cudaFree(ctx->dFlagList2); ctx->dFlagList2 = nullptr; }
     if (ctx->dIncumbent) { cudaFree(ctx->dIncumbent); ctx->dIncumbent = nullptr; }
     if (ctx->dFlagBits) { cudaFree(ctx->dFlagBits); ctx->dFlagBits = nullptr; }
     if (ctx->dAppendInfo) { cudaFree(ctx->dAppendInfo); ctx->dAppendInfo = nullptr; }
@@ -742,6 +743,20 @@ extern "C" int bo_set_option(bo_ctx *ctx, const char *key, double value) {
         ctx->oz_cluster = v;
         return BO_OK;
     }
+    if (strcmp(key, "oz_tiered") == 0) {
+        ctx->oz_tiered = value != 0.0;
+        return BO_OK;
+    }
+    if (strcmp(key, "oz_tier_frac") == 0) {
+        if (!(value >= 0.0 && value <= 1.0)) return bo_set_err(ctx, BO_ERR_ARG, "oz_tier_frac must lie in [0, 1]");
+        ctx->oz_tier_frac = value;
+        return BO_OK;
+    }
+    if (strcmp(key, "oz_tier_min") == 0) {
+        if (!(value >= 1.0)) return bo_set_err(ctx, BO_ERR_ARG, "oz_tier_min must be >= 1");
+        ctx->oz_tier_min = (int64_t)value;
+        return BO_OK;
+    }
     return bo_set_err(ctx, BO_ERR_ARG, "bo_set_option: unknown key '%s'", key);
 }
 
@@ -752,7 +767,7 @@ extern "C" int bo_ozaki_error_bound(bo_ctx *ctx, double *errk) {
     const int S = bo_ozaki_choose_slices(ctx, ctx->prec_tol);
     if (S < 1) return BO_ERR_CUDA;
     BO_TRY(bo_ozaki_prepare(ctx, S));
-    BO_TRY(bo_ozaki_error_scale(ctx, S));
+    BO_TRY(bo_ozaki_error_scale(ctx, S, ctx->oz_extra, 0));
     for (int s = 0; s < ctx->S; ++s) errk[s] = ctx->h_errk[s];
     return BO_OK;
 }
@@ -768,7 +783,19 @@ extern "C" int bo_rescue_info(bo_ctx *ctx, int *int8_path, int64_t *flagged, int
 extern "C" int bo_precision_info(bo_ctx *ctx, int *prec, int *slices) {
     if (!ctx) return BO_ERR_ARG;
     if (prec) *prec = ctx->prec;
-    if (slices) *slices = (ctx->prec == BO_PREC_OZAKI) ? ctx->oz_slices * 2 + (ctx->oz_extra ? 1 : 0) : 0;
+    // (the level most candidates of the last pass ran at; before the first pass, the level the tolerance selects)
+    if (slices) *slices = (ctx->prec == BO_PREC_OZAKI) ? (ctx->oz_last_rest ? ctx->oz_last_rest : ctx->oz_slices * 2 + (ctx->oz_extra ? 1 : 0)) : 0;
+    return BO_OK;
+}
+
+extern "C" int bo_tier_info(bo_ctx *ctx, int *level_first, int *level_rest, int *level_tier2, int64_t *first_flagged,
+                            int64_t *fp64_rescored) {
+    if (!ctx) return BO_ERR_ARG;
+    if (level_first) *level_first = ctx->oz_last_first;
+    if (level_rest) *level_rest = ctx->oz_last_rest;
+    if (level_tier2) *level_tier2 = ctx->oz_last_tier2;
+    if (first_flagged) *first_flagged = ctx->oz_last_first_flagged;
+    if (fp64_rescored) *fp64_rescored = ctx->oz_last_flagged;
     return BO_OK;
 }
 

@@ -52,6 +52,7 @@ struct bo_chol_graph {
 };
 
 #define BO_CHOL_MAX_LANES 8
+#define BO_OZ_ERRK_SLOTS 4
 
 struct bo_ctx {
     int device = 0;
@@ -170,10 +171,20 @@ struct bo_ctx {
     double oz_rescue_floor = 1e-12;
     double oz_demote_frac = 0.25;       // a pass that rescues more than this fraction sends later passes to FP64
     bool oz_demoted = false;
-    int64_t oz_last_total = 0, oz_last_flagged = 0;
+    int64_t oz_last_total = 0, oz_last_flagged = 0;      // flagged = candidates re-scored on the FP64 path
+    // tiers of the last int8 pass: levels are 2 S + extra; first = candidate chunk 0, rest = the other chunks,
+    // tier2 = the level the flagged candidates were re-scored at before FP64 (0: went straight to FP64)
+    int oz_last_first = 0, oz_last_rest = 0, oz_last_tier2 = 0;
+    int64_t oz_last_first_flagged = 0;
+    bool oz_tiered = true;              // main pass one half-level below the selected one when few candidates need more
+    double oz_tier_frac = 0.10;         // ... i.e. when at most this fraction of the first chunk is flagged there
+    int64_t oz_tier_min = 4096;         // flagged lists shorter than this go straight to FP64
     int oz_last_path = 0;               // 1: the last scoring pass ran the int8-slice contraction
     double *dErrEst = nullptr, *dErrK = nullptr, *dRescue = nullptr;
     int *dFlagList = nullptr;
+    double *dErrEst2 = nullptr, *dRescue2 = nullptr;      // second tier's own scratch (the first tier's stays live)
+    int *dFlagList2 = nullptr;
+    size_t errest2_capacity = 0, rescue2_capacity = 0, flaglist2_capacity = 0;
     unsigned long long *dFlagBits = nullptr;
     size_t errest_capacity = 0, errk_capacity = 0, rescue_capacity = 0, flaglist_capacity = 0, flagbits_capacity = 0;
     std::vector<double> h_errk;
@@ -273,10 +284,10 @@ int bo_thompson_build_init(bo_ctx *ctx);
 int bo_ozaki_prepare(bo_ctx *ctx, int S);
 int bo_ozaki_append_row(bo_ctx *ctx, int row);
 int bo_ozaki_choose_slices(bo_ctx *ctx, double tol);
-int bo_ozaki_error_scale(bo_ctx *ctx, int S);
+int bo_ozaki_error_scale(bo_ctx *ctx, int S, bool extra, int slot);
 int bo_ozaki_slice(bo_ctx *ctx, int s, int S, const double *dXc, int64_t c0, int mc, int mcp, int buf,
                    cudaStream_t stream);
-int bo_ozaki_contract(bo_ctx *ctx, int s, int S, int mcp, int buf, double *mu, double *s2, int32_t *dbg);
+int bo_ozaki_contract(bo_ctx *ctx, int s, int S, bool extra, int mcp, int buf, double *mu, double *s2, int32_t *dbg);
 int bo_ozaki_reserve(bo_ctx *ctx, int S, int mcp_max, int nbuf);
 bool bo_thompson_ozaki_usable(bo_ctx *ctx, int64_t M);
 int64_t bo_thompson_ozaki_blocks(int64_t M);

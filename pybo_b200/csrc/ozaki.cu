@@ -1025,7 +1025,7 @@ int bo_ozaki_init(bo_ctx *ctx) {
 // Build the slice planes of W for hyper-sample s (S slices) into ctx->dWs.
 int bo_ozaki_prepare(bo_ctx *ctx, int S) {
     const int np = ctx->np, ns = ctx->S;
-    if (ctx->oz_ready && ctx->oz_slices == S) return BO_OK;
+    if (ctx->oz_ready && ctx->oz_slices >= S) return BO_OK;       // digit planes are a prefix code: more is fine
     BO_TRY(bo_reserve(ctx, &ctx->dWs, &ctx->ws_capacity, (size_t)ns * S * np * np));
     BO_TRY(bo_reserve(ctx, &ctx->dRowScale, &ctx->rowscale_capacity, (size_t)ns * np));
     BO_TRY(bo_reserve(ctx, &ctx->dRowExp, &ctx->rowexp_capacity, (size_t)ns * np + ns));
@@ -1128,16 +1128,19 @@ int bo_ozaki_choose_slices(bo_ctx *ctx, double tol) {
 // x six levels x 73 k candidates incl. 8 k placed on top of observations): max |ds2| / (est sqrt(q rho)) = 0.85,
 // median 0.03 -- the factor 2 leaves > 2.3x on the worst case seen (profiles/r2_oz_calib.txt).
 #define OZ_ERR_SAFETY 2.0
-int bo_ozaki_error_scale(bo_ctx *ctx, int S) {
+int bo_ozaki_error_scale(bo_ctx *ctx, int S, bool extra, int slot) {
     const int ns = ctx->S;
     ctx->h_errk.assign(ns, 0.0);
     for (int s = 0; s < ns; ++s) {
         const double est = 8.0 * sqrt((double)ctx->np) * ldexp(1.0, ctx->h_emax[s]) * sqrt(ctx->h_rho[s]) * ldexp(1.0, -8 * S) /
-                           (ctx->oz_extra ? 32.0 : 1.0);
+                           (extra ? 32.0 : 1.0);
         ctx->h_errk[s] = OZ_ERR_SAFETY * est;
     }
-    BO_TRY(bo_reserve(ctx, &ctx->dErrK, &ctx->errk_capacity, (size_t)ns));
-    BO_CUDA(ctx, cudaMemcpyAsync(ctx->dErrK, ctx->h_errk.data(), sizeof(double) * ns, cudaMemcpyHostToDevice, ctx->stream));
+    // BO_OZ_ERRK_SLOTS scales per context: one per level a pass can mix (score.cu run_oz)
+    BO_TRY(bo_reserve(ctx, &ctx->dErrK, &ctx->errk_capacity, (size_t)ns * BO_OZ_ERRK_SLOTS));
+    // (pageable source: the copy is staged before the call returns, h_errk may be rewritten right away)
+    BO_CUDA(ctx, cudaMemcpyAsync(ctx->dErrK + (size_t)slot * ns, ctx->h_errk.data(), sizeof(double) * ns, cudaMemcpyHostToDevice,
+                                 ctx->stream));
     return BO_OK;
 }
 
@@ -1208,11 +1211,12 @@ int bo_ozaki_slice(bo_ctx *ctx, int s, int S, const double *dXc, int64_t c0, int
 }
 
 // mu_s, s2_s of the candidates sliced into buffer `buf`: the tcgen05 contraction + reductions.
-int bo_ozaki_contract(bo_ctx *ctx, int s, int S, int mcp, int buf, double *mu, double *s2, int32_t *dbg) {
+int bo_ozaki_contract(bo_ctx *ctx, int s, int S, bool extra, int mcp, int buf, double *mu, double *s2, int32_t *dbg) {
     const int np = ctx->np;
     const int8_t *Kss = ctx->dKss + (size_t)buf * ctx->kss_stride;
     CUtensorMap tmB;
-    BO_TRY(make_tmap(ctx, &tmB, ctx->dWs + (size_t)s * S * np * np, np, np, S, OZ_BN));
+    // (the planes were built for ctx->oz_slices >= S digits; a lower level reads the leading S of them)
+    BO_TRY(make_tmap(ctx, &tmB, ctx->dWs + (size_t)s * ctx->oz_slices * np * np, np, np, S, OZ_BN));
     const int nb = np / OZ_BN;
     {
         size_t need = (size_t)2 * nb * mcp;              // two partial sums per row block (one per half of the epilogue warps)
@@ -1221,7 +1225,6 @@ int bo_ozaki_contract(bo_ctx *ctx, int s, int S, int mcp, int buf, double *mu, d
     OzParams p = {};
     p.nrb = np / OZ_BN; p.nkb = np / OZ_BK; p.full_k = 0;
     p.S = S; p.nstages = oz_stage_count(S); p.ntiles = mcp / OZ_BM; p.mcp = mcp;
-    const bool extra = ctx->oz_extra;
     // exact int32 accumulation: up to S digit pairs per group, |digit| <= 128, k range <= np
     if ((int64_t)np * S >= (1 << 17))
         return bo_set_err(ctx, BO_ERR_ARG, "int8 path: n = %d with %d slices would overflow the int32 accumulators; use the FP64 path", np, S);
@@ -1618,7 +1621,7 @@ extern "C" int bo_ozaki_debug(bo_ctx *ctx, int S, int extra, int mc, const doubl
     BO_CUDA(ctx, cudaMemcpyAsync(dXc, Xc, sizeof(double) * mc * ctx->d, cudaMemcpyHostToDevice, ctx->stream));
     int rc = bo_ozaki_reserve(ctx, S, mcp, 1);
     if (rc == BO_OK) rc = bo_ozaki_slice(ctx, 0, S, dXc, 0, mc, mcp, 0, ctx->stream);
-    if (rc == BO_OK) rc = bo_ozaki_contract(ctx, 0, S, mcp, 0, dmu, dmu + mcp, acc ? dacc : nullptr);
+    if (rc == BO_OK) rc = bo_ozaki_contract(ctx, 0, S, ctx->oz_extra, mcp, 0, dmu, dmu + mcp, acc ? dacc : nullptr);
     cudaError_t e = cudaStreamSynchronize(ctx->stream);
     if (rc == BO_OK && e == cudaSuccess) {
         if (mu) cudaMemcpy(mu, dmu, sizeof(double) * mc, cudaMemcpyDeviceToHost);

@@ -891,39 +891,86 @@ static int run_fp64(bo_ctx *ctx, const ScoreRequest &rq) {
 
 // int8-slice path: slices -> tcgen05 contraction -> moments -> acquisition + error bound, chunk by chunk;
 // then the FP64 rescue of the candidates whose bound exceeds the tolerance.
-static int run_oz(bo_ctx *ctx, const ScoreRequest &rq, int oz_S) {
+// Precision levels of the int8-slice path are coded 2 S + extra (S slices per operand, `extra`: the digit pairs of
+// group g = S are accumulated too); one step up divides the error bound by 8 (extra on) or 32 (S + 1, extra off).
+static inline int lv_S(int L) { return L >> 1; }
+static inline bool lv_extra(int L) { return (L & 1) != 0; }
+
+#define OZ_TIER_MIN_CHUNKS 16
+
+struct OzLevels {
+    int first;      // level of candidate chunk 0
+    int rest;       // level of the other chunks; if first < rest the pass may lower it to `first` after chunk 0 (see run_oz)
+    int tier2;      // level the flagged candidates are re-scored at before the FP64 path takes what is left (0: none) ...
+    int sel;        // ... unless the whole pass ran below the level the tolerance selects: then that level is the next tier
+};
+
+static int64_t oz_chunk_candidates() {
+    static const int chunk_tiles = getenv("BO_OZ_CHUNK_TILES") ? atoi(getenv("BO_OZ_CHUNK_TILES")) : 256;
+    return (int64_t)(chunk_tiles > 0 ? chunk_tiles : 256) * 128;
+}
+
+// One pass of the int8-slice path over rq's candidates, then the repair of what it cannot certify:
+//   1. every chunk of 32 768 candidates: slice K*, contract on tcgen05, moments, acquisition + error bound
+//   2. flag the candidates whose bound exceeds the rescue tolerance, compact them (sorted)
+//   3. depth 0, long list, a higher level available: re-score the list on this same path at lv.tier2 (depth 1), which
+//      hands what it still cannot certify to the FP64 path; otherwise the FP64 path takes the list directly
+//   4. scatter back
+// Because every candidate that is not certified at 2.5e-7 is re-scored, the level of step 1 only decides the SPEED.
+// With lv.first < lv.rest (bo_score_run: one half-level below the level the tolerance selects) chunk 0 runs at the
+// lower level and its flagged fraction decides the level of the other chunks: <= oz_tier_frac -> they run at the
+// lower level too (2 of 15 digit-pair products saved at the headline shape), else at lv.rest.
+static int run_oz(bo_ctx *ctx, const ScoreRequest &rq, OzLevels lv, int depth, const double *gmax_outer, int64_t *fp64_count) {
     const int np = ctx->np, S = ctx->S, d = ctx->d;
     const int64_t M = rq.M;
-    static const int chunk_tiles = getenv("BO_OZ_CHUNK_TILES") ? atoi(getenv("BO_OZ_CHUNK_TILES")) : 256;
-    const int64_t chunk = (int64_t)(chunk_tiles > 0 ? chunk_tiles : 256) * 128;
+    const int64_t chunk = oz_chunk_candidates();
     const int64_t cap = bo_round_up64(M < chunk ? M : chunk, 128);
     BO_TRY(reserve_moments(ctx, np / 128, cap, S));
     // what the rescue pass looks at: mode 0 -> the acquisition value (not for the mean, which never goes through
     // the int8 contraction); mode 1 -> s2
     const bool rescue = ctx->oz_rescue && ((rq.mode == 0) ? (rq.acq != BO_ACQ_MEAN) : (rq.dS2 != nullptr));
-    const bool need_best = rq.want_best || (rescue && rq.mode == 0);
+    const bool own_max = rescue && rq.mode == 0 && !gmax_outer;       // the flag floor needs max |value|
+    const bool need_best = rq.want_best || own_max;
     if (rescue && M > (int64_t)0x7fffffff)
         return bo_set_err(ctx, BO_ERR_ARG, "int8 path: at most 2^31 - 1 candidates per call (the rescue list holds 32-bit indices)");
+    if (!rescue) lv.first = lv.rest;
     const int64_t nchunk = (M + chunk - 1) / chunk;
     const int64_t nblocks_total = nchunk * ((chunk + 255) / 256);
     if (need_best) BO_TRY(reserve_blocks(ctx, (size_t)(nblocks_total > ARGMAX_PASS_BLOCKS ? nblocks_total : ARGMAX_PASS_BLOCKS) + 8));
+    double **errest_p = depth ? &ctx->dErrEst2 : &ctx->dErrEst;
+    int **flag_p = depth ? &ctx->dFlagList2 : &ctx->dFlagList;
+    double **rescue_p = depth ? &ctx->dRescue2 : &ctx->dRescue;
+    const int slot_first = 2 * depth, slot_rest = 2 * depth + 1;
+    double floor_abs = 0.0;
     if (rescue) {
-        BO_TRY(bo_reserve(ctx, &ctx->dErrEst, &ctx->errest_capacity, (size_t)M));
-        BO_TRY(bo_reserve(ctx, &ctx->dFlagList, &ctx->flaglist_capacity, (size_t)M + 1));
-        BO_TRY(bo_ozaki_error_scale(ctx, oz_S));
+        BO_TRY(bo_reserve(ctx, errest_p, depth ? &ctx->errest2_capacity : &ctx->errest_capacity, (size_t)M));
+        BO_TRY(bo_reserve(ctx, flag_p, depth ? &ctx->flaglist2_capacity : &ctx->flaglist_capacity, (size_t)M + 1));
+        BO_TRY(bo_ozaki_error_scale(ctx, lv_S(lv.first), lv_extra(lv.first), slot_first));
+        BO_TRY(bo_ozaki_error_scale(ctx, lv_S(lv.rest), lv_extra(lv.rest), slot_rest));
+        if (rq.mode == 1) {                                // s2: floor 1e-9 * mean rho (the parity metric's floor)
+            for (int i = 0; i < S; ++i) floor_abs += ctx->h_rho[i];
+            floor_abs *= 1e-9 / S;
+        }
     }
+    double *errest = rescue ? *errest_p : nullptr;
+    int *flaglist = rescue ? *flag_p : nullptr;
+    int *count_dev = rescue ? flaglist + M : nullptr;
+    const double *xflag = rq.mode == 0 ? rq.dVal : rq.dS2;
+    const double floor_rel = rq.mode == 0 ? ctx->oz_rescue_floor : 0.0;
 
     // Software pipeline over work items (chunk, hyper-sample): the operand slicer of item w+1
     // runs on the low-priority side stream while the tcgen05 contraction of item w runs on
     // the main stream (different pipes: FP64/ALU vs tensor).  Two slice buffers.
     const int64_t nitems = nchunk * S;
-    BO_TRY(bo_ozaki_reserve(ctx, oz_S, (int)cap, nitems > 1 ? 2 : 1));
+    const int S_buf = lv_S(lv.first) > lv_S(lv.rest) ? lv_S(lv.first) : lv_S(lv.rest);
+    BO_TRY(bo_ozaki_reserve(ctx, S_buf, (int)cap, nitems > 1 ? 2 : 1));
     auto item = [&](int64_t w, int64_t &c0, int &mc, int &mcp, int &s) {
         c0 = (w / S) * chunk;
         s = (int)(w % S);
         mc = (int)((M - c0) < chunk ? (M - c0) : chunk);
         mcp = bo_round_up(mc, 128);
     };
+    auto level_of = [&](int64_t w) { return (w / S) == 0 ? lv.first : lv.rest; };
     int64_t c0; int mc, mcp, s;
     // Overlap is opt-in (BO_OZ_OVERLAP=1): on a power-capped B200 the two kernels only slow each
     // other down (measured: contraction 2.77 -> 3.56 ms per chunk), so by default both stages
@@ -934,23 +981,17 @@ static int run_oz(bo_ctx *ctx, const ScoreRequest &rq, int oz_S) {
     BO_CUDA(ctx, cudaEventRecord(ctx->ev_consumed[0], ctx->stream));
     BO_CUDA(ctx, cudaStreamWaitEvent(side, ctx->ev_consumed[0], 0));
     item(0, c0, mc, mcp, s);
-    BO_TRY(bo_ozaki_slice(ctx, s, oz_S, rq.dXc, c0, mc, mcp, 0, side));
+    BO_TRY(bo_ozaki_slice(ctx, s, lv_S(lv.first), rq.dXc, c0, mc, mcp, 0, side));
     BO_CUDA(ctx, cudaEventRecord(ctx->ev_sliced[0], side));
     int64_t blk0 = 0;
+    int64_t pilot_count = -1;
     for (int64_t w = 0; w < nitems; ++w) {
         const int buf = (int)(w & 1);
+        const int L = level_of(w);
         item(w, c0, mc, mcp, s);
         BO_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_sliced[buf], 0));
-        BO_TRY(bo_ozaki_contract(ctx, s, oz_S, mcp, buf, ctx->dMuS + (int64_t)s * mcp, ctx->dS2S + (int64_t)s * mcp, nullptr));
+        BO_TRY(bo_ozaki_contract(ctx, s, lv_S(L), lv_extra(L), mcp, buf, ctx->dMuS + (int64_t)s * mcp, ctx->dS2S + (int64_t)s * mcp, nullptr));
         BO_CUDA(ctx, cudaEventRecord(ctx->ev_consumed[buf], ctx->stream));
-        if (w + 1 < nitems) {
-            int64_t c1; int mc1, mcp1, s1;
-            item(w + 1, c1, mc1, mcp1, s1);
-            const int nbuf = (int)((w + 1) & 1);
-            if (w >= 1) BO_CUDA(ctx, cudaStreamWaitEvent(side, ctx->ev_consumed[nbuf], 0));
-            BO_TRY(bo_ozaki_slice(ctx, s1, oz_S, rq.dXc, c1, mc1, mcp1, nbuf, side));
-            BO_CUDA(ctx, cudaEventRecord(ctx->ev_sliced[nbuf], side));
-        }
         if (s == S - 1) {
             AcqParams ap = {};
             ap.mode = rq.mode; ap.acq = rq.acq; ap.param = rq.param;
@@ -961,7 +1002,11 @@ static int run_oz(bo_ctx *ctx, const ScoreRequest &rq, int oz_S) {
             ap.blkval = need_best ? ctx->dBlkVal : nullptr;
             ap.blkidx = need_best ? ctx->dBlkIdx : nullptr;
             ap.blk0 = blk0;
-            if (rescue) { ap.rhoS = ctx->dRho; ap.errK = ctx->dErrK; ap.errest = ctx->dErrEst; }
+            if (rescue) {
+                ap.rhoS = ctx->dRho;
+                ap.errK = ctx->dErrK + (size_t)((w / S) == 0 ? slot_first : slot_rest) * S;
+                ap.errest = errest;
+            }
             const int nb = (mc + 255) / 256;
             {
                 BO_LAUNCH(ctx, "acq_kernel");
@@ -969,6 +1014,47 @@ static int run_oz(bo_ctx *ctx, const ScoreRequest &rq, int oz_S) {
                 BO_CHECK_LAUNCH(ctx);
             }
             blk0 += nb;
+            if (w / S == 0 && lv.first < lv.rest) {
+                // pilot: how much of chunk 0 does the lower level leave to the tiers above it?  (floor from the
+                // chunk's own maximum, never above the global one: the estimate errs towards the higher level)
+                if (nchunk < OZ_TIER_MIN_CHUNKS) {
+                    pilot_count = mc;       // short passes: a failed pilot costs too much (bo_score_run does not ask for it)
+                } else {
+                    double *pmax = nullptr;
+                    if (rq.mode == 0) {
+                        pmax = gmax_outer ? const_cast<double *>(gmax_outer) : ctx->dBlkVal + ctx->blk_capacity - 2;
+                        if (!gmax_outer) {
+                            BO_LAUNCH(ctx, "argmax_final_kernel");
+                            argmax_final_kernel<<<1, 1024, 0, ctx->stream>>>(ctx->dBlkVal, ctx->dBlkIdx, blk0, pmax,
+                                                                            ctx->dBlkIdx + ctx->blk_capacity - 2, nullptr, 0);
+                            BO_CHECK_LAUNCH(ctx);
+                        }
+                    }
+                    BO_CUDA(ctx, cudaMemsetAsync(count_dev, 0, sizeof(int), ctx->stream));
+                    {
+                        BO_LAUNCH(ctx, "oz_flag_kernel");
+                        oz_flag_kernel<<<(mc + 255) / 256, 256, 0, ctx->stream>>>(mc, xflag, errest, ctx->oz_rescue_tol, floor_abs, floor_rel,
+                                                                                 pmax, flaglist, count_dev);
+                        BO_CHECK_LAUNCH(ctx);
+                    }
+                    int cnt = 0;
+                    BO_CUDA(ctx, cudaMemcpyAsync(&cnt, count_dev, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+                    BO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+                    pilot_count = cnt;
+                }
+                if ((double)pilot_count <= ctx->oz_tier_frac * (double)mc) {
+                    lv.rest = lv.first;
+                    BO_TRY(bo_ozaki_error_scale(ctx, lv_S(lv.rest), lv_extra(lv.rest), slot_rest));   // bound of the level that runs
+                }
+            }
+        }
+        if (w + 1 < nitems) {
+            int64_t c1; int mc1, mcp1, s1;
+            item(w + 1, c1, mc1, mcp1, s1);
+            const int nbuf = (int)((w + 1) & 1);
+            if (w >= 1) BO_CUDA(ctx, cudaStreamWaitEvent(side, ctx->ev_consumed[nbuf], 0));
+            BO_TRY(bo_ozaki_slice(ctx, s1, lv_S(level_of(w + 1)), rq.dXc, c1, mc1, mcp1, nbuf, side));
+            BO_CUDA(ctx, cudaEventRecord(ctx->ev_sliced[nbuf], side));
         }
     }
     double *gmax = ctx->dBlkVal ? ctx->dBlkVal + ctx->blk_capacity - 1 : nullptr;
@@ -978,36 +1064,35 @@ static int run_oz(bo_ctx *ctx, const ScoreRequest &rq, int oz_S) {
                                                         ctx->dBlkIdx + ctx->blk_capacity - 1, ctx->rec_ptr, ctx->rec_offset);
         BO_CHECK_LAUNCH(ctx);
     }
-    ctx->oz_last_total = M;
-    ctx->oz_last_flagged = 0;
+    if (gmax_outer) gmax = const_cast<double *>(gmax_outer);
+    if (fp64_count) *fp64_count = 0;
+    if (depth == 0) {
+        ctx->oz_last_total = M;
+        ctx->oz_last_flagged = 0;
+        ctx->oz_last_first = lv.first; ctx->oz_last_rest = lv.rest; ctx->oz_last_tier2 = 0;
+        ctx->oz_last_first_flagged = 0;
+    }
     if (!rescue) return BO_OK;
 
-    // ---- rescue: flag, compact (sorted), re-score in FP64, scatter ----
-    int *count_dev = ctx->dFlagList + M;
+    // ---- rescue: flag, compact (sorted), re-score (higher level, then FP64), scatter ----
     BO_CUDA(ctx, cudaMemsetAsync(count_dev, 0, sizeof(int), ctx->stream));
     {
-        double floor_abs = 0.0;
-        if (rq.mode == 1) {                                // s2: floor 1e-9 * mean rho (the parity metric's floor)
-            for (int i = 0; i < S; ++i) floor_abs += ctx->h_rho[i];
-            floor_abs *= 1e-9 / S;
-        }
         BO_LAUNCH(ctx, "oz_flag_kernel");
         const int nb = (int)((M + 255) / 256 < 1184 ? (M + 255) / 256 : 1184);
-        oz_flag_kernel<<<nb, 256, 0, ctx->stream>>>(M, rq.mode == 0 ? rq.dVal : rq.dS2, ctx->dErrEst, ctx->oz_rescue_tol,
-                                                    floor_abs, rq.mode == 0 ? ctx->oz_rescue_floor : 0.0,
-                                                    rq.mode == 0 ? gmax : nullptr, ctx->dFlagList, count_dev);
+        oz_flag_kernel<<<nb, 256, 0, ctx->stream>>>(M, xflag, errest, ctx->oz_rescue_tol, floor_abs, floor_rel,
+                                                    rq.mode == 0 ? gmax : nullptr, flaglist, count_dev);
         BO_CHECK_LAUNCH(ctx);
     }
     int count = 0;
     BO_CUDA(ctx, cudaMemcpyAsync(&count, count_dev, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     BO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    ctx->oz_last_flagged = count;
+    if (depth == 0) ctx->oz_last_first_flagged = count;
     if (count == 0) return BO_OK;
     if (count <= 8192) {
         int np2 = 1;
         while (np2 < count) np2 <<= 1;
         BO_LAUNCH(ctx, "oz_sort_small_kernel");
-        oz_sort_small_kernel<<<1, 1024, np2 * sizeof(int), ctx->stream>>>(ctx->dFlagList, count);
+        oz_sort_small_kernel<<<1, 1024, np2 * sizeof(int), ctx->stream>>>(flaglist, count);
         BO_CHECK_LAUNCH(ctx);
     } else {
         const int nwords = (int)((M + 63) / 64), nwb = (nwords + 1023) / 1024;
@@ -1015,17 +1100,17 @@ static int run_oz(bo_ctx *ctx, const ScoreRequest &rq, int oz_S) {
         int *blocksum = reinterpret_cast<int *>(ctx->dFlagBits + nwords);
         BO_CUDA(ctx, cudaMemsetAsync(ctx->dFlagBits, 0, sizeof(unsigned long long) * nwords, ctx->stream));
         ctx->launches += 3;
-        oz_mark_kernel<<<(count + 255) / 256, 256, 0, ctx->stream>>>(ctx->dFlagList, count, ctx->dFlagBits);
+        oz_mark_kernel<<<(count + 255) / 256, 256, 0, ctx->stream>>>(flaglist, count, ctx->dFlagBits);
         oz_wordcount_kernel<<<nwb, 1024, 0, ctx->stream>>>(ctx->dFlagBits, nwords, blocksum);
-        oz_compact_kernel<<<nwb, 1024, 0, ctx->stream>>>(ctx->dFlagBits, nwords, blocksum, ctx->dFlagList);
+        oz_compact_kernel<<<nwb, 1024, 0, ctx->stream>>>(ctx->dFlagBits, nwords, blocksum, flaglist);
         BO_CHECK_LAUNCH(ctx);
     }
     const size_t per = (size_t)d + 2;
-    BO_TRY(bo_reserve(ctx, &ctx->dRescue, &ctx->rescue_capacity, (size_t)count * per));
-    double *xr = ctx->dRescue, *ra = xr + (size_t)count * d, *rb = ra + count;
+    BO_TRY(bo_reserve(ctx, rescue_p, depth ? &ctx->rescue2_capacity : &ctx->rescue_capacity, (size_t)count * per));
+    double *xr = *rescue_p, *ra = xr + (size_t)count * d, *rb = ra + count;
     {
         BO_LAUNCH(ctx, "oz_gather_rows_kernel");
-        oz_gather_rows_kernel<<<(int)(((int64_t)count * d + 255) / 256), 256, 0, ctx->stream>>>(rq.dXc, d, ctx->dFlagList, count, xr);
+        oz_gather_rows_kernel<<<(int)(((int64_t)count * d + 255) / 256), 256, 0, ctx->stream>>>(rq.dXc, d, flaglist, count, xr);
         BO_CHECK_LAUNCH(ctx);
     }
     ScoreRequest r2;
@@ -1033,19 +1118,41 @@ static int run_oz(bo_ctx *ctx, const ScoreRequest &rq, int oz_S) {
     if (rq.mode == 0) r2.dVal = ra;
     else { r2.dMu = ra; r2.dS2 = rb; }
     r2.want_best = false;
-    BO_TRY(run_fp64(ctx, r2));
+    int64_t to_fp64 = count;
+    const int top = lv.first > lv.rest ? lv.first : lv.rest;
+    const int next = (lv.tier2 > 0 && top < lv.sel) ? lv.sel : lv.tier2;
+    if (depth == 0 && next > top && count >= ctx->oz_tier_min) {
+        OzLevels l2 = {next, next, 0, next};
+        BO_TRY(run_oz(ctx, r2, l2, 1, rq.mode == 0 ? gmax : nullptr, &to_fp64));
+        ctx->oz_last_tier2 = next;
+    } else {
+        BO_TRY(run_fp64(ctx, r2));
+    }
+    if (fp64_count) *fp64_count = to_fp64;
     {
         BO_LAUNCH(ctx, "oz_scatter_kernel");
         if (rq.mode == 0)
-            oz_scatter_kernel<<<(count + 255) / 256, 256, 0, ctx->stream>>>(ctx->dFlagList, count, ra, rq.dVal, nullptr, nullptr);
+            oz_scatter_kernel<<<(count + 255) / 256, 256, 0, ctx->stream>>>(flaglist, count, ra, rq.dVal, nullptr, nullptr);
         else
-            oz_scatter_kernel<<<(count + 255) / 256, 256, 0, ctx->stream>>>(ctx->dFlagList, count, ra, rq.dMu, rb, rq.dS2);
+            oz_scatter_kernel<<<(count + 255) / 256, 256, 0, ctx->stream>>>(flaglist, count, ra, rq.dMu, rb, rq.dS2);
         BO_CHECK_LAUNCH(ctx);
     }
+    if (depth != 0) return BO_OK;
+    ctx->oz_last_flagged = to_fp64;
     if (rq.want_best) BO_TRY(final_argmax_over(ctx, rq.dVal, M));
-    // a fit where the int8 path hands most of its work to the rescue (posterior variance collapsed over the
-    // whole candidate set, e.g. n = 1024 in d = 4) is an FP64 problem: later passes go there directly
-    if (M >= 4096 && (double)count > ctx->oz_demote_frac * (double)M) ctx->oz_demoted = true;
+    // a fit where the int8 path hands most of its work on (posterior variance collapsed over the whole candidate
+    // set, e.g. n = 1024 in d = 4) is an FP64 problem: later passes go there directly.  Judged on what the selected
+    // level (lv.rest, or everything when the pass ran at one level) left over.
+    {
+        double frac;
+        if (pilot_count >= 0 && lv.rest != lv.first && M > chunk)
+            frac = (double)(count - (pilot_count < count ? pilot_count : count)) / (double)(M - chunk);
+        else if (pilot_count >= 0 && lv.rest == lv.first && lv.tier2 > 0)
+            frac = (double)to_fp64 / (double)M;         // whole pass below the selected level: judge by what reached FP64
+        else
+            frac = (double)count / (double)M;
+        if (M >= 4096 && frac > ctx->oz_demote_frac) ctx->oz_demoted = true;
+    }
     return BO_OK;
 }
 
@@ -1060,12 +1167,24 @@ int bo_score_run(bo_ctx *ctx, const ScoreRequest &rq) {
     if (!oz) {
         ctx->oz_last_total = rq.M;
         ctx->oz_last_flagged = 0;
+        ctx->oz_last_first = ctx->oz_last_rest = ctx->oz_last_tier2 = 0;
+        ctx->oz_last_first_flagged = 0;
         return run_fp64(ctx, rq);
     }
     const int oz_S = bo_ozaki_choose_slices(ctx, ctx->prec_tol);
     if (oz_S < 1) return BO_ERR_CUDA;
-    BO_TRY(bo_ozaki_prepare(ctx, oz_S));
-    return run_oz(ctx, rq, oz_S);
+    const int L_sel = 2 * oz_S + (ctx->oz_extra ? 1 : 0);
+    OzLevels lv = {L_sel, L_sel, 0, L_sel};
+    // a pinned level (tol >= 2: tests, calibration) runs exactly as pinned: one level, flagged candidates to FP64
+    const bool pinned = ctx->prec_tol >= 2.0;
+    if (!pinned && ctx->oz_rescue && ctx->oz_tiered) {
+        const int L2 = L_sel + 1;                                   // one step up for the flagged list
+        if (lv_S(L2) <= 7 && (int64_t)ctx->np * lv_S(L2) < (1 << 17)) lv.tier2 = L2;
+        // (a pilot that fails has its whole chunk re-scored one level up: bounded at ~1/16 of the pass)
+        if (L_sel - 1 >= 6 && rq.M >= OZ_TIER_MIN_CHUNKS * oz_chunk_candidates() && lv.tier2 > 0) lv.first = L_sel - 1;
+    }
+    BO_TRY(bo_ozaki_prepare(ctx, lv.tier2 > 0 ? lv_S(lv.tier2) : oz_S));
+    return run_oz(ctx, rq, lv, 0, nullptr, nullptr);
 }
 
 

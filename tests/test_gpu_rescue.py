@@ -148,6 +148,57 @@ def test_rescue_pass_reports_and_repairs(ctx):
     assert rel_err(mu_d, gp.predict(X)[0], 1e-9) < TOL
 
 
+def test_tiered_levels_headline_shape_vs_fp64_and_oracle(ctx):
+    """Passes of >= 16 chunks run their first chunk one half-level below the level the tolerance selects and, if at
+    most 10 % of it is flagged there, the rest too; the flagged list is re-scored on the int8 path at the selected
+    level before FP64 takes what is left.  Every combination of tiers must meet the same 1e-6 against the FP64 path
+    (and the oracle on a slice) with identical arg max and top-10: the tiers only decide the speed."""
+    rng, X, y, rho, bias = problem(4096, 8, seed=0)
+    gp = GPOracle(1e-6, rho, 0.25 * np.ones(8), bias, "se")
+    gp.add_data(X, y)
+    ctx.fit("se", X, y, 0.25 * np.ones((1, 8)), [rho], [1e-6], [bias])
+    Xc = qmc.Sobol(d=8, scramble=False).random_base2(19)
+    target = float(gp.predict(X)[0].max())
+    ctx.set_precision(0, 1e-8)
+    ref, _, rbest = ctx.score(1, target, Xc, want_best=True)
+    rtop = ctx.topk(10)[0]
+    sl = slice(40000, 40400)
+    oref = gp.get_improvement(target, Xc[sl])
+    ctx.set_precision(1, 1e-8)
+    seen = {}
+    for label, opts in (("untiered", dict(oz_tiered=0)),
+                        ("tiered", dict(oz_tiered=1, oz_tier_frac=0.10, oz_tier_min=4096)),
+                        ("pilot fails", dict(oz_tiered=1, oz_tier_frac=0.0, oz_tier_min=4096)),
+                        ("straight to fp64", dict(oz_tiered=1, oz_tier_frac=0.10, oz_tier_min=1 << 30)),
+                        ("tier 2 on short lists", dict(oz_tiered=1, oz_tier_frac=0.0, oz_tier_min=1))):
+        for k, v in opts.items():
+            ctx.set_option(k, v)
+        ctx.set_rescue(True)                            # re-arm (a pass that hands > 25 % to FP64 demotes the fit)
+        val, _, best = ctx.score(1, target, Xc, want_best=True)
+        t = ctx.tier_info()
+        seen[label] = t
+        assert ctx.rescue_info()[0], label
+        assert rel_err(val, ref) < 2.5e-7, (label, t)
+        assert rel_err(val[sl], oref) < TOL, (label, t)
+        assert best[1] == rbest[1] and np.array_equal(ctx.topk(10)[0], rtop), (label, t)
+    for k, v in dict(oz_tiered=1, oz_tier_frac=0.10, oz_tier_min=4096).items():
+        ctx.set_option(k, v)
+    assert seen["untiered"]["first"] == seen["untiered"]["rest"] == (5, False) and seen["untiered"]["tier2"] is None
+    assert seen["tiered"]["first"] == (4, True) and seen["tiered"]["rest"] == (4, True), seen["tiered"]
+    assert seen["tiered"]["tier2"] == (5, False) and seen["tiered"]["fp64_rescored"] < seen["tiered"]["first_flagged"]
+    assert seen["pilot fails"]["first"] == (4, True) and seen["pilot fails"]["rest"] == (5, False)
+    assert seen["straight to fp64"]["tier2"] is None
+    assert seen["straight to fp64"]["fp64_rescored"] == seen["straight to fp64"]["first_flagged"] > 0
+    assert seen["tier 2 on short lists"]["tier2"] == (5, True)
+    # predict (s2 is what the tiers look at) on the same candidates
+    mu, s2 = ctx.predict(Xc)
+    assert ctx.tier_info()["first"] == (4, True)
+    ctx.set_precision(0, 1e-8)
+    rmu, rs2 = ctx.predict(Xc)
+    assert rel_err(mu, rmu, 1e-9) < TOL
+    assert np.max(np.abs(s2 - rs2) / np.maximum(np.abs(rs2), 1e-9 * rho)) < TOL
+
+
 def test_refit_with_other_shapes_keeps_scratch_valid(ctx):
     """Round-1 review: gradient scratch was guarded by one capacity (np * cap).  Refit the same handle with other
     n, S and d and take gradients at batch sizes that make each buffer grow independently."""
