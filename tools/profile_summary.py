@@ -53,7 +53,7 @@ for kern in kerns:
         raw = subprocess.run(['ncu', '-i', 'gpurun_out/prof_%s.ncu-rep' % kern, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
     rr = list(csv.reader(raw.splitlines()))
     h, u, v = rr[0], rr[1], rr[2]
-    lines = ["# ncu --set full --clock-control none -k regex:%s, first captured launch (bench.py --candidates 65536)" % kern, ""]
+    lines = ["# ncu --set full --clock-control none -k regex:%s, first captured launch after the skip (short bench.py --quick run)" % kern, ""]
     for k in want:
         if k in h:
             i = h.index(k); lines.append("%s = %s %s" % (k, v[i], u[i]))
