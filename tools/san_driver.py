@@ -2,6 +2,7 @@
 fit (Gram, Cholesky step kernel with its inter-CTA flags, trtri), FP64 scoring + gradients, the int8-slice
 tcgen05/TMA/TMEM path, top-k, device Sobol grid, incremental append, batched stand-alone Cholesky, Thompson on
 both paths.  Shapes are small: the sanitizer slows kernels 10-100x."""
+import os
 import sys
 
 import numpy as np
@@ -42,6 +43,22 @@ ctx.set_rescue(True, 1e-12, 1e-12)
 ctx.score(2, target, Xbig, want_best=True)
 print("rescue (everything flagged)", ctx.rescue_info())
 ctx.set_rescue(True)
+# tiers of the int8 path (sanitize.sh shrinks the chunks with BO_OZ_CHUNK_TILES so that 2^14 candidates are >= 16 chunks):
+# pilot passes -> whole pass one half-level down; pilot fails -> mixed levels; flagged list one tier up, then FP64
+ctx.set_precision(1, 1e-8)
+ctx.set_option("oz_tier_min", 1)
+for frac in (1.0, 0.0):
+    ctx.set_option("oz_tier_frac", frac)
+    ctx.set_rescue(True)
+    vt, _, bt = ctx.score(1, target, Xbig, want_best=True)
+    print("tiers", ctx.tier_info(), bt)
+    mt, st = ctx.predict(Xbig)
+    print("tiers (predict)", ctx.tier_info())
+ctx.set_option("oz_tier_frac", 0.1)
+ctx.set_option("oz_tier_min", 4096)
+if os.environ.get("SAN_ONLY") == "tiers":
+    print("ok (tiers only)")
+    sys.exit(0)
 ctx.set_precision(0)
 rec = ctx.score_incumbent(1, target, len(Xc), Xc, offset=5, flags=0)
 print("incumbent", ctx.incumbent_merge(rec, 1, 1))
