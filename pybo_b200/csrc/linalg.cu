@@ -756,6 +756,20 @@ static int chol_enqueue_lane(bo_ctx *ctx, const chol_lane &ln, bool split, int n
     return BO_OK;
 }
 
+// extra stream pairs + events of the batched factorisation (created once, outside any stream capture)
+static int chol_lanes_init(bo_ctx *ctx) {
+    if (ctx->chol_lane_fork) return BO_OK;
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    for (int l = 0; l < BO_CHOL_MAX_LANES - 1; ++l) {
+        BO_CUDA(ctx, cudaStreamCreateWithPriority(&ctx->chol_lane_main[l], cudaStreamNonBlocking, hi));
+        BO_CUDA(ctx, cudaStreamCreateWithPriority(&ctx->chol_lane_side[l], cudaStreamNonBlocking, lo));
+        for (int i = 0; i < 5; ++i) BO_CUDA(ctx, cudaEventCreateWithFlags(&ctx->chol_lane_ev[l][i], cudaEventDisableTiming));
+    }
+    BO_CUDA(ctx, cudaEventCreateWithFlags(&ctx->chol_lane_fork, cudaEventDisableTiming));
+    return BO_OK;
+}
+
 // Many matrices at once are factored as independent sub-batches on their own stream pairs: a sub-batch that sits in
 // its diagonal-block step (one CTA per matrix) leaves the SMs to the others' trailing updates.
 static int chol_enqueue(bo_ctx *ctx, int np, int batch, double *A, double *dinv, int *dInfo) {
@@ -769,16 +783,7 @@ static int chol_enqueue(bo_ctx *ctx, int np, int batch, double *A, double *dinv,
     static const int max_lanes = getenv("BO_CHOL_LANES") ? std::min(BO_CHOL_MAX_LANES, std::max(1, atoi(getenv("BO_CHOL_LANES")))) : 2;
     const int lanes = split ? std::min(max_lanes, batch / 2) : 1;
     if (lanes <= 1) return chol_enqueue_lane(ctx, l0, split, np, batch, A, dinv, dInfo, ctx->dCholFlags);
-    if (!ctx->chol_lane_fork) {
-        int lo = 0, hi = 0;
-        cudaDeviceGetStreamPriorityRange(&lo, &hi);
-        for (int l = 0; l < BO_CHOL_MAX_LANES - 1; ++l) {
-            BO_CUDA(ctx, cudaStreamCreateWithPriority(&ctx->chol_lane_main[l], cudaStreamNonBlocking, hi));
-            BO_CUDA(ctx, cudaStreamCreateWithPriority(&ctx->chol_lane_side[l], cudaStreamNonBlocking, lo));
-            for (int i = 0; i < 5; ++i) BO_CUDA(ctx, cudaEventCreateWithFlags(&ctx->chol_lane_ev[l][i], cudaEventDisableTiming));
-        }
-        BO_CUDA(ctx, cudaEventCreateWithFlags(&ctx->chol_lane_fork, cudaEventDisableTiming));
-    }
+    BO_TRY(chol_lanes_init(ctx));
     BO_CUDA(ctx, cudaEventRecord(ctx->chol_lane_fork, ctx->stream));                         // fork
     int b0 = 0;
     for (int l = 0; l < lanes; ++l) {
@@ -860,6 +865,7 @@ int bo_linalg_cholesky(bo_ctx *ctx, int np, int batch, double *A, double *dinv, 
         }
     }
     const int64_t l0 = ctx->launches;
+    BO_TRY(chol_lanes_init(ctx));
     BO_CUDA(ctx, cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
     const int rc = chol_enqueue(ctx, np, batch, A, dinv, dInfo);
     cudaGraph_t graph = nullptr;
