@@ -943,7 +943,8 @@ def main():
                     help="scoring contraction: error-bounded int8 slices on tcgen05 (default) or FP64 DMMA")
     ap.add_argument("--tol", type=float, default=1e-8,
                     help="ozaki: target abs error of V entries / sqrt(rho) (>= 2 pins the level, e.g. 5 or 5.5). "
-                         "Default 1e-8 -> 5 base-256 slices (15 digit pairs) at the headline shape")
+                         "Default 1e-8 selects 5 base-256 slices (15 digit pairs) at the headline shape; the tiers then run the main "
+                         "pass at 4 slices + extra (13 pairs) and re-score what it flags at 5")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 0)
     if args.impl == "reference":
