@@ -938,7 +938,7 @@ def main():
     ap.add_argument("--candidates", type=int, default=0, help="override candidates per GPU (profiling only)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--config-steps", type=int, default=3, help="timed steps of each other BASELINE config in `configs`")
-    ap.add_argument("--quick", action="store_true", help="headline numbers only (no configs / fp64 / faster-level legs)")
+    ap.add_argument("--quick", action="store_true", help="headline numbers only (no configs / fp64 / untiered legs)")
     ap.add_argument("--precision", default="ozaki", choices=["ozaki", "fp64"],
                     help="scoring contraction: error-bounded int8 slices on tcgen05 (default) or FP64 DMMA")
     ap.add_argument("--tol", type=float, default=1e-8,
