@@ -1121,7 +1121,9 @@ static int run_oz(bo_ctx *ctx, const ScoreRequest &rq, OzLevels lv, int depth, c
     int64_t to_fp64 = count;
     const int top = lv.first > lv.rest ? lv.first : lv.rest;
     const int next = (lv.tier2 > 0 && top < lv.sel) ? lv.sel : lv.tier2;
-    if (depth == 0 && next > top && count >= ctx->oz_tier_min) {
+    // (a list longer than the demotion threshold is a fit whose variance has collapsed over the candidate set: one more
+    //  digit rarely certifies it, it goes to FP64 directly and the fit is demoted below)
+    if (depth == 0 && next > top && count >= ctx->oz_tier_min && (double)count <= ctx->oz_demote_frac * (double)M) {
         OzLevels l2 = {next, next, 0, next};
         BO_TRY(run_oz(ctx, r2, l2, 1, rq.mode == 0 ? gmax : nullptr, &to_fp64));
         ctx->oz_last_tier2 = next;
