@@ -502,10 +502,10 @@ def our_arm(args):
         # algorithmic: n^2 (forward-substitution equivalent) + 4n (reductions) flop per candidate
         alg_flop_per_launch = (n * n + 4 * n) * (M * S * args.steps) / max(1, gk["launches"])
         # executed int8 products: the main pass at its level(s) plus the flagged list re-scored one tier up
-        chunk = 32768
+        first_len = 4096 if "first_chunk" in level else 0          # the pilot chunk of a tiered pass that kept the selected level
         first_pairs = level.get("first_chunk", {}).get("digit_pairs", pairs)
         t2 = level.get("flagged_rescored_at")
-        pair_cands = pairs * max(0, M - chunk) + first_pairs * min(M, chunk) + (t2["digit_pairs"] * level["flagged_by_main_pass"] if t2 else 0)
+        pair_cands = pairs * max(0, M - first_len) + first_pairs * min(M, first_len) + (t2["digit_pairs"] * level["flagged_by_main_pass"] if t2 else 0)
         exec_ops_per_launch = 2.0 * 64 * 64 * nb * (nb + 1) / 2 * (pair_cands * S * args.steps) / max(1, gk["launches"])
         avg_ms = gk["total_ms"] / max(1, gk["launches"])
         achieved = alg_flop_per_launch / (avg_ms * 1e-3) / 1e12 if avg_ms > 0 else 0.0

@@ -147,8 +147,8 @@ int bo_set_precision(bo_ctx *ctx, int prec, double tol);
  * Tiers (tolerance-selected levels only; a level pinned with tol >= 2 runs exactly as pinned): a flagged list of
  * >= 4096 candidates is first re-scored on the int8 path one level up and only what that cannot certify goes to FP64.
  * Since whatever is not certified is re-scored, the level of the main pass only decides the speed: on passes of
- * >= 4 chunks of 32 768 candidates the first chunk runs one half-level below the selected level, and if at most
- * 10 % of it is flagged there the rest of the pass does too. */
+ * >= 8 chunks of 32 768 candidates the first 4096 candidates run one half-level below the selected level, and if at
+ * most 10 % of them are flagged there the rest of the pass does too. */
 int bo_set_rescue(bo_ctx *ctx, int on, double tol, double floor_rel);
 /* what the last bo_score / bo_predict call did: int8_path = 1 if it ran the int8-slice
  * contraction, how many of its `total` candidates the rescue pass re-scored in FP64 */

@@ -896,7 +896,8 @@ static int run_fp64(bo_ctx *ctx, const ScoreRequest &rq) {
 static inline int lv_S(int L) { return L >> 1; }
 static inline bool lv_extra(int L) { return (L & 1) != 0; }
 
-#define OZ_TIER_MIN_CHUNKS 16
+#define OZ_TIER_MIN_CHUNKS 8
+#define OZ_PILOT_CANDIDATES 4096     // length of the pilot chunk of a tiered pass
 
 struct OzLevels {
     int first;      // level of candidate chunk 0
@@ -934,7 +935,11 @@ static int run_oz(bo_ctx *ctx, const ScoreRequest &rq, OzLevels lv, int depth, c
     if (rescue && M > (int64_t)0x7fffffff)
         return bo_set_err(ctx, BO_ERR_ARG, "int8 path: at most 2^31 - 1 candidates per call (the rescue list holds 32-bit indices)");
     if (!rescue) lv.first = lv.rest;
-    const int64_t nchunk = (M + chunk - 1) / chunk;
+    // candidate chunks: [0, first_size), then steps of `chunk`; the pilot chunk of a tiered pass is short (a pilot that
+    // fails has its flagged candidates re-scored one level up: 4096 of them at most, and 32 candidate tiles x np / 64
+    // row blocks still fill the machine)
+    const int64_t first_size = (lv.first < lv.rest && OZ_PILOT_CANDIDATES < chunk) ? OZ_PILOT_CANDIDATES : chunk;
+    const int64_t nchunk = M <= first_size ? 1 : 1 + (M - first_size + chunk - 1) / chunk;
     const int64_t nblocks_total = nchunk * ((chunk + 255) / 256);
     if (need_best) BO_TRY(reserve_blocks(ctx, (size_t)(nblocks_total > ARGMAX_PASS_BLOCKS ? nblocks_total : ARGMAX_PASS_BLOCKS) + 8));
     double **errest_p = depth ? &ctx->dErrEst2 : &ctx->dErrEst;
@@ -965,9 +970,11 @@ static int run_oz(bo_ctx *ctx, const ScoreRequest &rq, OzLevels lv, int depth, c
     const int S_buf = lv_S(lv.first) > lv_S(lv.rest) ? lv_S(lv.first) : lv_S(lv.rest);
     BO_TRY(bo_ozaki_reserve(ctx, S_buf, (int)cap, nitems > 1 ? 2 : 1));
     auto item = [&](int64_t w, int64_t &c0, int &mc, int &mcp, int &s) {
-        c0 = (w / S) * chunk;
+        const int64_t ci = w / S;
+        c0 = ci == 0 ? 0 : first_size + (ci - 1) * chunk;
         s = (int)(w % S);
-        mc = (int)((M - c0) < chunk ? (M - c0) : chunk);
+        const int64_t len = ci == 0 ? first_size : chunk;
+        mc = (int)((M - c0) < len ? (M - c0) : len);
         mcp = bo_round_up(mc, 128);
     };
     auto level_of = [&](int64_t w) { return (w / S) == 0 ? lv.first : lv.rest; };
@@ -1147,8 +1154,8 @@ static int run_oz(bo_ctx *ctx, const ScoreRequest &rq, OzLevels lv, int depth, c
     // level (lv.rest, or everything when the pass ran at one level) left over.
     {
         double frac;
-        if (pilot_count >= 0 && lv.rest != lv.first && M > chunk)
-            frac = (double)(count - (pilot_count < count ? pilot_count : count)) / (double)(M - chunk);
+        if (pilot_count >= 0 && lv.rest != lv.first && M > first_size)
+            frac = (double)(count - (pilot_count < count ? pilot_count : count)) / (double)(M - first_size);
         else if (pilot_count >= 0 && lv.rest == lv.first && lv.tier2 > 0)
             frac = (double)to_fp64 / (double)M;         // whole pass below the selected level: judge by what reached FP64
         else
@@ -1182,7 +1189,7 @@ int bo_score_run(bo_ctx *ctx, const ScoreRequest &rq) {
     if (!pinned && ctx->oz_rescue && ctx->oz_tiered) {
         const int L2 = L_sel + 1;                                   // one step up for the flagged list
         if (lv_S(L2) <= 7 && (int64_t)ctx->np * lv_S(L2) < (1 << 17)) lv.tier2 = L2;
-        // (a pilot that fails has its whole chunk re-scored one level up: bounded at ~1/16 of the pass)
+        // (a pilot that fails has its 4096 candidates re-scored one level up: < 2 % of a pass of this length)
         if (L_sel - 1 >= 6 && rq.M >= OZ_TIER_MIN_CHUNKS * oz_chunk_candidates() && lv.tier2 > 0) lv.first = L_sel - 1;
     }
     BO_TRY(bo_ozaki_prepare(ctx, lv.tier2 > 0 ? lv_S(lv.tier2) : oz_S));

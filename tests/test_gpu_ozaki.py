@@ -119,7 +119,7 @@ def test_ozaki_slice_count_follows_tolerance(ctx):
 
 def test_full_size_headline_shape_int8_vs_fp64_and_oracle(ctx):
     """BASELINE headline shape (RBF n=4096, d=8, EI) at bench.py's default tolerance (1e-8 -> 5 base-256
-    slices, 15 digit pairs): the int8-slice path against the FP64 path on 2^18 candidates (many
+    slices selected, tiers on): the int8-slice path against the FP64 path on 2^18 candidates (many
     32768-candidate chunks) and against the oracle on a slice; identical arg max and top-10."""
     gp = synth(4096, 8, "se", seed=0)
     ctx.fit("se", gp.X, gp.Y, gp.ell[None], [gp.rho], [gp.sn2], [gp.bias])
@@ -130,7 +130,10 @@ def test_full_size_headline_shape_int8_vs_fp64_and_oracle(ctx):
     ctx.set_precision(1, 1e-8)
     val, _, best = ctx.score(1, target, Xc, want_best=True)
     top8 = ctx.topk(10)
-    assert ctx.precision_info() == (1, 5, False)
+    # 1e-8 selects 5 slices; a pass of >= 8 chunks pilots 4096 candidates one half-level down (4 slices + extra) and
+    # keeps that level when at most 10 % of them are flagged (test_gpu_rescue.py::test_tiered_levels... pins each case)
+    t = ctx.tier_info()
+    assert ctx.precision_info()[0] == 1 and t["first"] == (4, True) and t["rest"] in ((4, True), (5, False)), t
     assert rel_err(val, f64val) < 2.5e-7                # measured: 4.9e-8 over 2^20 candidates; floor 1e-12 max
     assert best[1] == f64best[1] and np.array_equal(top8[0], top64[0])
     sl = slice(32700, 32900)

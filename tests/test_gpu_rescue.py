@@ -149,7 +149,7 @@ def test_rescue_pass_reports_and_repairs(ctx):
 
 
 def test_tiered_levels_headline_shape_vs_fp64_and_oracle(ctx):
-    """Passes of >= 16 chunks run their first chunk one half-level below the level the tolerance selects and, if at
+    """Passes of >= 8 chunks run their first 4096 candidates one half-level below the level the tolerance selects and, if at
     most 10 % of it is flagged there, the rest too; the flagged list is re-scored on the int8 path at the selected
     level before FP64 takes what is left.  Every combination of tiers must meet the same 1e-6 against the FP64 path
     (and the oracle on a slice) with identical arg max and top-10: the tiers only decide the speed."""

@@ -43,7 +43,7 @@ ctx.set_rescue(True, 1e-12, 1e-12)
 ctx.score(2, target, Xbig, want_best=True)
 print("rescue (everything flagged)", ctx.rescue_info())
 ctx.set_rescue(True)
-# tiers of the int8 path (sanitize.sh shrinks the chunks with BO_OZ_CHUNK_TILES so that 2^14 candidates are >= 16 chunks):
+# tiers of the int8 path (sanitize.sh shrinks the chunks with BO_OZ_CHUNK_TILES so that 2^14 candidates are >= 8 chunks):
 # pilot passes -> whole pass one half-level down; pilot fails -> mixed levels; flagged list one tier up, then FP64
 ctx.set_precision(1, 1e-8)
 ctx.set_option("oz_tier_min", 1)
