@@ -550,7 +550,7 @@ def our_arm(args):
 
     if level["path"] != "fp64":
         dtype = ("int8 slices: %d balanced base-256 digits per operand%s, exact int32 accumulation on tcgen05, f64 reassembly; "
-                 "f64 mean; candidates whose a-priori error bound exceeds 2.5e-7 re-scored%s in f64"
+                 "f64 mean; candidates whose a-priori error bound exceeds 5e-7 re-scored%s in f64"
                  % (level["slices"], " + first dropped pair group" if level["extra_group"] else "",
                     " with %d digits, what that cannot certify" % level["flagged_rescored_at"]["slices"] if level.get("flagged_rescored_at") else ""))
     else:

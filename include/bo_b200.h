@@ -141,7 +141,8 @@ int bo_set_precision(bo_ctx *ctx, int prec, double tol);
  * bound on the error the slice truncation leaves in its acquisition value (bo_predict: in s2);
  * candidates whose bound exceeds tol * max(|value|, floor_rel * max|value|) are re-scored on the
  * FP64 path inside the same call, so the int8 path meets `tol` wherever the FP64 path does.
- * Defaults: tol = 2.5e-7 (4x inside the 1e-6 parity bar), floor_rel = 1e-12.  A pass that has
+ * Defaults: tol = 5e-7 (2x inside the 1e-6 parity bar; the bound itself sits > 2.3x above the largest error the
+ * calibration has seen, profiles/r2_oz_calib.txt), floor_rel = 1e-12.  A pass that has
  * to rescue more than a quarter of its candidates sends the following passes on this fit
  * straight to the FP64 path.
  * Tiers (tolerance-selected levels only; a level pinned with tol >= 2 runs exactly as pinned): a flagged list of

@@ -356,7 +356,7 @@ class Context(object):
         """Tuning knobs that do not change results (bo_set_option), e.g. ("oz_cluster", 2)."""
         self._check(self._lib.bo_set_option(self._h, key.encode(), float(value)))
 
-    def set_rescue(self, on=True, tol=2.5e-7, floor_rel=1e-12):
+    def set_rescue(self, on=True, tol=5e-7, floor_rel=1e-12):
         """FP64 rescue pass of the int8-slice path (bo_set_rescue)."""
         self._check(self._lib.bo_set_rescue(self._h, 1 if on else 0, float(tol), float(floor_rel)))
 

@@ -167,7 +167,7 @@ struct bo_ctx {
     // -> compact FP64 re-score -> scatter
     int oz_cluster = 0;                 // CTAs per cluster of the scoring contraction (0: library default)
     bool oz_rescue = true;
-    double oz_rescue_tol = 2.5e-7;      // flag when the bound exceeds tol * max(|value|, floor * max |value|)
+    double oz_rescue_tol = 5e-7;        // flag when the bound exceeds tol * max(|value|, floor * max |value|): 2x inside the 1e-6 bar
     double oz_rescue_floor = 1e-12;
     double oz_demote_frac = 0.25;       // a pass that rescues more than this fraction sends later passes to FP64
     bool oz_demoted = false;

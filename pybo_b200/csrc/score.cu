@@ -917,7 +917,7 @@ static int64_t oz_chunk_candidates() {
 //   3. depth 0, long list, a higher level available: re-score the list on this same path at lv.tier2 (depth 1), which
 //      hands what it still cannot certify to the FP64 path; otherwise the FP64 path takes the list directly
 //   4. scatter back
-// Because every candidate that is not certified at 2.5e-7 is re-scored, the level of step 1 only decides the SPEED.
+// Because every candidate that is not certified at the rescue tolerance (5e-7) is re-scored, the level of step 1 only decides the SPEED.
 // With lv.first < lv.rest (bo_score_run: one half-level below the level the tolerance selects) chunk 0 runs at the
 // lower level and its flagged fraction decides the level of the other chunks: <= oz_tier_frac -> they run at the
 // lower level too (2 of 15 digit-pair products saved at the headline shape), else at lv.rest.

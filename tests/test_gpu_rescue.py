@@ -126,7 +126,7 @@ def test_rescue_pass_reports_and_repairs(ctx):
     target = float(gp.predict(X)[0].max())
     ref = gp.get_improvement(target, Xc)
     ctx.set_precision(1, 4.0)
-    ctx.set_rescue(True, 2.5e-7, 1e-12)
+    ctx.set_rescue(True, 5e-7, 1e-12)
     val, _, best = ctx.score(1, target, Xc, want_best=True)
     ran8, rescued, total = ctx.rescue_info()
     assert ran8 and total == len(Xc) and 0 < rescued
@@ -178,7 +178,7 @@ def test_tiered_levels_headline_shape_vs_fp64_and_oracle(ctx):
         t = ctx.tier_info()
         seen[label] = t
         assert ctx.rescue_info()[0], label
-        assert rel_err(val, ref) < 2.5e-7, (label, t)
+        assert rel_err(val, ref) < 5e-7, (label, t)                # the rescue tolerance: what the path certifies
         assert rel_err(val[sl], oref) < TOL, (label, t)
         assert best[1] == rbest[1] and np.array_equal(ctx.topk(10)[0], rtop), (label, t)
     for k, v in dict(oz_tiered=1, oz_tier_frac=0.10, oz_tier_min=4096).items():

@@ -14,11 +14,14 @@ def main():
     ap.add_argument("--levels", default="4.0,4.5,5.0")
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--tiered", type=int, default=1)
+    ap.add_argument("--rescue-tol", type=float, default=0.0)
     a = ap.parse_args()
     args = argparse.Namespace(gpus=1)
     h = bench.Harness(args)
     w = bench.ScoringWorkload(h, a.workload)
     w.ctx.set_option("oz_tiered", a.tiered)
+    if a.rescue_tol > 0:
+        w.ctx.set_rescue(True, a.rescue_tol, 1e-12)
     for lv in [float(x) for x in a.levels.split(",") if x] + [1e-8]:
         w.set_path("ozaki", lv)
         for _ in range(2):
