@@ -160,7 +160,8 @@ int bo_rescue_info(bo_ctx *ctx, int *int8_path, int64_t *flagged, int64_t *total
  * (= bo_rescue_info's `flagged`).  All zero after a pass on the FP64 path. */
 int bo_tier_info(bo_ctx *ctx, int *level_first, int *level_rest, int *level_tier2, int64_t *first_flagged,
                  int64_t *fp64_rescored);
-/* tuning knobs that do not change results.  "oz_cluster": CTAs per thread-block cluster of the int8 scoring
+/* tuning knobs ("oz_cluster" leaves the results bit-identical, the tier knobs keep them within the rescue tolerance).
+ * "oz_cluster": CTAs per thread-block cluster of the int8 scoring
  * contraction (1, 2 or 4; 0 = library default): the CTAs of a cluster work on the same candidate tile and adjacent row
  * blocks of W and fetch the K* slice tile once, by TMA multicast.  "oz_tiered" (0 / 1, default 1), "oz_tier_frac"
  * (default 0.10), "oz_tier_min" (default 4096): the tiers described at bo_set_rescue (results stay within the rescue
