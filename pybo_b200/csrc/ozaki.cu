@@ -933,14 +933,29 @@ oz_score_kernel(const __grid_constant__ CUtensorMap tmapB, OzParams p) {
 
 // s2 = rho - sum_rb qpart (int8 contraction); mu = bias + rho * sum_blocks mupart (FP64 dot product
 // kappa . beta accumulated by the slicer); both in a fixed summation order
-__global__ void oz_moments_kernel(int nb, int nmu, int mcp, const double *__restrict__ qpart,
-                                  const double *__restrict__ mupart, double rho, double bias,
-                                  double *__restrict__ mu, double *__restrict__ s2) {
+// (the column sums keep their fixed order; the loads of 16 partials are issued together so that each thread has 16
+//  requests in flight instead of one dependent load per addition)
+__device__ __forceinline__ double oz_sum_ordered(const double *__restrict__ p, int n, int64_t stride) {
+    double acc = 0.0;
+    int i = 0;
+    for (; i + 16 <= n; i += 16) {
+        double v[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) v[k] = p[(int64_t)(i + k) * stride];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) acc += v[k];
+    }
+    for (; i < n; ++i) acc += p[(int64_t)i * stride];
+    return acc;
+}
+
+__global__ void __launch_bounds__(128)
+oz_moments_kernel(int nb, int nmu, int mcp, const double *__restrict__ qpart, const double *__restrict__ mupart, double rho,
+                  double bias, double *__restrict__ mu, double *__restrict__ s2) {
     const int m = blockIdx.x * blockDim.x + threadIdx.x;
     if (m >= mcp) return;
-    double q = 0.0, pm = 0.0;
-    for (int i = 0; i < nb; ++i) q += qpart[(int64_t)i * mcp + m];
-    for (int i = 0; i < nmu; ++i) pm += mupart[(int64_t)i * mcp + m];
+    const double q = oz_sum_ordered(qpart + m, nb, mcp);
+    const double pm = oz_sum_ordered(mupart + m, nmu, mcp);
     mu[m] = fma(rho, pm, bias);
     s2[m] = rho - q;
 }
@@ -1291,7 +1306,7 @@ int bo_ozaki_contract(bo_ctx *ctx, int s, int S, bool extra, int mcp, int buf, d
     }
     {
         BO_LAUNCH(ctx, "oz_moments_kernel");
-        oz_moments_kernel<<<(mcp + 255) / 256, 256, 0, ctx->stream>>>(
+        oz_moments_kernel<<<(mcp + 127) / 128, 128, 0, ctx->stream>>>(
             2 * nb, ctx->oz_mu_rows[buf], mcp, ctx->dOzQ, ctx->dOzMu + (size_t)buf * ctx->ozmu_stride, ctx->h_rho[s],
             ctx->h_bias[s], mu, s2);
         BO_CHECK_LAUNCH(ctx);
